@@ -1,0 +1,113 @@
+/*
+ * splat_b200.h — C ABI of the B200-native (sm_100a) differentiable Gaussian-splat rasterizer.
+ *
+ * Drop-in boundary for the native module the reference imports at
+ * gaussian_renderer/__init__.py:14 (`from diff_gaussian_rasterization import ...`): that package's
+ * `_C.rasterize_gaussians`, `_C.rasterize_gaussians_backward` and `_C.mark_visible` (third-party
+ * ingra14m/depth-diff-gaussian-rasterization @ f2d8fa9, pinned at reference README.md:28; call sites
+ * gaussian_renderer/__init__.py:94-102 and :106-114; surface restated in SURVEY.md §8b).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to contiguous fp32 (unless typed otherwise) on the device that is
+ *    current when the call is made; `stream` is a cudaStream_t passed as void* (NULL = legacy default);
+ *  - matrices are the reference's row-vector tensors (scene/cameras.py:68-73): m[4*c + r] = element (r,c);
+ *  - scratch memory is owned by the CALLER: the library asks for it through `sfb_alloc_fn` callbacks, the
+ *    same contract as the external rasterizer's std::function<char*(size_t)> resize lambdas, so that the
+ *    host framework (torch) owns every byte and the three buffers can live in an autograd ctx;
+ *  - every entry point returns 0 on success, a negative code on error (sfb_last_error() has the text).
+ *    There is no CPU fallback: a missing/failed GPU is an error.
+ */
+#ifndef SPLAT_B200_H
+#define SPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Must return a device pointer to at least `bytes` bytes, 256-byte aligned, valid until the caller
+ * releases the buffer it belongs to (after backward).  Called at most once per buffer per forward. */
+typedef void* (*sfb_alloc_fn)(void* user, size_t bytes);
+
+#define SFB_OK 0
+#define SFB_ERR_CUDA -1
+#define SFB_ERR_ARG -2
+#define SFB_ERR_ALLOC -3
+
+/* ABI version of this header; bumped on any signature change. */
+int sfb_abi_version(void);
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* sfb_last_error(void);
+
+/* Forward.  Replaces _C.rasterize_gaussians (reference call site
+ * gaussian_renderer/__init__.py:94-102).
+ *   P                 number of Gaussians;  sh_degree active degree (0..3);  M = coefficients per Gaussian
+ *                     in `shs` ([P][M][3]);  exactly one of shs / colors_precomp ([P][3]) is non-NULL;
+ *                     exactly one of (scales [P][3], rotations [P][4]) / cov3D_precomp ([P][6]) is non-NULL
+ *   opacities [P]     bg [3]   viewmatrix, projmatrix [16]   campos [3]
+ *   out_color [3][H][W]   out_depth [1][H][W]   radii [P] (int32)      — caller-allocated outputs
+ *   geom/binning/img  scratch allocators; the returned base pointers + *num_rendered must be handed to
+ *                     sfb_rasterize_backward unchanged.
+ * One blocking 4-byte device->host read (num_rendered) per call, like the reference. */
+int sfb_rasterize_forward(
+    int P, int sh_degree, int M, int W, int H,
+    const float* bg, const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier, const float* rotations,
+    const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, int prefiltered,
+    float* out_color, float* out_depth, int* radii,
+    sfb_alloc_fn geom_alloc, void* geom_user,
+    sfb_alloc_fn binning_alloc, void* binning_user,
+    sfb_alloc_fn img_alloc, void* img_user,
+    int* num_rendered, int debug, void* stream);
+
+/* Backward.  Replaces _C.rasterize_gaussians_backward.  dL_dout_color [3][H][W] is the
+ * cotangent of out_color.  Outputs (all caller-allocated, fully written by the call — no pre-zeroing
+ * needed): dL_dmeans2D [P][3] (xy = gradient w.r.t. the NDC-scaled screen mean, z = 0; this is what
+ * lands in viewspace_points.grad, scene/gaussian_model.py:429), dL_dcolors [P][3], dL_dopacity [P][1],
+ * dL_dmeans3D [P][3], dL_dcov3D [P][6], dL_dsh [P][M][3] (may be NULL when shs is NULL),
+ * dL_dscales [P][3], dL_drotations [P][4] (may be NULL when cov3D_precomp is given). */
+int sfb_rasterize_backward(
+    int P, int sh_degree, int M, int num_rendered, int W, int H,
+    const float* bg, const float* means3D, const float* shs, const float* colors_precomp,
+    const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, const int* radii,
+    void* geom_buffer, void* binning_buffer, void* img_buffer,
+    const float* dL_dout_color,
+    float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D, float* dL_dcov3D,
+    float* dL_dsh, float* dL_dscales, float* dL_drotations,
+    int debug, void* stream);
+
+/* Replaces _C.mark_visible: present[i] = 1 iff the view-space z of means3D[i] is > 0.2. */
+int sfb_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream);
+
+/* Inspection of the opaque scratch buffers (parity tests compare these with the oracle bit-for-bit).
+ * Each output may be NULL.  means2D [P][2], depths [P], cov3D [P][6], conic_opacity [P][4], rgb [P][3],
+ * clamped [P][3] (uint8), tiles_touched [P] (uint32).  */
+int sfb_export_geom(int P, const void* geom_buffer, float* means2D, float* depths, float* cov3D,
+                    float* conic_opacity, float* rgb, uint8_t* clamped, uint32_t* tiles_touched, void* stream);
+/* point_list_keys [R] (uint64: tile<<32 | depth bits), point_list [R] (uint32), ranges [T][2] (uint32). */
+int sfb_export_binning(int P, int num_rendered, int W, int H, const void* geom_buffer,
+                       const void* binning_buffer, uint64_t* point_list_keys, uint32_t* point_list,
+                       uint32_t* ranges, void* stream);
+/* final_T [H][W], n_contrib [H][W] (uint32; position+1 of the last contributor in the tile list). */
+int sfb_export_img(int W, int H, const void* img_buffer, float* final_T, uint32_t* n_contrib, void* stream);
+
+/* Per-stage device timing with CUDA events recorded on the launching stream (bench.py's roofline leg).
+ * which = 0: forward stages, 1: backward stages.  sfb_profile_read waits for the stage events of the last
+ * call made with profiling enabled and writes their durations (ms); returns the number of stages. */
+void sfb_profile_enable(int on);
+int sfb_profile_read(int which, float* ms, int max_stages);
+const char* sfb_profile_stage_name(int which, int stage);
+
+/* Number of kernel launches issued by the last forward / backward on the calling thread. */
+int sfb_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLAT_B200_H */

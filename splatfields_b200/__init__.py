@@ -1,0 +1,7 @@
+"""splatfields_b200 — B200-native (sm_100a) differentiable Gaussian-splat rasterizer: a drop-in for the
+`diff_gaussian_rasterization` extension behind the reference's gaussian_renderer.render().
+See DESIGN.md for the path, the boundary and the kernels."""
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians  # noqa: F401
+from .renderer import render  # noqa: F401
+
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "render"]

@@ -1,0 +1,99 @@
+"""ctypes binding of libsplat_b200.so (the C ABI in include/splat_b200.h).
+
+There is deliberately NO fallback: if the library is missing or does not load, importing the product
+path raises.  (The CPU oracle under oracle/ is test infrastructure and is never imported from here.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsplat_b200.so")
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+_lib = None
+
+# every symbol include/splat_b200.h declares
+SYMBOLS = (
+    "sfb_abi_version", "sfb_last_error", "sfb_rasterize_forward", "sfb_rasterize_backward", "sfb_mark_visible",
+    "sfb_export_geom", "sfb_export_binning", "sfb_export_img", "sfb_last_launch_count",
+    "sfb_profile_enable", "sfb_profile_read", "sfb_profile_stage_name",
+)
+
+
+class SplatB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the library; raise loudly when it has not been built (python -m splatfields_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SplatB200Error(
+            f"{LIB_PATH} not found: build it with `python -m splatfields_b200.build` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the rasterizer.")
+    lib = C.CDLL(LIB_PATH)
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    lib.sfb_abi_version.restype = ci
+    lib.sfb_last_error.restype = C.c_char_p
+    lib.sfb_last_launch_count.restype = ci
+    lib.sfb_rasterize_forward.restype = ci
+    lib.sfb_rasterize_forward.argtypes = [
+        ci, ci, ci, ci, ci,                       # P, sh_degree, M, W, H
+        vp, vp, vp, vp, vp, vp, cf, vp, vp,       # bg, means3D, shs, colors, opacities, scales, mod, rot, cov3D
+        vp, vp, vp, cf, cf, ci,                   # view, proj, campos, tanfovx, tanfovy, prefiltered
+        vp, vp, vp,                               # out_color, out_depth, radii
+        ALLOC_FN, vp, ALLOC_FN, vp, ALLOC_FN, vp,
+        C.POINTER(ci), ci, vp]
+    lib.sfb_rasterize_backward.restype = ci
+    lib.sfb_rasterize_backward.argtypes = [
+        ci, ci, ci, ci, ci, ci,                   # P, sh_degree, M, R, W, H
+        vp, vp, vp, vp, vp, cf, vp, vp,           # bg, means3D, shs, colors, scales, mod, rot, cov3D
+        vp, vp, vp, cf, cf, vp,                   # view, proj, campos, tanfovx, tanfovy, radii
+        vp, vp, vp, vp,                           # geom, binning, img, dL_dout_color
+        vp, vp, vp, vp, vp, vp, vp, vp,           # 8 gradient outputs
+        ci, vp]
+    lib.sfb_mark_visible.restype = ci
+    lib.sfb_mark_visible.argtypes = [ci, vp, vp, vp, vp, vp]
+    lib.sfb_export_geom.restype = ci
+    lib.sfb_export_geom.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.sfb_export_binning.restype = ci
+    lib.sfb_export_binning.argtypes = [ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
+    lib.sfb_export_img.restype = ci
+    lib.sfb_export_img.argtypes = [ci, ci, vp, vp, vp, vp]
+    lib.sfb_profile_enable.restype = None
+    lib.sfb_profile_enable.argtypes = [ci]
+    lib.sfb_profile_read.restype = ci
+    lib.sfb_profile_read.argtypes = [ci, C.POINTER(cf), ci]
+    lib.sfb_profile_stage_name.restype = C.c_char_p
+    lib.sfb_profile_stage_name.argtypes = [ci, ci]
+    if lib.sfb_abi_version() != 1:
+        raise SplatB200Error("libsplat_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().sfb_last_error().decode("utf-8", "replace")
+        if rc == -2:
+            raise Exception(msg)   # argument errors surface like the reference's Python exceptions
+        raise SplatB200Error(f"libsplat_b200 error {rc}: {msg}")
+
+
+def profile_enable(on: bool):
+    load().sfb_profile_enable(int(bool(on)))
+
+
+def profile_read(which: int) -> dict:
+    """{stage name: ms} of the last forward (which=0) / backward (which=1) run with profiling enabled."""
+    lib = load()
+    buf = (C.c_float * 8)()
+    n = lib.sfb_profile_read(which, buf, 8)
+    if n < 0:
+        check(n)
+    return {lib.sfb_profile_stage_name(which, i).decode(): float(buf[i]) for i in range(n)}

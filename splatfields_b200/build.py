@@ -1,0 +1,65 @@
+"""In-tree build of libsplat_b200.so (sm_100a only) with plain nvcc — no torch types in the library.
+
+`python -m splatfields_b200.build` or `__graft_entry__.build()`.  The .so lands next to the sources
+(git-ignored, but it travels to the GPU box with the gpurun snapshot).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(CSRC, "build")
+LIB = os.path.join(HERE, "libsplat_b200.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# per-file extra flags: the preprocess kernel's float math feeds integer tile keys and must be
+# bit-reproducible against the CPU oracle -> no implicit FMA contraction there.
+EXTRA = {"preprocess.cu": ["-fmad=false"]}
+SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "render_fwd.cu", "render_bwd.cu", "geom_bwd.cu"]
+
+
+def nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale(out: str, deps) -> bool:
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(BUILD, exist_ok=True)
+    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "splat_b200.h"), __file__]
+    objs = []
+    for src in SOURCES:
+        sp = os.path.join(CSRC, src)
+        op = os.path.join(BUILD, src.replace(".cu", ".o"))
+        objs.append(op)
+        if force or _stale(op, [sp] + hdrs):
+            cmd = [nvcc()] + ARCH + COMMON + EXTRA.get(src, []) + ["-c", sp, "-o", op]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            log = os.path.join(BUILD, src + ".ptxas.log")
+            with open(log, "w") as f:
+                f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+            if verbose or r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {src}")
+    if force or _stale(LIB, objs):
+        cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

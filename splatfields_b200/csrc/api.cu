@@ -1,0 +1,328 @@
+// api.cu — the C ABI declared in include/splat_b200.h: host-side orchestration of the kernels.
+// Mirrors the control flow of the external rasterizer's forward/backward entry points
+// (SURVEY.md §3.2-3.3): preprocess -> [R to host] -> binning -> render ; render-bwd -> geometry-bwd.
+#include "../../include/splat_b200.h"
+#include "common.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int g_launches = 0;
+thread_local uint32_t* g_pinned = nullptr;  // pinned word the num_rendered counter is copied into
+thread_local cudaEvent_t g_evt = nullptr;
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+  char buf[512];
+  if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+  else snprintf(buf, sizeof(buf), "%s", what);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                        \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) return fail(SFB_ERR_CUDA, #call, e__);      \
+  } while (0)
+
+#define CK_LAUNCH(name, dbg, s)                                                     \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ == cudaSuccess && (dbg)) e__ = cudaStreamSynchronize(s);                \
+    if (e__ != cudaSuccess) return fail(SFB_ERR_CUDA, "kernel " name, e__);         \
+  } while (0)
+
+// ---- optional per-stage device timing (CUDA events on the launching stream) ----
+constexpr int MAX_STAGES = 8;
+const char* kFwdStages[] = {"preprocess", "depth_sort", "instance_scan", "duplicate", "tile_sort", "tile_ranges",
+                            "render_forward"};
+const char* kBwdStages[] = {"zero_grad_acc", "render_backward", "geom_backward"};
+thread_local bool g_prof = false;
+thread_local cudaEvent_t g_ev[2][MAX_STAGES][2];
+thread_local bool g_ev_made = false;
+thread_local bool g_ev_used[2][MAX_STAGES];
+
+void prof_begin(int which, int stage, cudaStream_t s) {
+  if (!g_prof) return;
+  if (!g_ev_made) {
+    for (int w = 0; w < 2; w++)
+      for (int i = 0; i < MAX_STAGES; i++) { cudaEventCreate(&g_ev[w][i][0]); cudaEventCreate(&g_ev[w][i][1]); }
+    g_ev_made = true;
+  }
+  if (stage == 0) for (int i = 0; i < MAX_STAGES; i++) g_ev_used[which][i] = false;
+  cudaEventRecord(g_ev[which][stage][0], s);
+  g_ev_used[which][stage] = true;
+}
+void prof_end(int which, int stage, cudaStream_t s) {
+  if (g_prof) cudaEventRecord(g_ev[which][stage][1], s);
+}
+
+int tile_sort_final(int T) {
+  int bits = sfb::tile_bits(T);
+  int npass = (bits + 7) / 8;
+  return npass & 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sfb_abi_version(void) { return 1; }
+const char* sfb_last_error(void) { return g_err.c_str(); }
+int sfb_last_launch_count(void) { return g_launches; }
+
+int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float* bg, const float* means3D,
+                          const float* shs, const float* colors_precomp, const float* opacities,
+                          const float* scales, float scale_modifier, const float* rotations,
+                          const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                          const float* campos, float tan_fovx, float tan_fovy, int prefiltered,
+                          float* out_color, float* out_depth, int* radii, sfb_alloc_fn geom_alloc,
+                          void* geom_user, sfb_alloc_fn binning_alloc, void* binning_user, sfb_alloc_fn img_alloc,
+                          void* img_user, int* num_rendered, int debug, void* stream) {
+  using namespace sfb;
+  g_err.clear();
+  g_launches = 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (num_rendered) *num_rendered = 0;
+  if (P < 0 || W <= 0 || H <= 0) return fail(SFB_ERR_ARG, "bad sizes");
+  if (!out_color || !out_depth || !bg || !geom_alloc || !binning_alloc || !img_alloc)
+    return fail(SFB_ERR_ARG, "null output / allocator");
+  const size_t HW = (size_t)H * W;
+  if (P == 0) {  // like the reference: nothing is launched, outputs are zero-filled
+    CK(cudaMemsetAsync(out_color, 0, 3 * HW * sizeof(float), s));
+    CK(cudaMemsetAsync(out_depth, 0, HW * sizeof(float), s));
+    return SFB_OK;
+  }
+  if (!means3D || !opacities || !viewmatrix || !projmatrix || !campos || !radii)
+    return fail(SFB_ERR_ARG, "null input");
+  if ((shs == nullptr) == (colors_precomp == nullptr))
+    return fail(SFB_ERR_ARG, "Please provide exactly one of either SHs or precomputed colors!");
+  const bool has_sr = scales != nullptr && rotations != nullptr;
+  if (has_sr == (cov3D_precomp != nullptr) || (scales == nullptr) != (rotations == nullptr))
+    return fail(SFB_ERR_ARG, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+  if (shs && (sh_degree < 0 || sh_degree > 3 || M < (sh_degree + 1) * (sh_degree + 1)))
+    return fail(SFB_ERR_ARG, "sh_degree / M mismatch (degree 0..3, M >= (degree+1)^2)");
+  const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y, T = gx * gy;
+  if (gx > 65535 || gy > 65535) return fail(SFB_ERR_ARG, "image too large for packed tile rectangles");
+
+  if (!g_pinned) CK(cudaHostAlloc((void**)&g_pinned, 64, cudaHostAllocDefault));
+  if (!g_evt) CK(cudaEventCreateWithFlags(&g_evt, cudaEventDisableTiming));
+
+  char* gchunk = (char*)geom_alloc(geom_user, GeomState::required((size_t)P));
+  if (!gchunk) return fail(SFB_ERR_ALLOC, "geometry buffer allocation failed");
+  GeomState g = GeomState::from_chunk(gchunk, (size_t)P);
+  char* ichunk = (char*)img_alloc(img_user, ImgState::required(HW));
+  if (!ichunk) return fail(SFB_ERR_ALLOC, "image buffer allocation failed");
+  ImgState img = ImgState::from_chunk(ichunk, HW);
+
+  FwdParams fp;
+  fp.P = P; fp.D = sh_degree; fp.M = M; fp.W = W; fp.H = H;
+  fp.bg = bg; fp.means3D = means3D; fp.shs = shs; fp.colors_precomp = colors_precomp; fp.opacities = opacities;
+  fp.scales = scales; fp.rotations = rotations; fp.cov3D_precomp = cov3D_precomp;
+  fp.viewmatrix = viewmatrix; fp.projmatrix = projmatrix; fp.campos = campos;
+  fp.scale_modifier = scale_modifier; fp.tan_fovx = tan_fovx; fp.tan_fovy = tan_fovy; fp.prefiltered = prefiltered;
+
+  // K1 (+ num_rendered reduction) ; the 4-byte read-back is issued right behind it so that the host
+  // wait overlaps the depth sort instead of draining the whole pipeline.
+  prof_begin(0, 0, s);
+  CK(cudaMemsetAsync(g.counters, 0, 8 * sizeof(uint32_t), s));
+  launch_preprocess(fp, g, radii, s);
+  prof_end(0, 0, s);
+  g_launches++;
+  CK_LAUNCH("preprocess", debug, s);
+  CK(cudaMemcpyAsync(g_pinned, g.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(g_evt, s));
+
+  // stage 1: stable sort of the Gaussians by depth bits (culled ones carry 0xFFFFFFFF and sink)
+  prof_begin(0, 1, s);
+  int dfinal = radix_sort_pairs(g.depth_key, g.depth_idx, g.sort_hist, P, 32, s, &g_launches);
+  prof_end(0, 1, s);
+  CK_LAUNCH("depth sort", debug, s);
+  const uint32_t* sorted_idx = g.depth_idx[dfinal];
+  prof_begin(0, 2, s);
+  launch_instance_block_sums(P, sorted_idx, g.tiles_touched, g.block_sums, s);
+  prof_end(0, 2, s);
+  g_launches += 2;
+  CK_LAUNCH("instance scan", debug, s);
+
+  CK(cudaEventSynchronize(g_evt));
+  const uint32_t R = *g_pinned;
+  if (R > 0x7FFFFFFFu) return fail(SFB_ERR_ARG, "num_rendered overflows int32");
+  if (num_rendered) *num_rendered = (int)R;
+
+  char* bchunk = (char*)binning_alloc(binning_user, BinState::required((size_t)R, (size_t)T));
+  if (!bchunk) return fail(SFB_ERR_ALLOC, "binning buffer allocation failed");
+  BinState b = BinState::from_chunk(bchunk, (size_t)R, (size_t)T);
+
+  int tfinal = 0;
+  if (R > 0) {
+    // stage 2: emit (tile, gaussian) instances in depth order; stage 3: stable sort by tile id
+    prof_begin(0, 3, s);
+    launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, b.tile_key[0], b.inst_idx[0], s);
+    prof_end(0, 3, s);
+    g_launches++;
+    CK_LAUNCH("duplicate", debug, s);
+    prof_begin(0, 4, s);
+    tfinal = radix_sort_pairs(b.tile_key, b.inst_idx, b.sort_hist, (int)R, tile_bits(T), s, &g_launches);
+    prof_end(0, 4, s);
+    CK_LAUNCH("tile sort", debug, s);
+  }
+  prof_begin(0, 5, s);
+  launch_tile_ranges((int)R, T, b.tile_key[tfinal], b.ranges, s);
+  prof_end(0, 5, s);
+  g_launches++;
+  CK_LAUNCH("tile ranges", debug, s);
+
+  prof_begin(0, 6, s);
+  launch_render_forward(W, H, b.ranges, b.inst_idx[tfinal], g.rec, bg, out_color, out_depth, img.final_T,
+                        img.n_contrib, s);
+  prof_end(0, 6, s);
+  g_launches++;
+  CK_LAUNCH("render forward", debug, s);
+  return SFB_OK;
+}
+
+int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W, int H, const float* bg,
+                           const float* means3D, const float* shs, const float* colors_precomp,
+                           const float* scales, float scale_modifier, const float* rotations,
+                           const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                           const float* campos, float tan_fovx, float tan_fovy, const int* radii,
+                           void* geom_buffer, void* binning_buffer, void* img_buffer,
+                           const float* dL_dout_color, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                           float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscales,
+                           float* dL_drotations, int debug, void* stream) {
+  using namespace sfb;
+  g_err.clear();
+  g_launches = 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (P == 0) return SFB_OK;
+  if (P < 0 || W <= 0 || H <= 0 || num_rendered < 0) return fail(SFB_ERR_ARG, "bad sizes");
+  if (!geom_buffer || !binning_buffer || !img_buffer) return fail(SFB_ERR_ARG, "null scratch buffer");
+  if (!dL_dout_color || !dL_dmeans2D || !dL_dcolors || !dL_dopacity || !dL_dmeans3D || !dL_dcov3D)
+    return fail(SFB_ERR_ARG, "null gradient buffer");
+  if (shs && !dL_dsh) return fail(SFB_ERR_ARG, "dL_dsh required with shs");
+  if (!cov3D_precomp && (!dL_dscales || !dL_drotations || !scales || !rotations))
+    return fail(SFB_ERR_ARG, "dL_dscales / dL_drotations required with scales / rotations");
+  const size_t HW = (size_t)H * W;
+  const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y, T = gx * gy;
+  char* gchunk = (char*)geom_buffer;
+  GeomState g = GeomState::from_chunk(gchunk, (size_t)P);
+  char* bchunk = (char*)binning_buffer;
+  BinState b = BinState::from_chunk(bchunk, (size_t)num_rendered, (size_t)T);
+  char* ichunk = (char*)img_buffer;
+  ImgState img = ImgState::from_chunk(ichunk, HW);
+  const int tfinal = num_rendered > 0 ? tile_sort_final(T) : 0;
+
+  prof_begin(1, 0, s);
+  CK(cudaMemsetAsync(g.grad, 0, sizeof(GradRec) * (size_t)P, s));
+  prof_end(1, 0, s);
+  prof_begin(1, 1, s);
+  launch_render_backward(W, H, b.ranges, b.inst_idx[tfinal], g.rec, bg, img.final_T, img.n_contrib,
+                         dL_dout_color, g.grad, s);
+  prof_end(1, 1, s);
+  g_launches++;
+  CK_LAUNCH("render backward", debug, s);
+
+  BwdParams bp;
+  bp.P = P; bp.D = sh_degree; bp.M = M; bp.W = W; bp.H = H;
+  bp.means3D = means3D; bp.shs = shs; bp.colors_precomp = colors_precomp; bp.scales = scales;
+  bp.rotations = rotations; bp.cov3D_precomp = cov3D_precomp;
+  bp.viewmatrix = viewmatrix; bp.projmatrix = projmatrix; bp.campos = campos;
+  bp.scale_modifier = scale_modifier; bp.tan_fovx = tan_fovx; bp.tan_fovy = tan_fovy; bp.radii = radii;
+  bp.dL_dmeans2D = dL_dmeans2D; bp.dL_dcolors = dL_dcolors; bp.dL_dopacity = dL_dopacity;
+  bp.dL_dmeans3D = dL_dmeans3D; bp.dL_dcov3D = dL_dcov3D; bp.dL_dsh = dL_dsh; bp.dL_dscales = dL_dscales;
+  bp.dL_drot = dL_drotations;
+  prof_begin(1, 2, s);
+  launch_geom_backward(bp, g, s);
+  prof_end(1, 2, s);
+  g_launches++;
+  CK_LAUNCH("geometry backward", debug, s);
+  return SFB_OK;
+}
+
+void sfb_profile_enable(int on) { g_prof = on != 0; }
+
+int sfb_profile_read(int which, float* ms, int max_stages) {
+  g_err.clear();
+  if (which < 0 || which > 1 || !ms) return fail(SFB_ERR_ARG, "bad arguments");
+  const int n = which == 0 ? 7 : 3;
+  int out = 0;
+  for (int i = 0; i < n && i < max_stages; i++, out++) {
+    ms[i] = 0.f;
+    if (!g_ev_made || !g_ev_used[which][i]) continue;
+    cudaError_t e = cudaEventSynchronize(g_ev[which][i][1]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms[i], g_ev[which][i][0], g_ev[which][i][1]);
+    if (e != cudaSuccess) return fail(SFB_ERR_CUDA, "profile read", e);
+  }
+  return out;
+}
+
+const char* sfb_profile_stage_name(int which, int stage) {
+  if (which == 0 && stage >= 0 && stage < 7) return kFwdStages[stage];
+  if (which == 1 && stage >= 0 && stage < 3) return kBwdStages[stage];
+  return "";
+}
+
+int sfb_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream) {
+  (void)projmatrix;
+  g_err.clear();
+  if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(SFB_ERR_ARG, "bad arguments");
+  sfb::launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+  CK_LAUNCH("mark_visible", 0, (cudaStream_t)stream);
+  return SFB_OK;
+}
+
+int sfb_export_geom(int P, const void* geom_buffer, float* means2D, float* depths, float* cov3D,
+                    float* conic_opacity, float* rgb, uint8_t* clamped, uint32_t* tiles_touched, void* stream) {
+  using namespace sfb;
+  g_err.clear();
+  if (P <= 0 || !geom_buffer) return fail(SFB_ERR_ARG, "bad arguments");
+  char* gchunk = (char*)geom_buffer;
+  GeomState g = GeomState::from_chunk(gchunk, (size_t)P);
+  launch_export_geom(P, g, means2D, depths, cov3D, conic_opacity, rgb, clamped, tiles_touched, (cudaStream_t)stream);
+  CK_LAUNCH("export_geom", 0, (cudaStream_t)stream);
+  return SFB_OK;
+}
+
+int sfb_export_binning(int P, int num_rendered, int W, int H, const void* geom_buffer,
+                       const void* binning_buffer, uint64_t* point_list_keys, uint32_t* point_list,
+                       uint32_t* ranges, void* stream) {
+  using namespace sfb;
+  g_err.clear();
+  cudaStream_t s = (cudaStream_t)stream;
+  if (P <= 0 || !geom_buffer || !binning_buffer) return fail(SFB_ERR_ARG, "bad arguments");
+  const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y, T = gx * gy;
+  char* gchunk = (char*)geom_buffer;
+  GeomState g = GeomState::from_chunk(gchunk, (size_t)P);
+  char* bchunk = (char*)binning_buffer;
+  BinState b = BinState::from_chunk(bchunk, (size_t)num_rendered, (size_t)T);
+  const int tfinal = num_rendered > 0 ? tile_sort_final(T) : 0;
+  if (point_list_keys)
+    launch_export_keys(num_rendered, b.tile_key[tfinal], b.inst_idx[tfinal], g.rec, point_list_keys, s);
+  if (point_list && num_rendered > 0)
+    CK(cudaMemcpyAsync(point_list, b.inst_idx[tfinal], sizeof(uint32_t) * (size_t)num_rendered,
+                       cudaMemcpyDeviceToDevice, s));
+  if (ranges) CK(cudaMemcpyAsync(ranges, b.ranges, sizeof(uint2) * (size_t)T, cudaMemcpyDeviceToDevice, s));
+  CK_LAUNCH("export_binning", 0, s);
+  return SFB_OK;
+}
+
+int sfb_export_img(int W, int H, const void* img_buffer, float* final_T, uint32_t* n_contrib, void* stream) {
+  using namespace sfb;
+  g_err.clear();
+  cudaStream_t s = (cudaStream_t)stream;
+  if (W <= 0 || H <= 0 || !img_buffer) return fail(SFB_ERR_ARG, "bad arguments");
+  const size_t HW = (size_t)H * W;
+  char* ichunk = (char*)img_buffer;
+  ImgState img = ImgState::from_chunk(ichunk, HW);
+  if (final_T) CK(cudaMemcpyAsync(final_T, img.final_T, sizeof(float) * HW, cudaMemcpyDeviceToDevice, s));
+  if (n_contrib) CK(cudaMemcpyAsync(n_contrib, img.n_contrib, sizeof(uint32_t) * HW, cudaMemcpyDeviceToDevice, s));
+  return SFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+// common.cuh — shared types, scratch-buffer layouts and launch prototypes of the sm_100a rasterizer.
+// Path and boundary: DESIGN.md §1-2; reference surface: SURVEY.md §8b (the external
+// diff_gaussian_rasterization extension imported at gaussian_renderer/__init__.py:14).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace sfb {
+
+constexpr int TILE_X = 16;
+constexpr int TILE_Y = 16;
+constexpr int TILE_PIX = TILE_X * TILE_Y;
+constexpr int NUM_SMS_B200 = 148;
+
+// One record per Gaussian, written by preprocess, gathered (L2-resident) by both render kernels.
+// 48 bytes = three 16-byte loads, always exactly two 32-byte sectors.
+struct __align__(16) SplatRec {
+  float x, y, conA, conB;   // screen mean (pixels), conic A, B
+  float conC, opacity, depth, r;
+  float g, b, pad0, pad1;
+};
+static_assert(sizeof(SplatRec) == 48, "SplatRec must be 48 bytes");
+
+// Per-Gaussian gradient accumulator filled by the backward render (atomics), consumed by the
+// per-Gaussian backward.  Same 48-byte shape so one splat's partials share two sectors.
+struct __align__(16) GradRec {
+  float dx, dy, dA, dB;     // d/d(NDC-scaled mean) x,y ; d/d conic A, B (true derivatives)
+  float dC, dop, dr, dg;    // d/d conic C ; d/d opacity ; d/d rgb
+  float db, pad0, pad1, pad2;
+};
+static_assert(sizeof(GradRec) == 48, "GradRec must be 48 bytes");
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename T>
+__host__ __device__ inline T* carve(char*& p, size_t n) {
+  size_t off = align_up(reinterpret_cast<size_t>(p), 256);
+  T* r = reinterpret_cast<T*>(off);
+  p = reinterpret_cast<char*>(r + n);
+  return r;
+}
+
+// Radix-sort geometry shared by histogram / scatter kernels.
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_IPT = 16;                          // items per thread
+constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;    // items per block
+constexpr int SORT_MAX_BINS = 256;
+__host__ __device__ inline int sort_blocks(int n) { return (n + SORT_TILE - 1) / SORT_TILE; }
+
+// ---- P-sized scratch ("geomBuffer") ----
+struct GeomState {
+  SplatRec* rec;            // [P]
+  float* cov3D;             // [6P]   (kept for the backward; also the precomputed-cov path)
+  uint32_t* tiles_touched;  // [P]
+  uint2* rect;              // [P]    packed tile rectangle: x = xmin | ymin<<16, y = xmax | ymax<<16
+  uint8_t* clamped;         // [P]    bit c set: channel c was clamped at 0
+  uint32_t* depth_key[2];   // [P]    ping-pong keys of the depth sort (0xFFFFFFFF = culled)
+  uint32_t* depth_idx[2];   // [P]    ping-pong values (Gaussian index)
+  uint32_t* sort_hist;      // [SORT_MAX_BINS * sort_blocks(P)]
+  uint32_t* block_sums;     // [sort_blocks(P) + 1]   per-block instance counts in depth order, then scanned
+  uint32_t* counters;       // [8]    [0] = num_rendered, [1] = num_visible
+  GradRec* grad;            // [P]    backward accumulators
+
+  static GeomState from_chunk(char*& chunk, size_t P) {
+    GeomState g;
+    g.rec = carve<SplatRec>(chunk, P);
+    g.cov3D = carve<float>(chunk, 6 * P);
+    g.tiles_touched = carve<uint32_t>(chunk, P);
+    g.rect = carve<uint2>(chunk, P);
+    g.clamped = carve<uint8_t>(chunk, P);
+    for (int i = 0; i < 2; i++) g.depth_key[i] = carve<uint32_t>(chunk, P);
+    for (int i = 0; i < 2; i++) g.depth_idx[i] = carve<uint32_t>(chunk, P);
+    g.sort_hist = carve<uint32_t>(chunk, (size_t)SORT_MAX_BINS * (sort_blocks((int)P) + 1) + 16);
+    g.block_sums = carve<uint32_t>(chunk, (size_t)sort_blocks((int)P) + 2);
+    g.counters = carve<uint32_t>(chunk, 8);
+    g.grad = carve<GradRec>(chunk, P);
+    return g;
+  }
+  static size_t required(size_t P) {
+    char* p = nullptr;
+    from_chunk(p, P);
+    return reinterpret_cast<size_t>(p) + 256;
+  }
+};
+
+// ---- R-sized scratch ("binningBuffer") ----
+struct BinState {
+  uint32_t* tile_key[2];    // [R]  ping-pong tile ids
+  uint32_t* inst_idx[2];    // [R]  ping-pong Gaussian indices; inst_idx[final] is the point list
+  uint32_t* sort_hist;      // [SORT_MAX_BINS * sort_blocks(R)]
+  uint2* ranges;            // [T]
+  int final_buf;            // which ping-pong half holds the sorted result (set by the host)
+
+  static BinState from_chunk(char*& chunk, size_t R, size_t T) {
+    BinState b;
+    for (int i = 0; i < 2; i++) b.tile_key[i] = carve<uint32_t>(chunk, R);
+    for (int i = 0; i < 2; i++) b.inst_idx[i] = carve<uint32_t>(chunk, R);
+    b.sort_hist = carve<uint32_t>(chunk, (size_t)SORT_MAX_BINS * (sort_blocks((int)R) + 1) + 16);
+    b.ranges = carve<uint2>(chunk, T);
+    b.final_buf = 0;
+    return b;
+  }
+  static size_t required(size_t R, size_t T) {
+    char* p = nullptr;
+    from_chunk(p, R, T);
+    return reinterpret_cast<size_t>(p) + 256;
+  }
+};
+
+// ---- pixel-sized scratch ("imgBuffer") ----
+struct ImgState {
+  float* final_T;           // [H*W]
+  uint32_t* n_contrib;      // [H*W]
+  static ImgState from_chunk(char*& chunk, size_t N) {
+    ImgState s;
+    s.final_T = carve<float>(chunk, N);
+    s.n_contrib = carve<uint32_t>(chunk, N);
+    return s;
+  }
+  static size_t required(size_t N) {
+    char* p = nullptr;
+    from_chunk(p, N);
+    return reinterpret_cast<size_t>(p) + 256;
+  }
+};
+
+// Number of tile-id bits the tile sort has to cover.
+inline int tile_bits(int num_tiles) {
+  int b = 1;
+  while ((1 << b) < num_tiles) b++;
+  return b;
+}
+
+// ------------------------------------------------------------------ launchers (one per .cu file)
+struct FwdParams {
+  int P, D, M, W, H;
+  const float *bg, *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *cov3D_precomp;
+  const float *viewmatrix, *projmatrix, *campos;
+  float scale_modifier, tan_fovx, tan_fovy;
+  int prefiltered;
+};
+
+// preprocess.cu
+void launch_preprocess(const FwdParams& p, const GeomState& g, int* radii, cudaStream_t s);
+void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
+void launch_export_geom(int P, const GeomState& g, float* means2D, float* depths, float* cov3D,
+                        float* conic_opacity, float* rgb, uint8_t* clamped, uint32_t* tiles_touched,
+                        cudaStream_t s);
+
+// binning.cu
+// Stable LSD radix sort of (key, value) pairs on key bits [0, nbits); returns the index (0/1) of the
+// ping-pong half that holds the result.  hist must hold SORT_MAX_BINS * (sort_blocks(n) + 1) words.
+int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
+                     int* launches);
+void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
+                                uint32_t* block_sums, cudaStream_t s);
+void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
+                      const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
+                      uint32_t* inst_idx, cudaStream_t s);
+void launch_tile_ranges(int R, int T, const uint32_t* sorted_tile_keys, uint2* ranges, cudaStream_t s);
+void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_list, const SplatRec* rec,
+                        uint64_t* out_keys, cudaStream_t s);
+
+// render_fwd.cu
+void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
+                           const float* bg, float* out_color, float* out_depth, float* final_T,
+                           uint32_t* n_contrib, cudaStream_t s);
+
+// render_bwd.cu
+void launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
+                            const float* bg, const float* final_T, const uint32_t* n_contrib,
+                            const float* dL_dpixels, GradRec* grad, cudaStream_t s);
+
+// geom_bwd.cu
+struct BwdParams {
+  int P, D, M, W, H;
+  const float *means3D, *shs, *colors_precomp, *scales, *rotations, *cov3D_precomp;
+  const float *viewmatrix, *projmatrix, *campos;
+  float scale_modifier, tan_fovx, tan_fovy;
+  const int* radii;
+  float *dL_dmeans2D, *dL_dcolors, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drot;
+};
+void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s);
+
+}  // namespace sfb

@@ -1,0 +1,297 @@
+// geom_bwd.cu — K8 + K9 fused: per-Gaussian backward of the EWA projection, the screen-space mean,
+// the SH colour and the 3D covariance.
+//
+// One thread per Gaussian.  Inputs are the pixel sums the backward render left in GradRec; every output
+// row is written exactly once (zeros for culled Gaussians), so the caller never has to pre-zero the
+// ~256 B/Gaussian of gradient tensors — that removes a full memset pass over the largest buffers
+// (dL_dsh alone is 192 B/Gaussian at degree 3).
+#include "common.cuh"
+
+namespace sfb {
+
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+__constant__ float SHB_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float SHB_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                -0.5900435899266435f};
+
+struct CamB {
+  float view[16], proj[16], campos[3];
+};
+
+// VEC: shs / dL_dsh rows are 16-byte aligned and 3*M is a multiple of 4 -> 128-bit loads and stores.
+template <int D, bool VEC>
+__global__ void __launch_bounds__(256) geom_backward_kernel(BwdParams p, GeomState g) {
+  __shared__ CamB cam;
+  if (threadIdx.x < 16) {
+    cam.view[threadIdx.x] = p.viewmatrix[threadIdx.x];
+    cam.proj[threadIdx.x] = p.projmatrix[threadIdx.x];
+  }
+  if (threadIdx.x < 3) cam.campos[threadIdx.x] = p.campos[threadIdx.x];
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.P) return;
+  const size_t i = (size_t)idx;
+  const bool visible = p.radii[idx] > 0;
+
+  float dmean[3] = {0.f, 0.f, 0.f};
+  float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float dscale[3] = {0.f, 0.f, 0.f};
+  float drot[4] = {0.f, 0.f, 0.f, 0.f};
+  float gm2[2] = {0.f, 0.f};
+  float gcol[3] = {0.f, 0.f, 0.f};
+  float gop = 0.f;
+  constexpr int NB = (D + 1) * (D + 1);
+
+  if (visible) {
+    const float4* gp = reinterpret_cast<const float4*>(g.grad + idx);
+    const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2];
+    gm2[0] = g0.x; gm2[1] = g0.y;
+    const float gA = g0.z, gB = g0.w, gC = g1.x;
+    gop = g1.y;
+    gcol[0] = g1.z; gcol[1] = g1.w; gcol[2] = g2.x;
+
+    const float mean[3] = {p.means3D[3 * i], p.means3D[3 * i + 1], p.means3D[3 * i + 2]};
+    float c6[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) c6[k] = g.cov3D[6 * i + k];
+    const float fx = (float)p.W / (2.0f * p.tan_fovx), fy = (float)p.H / (2.0f * p.tan_fovy);
+
+    // ---- conic -> cov2D -> (Sigma3D, view-space t) ----
+    float t[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      t[r] = cam.view[r] * mean[0] + cam.view[4 + r] * mean[1] + cam.view[8 + r] * mean[2] + cam.view[12 + r];
+    const float limx = 1.3f * p.tan_fovx, limy = 1.3f * p.tan_fovy;
+    const float txtz = t[0] / t[2], tytz = t[1] / t[2];
+    const float xmul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+    const float ymul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+    t[0] = fminf(limx, fmaxf(-limx, txtz)) * t[2];
+    t[1] = fminf(limy, fmaxf(-limy, tytz)) * t[2];
+    const float itz = 1.f / t[2], itz2 = itz * itz, itz3 = itz2 * itz;
+    const float J00 = fx * itz, J02 = -(fx * t[0]) * itz2, J11 = fy * itz, J12 = -(fy * t[1]) * itz2;
+    float m0[3], m1[3], v0[3], v1[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      m0[j] = J00 * cam.view[4 * j + 0] + J02 * cam.view[4 * j + 2];
+      m1[j] = J11 * cam.view[4 * j + 1] + J12 * cam.view[4 * j + 2];
+    }
+    v0[0] = c6[0] * m0[0] + c6[1] * m0[1] + c6[2] * m0[2];
+    v0[1] = c6[1] * m0[0] + c6[3] * m0[1] + c6[4] * m0[2];
+    v0[2] = c6[2] * m0[0] + c6[4] * m0[1] + c6[5] * m0[2];
+    v1[0] = c6[0] * m1[0] + c6[1] * m1[1] + c6[2] * m1[2];
+    v1[1] = c6[1] * m1[0] + c6[3] * m1[1] + c6[4] * m1[2];
+    v1[2] = c6[2] * m1[0] + c6[4] * m1[1] + c6[5] * m1[2];
+    const float a = m0[0] * v0[0] + m0[1] * v0[1] + m0[2] * v0[2] + 0.3f;
+    const float b = m1[0] * v0[0] + m1[1] * v0[1] + m1[2] * v0[2];
+    const float c = m1[0] * v1[0] + m1[1] * v1[1] + m1[2] * v1[2] + 0.3f;
+    const float denom = a * c - b * b;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+    if (denom2inv != 0.f) {
+      dL_da = denom2inv * (-c * c * gA + b * c * gB + (denom - a * c) * gC);
+      dL_dc = denom2inv * (-a * a * gC + a * b * gB + (denom - a * c) * gA);
+      dL_db = denom2inv * (2.f * b * c * gA - (denom + 2.f * b * b) * gB + 2.f * a * b * gC);
+      dcov[0] = m0[0] * m0[0] * dL_da + m0[0] * m1[0] * dL_db + m1[0] * m1[0] * dL_dc;
+      dcov[3] = m0[1] * m0[1] * dL_da + m0[1] * m1[1] * dL_db + m1[1] * m1[1] * dL_dc;
+      dcov[5] = m0[2] * m0[2] * dL_da + m0[2] * m1[2] * dL_db + m1[2] * m1[2] * dL_dc;
+      dcov[1] = 2.f * m0[0] * m0[1] * dL_da + (m0[0] * m1[1] + m0[1] * m1[0]) * dL_db + 2.f * m1[0] * m1[1] * dL_dc;
+      dcov[2] = 2.f * m0[0] * m0[2] * dL_da + (m0[0] * m1[2] + m0[2] * m1[0]) * dL_db + 2.f * m1[0] * m1[2] * dL_dc;
+      dcov[4] = 2.f * m0[2] * m0[1] * dL_da + (m0[1] * m1[2] + m0[2] * m1[1]) * dL_db + 2.f * m1[1] * m1[2] * dL_dc;
+    }
+    float dJ00 = 0.f, dJ02 = 0.f, dJ11 = 0.f, dJ12 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const float dm0 = 2.f * v0[j] * dL_da + v1[j] * dL_db;
+      const float dm1 = 2.f * v1[j] * dL_dc + v0[j] * dL_db;
+      dJ00 += cam.view[4 * j + 0] * dm0;
+      dJ02 += cam.view[4 * j + 2] * dm0;
+      dJ11 += cam.view[4 * j + 1] * dm1;
+      dJ12 += cam.view[4 * j + 2] * dm1;
+    }
+    const float dtx = xmul * -fx * itz2 * dJ02;
+    const float dty = ymul * -fy * itz2 * dJ12;
+    const float dtz = -fx * itz2 * dJ00 - fy * itz2 * dJ11 + (2.f * fx * t[0]) * itz3 * dJ02 +
+                      (2.f * fy * t[1]) * itz3 * dJ12;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      dmean[j] = cam.view[4 * j + 0] * dtx + cam.view[4 * j + 1] * dty + cam.view[4 * j + 2] * dtz;
+
+    // ---- NDC-scaled screen mean -> mean3D ----
+    {
+      float h[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+        h[r] = cam.proj[r] * mean[0] + cam.proj[4 + r] * mean[1] + cam.proj[8 + r] * mean[2] + cam.proj[12 + r];
+      const float m_w = 1.0f / (h[3] + 0.0000001f);
+      const float mul1 = h[0] * m_w * m_w, mul2 = h[1] * m_w * m_w;
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+        dmean[j] += (cam.proj[4 * j + 0] * m_w - cam.proj[4 * j + 3] * mul1) * gm2[0] +
+                    (cam.proj[4 * j + 1] * m_w - cam.proj[4 * j + 3] * mul2) * gm2[1];
+    }
+
+    // ---- colour -> SH coefficients and view direction ----
+    if (p.shs) {
+      constexpr int NF4 = (3 * NB + 3) / 4;   // float4s that hold the active coefficients
+      float sh[NF4 * 4];
+      float dshv[NF4 * 4];
+      {
+        const float* shp = p.shs + i * p.M * 3;
+        if (VEC) {
+#pragma unroll
+          for (int k = 0; k < NF4; k++) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(shp) + k);
+            sh[4 * k] = q.x; sh[4 * k + 1] = q.y; sh[4 * k + 2] = q.z; sh[4 * k + 3] = q.w;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 3 * NB; k++) sh[k] = __ldg(shp + k);
+        }
+      }
+      float* dsh = p.dL_dsh + i * p.M * 3;
+      const float vx = mean[0] - cam.campos[0], vy = mean[1] - cam.campos[1], vz = mean[2] - cam.campos[2];
+      const float sum2 = vx * vx + vy * vy + vz * vz;
+      const float ilen = rsqrtf(sum2);
+      const float x = vx * ilen, y = vy * ilen, z = vz * ilen;
+      const uint8_t cm = g.clamped[idx];
+      float gc[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) gc[ch] = ((cm >> ch) & 1) ? 0.f : gcol[ch];
+      float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+      float basis[NB];
+      basis[0] = SH_C0;
+      float xx = 0, yy = 0, zz = 0, xy = 0, yz = 0, xz = 0;
+      if (D > 0) { basis[1] = -SH_C1 * y; basis[2] = SH_C1 * z; basis[3] = -SH_C1 * x; }
+      if (D > 1) {
+        xx = x * x; yy = y * y; zz = z * z; xy = x * y; yz = y * z; xz = x * z;
+        basis[4] = SHB_C2[0] * xy; basis[5] = SHB_C2[1] * yz; basis[6] = SHB_C2[2] * (2.f * zz - xx - yy);
+        basis[7] = SHB_C2[3] * xz; basis[8] = SHB_C2[4] * (xx - yy);
+      }
+      if (D > 2) {
+        basis[9] = SHB_C3[0] * y * (3.f * xx - yy); basis[10] = SHB_C3[1] * xy * z;
+        basis[11] = SHB_C3[2] * y * (4.f * zz - xx - yy); basis[12] = SHB_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+        basis[13] = SHB_C3[4] * x * (4.f * zz - xx - yy); basis[14] = SHB_C3[5] * z * (xx - yy);
+        basis[15] = SHB_C3[6] * x * (xx - 3.f * yy);
+      }
+#pragma unroll
+      for (int k = 0; k < NF4 * 4; k++) dshv[k] = 0.f;
+#pragma unroll
+      for (int k = 0; k < NB; k++) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) dshv[3 * k + ch] = basis[k] * gc[ch];
+      }
+      if (VEC) {
+        float4* d4 = reinterpret_cast<float4*>(dsh);
+#pragma unroll
+        for (int k = 0; k < NF4; k++) d4[k] = make_float4(dshv[4 * k], dshv[4 * k + 1], dshv[4 * k + 2], dshv[4 * k + 3]);
+        for (int k = NF4; k < (3 * p.M) / 4; k++) d4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3 * NB; k++) dsh[k] = dshv[k];
+        for (int k = 3 * NB; k < 3 * p.M; k++) dsh[k] = 0.f;
+      }
+      if (D > 0) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+          float rx = -SH_C1 * sh[3 * 3 + ch], ry = -SH_C1 * sh[1 * 3 + ch], rz = SH_C1 * sh[2 * 3 + ch];
+          if (D > 1) {
+            const float s4 = sh[4 * 3 + ch], s5 = sh[5 * 3 + ch], s6 = sh[6 * 3 + ch], s7 = sh[7 * 3 + ch],
+                        s8 = sh[8 * 3 + ch];
+            rx += SHB_C2[0] * y * s4 + SHB_C2[2] * 2.f * -x * s6 + SHB_C2[3] * z * s7 + SHB_C2[4] * 2.f * x * s8;
+            ry += SHB_C2[0] * x * s4 + SHB_C2[1] * z * s5 + SHB_C2[2] * 2.f * -y * s6 + SHB_C2[4] * 2.f * -y * s8;
+            rz += SHB_C2[1] * y * s5 + SHB_C2[2] * 4.f * z * s6 + SHB_C2[3] * x * s7;
+            if (D > 2) {
+              const float s9 = sh[9 * 3 + ch], s10 = sh[10 * 3 + ch], s11 = sh[11 * 3 + ch], s12 = sh[12 * 3 + ch],
+                          s13 = sh[13 * 3 + ch], s14 = sh[14 * 3 + ch], s15 = sh[15 * 3 + ch];
+              rx += SHB_C3[0] * s9 * 6.f * xy + SHB_C3[1] * s10 * yz + SHB_C3[2] * s11 * -2.f * xy +
+                    SHB_C3[3] * s12 * -6.f * xz + SHB_C3[4] * s13 * (-3.f * xx + 4.f * zz - yy) +
+                    SHB_C3[5] * s14 * 2.f * xz + SHB_C3[6] * s15 * 3.f * (xx - yy);
+              ry += SHB_C3[0] * s9 * 3.f * (xx - yy) + SHB_C3[1] * s10 * xz +
+                    SHB_C3[2] * s11 * (-3.f * yy + 4.f * zz - xx) + SHB_C3[3] * s12 * -6.f * yz +
+                    SHB_C3[4] * s13 * -2.f * xy + SHB_C3[5] * s14 * -2.f * yz + SHB_C3[6] * s15 * -6.f * xy;
+              rz += SHB_C3[1] * s10 * xy + SHB_C3[2] * s11 * 8.f * yz + SHB_C3[3] * s12 * 3.f * (2.f * zz - xx - yy) +
+                    SHB_C3[4] * s13 * 8.f * xz + SHB_C3[5] * s14 * (xx - yy);
+            }
+          }
+          ddx += rx * gc[ch]; ddy += ry * gc[ch]; ddz += rz * gc[ch];
+        }
+        const float invsum32 = ilen * ilen * ilen;
+        dmean[0] += ((sum2 - vx * vx) * ddx - vy * vx * ddy - vz * vx * ddz) * invsum32;
+        dmean[1] += (-vx * vy * ddx + (sum2 - vy * vy) * ddy - vz * vy * ddz) * invsum32;
+        dmean[2] += (-vx * vz * ddx - vy * vz * ddy + (sum2 - vz * vz) * ddz) * invsum32;
+      }
+    }
+
+    // ---- Sigma3D -> scale, quaternion ----
+    if (!p.cov3D_precomp) {
+      const float qr = p.rotations[4 * i], qx = p.rotations[4 * i + 1], qy = p.rotations[4 * i + 2],
+                  qz = p.rotations[4 * i + 3];
+      float R[9];
+      R[0] = 1.f - 2.f * (qy * qy + qz * qz); R[1] = 2.f * (qx * qy - qr * qz); R[2] = 2.f * (qx * qz + qr * qy);
+      R[3] = 2.f * (qx * qy + qr * qz); R[4] = 1.f - 2.f * (qx * qx + qz * qz); R[5] = 2.f * (qy * qz - qr * qx);
+      R[6] = 2.f * (qx * qz - qr * qy); R[7] = 2.f * (qy * qz + qr * qx); R[8] = 1.f - 2.f * (qx * qx + qy * qy);
+      const float s[3] = {p.scale_modifier * p.scales[3 * i], p.scale_modifier * p.scales[3 * i + 1],
+                          p.scale_modifier * p.scales[3 * i + 2]};
+      const float Gm[9] = {dcov[0], 0.5f * dcov[1], 0.5f * dcov[2], 0.5f * dcov[1], dcov[3], 0.5f * dcov[4],
+                           0.5f * dcov[2], 0.5f * dcov[4], dcov[5]};
+      float Dr[9];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float ds = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < 3; k++) acc += Gm[3 * r + k] * (R[3 * k + j] * s[j]);
+          const float dLm = 2.f * acc;
+          ds += dLm * R[3 * r + j];
+          Dr[3 * r + j] = dLm * s[j];
+        }
+        dscale[j] = p.scale_modifier * ds;
+      }
+      drot[0] = 2.f * (qz * (Dr[3] - Dr[1]) + qy * (Dr[2] - Dr[6]) + qx * (Dr[7] - Dr[5]));
+      drot[1] = 2.f * (qy * (Dr[1] + Dr[3]) + qz * (Dr[2] + Dr[6]) + qr * (Dr[7] - Dr[5])) - 4.f * qx * (Dr[4] + Dr[8]);
+      drot[2] = 2.f * (qx * (Dr[1] + Dr[3]) + qr * (Dr[2] - Dr[6]) + qz * (Dr[5] + Dr[7])) - 4.f * qy * (Dr[0] + Dr[8]);
+      drot[3] = 2.f * (qr * (Dr[3] - Dr[1]) + qx * (Dr[2] + Dr[6]) + qy * (Dr[5] + Dr[7])) - 4.f * qz * (Dr[0] + Dr[4]);
+    }
+  } else if (p.shs) {
+    float* dsh = p.dL_dsh + i * p.M * 3;
+    if (VEC) {
+      float4* d4 = reinterpret_cast<float4*>(dsh);
+      for (int k = 0; k < (3 * p.M) / 4; k++) d4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int k = 0; k < 3 * p.M; k++) dsh[k] = 0.f;
+    }
+  }
+
+  p.dL_dmeans3D[3 * i] = dmean[0]; p.dL_dmeans3D[3 * i + 1] = dmean[1]; p.dL_dmeans3D[3 * i + 2] = dmean[2];
+  p.dL_dmeans2D[3 * i] = gm2[0]; p.dL_dmeans2D[3 * i + 1] = gm2[1]; p.dL_dmeans2D[3 * i + 2] = 0.f;
+  p.dL_dcolors[3 * i] = gcol[0]; p.dL_dcolors[3 * i + 1] = gcol[1]; p.dL_dcolors[3 * i + 2] = gcol[2];
+  p.dL_dopacity[i] = gop;
+#pragma unroll
+  for (int k = 0; k < 6; k++) p.dL_dcov3D[6 * i + k] = dcov[k];
+  if (p.dL_dscales) { p.dL_dscales[3 * i] = dscale[0]; p.dL_dscales[3 * i + 1] = dscale[1]; p.dL_dscales[3 * i + 2] = dscale[2]; }
+  if (p.dL_drot) { p.dL_drot[4 * i] = drot[0]; p.dL_drot[4 * i + 1] = drot[1]; p.dL_drot[4 * i + 2] = drot[2]; p.dL_drot[4 * i + 3] = drot[3]; }
+}
+
+void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s) {
+  if (p.P <= 0) return;
+  const int blocks = (p.P + 255) / 256;
+  const bool vec = p.shs && ((p.M * 3) % 4 == 0) && ((reinterpret_cast<size_t>(p.shs) & 15) == 0) &&
+                   ((reinterpret_cast<size_t>(p.dL_dsh) & 15) == 0);
+#define SFB_GB(DD)                                                              \
+  if (vec) geom_backward_kernel<DD, true><<<blocks, 256, 0, s>>>(p, g);         \
+  else     geom_backward_kernel<DD, false><<<blocks, 256, 0, s>>>(p, g);
+  switch (p.shs ? p.D : 0) {
+    case 0: SFB_GB(0) break;
+    case 1: SFB_GB(1) break;
+    case 2: SFB_GB(2) break;
+    default: SFB_GB(3) break;
+  }
+#undef SFB_GB
+}
+
+}  // namespace sfb

@@ -1,0 +1,97 @@
+// render_fwd.cu — K6: per-16x16-tile front-to-back alpha compositing (RGB + depth).
+// Restates the external rasterizer's forward render: for every pixel
+// walk the tile's depth-ordered list; alpha = min(0.99, o * exp(power)); skip alpha < 1/255; stop before
+// the contributor that would push T below 1e-4; C += rgb*alpha*T, D += depth*alpha*T; out = C + T*bg.
+//
+// One CTA per tile, 256 threads = one pixel each; a warp covers an 8x4 pixel patch (not a 16x2 strip)
+// so that the pixels of a warp see nearly the same set of contributing splats.  The tile's list is
+// consumed in batches of 256: every thread gathers one 48-byte SplatRec (three 16-byte loads out of L2,
+// where the whole record array of a 1M-splat scene stays resident) into shared memory, then all threads
+// sweep the batch reading the records as warp-wide broadcasts.
+#include "common.cuh"
+
+namespace sfb {
+
+constexpr int RB = 256;  // batch = block size
+
+__global__ void __launch_bounds__(RB)
+render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
+                      const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ rec,
+                      const float* __restrict__ bg, float* __restrict__ out_color,
+                      float* __restrict__ out_depth, float* __restrict__ final_T,
+                      uint32_t* __restrict__ n_contrib) {
+  __shared__ float4 s_q0[RB];  // x, y, conA, conB
+  __shared__ float4 s_q1[RB];  // conC, opacity, depth, r
+  __shared__ float2 s_q2[RB];  // g, b
+
+  const int tile = blockIdx.x;
+  const int tile_x = tile % grid_x, tile_y = tile / grid_x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int px = tile_x * TILE_X + (warp & 1) * 8 + (lane & 7);
+  const int py = tile_y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const float pixfx = (float)px, pixfy = (float)py;
+
+  const uint2 range = ranges[tile];
+  int todo = (int)(range.y - range.x);
+  bool done = !inside;
+
+  float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
+  uint32_t contributor = 0, last_contributor = 0;
+
+  for (int base = 0; todo > 0; base += RB, todo -= RB) {
+    if (__syncthreads_count(done) == RB) break;
+    if ((int)threadIdx.x < todo) {
+      uint32_t id = point_list[range.x + base + threadIdx.x];
+      const float4* rp = reinterpret_cast<const float4*>(rec + id);
+      float4 a = __ldg(rp), b = __ldg(rp + 1), c = __ldg(rp + 2);
+      s_q0[threadIdx.x] = a;
+      s_q1[threadIdx.x] = b;
+      s_q2[threadIdx.x] = make_float2(c.x, c.y);
+    }
+    __syncthreads();
+    const int n = todo < RB ? todo : RB;
+    for (int j = 0; !done && j < n; j++) {
+      contributor++;
+      const float4 q0 = s_q0[j];
+      const float dx = q0.x - pixfx, dy = q0.y - pixfy;
+      const float4 q1 = s_q1[j];
+      // -0.5f*(A*dx*dx + C*dy*dy) - B*dx*dy, in the op order nvcc gives that expression
+      const float s = __fmaf_rn(__fmul_rn(q0.z, dx), dx, __fmul_rn(__fmul_rn(q1.x, dy), dy));
+      const float power = __fmaf_rn(s, -0.5f, -__fmul_rn(__fmul_rn(q0.w, dx), dy));
+      if (power > 0.0f) continue;
+      const float alpha = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
+      if (alpha < 1.0f / 255.0f) continue;
+      const float test_T = __fmul_rn(T, 1.0f - alpha);
+      if (test_T < 0.0001f) { done = true; continue; }
+      const float w = __fmul_rn(alpha, T);
+      const float2 q2 = s_q2[j];
+      C0 = __fmaf_rn(q1.w, w, C0);
+      C1 = __fmaf_rn(q2.x, w, C1);
+      C2 = __fmaf_rn(q2.y, w, C2);
+      Dp = __fmaf_rn(q1.z, w, Dp);
+      T = test_T;
+      last_contributor = contributor;
+    }
+  }
+  if (inside) {
+    const size_t pix = (size_t)py * W + px;
+    const size_t HW = (size_t)H * W;
+    final_T[pix] = T;
+    n_contrib[pix] = last_contributor;
+    out_color[pix] = __fmaf_rn(T, bg[0], C0);
+    out_color[HW + pix] = __fmaf_rn(T, bg[1], C1);
+    out_color[2 * HW + pix] = __fmaf_rn(T, bg[2], C2);
+    out_depth[pix] = Dp;
+  }
+}
+
+void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
+                           const float* bg, float* out_color, float* out_depth, float* final_T,
+                           uint32_t* n_contrib, cudaStream_t s) {
+  const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+  render_forward_kernel<<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, out_color, out_depth,
+                                                final_T, n_contrib);
+}
+
+}  // namespace sfb

@@ -1,0 +1,222 @@
+"""Host-side mirror of the `diff_gaussian_rasterization` Python surface the reference imports at
+gaussian_renderer/__init__.py:14 and drives at :59-72, :74, :94-102, :106-114:
+
+    GaussianRasterizationSettings (NamedTuple, 12 fields)
+    GaussianRasterizer(nn.Module).forward(means3D, means2D, opacities, shs=None, colors_precomp=None,
+                                          scales=None, rotations=None, cov3D_precomp=None)
+        -> (color [3,H,W], radii [P] int32, depth [1,H,W])
+    GaussianRasterizer.markVisible(positions) -> bool [P]
+
+Same names, argument meaning, return order and error messages; the compute is the sm_100a library behind
+the C ABI (include/splat_b200.h).  torch is used for device memory, streams and autograd glue only.
+"""
+from __future__ import annotations
+
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+def _ptr(t):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+def _prep(t, name=None):
+    """contiguous fp32 CUDA tensor with a 16-byte aligned base (the kernels use 128-bit accesses)."""
+    if t is None or t.numel() == 0:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone()
+    return t
+
+
+class _Scratch:
+    """The three caller-owned scratch buffers; torch owns the bytes, the library asks via callbacks."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+        self._cbs = {}
+        for name in ("geom", "binning", "img"):
+            self._cbs[name] = _lib.ALLOC_FN(self._make(name))
+
+    def _make(self, name):
+        def alloc(_user, nbytes):
+            t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=self.device)
+            self.bufs[name] = t
+            return t.data_ptr()
+        return alloc
+
+    def cb(self, name):
+        return self._cbs[name]
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs):
+    lib = _lib.load()
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise Exception("means3D must have dimensions (num_points, 3)")
+    if not means3D.is_cuda:
+        raise _lib.SplatB200Error("the rasterizer runs on CUDA tensors only (no CPU fallback)")
+    dev = means3D.device
+    P = means3D.shape[0]
+    H, W = int(rs.image_height), int(rs.image_width)
+    means3D_c = _prep(means3D)
+    sh_c, col_c = _prep(sh), _prep(colors_precomp)
+    op_c, sc_c, rot_c, cov_c = _prep(opacities), _prep(scales), _prep(rotations), _prep(cov3Ds_precomp)
+    bg, vm, pm, cp = _prep(rs.bg.to(dev)), _prep(rs.viewmatrix.to(dev)), _prep(rs.projmatrix.to(dev)), _prep(rs.campos.to(dev))
+    M = 0 if sh_c is None else (sh_c.shape[1] if sh_c.dim() == 3 else sh_c.numel() // (3 * P))
+    color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+    depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+    radii = torch.empty((P,), dtype=torch.int32, device=dev)
+    scratch = _Scratch(dev)
+    import ctypes as C
+    nr = C.c_int(0)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.sfb_rasterize_forward(
+            P, int(rs.sh_degree), int(M), W, H,
+            _ptr(bg), _ptr(means3D_c), _ptr(sh_c), _ptr(col_c), _ptr(op_c), _ptr(sc_c), float(rs.scale_modifier),
+            _ptr(rot_c), _ptr(cov_c), _ptr(vm), _ptr(pm), _ptr(cp), float(rs.tanfovx), float(rs.tanfovy),
+            int(bool(rs.prefiltered)), _ptr(color), _ptr(depth), _ptr(radii),
+            scratch.cb("geom"), None, scratch.cb("binning"), None, scratch.cb("img"), None,
+            C.byref(nr), int(bool(rs.debug)), stream)
+    _lib.check(rc)
+    empty = torch.empty(0, dtype=torch.uint8, device=dev)
+    geom, binning, img = (scratch.bufs.get(k, empty) for k in ("geom", "binning", "img"))
+    saved = (means3D_c, sh_c, col_c, sc_c, rot_c, cov_c, bg, vm, pm, cp)
+    return int(nr.value), color, depth, radii, geom, binning, img, M, saved
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        rs = raster_settings
+        args = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs)
+        if rs.debug:
+            try:
+                out = _forward_impl(*args)
+            except Exception as ex:
+                torch.save(tuple(a.detach().cpu() if torch.is_tensor(a) else a for a in args[:-1]), "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            out = _forward_impl(*args)
+        num_rendered, color, depth, radii, geom, binning, img, M, saved = out
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.M = M
+        ctx.shapes = tuple(None if t is None else t.shape for t in
+                           (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
+        ctx.saved_inputs = saved
+        ctx.save_for_backward(radii, geom, binning, img)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii, _grad_depth):
+        # Like the pinned reference build, depth is a forward-only output: its cotangent is not
+        # propagated (every shipped recipe keeps lambda_depth = 0).
+        lib = _lib.load()
+        rs = ctx.raster_settings
+        radii, geom, binning, img = ctx.saved_tensors
+        means3D, sh, col, sc, rot, cov, bg, vm, pm, cp = ctx.saved_inputs
+        sh_means3D, sh_means2D, sh_sh, sh_col, sh_op, sh_sc, sh_rot, sh_cov = ctx.shapes
+        dev = means3D.device
+        P = means3D.shape[0]
+        H, W = int(rs.image_height), int(rs.image_width)
+        M = ctx.M
+        f32 = dict(dtype=torch.float32, device=dev)
+        dL_dmeans3D = torch.empty((P, 3), **f32)
+        dL_dmeans2D = torch.empty((P, 3), **f32)
+        dL_dcolors = torch.empty((P, 3), **f32)
+        dL_dopacity = torch.empty((P, 1), **f32)
+        dL_dcov3D = torch.empty((P, 6), **f32)
+        dL_dsh = torch.empty((P, M, 3), **f32) if sh is not None else None
+        dL_dscales = torch.empty((P, 3), **f32) if cov is None else None
+        dL_drot = torch.empty((P, 4), **f32) if cov is None else None
+        g = _prep(grad_out_color)
+        if P > 0:
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                rc = lib.sfb_rasterize_backward(
+                    P, int(rs.sh_degree), int(M), int(ctx.num_rendered), W, H,
+                    _ptr(bg), _ptr(means3D), _ptr(sh), _ptr(col), _ptr(sc), float(rs.scale_modifier), _ptr(rot),
+                    _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cp), float(rs.tanfovx), float(rs.tanfovy), _ptr(radii),
+                    _ptr(geom), _ptr(binning), _ptr(img), _ptr(g),
+                    _ptr(dL_dmeans2D), _ptr(dL_dcolors), _ptr(dL_dopacity), _ptr(dL_dmeans3D), _ptr(dL_dcov3D),
+                    _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drot), int(bool(rs.debug)), stream)
+            _lib.check(rc)
+
+        def shaped(t, shape):
+            return None if (t is None or shape is None) else t.reshape(shape)
+        grads = (
+            shaped(dL_dmeans3D, sh_means3D),
+            shaped(dL_dmeans2D, sh_means2D),
+            shaped(dL_dsh, sh_sh),
+            shaped(dL_dcolors, sh_col) if col is not None else None,
+            shaped(dL_dopacity, sh_op),
+            shaped(dL_dscales, sh_sc),
+            shaped(dL_drot, sh_rot),
+            shaped(dL_dcov3D, sh_cov) if cov is not None else None,
+            None,
+        )
+        return grads
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            lib = _lib.load()
+            pos = _prep(positions)
+            P = positions.shape[0]
+            out = torch.empty((P,), dtype=torch.uint8, device=positions.device)
+            vm, pm = _prep(rs.viewmatrix.to(positions.device)), _prep(rs.projmatrix.to(positions.device))
+            if P > 0:
+                with torch.cuda.device(positions.device):
+                    stream = torch.cuda.current_stream(positions.device).cuda_stream
+                    _lib.check(lib.sfb_mark_visible(P, _ptr(pos), _ptr(vm), _ptr(pm), _ptr(out), stream))
+            return out.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        rs = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, rs)

@@ -1,0 +1,93 @@
+"""CPU: the C-ABI library loads and exports every symbol include/splat_b200.h declares; the Python
+mirror keeps the reference's names, field order and error messages.  No compute calls (no GPU here)."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _built():
+    from splatfields_b200 import build
+    build.build()
+
+
+def test_library_exports_every_declared_symbol():
+    _built()
+    from splatfields_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "splat_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(sfb_[a-z_0-9]+)\s*\(", hdr)) - {"sfb_alloc_fn"})
+    assert len(declared) >= 9
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(_lib.SYMBOLS) == declared
+    assert lib.sfb_abi_version() == 1
+    assert lib.sfb_last_error() == b""
+
+
+def test_library_is_sm100a_only():
+    _built()
+    import subprocess
+    from splatfields_b200 import _lib
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_settings_fields_match_reference_order():
+    from splatfields_b200 import GaussianRasterizationSettings
+    # gaussian_renderer/__init__.py:59-72 passes exactly these keywords
+    assert GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "sh_degree", "campos", "prefiltered", "debug")
+
+
+def test_alias_package_resolves_like_the_reference_import():
+    import diff_gaussian_rasterization as D
+    from splatfields_b200 import rasterizer
+    assert D.GaussianRasterizer is rasterizer.GaussianRasterizer
+    assert D.GaussianRasterizationSettings is rasterizer.GaussianRasterizationSettings
+
+
+def _rast():
+    from splatfields_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    rs = GaussianRasterizationSettings(16, 16, 0.5, 0.5, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0,
+                                       torch.zeros(3), False, False)
+    return GaussianRasterizer(rs)
+
+
+def test_argument_validation_messages():
+    r = _rast()
+    m = torch.zeros(4, 3)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(means3D=m, means2D=m, opacities=torch.ones(4, 1), scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(means3D=m, means2D=m, opacities=torch.ones(4, 1), shs=torch.zeros(4, 1, 3), colors_precomp=torch.zeros(4, 3),
+          scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=m, means2D=m, opacities=torch.ones(4, 1), colors_precomp=torch.zeros(4, 3))
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=m, means2D=m, opacities=torch.ones(4, 1), colors_precomp=torch.zeros(4, 3),
+          scales=torch.ones(4, 3), rotations=torch.ones(4, 4), cov3D_precomp=torch.zeros(4, 6))
+
+
+def test_no_cpu_fallback():
+    """CPU tensors must fail loudly, not silently run somewhere else."""
+    from splatfields_b200._lib import SplatB200Error
+    r = _rast()
+    m = torch.zeros(4, 3)
+    with pytest.raises(SplatB200Error, match="no CPU fallback"):
+        r(means3D=m, means2D=m, opacities=torch.ones(4, 1), colors_precomp=torch.zeros(4, 3),
+          scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "splatfields_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "splat_oracle" not in txt, f
