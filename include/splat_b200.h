@@ -97,12 +97,14 @@ int sfb_export_binning(int P, int num_rendered, int W, int H, const void* geom_b
 /* final_T [H][W], n_contrib [H][W] (uint32; position+1 of the last contributor in the tile list). */
 int sfb_export_img(int W, int H, const void* img_buffer, float* final_T, uint32_t* n_contrib, void* stream);
 
-/* Per-stage device timing with CUDA events recorded on the launching stream (bench.py's roofline leg).
- * which = 0: forward stages, 1: backward stages.  sfb_profile_read waits for the stage events of the last
- * call made with profiling enabled and writes their durations (ms); returns the number of stages. */
+/* Per-kernel device timing with CUDA events recorded on the launching stream (bench.py's roofline leg).
+ * While enabled, every kernel of a forward (which = 0) / backward (which = 1) call is bracketed by an event
+ * pair; sfb_profile_read waits for the records of the last such call and writes their durations (ms),
+ * returning the record count; sfb_profile_name(which, i) names record i ("tile_sort.scatter", ...). */
 void sfb_profile_enable(int on);
-int sfb_profile_read(int which, float* ms, int max_stages);
-const char* sfb_profile_stage_name(int which, int stage);
+int sfb_profile_count(int which);
+int sfb_profile_read(int which, float* ms, int max_records);
+const char* sfb_profile_name(int which, int i);
 
 /* Number of kernel launches issued by the last forward / backward on the calling thread. */
 int sfb_last_launch_count(void);

@@ -58,7 +58,7 @@ def main():
     color, radii = step()
     color.backward(G)
     torch.cuda.synchronize()
-    pf, pb = _lib.profile_read(0), _lib.profile_read(1)
+    pf, pb = dict(_lib.profile_read(0)), dict(_lib.profile_read(1))
     _lib.profile_enable(False)
     med = lambda x: float(np.median(x))
     T = ((W + 15) // 16) * ((H + 15) // 16)

@@ -19,7 +19,7 @@ _lib = None
 SYMBOLS = (
     "sfb_abi_version", "sfb_last_error", "sfb_rasterize_forward", "sfb_rasterize_backward", "sfb_mark_visible",
     "sfb_export_geom", "sfb_export_binning", "sfb_export_img", "sfb_last_launch_count",
-    "sfb_profile_enable", "sfb_profile_read", "sfb_profile_stage_name",
+    "sfb_profile_enable", "sfb_profile_count", "sfb_profile_read", "sfb_profile_name",
 )
 
 
@@ -69,8 +69,10 @@ def load():
     lib.sfb_profile_enable.argtypes = [ci]
     lib.sfb_profile_read.restype = ci
     lib.sfb_profile_read.argtypes = [ci, C.POINTER(cf), ci]
-    lib.sfb_profile_stage_name.restype = C.c_char_p
-    lib.sfb_profile_stage_name.argtypes = [ci, ci]
+    lib.sfb_profile_count.restype = ci
+    lib.sfb_profile_count.argtypes = [ci]
+    lib.sfb_profile_name.restype = C.c_char_p
+    lib.sfb_profile_name.argtypes = [ci, ci]
     if lib.sfb_abi_version() != 1:
         raise SplatB200Error("libsplat_b200.so ABI version mismatch; rebuild")
     _lib = lib
@@ -89,11 +91,11 @@ def profile_enable(on: bool):
     load().sfb_profile_enable(int(bool(on)))
 
 
-def profile_read(which: int) -> dict:
-    """{stage name: ms} of the last forward (which=0) / backward (which=1) run with profiling enabled."""
+def profile_read(which: int) -> list:
+    """[(kernel name, ms), ...] of the last forward (which=0) / backward (which=1) run with profiling on."""
     lib = load()
-    buf = (C.c_float * 8)()
-    n = lib.sfb_profile_read(which, buf, 8)
+    buf = (C.c_float * 64)()
+    n = lib.sfb_profile_read(which, buf, 64)
     if n < 0:
         check(n)
-    return {lib.sfb_profile_stage_name(which, i).decode(): float(buf[i]) for i in range(n)}
+    return [(lib.sfb_profile_name(which, i).decode(), float(buf[i])) for i in range(n)]

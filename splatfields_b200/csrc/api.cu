@@ -36,30 +36,18 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
     if (e__ != cudaSuccess) return fail(SFB_ERR_CUDA, "kernel " name, e__);         \
   } while (0)
 
-// ---- optional per-stage device timing (CUDA events on the launching stream) ----
-constexpr int MAX_STAGES = 8;
-const char* kFwdStages[] = {"preprocess", "depth_sort", "instance_scan", "duplicate", "tile_sort", "tile_ranges",
-                            "render_forward"};
-const char* kBwdStages[] = {"zero_grad_acc", "render_backward", "geom_backward"};
+// ---- optional per-kernel device timing (CUDA events on the launching stream) ----
+// Every kernel launch is bracketed by an event pair when profiling is on; records of the last forward
+// (which = 0) and backward (which = 1) are kept until the next profiled call.
+constexpr int MAX_REC = 48;
+const char* const kDepthSortNames[3] = {"depth_sort.hist", "depth_sort.scan", "depth_sort.scatter"};
+const char* const kTileSortNames[3] = {"tile_sort.hist", "tile_sort.scan", "tile_sort.scatter"};
+struct ProfRec { const char* name; cudaEvent_t a, b; };
 thread_local bool g_prof = false;
-thread_local cudaEvent_t g_ev[2][MAX_STAGES][2];
-thread_local bool g_ev_made = false;
-thread_local bool g_ev_used[2][MAX_STAGES];
-
-void prof_begin(int which, int stage, cudaStream_t s) {
-  if (!g_prof) return;
-  if (!g_ev_made) {
-    for (int w = 0; w < 2; w++)
-      for (int i = 0; i < MAX_STAGES; i++) { cudaEventCreate(&g_ev[w][i][0]); cudaEventCreate(&g_ev[w][i][1]); }
-    g_ev_made = true;
-  }
-  if (stage == 0) for (int i = 0; i < MAX_STAGES; i++) g_ev_used[which][i] = false;
-  cudaEventRecord(g_ev[which][stage][0], s);
-  g_ev_used[which][stage] = true;
-}
-void prof_end(int which, int stage, cudaStream_t s) {
-  if (g_prof) cudaEventRecord(g_ev[which][stage][1], s);
-}
+thread_local int g_which = 0;
+thread_local ProfRec g_rec[2][MAX_REC];
+thread_local int g_nrec[2] = {0, 0};
+thread_local bool g_rec_made = false;
 
 int tile_sort_final(int T) {
   int bits = sfb::tile_bits(T);
@@ -68,6 +56,28 @@ int tile_sort_final(int T) {
 }
 
 }  // namespace
+
+namespace sfb {
+void prof_begin(const char* name, cudaStream_t s) {
+  if (!g_prof) return;
+  if (!g_rec_made) {
+    for (int w = 0; w < 2; w++)
+      for (int i = 0; i < MAX_REC; i++) { cudaEventCreate(&g_rec[w][i].a); cudaEventCreate(&g_rec[w][i].b); }
+    g_rec_made = true;
+  }
+  int& n = g_nrec[g_which];
+  if (n >= MAX_REC) return;
+  g_rec[g_which][n].name = name;
+  cudaEventRecord(g_rec[g_which][n].a, s);
+}
+void prof_end(cudaStream_t s) {
+  if (!g_prof) return;
+  int& n = g_nrec[g_which];
+  if (n >= MAX_REC) return;
+  cudaEventRecord(g_rec[g_which][n].b, s);
+  n++;
+}
+}  // namespace sfb
 
 extern "C" {
 
@@ -128,24 +138,21 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
 
   // K1 (+ num_rendered reduction) ; the 4-byte read-back is issued right behind it so that the host
   // wait overlaps the depth sort instead of draining the whole pipeline.
-  prof_begin(0, 0, s);
+  g_which = 0; g_nrec[0] = 0;
+  prof_begin("preprocess", s);
   CK(cudaMemsetAsync(g.counters, 0, 8 * sizeof(uint32_t), s));
   launch_preprocess(fp, g, radii, s);
-  prof_end(0, 0, s);
+  prof_end(s);
   g_launches++;
   CK_LAUNCH("preprocess", debug, s);
   CK(cudaMemcpyAsync(g_pinned, g.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(g_evt, s));
 
   // stage 1: stable sort of the Gaussians by depth bits (culled ones carry 0xFFFFFFFF and sink)
-  prof_begin(0, 1, s);
-  int dfinal = radix_sort_pairs(g.depth_key, g.depth_idx, g.sort_hist, P, 32, s, &g_launches);
-  prof_end(0, 1, s);
+  int dfinal = radix_sort_pairs(g.depth_key, g.depth_idx, g.sort_hist, P, 32, s, &g_launches, kDepthSortNames);
   CK_LAUNCH("depth sort", debug, s);
   const uint32_t* sorted_idx = g.depth_idx[dfinal];
-  prof_begin(0, 2, s);
   launch_instance_block_sums(P, sorted_idx, g.tiles_touched, g.block_sums, s);
-  prof_end(0, 2, s);
   g_launches += 2;
   CK_LAUNCH("instance scan", debug, s);
 
@@ -161,26 +168,24 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   int tfinal = 0;
   if (R > 0) {
     // stage 2: emit (tile, gaussian) instances in depth order; stage 3: stable sort by tile id
-    prof_begin(0, 3, s);
+    prof_begin("duplicate", s);
     launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, b.tile_key[0], b.inst_idx[0], s);
-    prof_end(0, 3, s);
+    prof_end(s);
     g_launches++;
     CK_LAUNCH("duplicate", debug, s);
-    prof_begin(0, 4, s);
-    tfinal = radix_sort_pairs(b.tile_key, b.inst_idx, b.sort_hist, (int)R, tile_bits(T), s, &g_launches);
-    prof_end(0, 4, s);
-    CK_LAUNCH("tile sort", debug, s);
+      tfinal = radix_sort_pairs(b.tile_key, b.inst_idx, b.sort_hist, (int)R, tile_bits(T), s, &g_launches, kTileSortNames);
+      CK_LAUNCH("tile sort", debug, s);
   }
-  prof_begin(0, 5, s);
+  prof_begin("tile_ranges", s);
   launch_tile_ranges((int)R, T, b.tile_key[tfinal], b.ranges, s);
-  prof_end(0, 5, s);
+  prof_end(s);
   g_launches++;
   CK_LAUNCH("tile ranges", debug, s);
 
-  prof_begin(0, 6, s);
+  prof_begin("render_forward", s);
   launch_render_forward(W, H, b.ranges, b.inst_idx[tfinal], g.rec, bg, out_color, out_depth, img.final_T,
                         img.n_contrib, s);
-  prof_end(0, 6, s);
+  prof_end(s);
   g_launches++;
   CK_LAUNCH("render forward", debug, s);
   return SFB_OK;
@@ -217,13 +222,14 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   ImgState img = ImgState::from_chunk(ichunk, HW);
   const int tfinal = num_rendered > 0 ? tile_sort_final(T) : 0;
 
-  prof_begin(1, 0, s);
+  g_which = 1; g_nrec[1] = 0;
+  prof_begin("zero_grad_acc", s);
   CK(cudaMemsetAsync(g.grad, 0, sizeof(GradRec) * (size_t)P, s));
-  prof_end(1, 0, s);
-  prof_begin(1, 1, s);
+  prof_end(s);
+  prof_begin("render_backward", s);
   launch_render_backward(W, H, b.ranges, b.inst_idx[tfinal], g.rec, bg, img.final_T, img.n_contrib,
                          dL_dout_color, g.grad, s);
-  prof_end(1, 1, s);
+  prof_end(s);
   g_launches++;
   CK_LAUNCH("render backward", debug, s);
 
@@ -236,9 +242,9 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   bp.dL_dmeans2D = dL_dmeans2D; bp.dL_dcolors = dL_dcolors; bp.dL_dopacity = dL_dopacity;
   bp.dL_dmeans3D = dL_dmeans3D; bp.dL_dcov3D = dL_dcov3D; bp.dL_dsh = dL_dsh; bp.dL_dscales = dL_dscales;
   bp.dL_drot = dL_drotations;
-  prof_begin(1, 2, s);
+  prof_begin("geom_backward", s);
   launch_geom_backward(bp, g, s);
-  prof_end(1, 2, s);
+  prof_end(s);
   g_launches++;
   CK_LAUNCH("geometry backward", debug, s);
   return SFB_OK;
@@ -246,24 +252,23 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
 
 void sfb_profile_enable(int on) { g_prof = on != 0; }
 
-int sfb_profile_read(int which, float* ms, int max_stages) {
+int sfb_profile_count(int which) { return (which == 0 || which == 1) ? g_nrec[which] : 0; }
+
+int sfb_profile_read(int which, float* ms, int max_records) {
   g_err.clear();
   if (which < 0 || which > 1 || !ms) return fail(SFB_ERR_ARG, "bad arguments");
-  const int n = which == 0 ? 7 : 3;
   int out = 0;
-  for (int i = 0; i < n && i < max_stages; i++, out++) {
+  for (int i = 0; i < g_nrec[which] && i < max_records; i++, out++) {
     ms[i] = 0.f;
-    if (!g_ev_made || !g_ev_used[which][i]) continue;
-    cudaError_t e = cudaEventSynchronize(g_ev[which][i][1]);
-    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms[i], g_ev[which][i][0], g_ev[which][i][1]);
+    cudaError_t e = cudaEventSynchronize(g_rec[which][i].b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms[i], g_rec[which][i].a, g_rec[which][i].b);
     if (e != cudaSuccess) return fail(SFB_ERR_CUDA, "profile read", e);
   }
   return out;
 }
 
-const char* sfb_profile_stage_name(int which, int stage) {
-  if (which == 0 && stage >= 0 && stage < 7) return kFwdStages[stage];
-  if (which == 1 && stage >= 0 && stage < 3) return kBwdStages[stage];
+const char* sfb_profile_name(int which, int i) {
+  if ((which == 0 || which == 1) && i >= 0 && i < g_nrec[which]) return g_rec[which][i].name;
   return "";
 }
 

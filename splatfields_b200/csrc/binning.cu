@@ -161,7 +161,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 }
 
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
-                     int* launches) {
+                     int* launches, const char* const* names) {
   if (n <= 0 || nbits <= 0) return 0;
   const int npass = (nbits + 7) / 8;
   const int nblocks = sort_blocks(n);
@@ -170,11 +170,17 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n
     // spread the bits evenly over the passes (12 -> 6+6, 13 -> 7+6, 32 -> 8x4)
     int bits = (nbits - shift + (npass - pass) - 1) / (npass - pass);
     int bins = 1 << bits;
+    prof_begin(names[0], s);
     radix_hist_kernel<<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], n, shift, bins, nblocks, hist);
+    prof_end(s);
     uint32_t* totals = hist + (size_t)SORT_MAX_BINS * nblocks;
+    prof_begin(names[1], s);
     scan_exclusive_kernel<<<bins, 1024, 0, s>>>(hist, nblocks, totals);  // one row (digit) per block
+    prof_end(s);
+    prof_begin(names[2], s);
     radix_scatter_kernel<<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
                                                           shift, bins, nblocks, hist, totals);
+    prof_end(s);
     if (launches) *launches += 3;
     cur ^= 1;
     shift += bits;
@@ -207,8 +213,12 @@ instance_block_sums_kernel(int P, const uint32_t* __restrict__ sorted_idx,
 void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
                                 uint32_t* block_sums, cudaStream_t s) {
   int nb = (P + DUP_GPB - 1) / DUP_GPB;
+  prof_begin("instance_block_sums", s);
   instance_block_sums_kernel<<<nb, DUP_THREADS, 0, s>>>(P, sorted_idx, tiles_touched, block_sums);
+  prof_end(s);
+  prof_begin("instance_block_scan", s);
   scan_exclusive_kernel<<<1, 1024, 0, s>>>(block_sums, nb, nullptr);
+  prof_end(s);
 }
 
 // Each block expands DUP_GPB depth-ranked Gaussians.  Output slot k of the block is produced by the

@@ -132,6 +132,10 @@ inline int tile_bits(int num_tiles) {
   return b;
 }
 
+// per-kernel profiling brackets (api.cu); no-ops unless sfb_profile_enable(1)
+void prof_begin(const char* name, cudaStream_t s);
+void prof_end(cudaStream_t s);
+
 // ------------------------------------------------------------------ launchers (one per .cu file)
 struct FwdParams {
   int P, D, M, W, H;
@@ -152,7 +156,7 @@ void launch_export_geom(int P, const GeomState& g, float* means2D, float* depths
 // Stable LSD radix sort of (key, value) pairs on key bits [0, nbits); returns the index (0/1) of the
 // ping-pong half that holds the result.  hist must hold SORT_MAX_BINS * (sort_blocks(n) + 1) words.
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
-                     int* launches);
+                     int* launches, const char* const* names /* {hist, scan, scatter} */);
 void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
                                 uint32_t* block_sums, cudaStream_t s);
 void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,

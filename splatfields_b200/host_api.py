@@ -1,0 +1,148 @@
+"""Host-side drivers above the rasterizer:
+
+* ViewParallelRasterizer — the multi-GPU unit of BASELINE.json's metric: one process per GPU, splats
+  replicated, each rank renders ITS camera (the reference renders the views of one iteration serially in
+  the loop at train.py:169 and averages the losses at train.py:242); the per-splat gradients of all
+  ranks are summed by ONE NCCL all-reduce over a flat fp32 slab [59, P] that the backward kernel writes
+  directly (no gather / flatten copy).
+* forward_backward_host — the same step for callers that hold HOST buffers: pinned host -> device copies
+  of every input, forward + backward, device -> pinned host copies of image, depth, radii and gradients.
+
+torch is plumbing here (device memory, streams, torch.distributed); the compute is libsplat_b200.so.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib, rasterizer
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+
+# (name, floats per splat) in slab order
+SLAB_FIELDS_SH = (("means3D", 3), ("opacities", 1), ("scales", 3), ("rotations", 4), ("shs", 48))
+SLAB_FIELDS_RGB = (("means3D", 3), ("opacities", 1), ("scales", 3), ("rotations", 4), ("colors_precomp", 3))
+
+
+class ViewParallelRasterizer:
+    def __init__(self, scene: dict, camera, H: int, W: int, sh_degree: int, device, world_size: int = 1,
+                 bg=(1.0, 1.0, 1.0)):
+        self.device = torch.device(device)
+        self.world = int(world_size)
+        self.H, self.W = H, W
+        self.P = scene["means3D"].shape[0]
+        self.params = {k: v.detach().to(self.device, copy=True).contiguous().requires_grad_(True)
+                       for k, v in scene.items()}
+        cam = camera.to(self.device)
+        self.settings = GaussianRasterizationSettings(
+            image_height=H, image_width=W, tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5),
+            bg=torch.tensor(bg, dtype=torch.float32, device=self.device), scale_modifier=1.0,
+            viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, sh_degree=sh_degree,
+            campos=cam.camera_center, prefiltered=False, debug=False)
+        self.rast = GaussianRasterizer(self.settings)
+        self.means2D = torch.zeros(self.P, 3, device=self.device, requires_grad=True)
+        self.fields = SLAB_FIELDS_SH if "shs" in scene else SLAB_FIELDS_RGB
+        self.floats_per_splat = sum(n for _, n in self.fields)
+        # the flat gradient slab: field-major [sum(n), P] so every field is one contiguous run
+        self.slab = torch.empty(self.floats_per_splat * self.P, dtype=torch.float32, device=self.device)
+        self.last = None
+
+    # -- one fwd + bwd (+ all-reduce); returns the number of kernel launches issued
+    def step(self, cotangent: torch.Tensor, keep: bool = False) -> int:
+        p = self.params
+        for v in p.values():
+            v.grad = None
+        self.means2D.grad = None
+        lib = _lib.load()
+        color, radii, depth = self.rast(means3D=p["means3D"], means2D=self.means2D, opacities=p["opacities"],
+                                        shs=p.get("shs"), colors_precomp=p.get("colors_precomp"),
+                                        scales=p["scales"], rotations=p["rotations"])
+        n = lib.sfb_last_launch_count()
+        rasterizer.set_grad_arena(self.slab, self.fields)
+        try:
+            # mean over views (train.py:242) folded into the cotangent: backward is linear in it
+            color.backward(cotangent if self.world == 1 else cotangent * (1.0 / self.world))
+        finally:
+            rasterizer.set_grad_arena(None, None)
+        n += lib.sfb_last_launch_count()
+        # normally a no-op: the backward kernel already wrote into the slab slices (the .grad tensors ARE
+        # those slices); copy only if autograd handed back separate storage.
+        for name, dst in self.grads().items():
+            g = p[name].grad
+            if g is None:
+                dst.zero_()
+            elif g.data_ptr() != dst.data_ptr():
+                dst.copy_(g.reshape(-1))
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.slab, op=dist.ReduceOp.SUM)
+            n += 1
+        if keep:
+            self.last = (color.detach(), radii, depth.detach())
+        return n
+
+    def grads(self) -> dict:
+        out, off = {}, 0
+        for name, n in self.fields:
+            out[name] = self.slab[off * self.P:(off + n) * self.P]
+            off += n
+        return out
+
+    # -- tile-list statistics of this rank's view (for the bench's roofline accounting)
+    def list_stats(self) -> dict:
+        import ctypes as C  # noqa: F401
+        lib = _lib.load()
+        p = self.params
+        color, radii, depth = self.rast(means3D=p["means3D"], means2D=self.means2D, opacities=p["opacities"],
+                                        shs=p.get("shs"), colors_precomp=p.get("colors_precomp"),
+                                        scales=p["scales"], rotations=p["rotations"])
+        fn = color.grad_fn
+        radii_s, geom, binning, img = fn.saved_tensors
+        R = fn.num_rendered
+        H, W = self.H, self.W
+        gx, gy = (W + 15) // 16, (H + 15) // 16
+        T = gx * gy
+        ranges = torch.zeros(T, 2, dtype=torch.int32, device=self.device)
+        _lib.check(lib.sfb_export_binning(self.P, R, W, H, geom.data_ptr(), binning.data_ptr(), None, None,
+                                          ranges.data_ptr(), None))
+        nc = torch.zeros(H, W, dtype=torch.int32, device=self.device)
+        _lib.check(lib.sfb_export_img(W, H, img.data_ptr(), None, nc.data_ptr(), None))
+        torch.cuda.synchronize()
+        lens = (ranges[:, 1] - ranges[:, 0]).long()
+        pad = torch.zeros(gy * 16, gx * 16, dtype=torch.int64, device=self.device)
+        pad[:H, :W] = nc.long()
+        tmax = pad.reshape(gy, 16, gx, 16).amax(dim=(1, 3)).reshape(-1)      # deepest contributor per tile
+        # entries the forward sweeps: whole 256-batches until every pixel of the tile is done (<= list length);
+        # entries the backward sweeps: up to the deepest last contributor.
+        r_bwd = int(torch.minimum(tmax, lens).sum())
+        r_fwd = int(torch.minimum(((tmax + 256) // 256) * 256, lens).sum())
+        return dict(R=int(R), visible=int((radii > 0).sum()), mean_list=float(lens.float().mean()),
+                    max_list=int(lens.max()), R_fwd=r_fwd, R_bwd=r_bwd)
+
+    # -- pinned host mirrors of every input and output of one step
+    def pinned_host_buffers(self, scene: dict, cotangent: torch.Tensor):
+        pin = lambda t: t.detach().cpu().contiguous().pin_memory()
+        host_in = {k: pin(v) for k, v in scene.items()}
+        host_in["dL_dcolor"] = pin(cotangent)
+        host_out = dict(color=torch.empty(3, self.H, self.W).pin_memory(),
+                        depth=torch.empty(1, self.H, self.W).pin_memory(),
+                        radii=torch.empty(self.P, dtype=torch.int32).pin_memory(),
+                        grads=torch.empty(self.floats_per_splat * self.P).pin_memory())
+        self._cot_dev = torch.empty_like(cotangent, device=self.device)
+        return host_in, host_out
+
+
+def forward_backward_host(vp: ViewParallelRasterizer, host_in: dict, host_out: dict) -> None:
+    """HOST buffers in, HOST buffers out: H2D of all splat parameters + cotangent, fwd + bwd
+    (+ all-reduce), D2H of image, depth, radii and the gradient slab; returns when the host buffers are valid."""
+    with torch.no_grad():
+        for k, v in vp.params.items():
+            v.copy_(host_in[k], non_blocking=True)
+        vp._cot_dev.copy_(host_in["dL_dcolor"], non_blocking=True)
+    vp.step(vp._cot_dev, keep=True)
+    color, radii, depth = vp.last
+    host_out["color"].copy_(color, non_blocking=True)
+    host_out["depth"].copy_(depth, non_blocking=True)
+    host_out["radii"].copy_(radii, non_blocking=True)
+    host_out["grads"].copy_(vp.slab, non_blocking=True)
+    torch.cuda.current_stream(vp.device).synchronize()

@@ -35,6 +35,33 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
+# Optional gradient arena: when set, backward writes the parameter gradients straight into slices of one
+# caller-owned flat fp32 slab (the buffer a view-parallel trainer hands to NCCL all-reduce) instead of
+# allocating separate tensors.  fields = ((input name, floats per splat), ...) in slab order.
+_ARENA = None
+
+
+def set_grad_arena(slab, fields):
+    global _ARENA
+    _ARENA = None if slab is None else (slab, tuple(fields))
+
+
+def _arena_out(name, P, shape, **f32):
+    if _ARENA is not None:
+        slab, fields = _ARENA
+        off = 0
+        for fname, n in fields:
+            if fname == name:
+                numel = 1
+                for d in shape:
+                    numel *= d
+                if numel == n * P and (off + n) * P <= slab.numel():
+                    return slab[off * P:(off + n) * P].view(shape)
+                break
+            off += n
+    return torch.empty(shape, **f32)
+
+
 def _ptr(t):
     return None if t is None or t.numel() == 0 else t.data_ptr()
 
@@ -154,14 +181,14 @@ class _RasterizeGaussians(torch.autograd.Function):
         H, W = int(rs.image_height), int(rs.image_width)
         M = ctx.M
         f32 = dict(dtype=torch.float32, device=dev)
-        dL_dmeans3D = torch.empty((P, 3), **f32)
+        dL_dmeans3D = _arena_out("means3D", P, (P, 3), **f32)
         dL_dmeans2D = torch.empty((P, 3), **f32)
-        dL_dcolors = torch.empty((P, 3), **f32)
-        dL_dopacity = torch.empty((P, 1), **f32)
-        dL_dcov3D = torch.empty((P, 6), **f32)
-        dL_dsh = torch.empty((P, M, 3), **f32) if sh is not None else None
-        dL_dscales = torch.empty((P, 3), **f32) if cov is None else None
-        dL_drot = torch.empty((P, 4), **f32) if cov is None else None
+        dL_dcolors = _arena_out("colors_precomp", P, (P, 3), **f32)
+        dL_dopacity = _arena_out("opacities", P, (P, 1), **f32)
+        dL_dcov3D = _arena_out("cov3D_precomp", P, (P, 6), **f32)
+        dL_dsh = _arena_out("shs", P, (P, M, 3), **f32) if sh is not None else None
+        dL_dscales = _arena_out("scales", P, (P, 3), **f32) if cov is None else None
+        dL_drot = _arena_out("rotations", P, (P, 4), **f32) if cov is None else None
         g = _prep(grad_out_color)
         if P > 0:
             with torch.cuda.device(dev):

@@ -1,0 +1,89 @@
+"""CPU, world_size = 2 over gloo: the host logic of the view-parallel path — gradient slab carving,
+1/world folded into the cotangent, ONE all-reduce(SUM) — reproduces the reference's serial multi-view
+accumulation (train.py:169 loop, train.py:242 mean of the per-view losses).  The rasterizer itself is
+replaced by a tiny differentiable stand-in (no GPU here); the CUDA path is covered by -m gpu tests."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from splatfields_b200 import synth
+from splatfields_b200.host_api import SLAB_FIELDS_SH, ViewParallelRasterizer
+
+
+class _StubRast(torch.nn.Module):
+    """colour[3,H,W] as a smooth function of every parameter and of the camera (so views differ)."""
+
+    def __init__(self, cam, H, W):
+        super().__init__()
+        self.cam, self.H, self.W = cam, H, W
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        hom = torch.cat([means3D, torch.ones_like(means3D[:, :1])], 1) @ self.cam.full_proj_transform
+        w = torch.sigmoid(hom[:, :1]) * opacities * scales.sum(1, keepdim=True) * (rotations ** 2).sum(1, keepdim=True)
+        feat = (shs * torch.linspace(0.5, 1.5, shs.shape[1])[None, :, None]).sum(1)        # [P,3]
+        img = (w * feat).t() @ torch.sin(torch.arange(means3D.shape[0] * self.H * self.W, dtype=torch.float32)
+                                         .reshape(means3D.shape[0], self.H * self.W) * 0.01)
+        color = img.reshape(3, self.H, self.W) + 0.0 * means2D.sum()
+        return color, torch.ones(means3D.shape[0], dtype=torch.int32), color[:1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P, H, W = 40, 8, 12
+        sc = synth.make_scene(P, 5)
+        cam = synth.orbit_camera(rank, H, W)
+        vp = ViewParallelRasterizer(sc, cam, H, W, 3, device="cpu", world_size=world)
+        vp.rast = _StubRast(cam, H, W)
+        G = torch.randn(3, H, W, generator=torch.Generator().manual_seed(100 + rank))
+        vp.step(G)
+        got = {k: v.clone() for k, v in vp.grads().items()}
+        if rank == 0:
+            # serial reference: loop over the views, mean of the losses, one backward
+            leaves = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+            losses = []
+            for r in range(world):
+                c = synth.orbit_camera(r, H, W)
+                Gr = torch.randn(3, H, W, generator=torch.Generator().manual_seed(100 + r))
+                col, _, _ = _StubRast(c, H, W)(leaves["means3D"], torch.zeros(P, 3), leaves["opacities"],
+                                               shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+                losses.append((col * Gr).sum())
+            (sum(losses) / world).backward()
+            ok = all(torch.allclose(got[n], leaves[n].grad.reshape(-1), rtol=1e-4, atol=1e-5) for n, _ in SLAB_FIELDS_SH)
+            ret.put(bool(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_view_parallel_allreduce_matches_serial_mean():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) is True
+
+
+def test_slab_layout():
+    sc = synth.make_scene(16, 1)
+    vp = ViewParallelRasterizer(sc, synth.orbit_camera(0, 16, 16), 16, 16, 3, device="cpu")
+    g = vp.grads()
+    assert [k for k in g] == ["means3D", "opacities", "scales", "rotations", "shs"]
+    assert vp.slab.numel() == 59 * 16 and sum(v.numel() for v in g.values()) == 59 * 16
+    # slices tile the slab without gaps, in order
+    off = 0
+    for v in g.values():
+        assert v.data_ptr() == vp.slab.data_ptr() + 4 * off
+        off += v.numel()
