@@ -56,14 +56,23 @@ class ClockSampler:
         self.proc = None
         self.lines = []
 
-    def start(self):
+    def start(self, wait_first_sample_s: float = 5.0):
+        """Start polling and wait until nvidia-smi has delivered its first sample, so that its start-up
+        (NVML initialisation takes the driver lock) never falls inside a timed region."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < wait_first_sample_s:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Samples taken from now on belong to the timed regions."""
+        self.first = len(self.lines)
 
     def _pump(self):
         for ln in self.proc.stdout:
@@ -79,7 +88,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "first", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -128,7 +137,7 @@ def run_reference(args):
         return
     from oracle import oracle as O
     O.build()
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     O.set_num_threads(cores)
     cfg, sc, cam, G = make_workload(0)
     for _ in range(args.warmup):
@@ -202,14 +211,16 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing: `value` ----
-    for _ in range(max(args.warmup, 3)):
-        vp.step(Gd)
-    sync_all()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        vp.step(Gd)
+    sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    if rank == 0:
+        sampler.mark()
     e0.record()
     launches = 0
     for _ in range(args.steps):
@@ -219,7 +230,6 @@ def run_ours(args):
     ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if dist is not None:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop() if rank == 0 else None
     ms_step = float(ms_total.item()) / args.steps
     value = world * P / (ms_step * 1e-3) / 1e6
 
@@ -239,6 +249,7 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     ms_e2e_step = float(ms_e2e.item()) / args.steps
+    clocks = sampler.stop() if rank == 0 else None     # samples span both timed regions (value + e2e)
     h2d = sum(t.numel() * t.element_size() for t in host_in.values())
     d2h = sum(t.numel() * t.element_size() for t in host_out.values())
     e2e = {"value": world * P / (ms_e2e_step * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e_step,
@@ -280,7 +291,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         O.build()
-        O.set_num_threads(os.cpu_count() or 1)
+        O.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
         t, _f = oracle_step(O, sc, cam, cfg, G)
         cpu_baseline = {"value": P / t / 1e6, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
                         "sample": f"1 full fwd+bwd step of {WORKLOAD} ({t:.2f} s of wall time on all host threads)"}
@@ -308,8 +319,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

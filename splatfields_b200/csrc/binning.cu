@@ -12,6 +12,7 @@
 //
 // All of this is integer work bound by HBM/L2 traffic; no tensor cores.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace sfb {
 
@@ -160,7 +161,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   }
 }
 
-int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
+static int radix_sort_pairs_legacy(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
                      int* launches, const char* const* names) {
   if (n <= 0 || nbits <= 0) return 0;
   const int npass = (nbits + 7) / 8;
@@ -186,6 +187,200 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n
     shift += bits;
   }
   return cur;
+}
+
+
+// ------------------------------------------------------------------ onesweep radix sort (default)
+// One kernel per digit pass: a block takes a ticket, ranks its 4096 (key, value) pairs stably, publishes
+// its per-digit counts and obtains its global offsets by DECOUPLED LOOK-BACK over the predecessors'
+// published counts (flag | value in one word: 1 = block aggregate, 2 = inclusive prefix), stages the pairs
+// in shared memory in sorted order and writes them out as coalesced per-digit runs.  Keys and values are
+// read once and written once per pass; the digit histograms of ALL passes come from one up-front sweep.
+constexpr uint32_t OS_FLAG_AGG = 1u << 30, OS_FLAG_INC = 2u << 30, OS_VAL_MASK = (1u << 30) - 1u;
+constexpr int OS_MAX_PASSES = 4;
+
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_hist_all_kernel(const uint32_t* __restrict__ keys, int n, int npass, int4 shifts, int4 nbins,
+                      uint32_t* __restrict__ hist_all /* [npass][SORT_MAX_BINS] */) {
+  __shared__ uint32_t s_h[OS_MAX_PASSES][SORT_MAX_BINS];
+  for (int i = threadIdx.x; i < OS_MAX_PASSES * SORT_MAX_BINS; i += SORT_THREADS) (&s_h[0][0])[i] = 0;
+  __syncthreads();
+  const int sh[4] = {shifts.x, shifts.y, shifts.z, shifts.w};
+  const int nb[4] = {nbins.x, nbins.y, nbins.z, nbins.w};
+  const int stride = gridDim.x * SORT_THREADS;
+  for (int k = blockIdx.x * SORT_THREADS + threadIdx.x; k < n; k += stride) {
+    const uint32_t key = keys[k];
+#pragma unroll
+    for (int p = 0; p < OS_MAX_PASSES; p++)
+      if (p < npass) atomicAdd(&s_h[p][(key >> sh[p]) & (uint32_t)(nb[p] - 1)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npass * SORT_MAX_BINS; i += SORT_THREADS) {
+    const uint32_t v = (&s_h[0][0])[i];
+    if (v) atomicAdd(&hist_all[i], v);
+  }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift, int bins,
+                     const uint32_t* __restrict__ digit_totals /* [SORT_MAX_BINS] for this pass */,
+                     uint32_t* __restrict__ tile_state /* [nblocks][bins], zeroed */,
+                     uint32_t* __restrict__ ticket /* zeroed */) {
+  constexpr int NW = SORT_THREADS / 32;
+  __shared__ uint32_t s_cnt[NW][SORT_MAX_BINS];   // per-warp digit counts -> exclusive-over-warps prefixes
+  __shared__ uint32_t s_lstart[SORT_MAX_BINS];    // block-local start of each digit run
+  __shared__ int32_t s_gofs[SORT_MAX_BINS];       // global position - local position, per digit
+  __shared__ uint32_t s_key[SORT_TILE];
+  __shared__ uint32_t s_val[SORT_TILE];
+  __shared__ uint32_t s_wsum[NW];
+  __shared__ uint32_t s_ticket;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t mask = (uint32_t)bins - 1;
+  for (int i = threadIdx.x; i < NW * SORT_MAX_BINS; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int blk = (int)s_ticket;
+
+  // ---- stable ranking inside the block (sequential order = warp, item, lane) ----
+  const int seg = blk * SORT_TILE + warp * (32 * SORT_IPT);
+  uint32_t key[SORT_IPT], rank[SORT_IPT];
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < SORT_IPT; i++) {
+    const int k = seg + i * 32 + lane;
+    const bool valid = k < n;
+    key[i] = valid ? keys_in[k] : 0xFFFFFFFFu;
+    const uint32_t d = (key[i] >> shift) & mask;
+    const uint32_t md = valid ? d : 0xFFFFu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, md);
+    const uint32_t before = __popc(peers & lt_mask);
+    uint32_t prev = 0;
+    if (valid && before == 0) {
+      prev = s_cnt[warp][d];
+      s_cnt[warp][d] = prev + __popc(peers);
+    }
+    prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
+    rank[i] = prev + before;
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- per digit (one thread each): block count, publish, look back, global base ----
+  uint32_t my_count = 0, dtotal = 0;
+  const int d = threadIdx.x;
+  if (d < bins) {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) { const uint32_t c = s_cnt[w][d]; s_cnt[w][d] = run; run += c; }
+    my_count = run;
+    dtotal = digit_totals[d];
+    volatile uint32_t* st = tile_state;
+    st[(size_t)blk * bins + d] = (blk == 0 ? OS_FLAG_INC : OS_FLAG_AGG) | my_count;
+  }
+  // block-wide exclusive scans: of the block's digit counts (local starts) and of the digit totals (bases)
+  uint32_t inc_c = my_count, inc_t = dtotal;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t a = __shfl_up_sync(0xffffffffu, inc_c, o), b2 = __shfl_up_sync(0xffffffffu, inc_t, o);
+    if (lane >= o) { inc_c += a; inc_t += b2; }
+  }
+  __shared__ uint32_t s_wsum_t[NW];
+  if (lane == 31) { s_wsum[warp] = inc_c; s_wsum_t[warp] = inc_t; }
+  __syncthreads();
+  uint32_t wb_c = 0, wb_t = 0;
+  for (int w = 0; w < warp; w++) { wb_c += s_wsum[w]; wb_t += s_wsum_t[w]; }
+  const uint32_t lstart = wb_c + inc_c - my_count;     // local start of digit d inside the block
+  const uint32_t dbase = wb_t + inc_t - dtotal;        // global start of digit d
+  if (d < bins) {
+    uint32_t excl = 0;
+    if (blk > 0) {
+      volatile uint32_t* st = tile_state;
+      int p = blk - 1;
+      while (true) {
+        const uint32_t v = st[(size_t)p * bins + d];
+        const uint32_t f = v & ~OS_VAL_MASK;
+        if (f == 0u) continue;                          // predecessor not published yet: spin
+        excl += v & OS_VAL_MASK;
+        if (f == OS_FLAG_INC) break;
+        p--;
+      }
+      st[(size_t)blk * bins + d] = OS_FLAG_INC | (excl + my_count);
+    }
+    s_lstart[d] = lstart;
+    s_gofs[d] = (int32_t)(dbase + excl) - (int32_t)lstart;
+  }
+  __syncthreads();
+
+  // ---- stage in shared memory in sorted order, then write coalesced runs ----
+#pragma unroll
+  for (int i = 0; i < SORT_IPT; i++) {
+    const int k = seg + i * 32 + lane;
+    if (k < n) {
+      const uint32_t dd = (key[i] >> shift) & mask;
+      const uint32_t lp = s_lstart[dd] + s_cnt[warp][dd] + rank[i];
+      s_key[lp] = key[i];
+      s_val[lp] = vals_in[k];
+    }
+  }
+  __syncthreads();
+  const int cnt_blk = min(SORT_TILE, n - blk * SORT_TILE);
+  for (int q = threadIdx.x; q < cnt_blk; q += SORT_THREADS) {
+    const uint32_t kk = s_key[q];
+    const uint32_t dd = (kk >> shift) & mask;
+    const int32_t dst = (int32_t)q + s_gofs[dd];
+    keys_out[dst] = kk;
+    vals_out[dst] = s_val[q];
+  }
+}
+
+static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint32_t* scratch, int n, int nbits,
+                                     cudaStream_t s, int* launches, const char* const* names) {
+  const int npass = (nbits + 7) / 8;
+  const int nblocks = sort_blocks(n);
+  // scratch layout: [hist_all: 4*256][tickets: 8][tile_state: npass * nblocks * bins]
+  uint32_t* hist_all = scratch;
+  uint32_t* tickets = scratch + OS_MAX_PASSES * SORT_MAX_BINS;
+  uint32_t* state0 = tickets + 8;
+  int shifts[4] = {0, 0, 0, 0}, nbins[4] = {1, 1, 1, 1};
+  int shift = 0;
+  size_t state_words = 0;
+  for (int pass = 0; pass < npass; pass++) {
+    const int bits = (nbits - shift + (npass - pass) - 1) / (npass - pass);
+    shifts[pass] = shift;
+    nbins[pass] = 1 << bits;
+    state_words += (size_t)nblocks * nbins[pass];
+    shift += bits;
+  }
+  cudaMemsetAsync(scratch, 0, sizeof(uint32_t) * (OS_MAX_PASSES * SORT_MAX_BINS + 8 + state_words), s);
+  prof_begin(names[0], s);
+  const int hblocks = min(nblocks, 4 * NUM_SMS_B200);
+  radix_hist_all_kernel<<<hblocks, SORT_THREADS, 0, s>>>(keys[0], n, npass, make_int4(shifts[0], shifts[1], shifts[2], shifts[3]),
+                                                          make_int4(nbins[0], nbins[1], nbins[2], nbins[3]), hist_all);
+  prof_end(s);
+  if (launches) *launches += 1;
+  int cur = 0;
+  uint32_t* state = state0;
+  for (int pass = 0; pass < npass; pass++) {
+    prof_begin(names[2], s);
+    onesweep_pass_kernel<<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
+                                                          shifts[pass], nbins[pass], hist_all + pass * SORT_MAX_BINS,
+                                                          state, tickets + pass);
+    prof_end(s);
+    if (launches) *launches += 1;
+    state += (size_t)nblocks * nbins[pass];
+    cur ^= 1;
+  }
+  return cur;
+}
+
+int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
+                     int* launches, const char* const* names) {
+  if (n <= 0 || nbits <= 0) return 0;
+  static int legacy = -1;
+  if (legacy < 0) { const char* e = getenv("SFB_SORT"); legacy = (e && e[0] == 'l') ? 1 : 0; }
+  if (legacy) return radix_sort_pairs_legacy(keys, vals, hist, n, nbits, s, launches, names);
+  return radix_sort_pairs_onesweep(keys, vals, hist, n, nbits, s, launches, names);
 }
 
 // ------------------------------------------------------------------ instance emission in depth order

@@ -18,9 +18,24 @@ constexpr int NUM_SMS_B200 = 148;
 struct __align__(16) SplatRec {
   float x, y, conA, conB;   // screen mean (pixels), conic A, B
   float conC, opacity, depth, r;
-  float g, b, pad0, pad1;
+  float g, b, hx, hy;       // hx, hy: conservative half-extents of the alpha >= 1/255 footprint (-1: never)
 };
 static_assert(sizeof(SplatRec) == 48, "SplatRec must be 48 bytes");
+
+// Bit w of the returned mask is set iff the splat's footprint box can touch the 8x4-pixel patch of warp w
+// (patch w: x-half w&1, y-quarter w>>1) of the 16x16 tile whose first pixel is (tx0, ty0).
+__device__ __forceinline__ uint32_t patch_mask(float x, float y, float hx, float hy, float tx0, float ty0) {
+  if (hx < 0.f) return 0u;
+  const float xl = x - hx, xh = x + hx, yl = y - hy, yh = y + hy;
+  uint32_t mx = 0u;
+  if (xh >= tx0 && xl <= tx0 + 7.f) mx |= 1u;
+  if (xh >= tx0 + 8.f && xl <= tx0 + 15.f) mx |= 2u;
+  uint32_t m = 0u;
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+    if (yh >= ty0 + 4.f * r && yl <= ty0 + 4.f * r + 3.f) m |= mx << (2 * r);
+  return m;
+}
 
 // Per-Gaussian gradient accumulator filled by the backward render (atomics), consumed by the
 // per-Gaussian backward.  Same 48-byte shape so one splat's partials share two sectors.
@@ -47,6 +62,11 @@ constexpr int SORT_IPT = 16;                          // items per thread
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;    // items per block
 constexpr int SORT_MAX_BINS = 256;
 __host__ __device__ inline int sort_blocks(int n) { return (n + SORT_TILE - 1) / SORT_TILE; }
+// words of sort scratch for n items: 4 digit histograms + tickets + one look-back state row per pass
+// (worst case 4 passes x 256 bins), which also covers the legacy path's [bins][blocks] histogram + totals.
+__host__ __device__ inline size_t sort_scratch_words(size_t n) {
+  return (size_t)4 * SORT_MAX_BINS + 8 + (size_t)4 * SORT_MAX_BINS * (size_t)(sort_blocks((int)n) + 1) + 16;
+}
 
 // ---- P-sized scratch ("geomBuffer") ----
 struct GeomState {
@@ -71,7 +91,7 @@ struct GeomState {
     g.clamped = carve<uint8_t>(chunk, P);
     for (int i = 0; i < 2; i++) g.depth_key[i] = carve<uint32_t>(chunk, P);
     for (int i = 0; i < 2; i++) g.depth_idx[i] = carve<uint32_t>(chunk, P);
-    g.sort_hist = carve<uint32_t>(chunk, (size_t)SORT_MAX_BINS * (sort_blocks((int)P) + 1) + 16);
+    g.sort_hist = carve<uint32_t>(chunk, sort_scratch_words(P));
     g.block_sums = carve<uint32_t>(chunk, (size_t)sort_blocks((int)P) + 2);
     g.counters = carve<uint32_t>(chunk, 8);
     g.grad = carve<GradRec>(chunk, P);
@@ -96,7 +116,7 @@ struct BinState {
     BinState b;
     for (int i = 0; i < 2; i++) b.tile_key[i] = carve<uint32_t>(chunk, R);
     for (int i = 0; i < 2; i++) b.inst_idx[i] = carve<uint32_t>(chunk, R);
-    b.sort_hist = carve<uint32_t>(chunk, (size_t)SORT_MAX_BINS * (sort_blocks((int)R) + 1) + 16);
+    b.sort_hist = carve<uint32_t>(chunk, sort_scratch_words(R));
     b.ranges = carve<uint2>(chunk, T);
     b.final_buf = 0;
     return b;
@@ -154,7 +174,7 @@ void launch_export_geom(int P, const GeomState& g, float* means2D, float* depths
 
 // binning.cu
 // Stable LSD radix sort of (key, value) pairs on key bits [0, nbits); returns the index (0/1) of the
-// ping-pong half that holds the result.  hist must hold SORT_MAX_BINS * (sort_blocks(n) + 1) words.
+// ping-pong half that holds the result.  hist must hold sort_scratch_words(n) words.
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
                      int* launches, const char* const* names /* {hist, scan, scatter} */);
 void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_t* tiles_touched,

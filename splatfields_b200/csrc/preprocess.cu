@@ -219,10 +219,27 @@ preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
             load_sh<D, VEC_SH>(p.shs, idx, p.M, sh);
             sh_to_rgb<D>(sh, mean, cam.campos, rgb, clamp_mask);
           }
+          // Conservative half-extents (pixels) of the region where this splat can reach alpha >= 1/255:
+          // alpha = o*exp(-q/2) >= 1/255  <=>  q <= tau = 2 ln(255 o); the AABB of {d^T Sigma^-1 d <= tau} is
+          // sqrt(tau * Sigma_xx), sqrt(tau * Sigma_yy) with Sigma the dilated 2D covariance (a, c above).
+          // +2 % and +0.5 px absorb the rounding of the fp32 conic inversion; ill-conditioned splats
+          // (lambda1/lambda2 > 1e4) and NaN opacities are never culled.  The render kernels use this ONLY to
+          // skip (splat, 8x4-pixel patch) pairs that provably fail the reference's own alpha test, so the
+          // composited result is unchanged bit for bit.
+          const float opac = __ldg(p.opacities + idx);
+          float hx, hy;
+          if (opac != opac) { hx = hy = 3.0e38f; }
+          else if (opac < 1.0f / 255.0f) { hx = hy = -1.f; }   // alpha <= o < 1/255 everywhere
+          else {
+            const float tau = fmaxf(0.f, 2.f * logf(255.f * opac));
+            const bool ill = !(lambda2 > 0.f) || lambda1 > 1.0e4f * lambda2;
+            hx = ill ? 3.0e38f : 1.02f * sqrtf(tau * a) + 0.5f;
+            hy = ill ? 3.0e38f : 1.02f * sqrtf(tau * c) + 0.5f;
+          }
           float4* rp = reinterpret_cast<float4*>(g.rec + idx);
           rp[0] = make_float4(pix, piy, conA, conB);
-          rp[1] = make_float4(conC, __ldg(p.opacities + idx), p_view.z, rgb[0]);
-          rp[2] = make_float4(rgb[1], rgb[2], 0.f, 0.f);
+          rp[1] = make_float4(conC, opac, p_view.z, rgb[0]);
+          rp[2] = make_float4(rgb[1], rgb[2], hx, hy);
           out_radius = irad;
           my_tiles = (uint32_t)area;
           key = __float_as_uint(p_view.z);

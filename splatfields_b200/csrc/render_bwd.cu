@@ -11,6 +11,7 @@
 // Accumulation order differs from the reference's (as it does between two runs of the reference), so
 // parity here is tolerance-based: 1e-3 relative on every per-splat gradient.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace sfb {
 
@@ -20,6 +21,9 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// CULL: same per-warp footprint culling as the forward render (SplatRec::hx/hy): a warp skips splats that
+// cannot reach alpha >= 1/255 on any of its 32 pixels — pairs whose contribution is exactly zero.
+template <bool CULL>
 __global__ void __launch_bounds__(BB)
 render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
                        const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ rec,
@@ -32,6 +36,9 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
   __shared__ uint32_t s_id[BB];
   __shared__ float s_acc[BB * 9];
   __shared__ uint32_t s_max[BB / 32];
+  __shared__ uint8_t s_mask[CULL ? BB : 1];
+  __shared__ uint8_t s_list[CULL ? BB / 32 : 1][CULL ? BB : 1];
+  const float tx0 = (float)((blockIdx.x % grid_x) * TILE_X), ty0 = (float)((blockIdx.x / grid_x) * TILE_Y);
 
   const int tile = blockIdx.x;
   const int tile_x = tile % grid_x, tile_y = tile / grid_x;
@@ -65,6 +72,7 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
     // smem slot j holds list position top-1-j (back to front)
     const int n = top < BB ? top : BB;
     __syncthreads();
+    uint32_t mask = 0u;
     if ((int)threadIdx.x < n) {
       uint32_t id = point_list[range.x + (uint32_t)(top - 1 - (int)threadIdx.x)];
       const float4* rp = reinterpret_cast<const float4*>(rec + id);
@@ -73,12 +81,30 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
       s_q1[threadIdx.x] = b;
       s_q2[threadIdx.x] = make_float2(c.x, c.y);
       s_id[threadIdx.x] = id;
+      if (CULL) mask = patch_mask(a.x, a.y, c.z, c.w, tx0, ty0);
     }
+    if (CULL) s_mask[threadIdx.x] = (uint8_t)mask;
 #pragma unroll
     for (int k = 0; k < 9; k++) s_acc[k * BB + threadIdx.x] = 0.f;
     __syncthreads();
+    int nsweep = n;
+    if (CULL) {
+      int cnt = 0;
+      const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+      for (int c8 = 0; c8 < BB / 32; c8++) {
+        const int idx = c8 * 32 + lane;
+        const bool hit = (s_mask[idx] >> warp) & 1;
+        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) s_list[warp][cnt + __popc(bal & lt)] = (uint8_t)idx;
+        cnt += __popc(bal);
+      }
+      __syncwarp();
+      nsweep = cnt;
+    }
 
-    for (int j = 0; j < n; j++) {
+    for (int kk = 0; kk < nsweep; kk++) {
+      const int j = CULL ? (int)s_list[warp][kk] : kk;
       const uint32_t pos = (uint32_t)(top - 1 - j);
       float v[8], v8 = 0.f;
 #pragma unroll
@@ -177,8 +203,14 @@ void launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* p
                             const float* bg, const float* final_T, const uint32_t* n_contrib,
                             const float* dL_dpixels, GradRec* grad, cudaStream_t s) {
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
-  render_backward_kernel<<<gx * gy, BB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib,
-                                                 dL_dpixels, grad);
+  static int cull = -1;
+  if (cull < 0) { const char* e = getenv("SFB_NO_CULL"); cull = (e && e[0] == '1') ? 0 : 1; }
+  if (cull)
+    render_backward_kernel<true><<<gx * gy, BB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib,
+                                                         dL_dpixels, grad);
+  else
+    render_backward_kernel<false><<<gx * gy, BB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T,
+                                                          n_contrib, dL_dpixels, grad);
 }
 
 }  // namespace sfb

@@ -9,11 +9,17 @@
 // where the whole record array of a 1M-splat scene stays resident) into shared memory, then all threads
 // sweep the batch reading the records as warp-wide broadcasts.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace sfb {
 
 constexpr int RB = 256;  // batch = block size
 
+// CULL: each fetched splat gets an 8-bit mask of the 8x4 patches (= warps) its alpha >= 1/255 footprint box
+// can touch (SplatRec::hx/hy, computed conservatively in preprocess); every warp then sweeps only its own
+// compacted sub-list.  Skipped (splat, patch) pairs are pairs the reference's own `alpha < 1/255` test would
+// reject for all 32 pixels, so the output is bit-identical; the sweep shrinks ~3x on dense scenes.
+template <bool CULL>
 __global__ void __launch_bounds__(RB)
 render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
                       const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ rec,
@@ -23,6 +29,8 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
   __shared__ float4 s_q0[RB];  // x, y, conA, conB
   __shared__ float4 s_q1[RB];  // conC, opacity, depth, r
   __shared__ float2 s_q2[RB];  // g, b
+  __shared__ uint8_t s_mask[CULL ? RB : 1];
+  __shared__ uint8_t s_list[CULL ? RB / 32 : 1][CULL ? RB : 1];
 
   const int tile = blockIdx.x;
   const int tile_x = tile % grid_x, tile_y = tile / grid_x;
@@ -31,16 +39,18 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
   const int py = tile_y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
   const bool inside = px < W && py < H;
   const float pixfx = (float)px, pixfy = (float)py;
+  const float tx0 = (float)(tile_x * TILE_X), ty0 = (float)(tile_y * TILE_Y);
 
   const uint2 range = ranges[tile];
   int todo = (int)(range.y - range.x);
   bool done = !inside;
 
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
-  uint32_t contributor = 0, last_contributor = 0;
+  uint32_t last_contributor = 0;
 
   for (int base = 0; todo > 0; base += RB, todo -= RB) {
     if (__syncthreads_count(done) == RB) break;
+    uint32_t mask = 0u;
     if ((int)threadIdx.x < todo) {
       uint32_t id = point_list[range.x + base + threadIdx.x];
       const float4* rp = reinterpret_cast<const float4*>(rec + id);
@@ -48,11 +58,27 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
       s_q0[threadIdx.x] = a;
       s_q1[threadIdx.x] = b;
       s_q2[threadIdx.x] = make_float2(c.x, c.y);
+      if (CULL) mask = patch_mask(a.x, a.y, c.z, c.w, tx0, ty0);
     }
+    if (CULL) s_mask[threadIdx.x] = (uint8_t)mask;
     __syncthreads();
-    const int n = todo < RB ? todo : RB;
-    for (int j = 0; !done && j < n; j++) {
-      contributor++;
+    int n = todo < RB ? todo : RB;
+    if (CULL) {
+      int cnt = 0;
+      const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+      for (int c8 = 0; c8 < RB / 32; c8++) {
+        const int idx = c8 * 32 + lane;
+        const bool hit = (s_mask[idx] >> warp) & 1;
+        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) s_list[warp][cnt + __popc(bal & lt)] = (uint8_t)idx;
+        cnt += __popc(bal);
+      }
+      __syncwarp();
+      n = cnt;
+    }
+    for (int k = 0; !done && k < n; k++) {
+      const int j = CULL ? (int)s_list[warp][k] : k;
       const float4 q0 = s_q0[j];
       const float dx = q0.x - pixfx, dy = q0.y - pixfy;
       const float4 q1 = s_q1[j];
@@ -71,7 +97,7 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
       C2 = __fmaf_rn(q2.y, w, C2);
       Dp = __fmaf_rn(q1.z, w, Dp);
       T = test_T;
-      last_contributor = contributor;
+      last_contributor = (uint32_t)(base + j + 1);   // 1-based position in the tile list
     }
   }
   if (inside) {
@@ -86,12 +112,22 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
   }
 }
 
+static bool cull_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SFB_NO_CULL"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
                            const float* bg, float* out_color, float* out_depth, float* final_T,
                            uint32_t* n_contrib, cudaStream_t s) {
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
-  render_forward_kernel<<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, out_color, out_depth,
-                                                final_T, n_contrib);
+  if (cull_enabled())
+    render_forward_kernel<true><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, out_color, out_depth,
+                                                        final_T, n_contrib);
+  else
+    render_forward_kernel<false><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, out_color,
+                                                         out_depth, final_T, n_contrib);
 }
 
 }  // namespace sfb
