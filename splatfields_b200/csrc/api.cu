@@ -11,7 +11,7 @@
 namespace {
 
 thread_local std::string g_err;
-thread_local int g_launches = 0;
+int g_launches = 0;   // process-wide: autograd runs backward on its own thread
 thread_local uint32_t* g_pinned = nullptr;  // pinned word the num_rendered counter is copied into
 thread_local cudaEvent_t g_evt = nullptr;
 
@@ -43,11 +43,12 @@ constexpr int MAX_REC = 48;
 const char* const kDepthSortNames[3] = {"depth_sort.hist", "depth_sort.scan", "depth_sort.scatter"};
 const char* const kTileSortNames[3] = {"tile_sort.hist", "tile_sort.scan", "tile_sort.scatter"};
 struct ProfRec { const char* name; cudaEvent_t a, b; };
-thread_local bool g_prof = false;
-thread_local int g_which = 0;
-thread_local ProfRec g_rec[2][MAX_REC];
-thread_local int g_nrec[2] = {0, 0};
-thread_local bool g_rec_made = false;
+// process-wide (not thread_local): PyTorch runs the backward on an autograd worker thread
+bool g_prof = false;
+int g_which = 0;
+ProfRec g_rec[2][MAX_REC];
+int g_nrec[2] = {0, 0};
+bool g_rec_made = false;
 
 int tile_sort_final(int T) {
   int bits = sfb::tile_bits(T);

@@ -266,16 +266,20 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   }
   __syncthreads();
 
-  // ---- per digit (one thread each): block count, publish, look back, global base ----
+  // ---- per digit (one thread each): block count, publish the aggregate ----
+  __shared__ uint32_t s_count[SORT_MAX_BINS];
+  __shared__ uint32_t s_excl[SORT_MAX_BINS];
+  __shared__ uint32_t s_wsum_t[NW];
   uint32_t my_count = 0, dtotal = 0;
   const int d = threadIdx.x;
+  volatile uint32_t* st = tile_state;
   if (d < bins) {
     uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < NW; w++) { const uint32_t c = s_cnt[w][d]; s_cnt[w][d] = run; run += c; }
     my_count = run;
+    s_count[d] = run;
     dtotal = digit_totals[d];
-    volatile uint32_t* st = tile_state;
     st[(size_t)blk * bins + d] = (blk == 0 ? OS_FLAG_INC : OS_FLAG_AGG) | my_count;
   }
   // block-wide exclusive scans: of the block's digit counts (local starts) and of the digit totals (bases)
@@ -285,30 +289,47 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     const uint32_t a = __shfl_up_sync(0xffffffffu, inc_c, o), b2 = __shfl_up_sync(0xffffffffu, inc_t, o);
     if (lane >= o) { inc_c += a; inc_t += b2; }
   }
-  __shared__ uint32_t s_wsum_t[NW];
   if (lane == 31) { s_wsum[warp] = inc_c; s_wsum_t[warp] = inc_t; }
   __syncthreads();
   uint32_t wb_c = 0, wb_t = 0;
   for (int w = 0; w < warp; w++) { wb_c += s_wsum[w]; wb_t += s_wsum_t[w]; }
   const uint32_t lstart = wb_c + inc_c - my_count;     // local start of digit d inside the block
   const uint32_t dbase = wb_t + inc_t - dtotal;        // global start of digit d
-  if (d < bins) {
+
+  // ---- decoupled look-back, one WARP per digit: a window of 32 predecessors per probe ----
+  // (a single thread walking back one block per L2 round trip serialises a whole wave of blocks)
+  for (int dd = warp; dd < bins; dd += NW) {
     uint32_t excl = 0;
     if (blk > 0) {
-      volatile uint32_t* st = tile_state;
-      int p = blk - 1;
+      int base = blk - 1;
       while (true) {
-        const uint32_t v = st[(size_t)p * bins + d];
+        const int p = base - lane;
+        uint32_t v = 2u << 30;                                   // virtual block -1: inclusive prefix 0
+        if (p >= 0) v = st[(size_t)p * bins + dd];   // virtual block -1: inclusive 0
         const uint32_t f = v & ~OS_VAL_MASK;
-        if (f == 0u) continue;                          // predecessor not published yet: spin
-        excl += v & OS_VAL_MASK;
-        if (f == OS_FLAG_INC) break;
-        p--;
+        const uint32_t inc_m = __ballot_sync(0xffffffffu, f == OS_FLAG_INC);
+        const uint32_t zero_m = __ballot_sync(0xffffffffu, f == 0u);
+        if (inc_m) {
+          const int first = __ffs(inc_m) - 1;                       // nearest predecessor with an inclusive prefix
+          const uint32_t need = first == 31 ? 0xffffffffu : ((2u << first) - 1u);
+          if (zero_m & need) continue;                              // someone nearer is not published yet: spin
+          excl += __reduce_add_sync(0xffffffffu, lane <= first ? (v & OS_VAL_MASK) : 0u);
+          break;
+        }
+        if (zero_m) continue;                                       // spin
+        excl += __reduce_add_sync(0xffffffffu, v & OS_VAL_MASK);    // 32 aggregates, keep walking
+        base -= 32;
       }
-      st[(size_t)blk * bins + d] = OS_FLAG_INC | (excl + my_count);
     }
+    if (lane == 0) {
+      if (blk > 0) st[(size_t)blk * bins + dd] = OS_FLAG_INC | (excl + s_count[dd]);
+      s_excl[dd] = excl;
+    }
+  }
+  __syncthreads();
+  if (d < bins) {
     s_lstart[d] = lstart;
-    s_gofs[d] = (int32_t)(dbase + excl) - (int32_t)lstart;
+    s_gofs[d] = (int32_t)(dbase + s_excl[d]) - (int32_t)lstart;
   }
   __syncthreads();
 
@@ -416,9 +437,15 @@ void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_
   prof_end(s);
 }
 
-// Each block expands DUP_GPB depth-ranked Gaussians.  Output slot k of the block is produced by the
-// thread that owns k, which finds its source Gaussian by binary search over the block's exclusive
-// scan of tile counts: all stores are contiguous and coalesced no matter how skewed the counts are.
+// Each block expands DUP_GPB depth-ranked Gaussians into their (tile, gaussian) instances.  Output slot k
+// has to know which Gaussian it belongs to.  Instead of a per-slot binary search, the block works in rounds
+// of DUP_CHUNK slots: every Gaussian that STARTS inside the round marks its first slot with its (local
+// index + 1), the Gaussian spilling in from the previous round marks slot 0, and a block-wide running
+// maximum over the slots (indices increase with the slot) turns the marks into a per-slot owner.  All
+// global stores are then slot-strided, i.e. contiguous and coalesced no matter how skewed the counts are.
+constexpr int DUP_CHUNK = 4096;
+constexpr int DUP_SPT = DUP_CHUNK / DUP_THREADS;   // slots per thread in the scan (16)
+
 __global__ void __launch_bounds__(DUP_THREADS)
 duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
                  const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ rect,
@@ -428,6 +455,7 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
   __shared__ uint32_t s_gidx[DUP_GPB];
   __shared__ uint2 s_rect[DUP_GPB];
   __shared__ uint32_t s_warp[DUP_THREADS / 32];
+  __shared__ __align__(16) uint16_t s_own[DUP_CHUNK];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j0 = blockIdx.x * DUP_GPB;
   constexpr int PER = DUP_GPB / DUP_THREADS;  // consecutive ranks per thread
@@ -461,27 +489,85 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
     s_pref[DUP_GPB] = run;
   }
   __syncthreads();
-  uint32_t ex = s_warp[warp] + inc - tsum;
+  uint32_t start[PER];
+  {
+    uint32_t ex = s_warp[warp] + inc - tsum;
 #pragma unroll
-  for (int k = 0; k < PER; k++) { s_pref[threadIdx.x * PER + k] = ex; ex += cnt[k]; }
+    for (int k = 0; k < PER; k++) { start[k] = ex; s_pref[threadIdx.x * PER + k] = ex; ex += cnt[k]; }
+  }
   __syncthreads();
   const uint32_t total = s_pref[DUP_GPB];
   const uint32_t out0 = block_offsets[blockIdx.x];
-  for (uint32_t k = threadIdx.x; k < total; k += DUP_THREADS) {
-    // largest s with s_pref[s] <= k
-    int lo = 0, hi = DUP_GPB;
+
+  for (uint32_t cb = 0; cb < total; cb += DUP_CHUNK) {
+    // A: clear the marks (two 16-byte stores per thread)
+    reinterpret_cast<uint4*>(s_own)[threadIdx.x * 2] = make_uint4(0u, 0u, 0u, 0u);
+    reinterpret_cast<uint4*>(s_own)[threadIdx.x * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    // B: Gaussians starting in this round mark their first slot
 #pragma unroll
-    for (int it = 0; it < 10; it++) {  // log2(DUP_GPB)
-      int mid = (lo + hi) >> 1;
-      if (s_pref[mid] <= k) lo = mid; else hi = mid;
+    for (int k = 0; k < PER; k++)
+      if (cnt[k] > 0 && start[k] >= cb && start[k] < cb + DUP_CHUNK)
+        s_own[start[k] - cb] = (uint16_t)(threadIdx.x * PER + k + 1);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_own[0] == 0) {
+      // the Gaussian that spills in: largest s with s_pref[s] <= cb (it has a non-zero count)
+      int lo = 0, hi = DUP_GPB;
+#pragma unroll
+      for (int it = 0; it < 10; it++) {
+        int mid = (lo + hi) >> 1;
+        if (s_pref[mid] <= cb) lo = mid; else hi = mid;
+      }
+      s_own[0] = (uint16_t)(lo + 1);
     }
-    uint32_t t = k - s_pref[lo];
-    uint2 r = s_rect[lo];
-    uint32_t x0 = r.x & 0xFFFFu, y0 = r.x >> 16, x1 = r.y & 0xFFFFu;
-    uint32_t w = x1 - x0;
-    uint32_t yy = t / w, xx = t - yy * w;
-    tile_keys[out0 + k] = (y0 + yy) * (uint32_t)grid_x + (x0 + xx);
-    inst_idx[out0 + k] = s_gidx[lo];
+    __syncthreads();
+    // C: running maximum over the slots; thread t owns slots [16t, 16t+16)
+    uint32_t w8[DUP_SPT / 2];
+    {
+      const uint4 a4 = reinterpret_cast<const uint4*>(s_own)[threadIdx.x * 2];
+      const uint4 b4 = reinterpret_cast<const uint4*>(s_own)[threadIdx.x * 2 + 1];
+      w8[0] = a4.x; w8[1] = a4.y; w8[2] = a4.z; w8[3] = a4.w; w8[4] = b4.x; w8[5] = b4.y; w8[6] = b4.z; w8[7] = b4.w;
+    }
+    uint32_t m[DUP_SPT];
+    uint32_t run = 0;
+#pragma unroll
+    for (int q = 0; q < DUP_SPT; q++) {
+      const uint32_t v = (q & 1) ? (w8[q >> 1] >> 16) : (w8[q >> 1] & 0xFFFFu);
+      run = max(run, v);
+      m[q] = run;
+    }
+    uint32_t incm = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incm, o);
+      if (lane >= o) incm = max(incm, t);
+    }
+    if (lane == 31) s_warp[warp] = incm;
+    uint32_t exm = __shfl_up_sync(0xffffffffu, incm, 1);
+    if (lane == 0) exm = 0;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < DUP_THREADS / 32; w++)
+      if (w < warp) exm = max(exm, s_warp[w]);
+#pragma unroll
+    for (int q = 0; q < DUP_SPT / 2; q++)
+      w8[q] = max(exm, m[2 * q]) | (max(exm, m[2 * q + 1]) << 16);
+    reinterpret_cast<uint4*>(s_own)[threadIdx.x * 2] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+    reinterpret_cast<uint4*>(s_own)[threadIdx.x * 2 + 1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+    __syncthreads();
+    // D: slot-strided emission
+    const uint32_t nslots = min((uint32_t)DUP_CHUNK, total - cb);
+    for (uint32_t q = threadIdx.x; q < nslots; q += DUP_THREADS) {
+      const uint32_t sidx = (uint32_t)s_own[q] - 1u;
+      const uint32_t t = cb + q - s_pref[sidx];
+      const uint2 r = s_rect[sidx];
+      const uint32_t x0 = r.x & 0xFFFFu, y0 = r.x >> 16, x1 = r.y & 0xFFFFu;
+      const uint32_t w = x1 - x0;
+      const uint32_t yy = t / w, xx = t - yy * w;
+      tile_keys[out0 + cb + q] = (y0 + yy) * (uint32_t)grid_x + (x0 + xx);
+      inst_idx[out0 + cb + q] = s_gidx[sidx];
+    }
+    __syncthreads();
   }
 }
 
@@ -494,21 +580,36 @@ void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint3
 }
 
 // ------------------------------------------------------------------ tile ranges
-__global__ void tile_ranges_kernel(int R, const uint32_t* __restrict__ keys, uint2* __restrict__ ranges) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R) return;
-  uint32_t t = keys[i];
-  if (i == 0) ranges[t].x = 0;
-  else {
-    uint32_t prev = keys[i - 1];
-    if (prev != t) { ranges[prev].y = (uint32_t)i; ranges[t].x = (uint32_t)i; }
+// Four consecutive keys per thread (one 16-byte load) + the key before them.
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int R, const uint32_t* __restrict__ keys,
+                                                           uint2* __restrict__ ranges) {
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= R) return;
+  uint32_t k[4];
+  if (i0 + 3 < R) {
+    const uint4 v = *reinterpret_cast<const uint4*>(keys + i0);
+    k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) k[j] = (i0 + j < R) ? keys[i0 + j] : 0u;
   }
-  if (i == R - 1) ranges[t].y = (uint32_t)R;
+  uint32_t prev = i0 > 0 ? keys[i0 - 1] : 0u;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int i = i0 + j;
+    if (i < R) {
+      const uint32_t t = k[j];
+      if (i == 0) ranges[t].x = 0;
+      else if (prev != t) { ranges[prev].y = (uint32_t)i; ranges[t].x = (uint32_t)i; }
+      if (i == R - 1) ranges[t].y = (uint32_t)R;
+      prev = t;
+    }
+  }
 }
 
 void launch_tile_ranges(int R, int T, const uint32_t* sorted_tile_keys, uint2* ranges, cudaStream_t s) {
   cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)T, s);
-  if (R > 0) tile_ranges_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, sorted_tile_keys, ranges);
+  if (R > 0) tile_ranges_kernel<<<((R + 3) / 4 + 255) / 256, 256, 0, s>>>(R, sorted_tile_keys, ranges);
 }
 
 __global__ void export_keys_kernel(int R, const uint32_t* __restrict__ tile_keys,

@@ -3,11 +3,13 @@
 // final_T and the last contributor, walk the tile list backwards, rebuild alpha and T, and emit
 //   d/d rgb_i, d/d opacity_i, d/d conic_i (A,B,C), d/d mean2D_i (NDC-scaled: includes 0.5*W, 0.5*H).
 //
-// The reference issues 9 global float atomics per (pixel, contributor).  Here the 32 pixels of a warp
-// are first summed with a recursive-halving shuffle reduction (14 shuffles for 9 values, and the 8
-// results end up on 8 different lanes), those lanes add into a per-tile shared-memory accumulator, and
-// only one vectorised global reduction (2x red.global.add.v4.f32 + 1 scalar) is issued per
-// (tile, splat) instance: global atomic traffic drops from 9 * pixels * contributors to 3 * R.
+// The reference issues 9 global float atomics per (pixel, contributor).  Here each pixel only forms the
+// raw moments of s = dL/dG*G about the splat centre plus the three colour terms; the 32 pixels of a warp
+// are summed with a recursive-halving shuffle reduction (14 shuffles for 9 values, the results land on 9
+// different lanes), those lanes add into a per-tile shared-memory accumulator in one conflict-free
+// atomic, and at the end of a batch one thread per splat turns the moments into gradients and issues one
+// vectorised global reduction (2x red.global.add.v4.f32 + 1 scalar) per (tile, splat) instance: global
+// atomic traffic drops from 9 * pixels * contributors to 3 * R.
 // Accumulation order differs from the reference's (as it does between two runs of the reference), so
 // parity here is tolerance-based: 1e-3 relative on every per-splat gradient.
 #include "common.cuh"
@@ -57,6 +59,7 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
   float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f;
   if (inside) { dLp0 = dL_dpixels[pix]; dLp1 = dL_dpixels[HW + pix]; dLp2 = dL_dpixels[2 * HW + pix]; }
   const float bg_dot = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
+  const float Tf_bg = T_final * bg_dot;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
@@ -85,7 +88,7 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
     }
     if (CULL) s_mask[threadIdx.x] = (uint8_t)mask;
 #pragma unroll
-    for (int k = 0; k < 9; k++) s_acc[k * BB + threadIdx.x] = 0.f;
+    for (int k = 0; k < 9; k++) s_acc[k * BB + threadIdx.x] = 0.f;   // 9*BB floats, any order
     __syncthreads();
     int nsweep = n;
     if (CULL) {
@@ -106,14 +109,15 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
     for (int kk = 0; kk < nsweep; kk++) {
       const int j = CULL ? (int)s_list[warp][kk] : kk;
       const uint32_t pos = (uint32_t)(top - 1 - j);
-      float v[8], v8 = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; k++) v[k] = 0.f;
+      // Per-lane work is kept to the raw moments of  s = dL/dG * G  about the splat centre
+      //   S0 = s, Sx = s dx, Sy = s dy, Sxx = s dx^2, Sxy = s dx dy, Syy = s dy^2   and   w dL/dC_c,
+      // everything that is per-splat (conic, opacity, 0.5 W / 0.5 H) is applied once at flush time.
       bool contrib = false;
+      float dx = 0.f, dy = 0.f, sG = 0.f, wgt = 0.f;
       if (pos < my_last) {
         const float4 q0 = s_q0[j];
         const float4 q1 = s_q1[j];
-        const float dx = q0.x - pixfx, dy = q0.y - pixfy;
+        dx = q0.x - pixfx; dy = q0.y - pixfy;
         const float s = __fmaf_rn(__fmul_rn(q0.z, dx), dx, __fmul_rn(__fmul_rn(q1.x, dy), dy));
         const float power = __fmaf_rn(s, -0.5f, -__fmul_rn(__fmul_rn(q0.w, dx), dy));
         if (power <= 0.0f) {
@@ -122,33 +126,29 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
           if (alpha >= 1.0f / 255.0f) {
             contrib = true;
             const float2 q2 = s_q2[j];
-            T = T / (1.f - alpha);
-            const float dchannel_dcolor = alpha * T;
-            acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-            acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-            acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
+            const float inv = __fdividef(1.f, 1.f - alpha);
+            T *= inv;
+            wgt = alpha * T;
+            acc0 = fmaf(last_alpha, lc0 - acc0, acc0);
+            acc1 = fmaf(last_alpha, lc1 - acc1, acc1);
+            acc2 = fmaf(last_alpha, lc2 - acc2, acc2);
             lc0 = q1.w; lc1 = q2.x; lc2 = q2.y;
-            float dL_dalpha = (lc0 - acc0) * dLp0 + (lc1 - acc1) * dLp1 + (lc2 - acc2) * dLp2;
-            dL_dalpha *= T;
+            float dL_dalpha = (lc0 - acc0) * dLp0;
+            dL_dalpha = fmaf(lc1 - acc1, dLp1, dL_dalpha);
+            dL_dalpha = fmaf(lc2 - acc2, dLp2, dL_dalpha);
+            dL_dalpha = fmaf(dL_dalpha, T, -Tf_bg * inv);
             last_alpha = alpha;
-            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-            const float dL_dG = q1.y * dL_dalpha;
-            const float gdx = G * dx, gdy = G * dy;
-            const float dG_ddelx = -gdx * q0.z - gdy * q0.w;
-            const float dG_ddely = -gdy * q1.x - gdx * q0.w;
-            v[0] = dL_dG * dG_ddelx * ddelx_dx;
-            v[1] = dL_dG * dG_ddely * ddely_dy;
-            v[2] = -0.5f * gdx * dx * dL_dG;
-            v[3] = -gdx * dy * dL_dG;
-            v[4] = -0.5f * gdy * dy * dL_dG;
-            v[5] = G * dL_dalpha;
-            v[6] = dchannel_dcolor * dLp0;
-            v[7] = dchannel_dcolor * dLp1;
-            v8 = dchannel_dcolor * dLp2;
+            sG = q1.y * dL_dalpha * G;
           }
         }
       }
       if (!__any_sync(0xffffffffu, contrib)) continue;
+      float v[8], v8;
+      {
+        const float sx = sG * dx, sy = sG * dy;     // sG == 0 on lanes that do not contribute
+        v[0] = sG; v[1] = sx; v[2] = sy; v[3] = sx * dx; v[4] = sx * dy; v[5] = sy * dy;
+        v[6] = wgt * dLp0; v[7] = wgt * dLp1; v8 = wgt * dLp2;
+      }
       // recursive halving: 8 values over 32 lanes in 4+2+1+2 shuffles
       float w4[4];
 #pragma unroll
@@ -177,22 +177,30 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
       u += __shfl_xor_sync(0xffffffffu, u, 1);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v8 += __shfl_xor_sync(0xffffffffu, v8, o);
-      if ((lane & 3) == 0) {
-        const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-        atomicAdd(&s_acc[k * BB + j], u);
+      // lanes 0,4,..,28 hold values 0..7, lane 1 holds value 8: ONE atomic site, nine distinct banks
+      if ((lane & 3) == 0 || lane == 1) {
+        const int k = lane == 1 ? 8 : ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        atomicAdd(&s_acc[j * 9 + k], lane == 1 ? v8 : u);
       }
-      if (lane == 1) atomicAdd(&s_acc[8 * BB + j], v8);
     }
     __syncthreads();
     if ((int)threadIdx.x < n) {
       float a[9];
       bool nz = false;
 #pragma unroll
-      for (int k = 0; k < 9; k++) { a[k] = s_acc[k * BB + threadIdx.x]; nz |= (a[k] != 0.f); }
+      for (int k = 0; k < 9; k++) { a[k] = s_acc[threadIdx.x * 9 + k]; nz |= (a[k] != 0.f); }
       if (nz) {
+        const float4 q0 = s_q0[threadIdx.x];
+        const float4 q1 = s_q1[threadIdx.x];
+        const float conA = q0.z, conB = q0.w, conC = q1.x, op = q1.y;
+        // moments -> gradients: d/dmean (NDC-scaled), d/dconic (true derivatives), d/dopacity
+        const float gx = -(conA * a[1] + conB * a[2]) * ddelx_dx;
+        const float gy = -(conC * a[2] + conB * a[1]) * ddely_dy;
+        const float gA = -0.5f * a[3], gB = -a[4], gC = -0.5f * a[5];
+        const float gop = a[0] / op;      // sum of G * dL/dalpha  (op >= 1/255 whenever a[0] != 0)
         float* gp = reinterpret_cast<float*>(grad + s_id[threadIdx.x]);
-        red_add_v4(gp, a[0], a[1], a[2], a[3]);
-        red_add_v4(gp + 4, a[4], a[5], a[6], a[7]);
+        red_add_v4(gp, gx, gy, gA, gB);
+        red_add_v4(gp + 4, gC, a[0] != 0.f ? gop : 0.f, a[6], a[7]);
         atomicAdd(gp + 8, a[8]);
       }
     }
