@@ -198,13 +198,17 @@ static int radix_sort_pairs_legacy(uint32_t* keys[2], uint32_t* vals[2], uint32_
 // read once and written once per pass; the digit histograms of ALL passes come from one up-front sweep.
 constexpr uint32_t OS_FLAG_AGG = 1u << 30, OS_FLAG_INC = 2u << 30, OS_VAL_MASK = (1u << 30) - 1u;
 constexpr int OS_MAX_PASSES = 4;
+constexpr int OS_LB = 8;   // look-back probes in flight per digit
 
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_hist_all_kernel(const uint32_t* __restrict__ keys, int n, int npass, int4 shifts, int4 nbins,
                       uint32_t* __restrict__ hist_all /* [npass][SORT_MAX_BINS] */) {
-  __shared__ uint32_t s_h[OS_MAX_PASSES][SORT_MAX_BINS];
-  for (int i = threadIdx.x; i < OS_MAX_PASSES * SORT_MAX_BINS; i += SORT_THREADS) (&s_h[0][0])[i] = 0;
+  // one private histogram per warp: 8x fewer same-address collisions on the shared-memory atomics
+  constexpr int NW = SORT_THREADS / 32;
+  __shared__ uint32_t s_h[NW][OS_MAX_PASSES][SORT_MAX_BINS];
+  for (int i = threadIdx.x; i < NW * OS_MAX_PASSES * SORT_MAX_BINS; i += SORT_THREADS) (&s_h[0][0][0])[i] = 0;
   __syncthreads();
+  const int warp = threadIdx.x >> 5;
   const int sh[4] = {shifts.x, shifts.y, shifts.z, shifts.w};
   const int nb[4] = {nbins.x, nbins.y, nbins.z, nbins.w};
   const int stride = gridDim.x * SORT_THREADS;
@@ -212,27 +216,33 @@ radix_hist_all_kernel(const uint32_t* __restrict__ keys, int n, int npass, int4 
     const uint32_t key = keys[k];
 #pragma unroll
     for (int p = 0; p < OS_MAX_PASSES; p++)
-      if (p < npass) atomicAdd(&s_h[p][(key >> sh[p]) & (uint32_t)(nb[p] - 1)], 1u);
+      if (p < npass) atomicAdd(&s_h[warp][p][(key >> sh[p]) & (uint32_t)(nb[p] - 1)], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < npass * SORT_MAX_BINS; i += SORT_THREADS) {
-    const uint32_t v = (&s_h[0][0])[i];
+    uint32_t v = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) v += (&s_h[w][0][0])[i];
     if (v) atomicAdd(&hist_all[i], v);
   }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS)
+// IPT items per thread: 16 (4096-item tiles) for large inputs, 4 (1024-item tiles) when 4096-item tiles
+// would leave most SMs idle and every block a long latency chain.
+template <int IPT>
+__global__ void __launch_bounds__(SORT_THREADS, 3)
 onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift, int bins,
                      const uint32_t* __restrict__ digit_totals /* [SORT_MAX_BINS] for this pass */,
                      uint32_t* __restrict__ tile_state /* [nblocks][bins], zeroed */,
                      uint32_t* __restrict__ ticket /* zeroed */) {
   constexpr int NW = SORT_THREADS / 32;
+  constexpr int OS_TILE = SORT_THREADS * IPT;
   __shared__ uint32_t s_cnt[NW][SORT_MAX_BINS];   // per-warp digit counts -> exclusive-over-warps prefixes
   __shared__ uint32_t s_lstart[SORT_MAX_BINS];    // block-local start of each digit run
   __shared__ int32_t s_gofs[SORT_MAX_BINS];       // global position - local position, per digit
-  __shared__ uint32_t s_key[SORT_TILE];
-  __shared__ uint32_t s_val[SORT_TILE];
+  __shared__ uint32_t s_key[OS_TILE];
+  __shared__ uint32_t s_val[OS_TILE];
   __shared__ uint32_t s_wsum[NW];
   __shared__ uint32_t s_ticket;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -243,14 +253,19 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   const int blk = (int)s_ticket;
 
   // ---- stable ranking inside the block (sequential order = warp, item, lane) ----
-  const int seg = blk * SORT_TILE + warp * (32 * SORT_IPT);
-  uint32_t key[SORT_IPT], rank[SORT_IPT];
+  const int seg = blk * OS_TILE + warp * (32 * IPT);
+  uint32_t key[IPT], val[IPT], rank[IPT];
   const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
-  for (int i = 0; i < SORT_IPT; i++) {
+  for (int i = 0; i < IPT; i++) {   // all loads of the tile in flight before the first use
+    const int k = seg + i * 32 + lane;
+    key[i] = k < n ? keys_in[k] : 0xFFFFFFFFu;
+    val[i] = k < n ? vals_in[k] : 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < IPT; i++) {
     const int k = seg + i * 32 + lane;
     const bool valid = k < n;
-    key[i] = valid ? keys_in[k] : 0xFFFFFFFFu;
     const uint32_t d = (key[i] >> shift) & mask;
     const uint32_t md = valid ? d : 0xFFFFu;
     const uint32_t peers = __match_any_sync(0xffffffffu, md);
@@ -296,35 +311,38 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   const uint32_t lstart = wb_c + inc_c - my_count;     // local start of digit d inside the block
   const uint32_t dbase = wb_t + inc_t - dtotal;        // global start of digit d
 
-  // ---- decoupled look-back, one WARP per digit: a window of 32 predecessors per probe ----
-  // (a single thread walking back one block per L2 round trip serialises a whole wave of blocks)
-  for (int dd = warp; dd < bins; dd += NW) {
+  // ---- decoupled look-back, one thread per digit, OS_LB predecessors probed per round trip ----
+  // (the probes of one round are independent loads, so a chain of k not-yet-inclusive predecessors costs
+  //  k / OS_LB L2 latencies instead of k; partial progress is kept when a predecessor is not published yet)
+  if (d < bins) {
     uint32_t excl = 0;
     if (blk > 0) {
-      int base = blk - 1;
+      int p = blk - 1;
       while (true) {
-        const int p = base - lane;
-        uint32_t v = 2u << 30;                                   // virtual block -1: inclusive prefix 0
-        if (p >= 0) v = st[(size_t)p * bins + dd];   // virtual block -1: inclusive 0
-        const uint32_t f = v & ~OS_VAL_MASK;
-        const uint32_t inc_m = __ballot_sync(0xffffffffu, f == OS_FLAG_INC);
-        const uint32_t zero_m = __ballot_sync(0xffffffffu, f == 0u);
-        if (inc_m) {
-          const int first = __ffs(inc_m) - 1;                       // nearest predecessor with an inclusive prefix
-          const uint32_t need = first == 31 ? 0xffffffffu : ((2u << first) - 1u);
-          if (zero_m & need) continue;                              // someone nearer is not published yet: spin
-          excl += __reduce_add_sync(0xffffffffu, lane <= first ? (v & OS_VAL_MASK) : 0u);
-          break;
+        uint32_t v[OS_LB];
+#pragma unroll
+        for (int i = 0; i < OS_LB; i++) v[i] = (p - i >= 0) ? st[(size_t)(p - i) * bins + d] : (2u << 30);
+        uint32_t add = 0;
+        int adv = 0;
+        bool fin = false;
+#pragma unroll
+        for (int i = 0; i < OS_LB; i++) {
+          if (!fin && adv == i) {
+            const uint32_t f = v[i] & ~OS_VAL_MASK;
+            if (f != 0u) {
+              add += v[i] & OS_VAL_MASK;
+              adv++;
+              fin = (f == (2u << 30));
+            }
+          }
         }
-        if (zero_m) continue;                                       // spin
-        excl += __reduce_add_sync(0xffffffffu, v & OS_VAL_MASK);    // 32 aggregates, keep walking
-        base -= 32;
+        excl += add;
+        p -= adv;
+        if (fin) break;
       }
+      st[(size_t)blk * bins + d] = (2u << 30) | (excl + my_count);
     }
-    if (lane == 0) {
-      if (blk > 0) st[(size_t)blk * bins + dd] = OS_FLAG_INC | (excl + s_count[dd]);
-      s_excl[dd] = excl;
-    }
+    s_excl[d] = excl;
   }
   __syncthreads();
   if (d < bins) {
@@ -335,17 +353,17 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 
   // ---- stage in shared memory in sorted order, then write coalesced runs ----
 #pragma unroll
-  for (int i = 0; i < SORT_IPT; i++) {
+  for (int i = 0; i < IPT; i++) {
     const int k = seg + i * 32 + lane;
     if (k < n) {
       const uint32_t dd = (key[i] >> shift) & mask;
       const uint32_t lp = s_lstart[dd] + s_cnt[warp][dd] + rank[i];
       s_key[lp] = key[i];
-      s_val[lp] = vals_in[k];
+      s_val[lp] = val[i];
     }
   }
   __syncthreads();
-  const int cnt_blk = min(SORT_TILE, n - blk * SORT_TILE);
+  const int cnt_blk = min(OS_TILE, n - blk * OS_TILE);
   for (int q = threadIdx.x; q < cnt_blk; q += SORT_THREADS) {
     const uint32_t kk = s_key[q];
     const uint32_t dd = (kk >> shift) & mask;
@@ -358,7 +376,9 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint32_t* scratch, int n, int nbits,
                                      cudaStream_t s, int* launches, const char* const* names) {
   const int npass = (nbits + 7) / 8;
-  const int nblocks = sort_blocks(n);
+  const bool small = sort_blocks(n) < 4 * NUM_SMS_B200;       // < 4 tiles per SM with 4096-item tiles
+  const int tile = small ? SORT_THREADS * 4 : SORT_TILE;
+  const int nblocks = (n + tile - 1) / tile;
   // scratch layout: [hist_all: 4*256][tickets: 8][tile_state: npass * nblocks * bins]
   uint32_t* hist_all = scratch;
   uint32_t* tickets = scratch + OS_MAX_PASSES * SORT_MAX_BINS;
@@ -375,7 +395,7 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
   }
   cudaMemsetAsync(scratch, 0, sizeof(uint32_t) * (OS_MAX_PASSES * SORT_MAX_BINS + 8 + state_words), s);
   prof_begin(names[0], s);
-  const int hblocks = min(nblocks, 4 * NUM_SMS_B200);
+  const int hblocks = min(sort_blocks(n), 4 * NUM_SMS_B200);
   radix_hist_all_kernel<<<hblocks, SORT_THREADS, 0, s>>>(keys[0], n, npass, make_int4(shifts[0], shifts[1], shifts[2], shifts[3]),
                                                           make_int4(nbins[0], nbins[1], nbins[2], nbins[3]), hist_all);
   prof_end(s);
@@ -384,9 +404,14 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
   uint32_t* state = state0;
   for (int pass = 0; pass < npass; pass++) {
     prof_begin(names[2], s);
-    onesweep_pass_kernel<<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
-                                                          shifts[pass], nbins[pass], hist_all + pass * SORT_MAX_BINS,
-                                                          state, tickets + pass);
+    if (small)
+      onesweep_pass_kernel<4><<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
+                                                                shifts[pass], nbins[pass],
+                                                                hist_all + pass * SORT_MAX_BINS, state, tickets + pass);
+    else
+      onesweep_pass_kernel<16><<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
+                                                                 shifts[pass], nbins[pass],
+                                                                 hist_all + pass * SORT_MAX_BINS, state, tickets + pass);
     prof_end(s);
     if (launches) *launches += 1;
     state += (size_t)nblocks * nbins[pass];

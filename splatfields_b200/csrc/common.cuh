@@ -65,7 +65,11 @@ __host__ __device__ inline int sort_blocks(int n) { return (n + SORT_TILE - 1) /
 // words of sort scratch for n items: 4 digit histograms + tickets + one look-back state row per pass
 // (worst case 4 passes x 256 bins), which also covers the legacy path's [bins][blocks] histogram + totals.
 __host__ __device__ inline size_t sort_scratch_words(size_t n) {
-  return (size_t)4 * SORT_MAX_BINS + 8 + (size_t)4 * SORT_MAX_BINS * (size_t)(sort_blocks((int)n) + 1) + 16;
+  // (small inputs use 1024-item tiles: at most 4 * 4 * NUM_SMS_B200 of them)
+  const size_t blocks = (size_t)sort_blocks((int)n) + 1;
+  const size_t blocks_small = (n + 1023) / 1024 + 1;
+  const size_t nb = blocks < (size_t)4 * NUM_SMS_B200 ? blocks_small : blocks;
+  return (size_t)4 * SORT_MAX_BINS + 8 + (size_t)4 * SORT_MAX_BINS * nb + 16;
 }
 
 // ---- P-sized scratch ("geomBuffer") ----
