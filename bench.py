@@ -257,17 +257,23 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (profiled steps, outside the timed regions) ----
     roofline, stages = None, None
+    acc = {}
+    nprof = 5
+    # every rank runs the profiled steps (vp.step contains the all-reduce: collectives must stay symmetric);
+    # only rank 0 records and reads the per-kernel events.
     if rank == 0:
-        acc = {}
-        nprof = 5
         _lib.profile_enable(True)
-        for _ in range(nprof):
-            vp.step(Gd)
-            torch.cuda.synchronize()
+    for _ in range(nprof):
+        vp.step(Gd)
+        torch.cuda.synchronize()
+        if rank == 0:
             for which in (0, 1):
                 for name, ms in _lib.profile_read(which):
                     acc.setdefault(name, []).append(ms)
+    if rank == 0:
         _lib.profile_enable(False)
+    sync_all()
+    if rank == 0:
         # a kernel name can occur several times per step (radix passes): per-launch average duration
         per_step = {k: sum(v) / nprof for k, v in acc.items()}
         per_launch = {k: sum(v) / len(v) for k, v in acc.items()}
@@ -316,7 +322,20 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _watchdog(seconds):
+    """Hard stop: a hung collective must never hold a multi-GPU box for the whole lease."""
+    import signal
+
+    def _die(signum, frame):
+        sys.stderr.write(f"bench.py: watchdog fired after {seconds}s\n")
+        sys.stderr.flush()
+        os._exit(3)
+    signal.signal(signal.SIGALRM, _die)
+    signal.alarm(seconds)
+
+
 def main():
+    _watchdog(int(os.environ.get("BENCH_WATCHDOG_S", "900")))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

@@ -254,31 +254,36 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 
   // ---- stable ranking inside the block (sequential order = warp, item, lane) ----
   const int seg = blk * OS_TILE + warp * (32 * IPT);
-  uint32_t key[IPT], val[IPT], rank[IPT];
+  constexpr bool PRELOAD_VALS = IPT <= 8;     // register budget: values ride along only for small tiles
+  uint32_t key[IPT], val[PRELOAD_VALS ? IPT : 1], rank[IPT];
   const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int i = 0; i < IPT; i++) {   // all loads of the tile in flight before the first use
     const int k = seg + i * 32 + lane;
     key[i] = k < n ? keys_in[k] : 0xFFFFFFFFu;
-    val[i] = k < n ? vals_in[k] : 0u;
+    if (PRELOAD_VALS) val[i] = k < n ? vals_in[k] : 0u;
   }
+  // Round i ranks item i of every lane: lanes with equal digits find each other with match.any, the lowest
+  // of them fetch-and-adds the group size on the warp's digit counter (shared-memory atomic WITH return:
+  // the returned old value is the number of equal digits in earlier rounds).  The returned values are only
+  // consumed after the loop, so the 16 atomics pipeline instead of forming a load->store->load chain.
+  uint32_t packed[IPT];   // before | leader << 8
 #pragma unroll
   for (int i = 0; i < IPT; i++) {
     const int k = seg + i * 32 + lane;
     const bool valid = k < n;
     const uint32_t d = (key[i] >> shift) & mask;
-    const uint32_t md = valid ? d : 0xFFFFu;
+    const uint32_t md = valid ? d : 0xFFFFu;   // invalid lanes: a digit no valid lane can match
     const uint32_t peers = __match_any_sync(0xffffffffu, md);
     const uint32_t before = __popc(peers & lt_mask);
     uint32_t prev = 0;
-    if (valid && before == 0) {
-      prev = s_cnt[warp][d];
-      s_cnt[warp][d] = prev + __popc(peers);
-    }
-    prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
-    rank[i] = prev + before;
-    __syncwarp();
+    if (valid && before == 0) prev = atomicAdd(&s_cnt[warp][d], (uint32_t)__popc(peers));
+    rank[i] = prev;
+    packed[i] = before | ((uint32_t)(__ffs(peers) - 1) << 8);
   }
+#pragma unroll
+  for (int i = 0; i < IPT; i++)
+    rank[i] = __shfl_sync(0xffffffffu, rank[i], packed[i] >> 8) + (packed[i] & 0xFFu);
   __syncthreads();
 
   // ---- per digit (one thread each): block count, publish the aggregate ----
@@ -359,7 +364,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
       const uint32_t dd = (key[i] >> shift) & mask;
       const uint32_t lp = s_lstart[dd] + s_cnt[warp][dd] + rank[i];
       s_key[lp] = key[i];
-      s_val[lp] = val[i];
+      s_val[lp] = PRELOAD_VALS ? val[i] : vals_in[k];
     }
   }
   __syncthreads();

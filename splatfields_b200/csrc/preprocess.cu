@@ -9,6 +9,7 @@
 // bit-identical with the CPU oracle (gcc -ffp-contract=off) — DESIGN.md "canonical op order".
 // The kernel is HBM-bound (≈236 B in, ≈110 B out per Gaussian); the extra FMULs are free.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace sfb {
 
@@ -99,11 +100,28 @@ __device__ __forceinline__ void sh_to_rgb(const float* sh, float3 mean, const fl
   }
 }
 
-template <int D, bool VEC_SH>
+// TMA_SH: the block's SH rows (256 x M*3 floats, one contiguous slab of the [P][M][3] tensor) are brought
+// into shared memory by ONE bulk async copy (cp.async.bulk -> UBLKCP) issued at kernel start and awaited on an
+// mbarrier only where the colours are needed, so the 192 B/Gaussian stream overlaps the projection math and
+// reaches DRAM as full sequential bursts instead of 32 strided 16-byte requests per load instruction.
+template <int D, bool VEC_SH, bool TMA_SH>
 __global__ void __launch_bounds__(256)
 preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
   __shared__ Cam cam;
   __shared__ uint32_t s_tiles[8];
+  __shared__ uint64_t s_bar;
+  extern __shared__ __align__(128) float s_shrows[];
+  if (TMA_SH) {
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int row0 = blockIdx.x * 256;
+      const int rows = min(256, p.P - row0);
+      const uint32_t bytes = (uint32_t)rows * (uint32_t)p.M * 12u;
+      mbar_expect_tx(&s_bar, bytes);
+      bulk_g2s(s_shrows, p.shs + (size_t)row0 * p.M * 3, bytes, &s_bar);
+    }
+  }
   if (threadIdx.x < 16) {
     cam.view[threadIdx.x] = p.viewmatrix[threadIdx.x];
     cam.proj[threadIdx.x] = p.projmatrix[threadIdx.x];
@@ -216,7 +234,18 @@ preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
             rgb[2] = __ldg(p.colors_precomp + 3 * (size_t)idx + 2);
           } else {
             float sh[((3 * (D + 1) * (D + 1) + 3) / 4) * 4];
-            load_sh<D, VEC_SH>(p.shs, idx, p.M, sh);
+            if (TMA_SH) {
+              mbar_wait(&s_bar, 0);
+              constexpr int NV = (3 * (D + 1) * (D + 1) + 3) / 4;
+              const float4* row = reinterpret_cast<const float4*>(s_shrows + (size_t)threadIdx.x * p.M * 3);
+#pragma unroll
+              for (int i = 0; i < NV; i++) {
+                const float4 v = row[i];
+                sh[4 * i + 0] = v.x; sh[4 * i + 1] = v.y; sh[4 * i + 2] = v.z; sh[4 * i + 3] = v.w;
+              }
+            } else {
+              load_sh<D, VEC_SH>(p.shs, idx, p.M, sh);
+            }
             sh_to_rgb<D>(sh, mean, cam.campos, rgb, clamp_mask);
           }
           // Conservative half-extents (pixels) of the region where this splat can reach alpha >= 1/255:
@@ -254,6 +283,7 @@ preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
     g.depth_key[0][idx] = key;
     g.depth_idx[0][idx] = (uint32_t)idx;
   }
+  if (TMA_SH) mbar_wait(&s_bar, 0);   // never retire the CTA with the bulk copy still landing in its smem
   // num_rendered = sum of tiles_touched: order-independent, so one atomic per block is exact.
   uint32_t v = my_tiles;
 #pragma unroll
@@ -268,12 +298,31 @@ preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
   }
 }
 
+static bool tma_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SFB_NO_TMA"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 template <int D>
 static void launch_pre_d(const FwdParams& p, const GeomState& g, int* radii, cudaStream_t s) {
   int blocks = (p.P + 255) / 256;
   bool vec = p.shs && ((p.M * 3) % 4 == 0) && ((reinterpret_cast<size_t>(p.shs) & 15) == 0);
-  if (vec) preprocess_kernel<D, true><<<blocks, 256, 0, s>>>(p, g, radii);
-  else     preprocess_kernel<D, false><<<blocks, 256, 0, s>>>(p, g, radii);
+  // the bulk-copy path moves whole rows: use it when every coefficient of the row is active
+  bool tma = vec && tma_enabled() && p.M == (D + 1) * (D + 1) && (size_t)256 * p.M * 12 <= 96 * 1024;
+  if (tma) {
+    const size_t smem = (size_t)256 * p.M * 12;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(preprocess_kernel<D, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr_set = true;
+    }
+    preprocess_kernel<D, true, true><<<blocks, 256, smem, s>>>(p, g, radii);
+  } else if (vec) {
+    preprocess_kernel<D, true, false><<<blocks, 256, 0, s>>>(p, g, radii);
+  } else {
+    preprocess_kernel<D, false, false><<<blocks, 256, 0, s>>>(p, g, radii);
+  }
 }
 
 void launch_preprocess(const FwdParams& p, const GeomState& g, int* radii, cudaStream_t s) {
