@@ -223,9 +223,11 @@ def run_ours(args):
         sampler.mark()
     e0.record()
     launches = 0
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         launches += vp.step(Gd)
     e1.record()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # CPU time to enqueue one step
     sync_all()
     ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if dist is not None:
@@ -312,7 +314,7 @@ def run_ours(args):
                                       f"1 all-reduce of [P,59] fp32 grads)" if world > 1 else "single view",
                        "l2": "inputs larger than L2 (236 MB of splat parameters + 0.5 GB of scratch per step "
                              "vs 126 MB L2)"},
-            "views_per_s": world / (ms_step * 1e-3),
+            "views_per_s": world / (ms_step * 1e-3), "host_enqueue_ms_per_step": host_enqueue_ms,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "stages": stages,
         }

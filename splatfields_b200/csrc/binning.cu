@@ -263,11 +263,9 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     key[i] = k < n ? keys_in[k] : 0xFFFFFFFFu;
     if (PRELOAD_VALS) val[i] = k < n ? vals_in[k] : 0u;
   }
-  // Round i ranks item i of every lane: lanes with equal digits find each other with match.any, the lowest
-  // of them fetch-and-adds the group size on the warp's digit counter (shared-memory atomic WITH return:
-  // the returned old value is the number of equal digits in earlier rounds).  The returned values are only
-  // consumed after the loop, so the 16 atomics pipeline instead of forming a load->store->load chain.
-  uint32_t packed[IPT];   // before | leader << 8
+  // Round i ranks item i of every lane: lanes with equal digits find each other with match.any; the lowest
+  // of them bumps the warp's private digit counter and broadcasts the old value.  (A returning shared-memory
+  // atomic instead of the load/store pair was measured slower on B200: 117 vs 85 us per 9M-item pass.)
 #pragma unroll
   for (int i = 0; i < IPT; i++) {
     const int k = seg + i * 32 + lane;
@@ -277,13 +275,14 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     const uint32_t peers = __match_any_sync(0xffffffffu, md);
     const uint32_t before = __popc(peers & lt_mask);
     uint32_t prev = 0;
-    if (valid && before == 0) prev = atomicAdd(&s_cnt[warp][d], (uint32_t)__popc(peers));
-    rank[i] = prev;
-    packed[i] = before | ((uint32_t)(__ffs(peers) - 1) << 8);
+    if (valid && before == 0) {
+      prev = s_cnt[warp][d];
+      s_cnt[warp][d] = prev + __popc(peers);
+    }
+    prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
+    rank[i] = prev + before;
+    __syncwarp();
   }
-#pragma unroll
-  for (int i = 0; i < IPT; i++)
-    rank[i] = __shfl_sync(0xffffffffu, rank[i], packed[i] >> 8) + (packed[i] & 0xFFu);
   __syncthreads();
 
   // ---- per digit (one thread each): block count, publish the aggregate ----

@@ -12,6 +12,7 @@ the C ABI (include/splat_b200.h).  torch is used for device memory, streams and 
 """
 from __future__ import annotations
 
+import threading
 from typing import NamedTuple
 
 import torch
@@ -79,24 +80,31 @@ def _prep(t, name=None):
 
 
 class _Scratch:
-    """The three caller-owned scratch buffers; torch owns the bytes, the library asks via callbacks."""
+    """The three caller-owned scratch buffers; torch owns the bytes, the library asks via callbacks.
+    The ctypes callback objects are created once per thread and reused (building a CFUNCTYPE thunk per
+    forward call costs tens of microseconds of pure host time on a ~1 ms step)."""
+
+    _tls = threading.local()
 
     def __init__(self, device):
         self.device = device
         self.bufs = {}
-        self._cbs = {}
-        for name in ("geom", "binning", "img"):
-            self._cbs[name] = _lib.ALLOC_FN(self._make(name))
+        tls = _Scratch._tls
+        if not hasattr(tls, "cbs"):
+            tls.cbs = {name: _lib.ALLOC_FN(_Scratch._make(name)) for name in ("geom", "binning", "img")}
+        tls.current = self
 
-    def _make(self, name):
+    @staticmethod
+    def _make(name):
         def alloc(_user, nbytes):
-            t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=self.device)
-            self.bufs[name] = t
+            cur = _Scratch._tls.current
+            t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=cur.device)
+            cur.bufs[name] = t
             return t.data_ptr()
         return alloc
 
     def cb(self, name):
-        return self._cbs[name]
+        return _Scratch._tls.cbs[name]
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
