@@ -37,6 +37,9 @@ __device__ __forceinline__ uint32_t patch_mask(float x, float y, float hx, float
   return m;
 }
 
+// Non-blocking L2 prefetch of the 128-byte line holding p (no register, no scoreboard).
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- TMA (bulk async copy) + mbarrier helpers: 1-D cp.async.bulk between global and shared memory ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

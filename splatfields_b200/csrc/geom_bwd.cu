@@ -26,8 +26,8 @@ struct CamB {
 // TMA: the block's SH rows arrive through one bulk async copy and its dL_dsh rows leave through one bulk
 // async store (cp.async.bulk both ways, UBLKCP.S.G / UBLKCP.G.S): each thread only touches its own 192-byte
 // row in shared memory (read, then overwritten in place with the gradient row; zeros for culled splats).
-template <int D, bool VEC, bool TMA>
-__global__ void __launch_bounds__(256) geom_backward_kernel(BwdParams p, GeomState g) {
+template <int D, bool VEC, bool TMA, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, GeomState g) {
   __shared__ CamB cam;
   __shared__ uint64_t s_bar;
   extern __shared__ __align__(128) float s_rows[];
@@ -54,6 +54,11 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(BwdParams p, GeomSta
   const size_t i = (size_t)(in_range ? idx : 0);
   const bool visible = in_range && p.radii[idx] > 0;
   float* my_row = TMA ? s_rows + (size_t)threadIdx.x * p.M * 3 : nullptr;
+  if (!TMA && visible && p.shs) {   // pull the SH row towards L2 while the covariance math runs
+    const char* row = reinterpret_cast<const char*>(p.shs + i * p.M * 3);
+    prefetch_l2(row);
+    prefetch_l2(row + 128);
+  }
 
   float dmean[3] = {0.f, 0.f, 0.f};
   float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -318,9 +323,13 @@ void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s
   const int blocks = (p.P + 255) / 256;
   const bool vec = p.shs && ((p.M * 3) % 4 == 0) && ((reinterpret_cast<size_t>(p.shs) & 15) == 0) &&
                    ((reinterpret_cast<size_t>(p.dL_dsh) & 15) == 0);
+  // bulk-copy (TMA) staging is opt-in (SFB_TMA=1): measured slower here (150 vs 134 us at 1M splats) —
+  // the whole 48 KB slab has to land before any thread of the CTA can start, and only 2 CTAs fit per SM.
   static int no_tma = -1;
-  if (no_tma < 0) { const char* e = getenv("SFB_NO_TMA"); no_tma = (e && e[0] == '1') ? 1 : 0; }
+  if (no_tma < 0) { const char* e = getenv("SFB_TMA"); no_tma = (e && e[0] == '1') ? 0 : 1; }
   const size_t smem = (size_t)256 * p.M * 12;
+  static int minb3 = -1;   // experiment: trade a few spills for 3 resident CTAs per SM
+  if (minb3 < 0) { const char* e = getenv("SFB_GEOM_MINB3"); minb3 = (e && e[0] == '1') ? 1 : 0; }
 #define SFB_GB(DD)                                                                                         \
   if (vec && !no_tma && p.M == (DD + 1) * (DD + 1) && smem <= 96 * 1024) {                                 \
     static bool attr_set = false;                                                                          \
@@ -330,7 +339,8 @@ void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s
       attr_set = true;                                                                                     \
     }                                                                                                      \
     geom_backward_kernel<DD, true, true><<<blocks, 256, smem, s>>>(p, g);                                  \
-  } else if (vec) geom_backward_kernel<DD, true, false><<<blocks, 256, 0, s>>>(p, g);                      \
+  } else if (vec && minb3 && DD == 3) geom_backward_kernel<3, true, false, 3><<<blocks, 256, 0, s>>>(p, g); \
+  else if (vec) geom_backward_kernel<DD, true, false><<<blocks, 256, 0, s>>>(p, g);                        \
   else            geom_backward_kernel<DD, false, false><<<blocks, 256, 0, s>>>(p, g);
   switch (p.shs ? p.D : 0) {
     case 0: SFB_GB(0) break;
