@@ -146,3 +146,73 @@ def forward_backward_host(vp: ViewParallelRasterizer, host_in: dict, host_out: d
     host_out["radii"].copy_(radii, non_blocking=True)
     host_out["grads"].copy_(vp.slab, non_blocking=True)
     torch.cuda.current_stream(vp.device).synchronize()
+
+
+class HostPipeline:
+    """Asynchronous HOST-buffer front end: `submit(host_in, host_out)` / `wait(ticket)`.
+
+    Every step still moves all of its inputs host->device and all of its results device->host, but on
+    three streams with double-buffered device staging, so that the upload of step k+1, the kernels of step
+    k and the download of step k-1 overlap (PCIe is full duplex; the kernels take ~1/4 of either copy).
+    """
+
+    def __init__(self, vp: ViewParallelRasterizer, depth: int = 2):
+        self.vp = vp
+        dev = vp.device
+        self.depth = depth
+        self.s_h2d = torch.cuda.Stream(dev)
+        self.s_comp = torch.cuda.Stream(dev)
+        self.s_d2h = torch.cuda.Stream(dev)
+        self.in_dev = [{k: torch.empty_like(v.detach()) for k, v in vp.params.items()} for _ in range(depth)]
+        self.cot_dev = [torch.empty(3, vp.H, vp.W, device=dev) for _ in range(depth)]
+        self.slabs = [torch.empty_like(vp.slab) for _ in range(depth)]
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_comp = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.live = [None] * depth       # keeps the per-step output tensors alive until their D2H is done
+        self.n = 0
+        for s in (self.s_h2d, self.s_comp, self.s_d2h):
+            s.wait_stream(torch.cuda.current_stream(dev))
+
+    def submit(self, host_in: dict, host_out: dict) -> int:
+        vp, k = self.vp, self.n
+        b = k % self.depth
+        # upload into staging set b (free once the compute that last read it has finished)
+        with torch.cuda.stream(self.s_h2d):
+            if k >= self.depth:
+                self.s_h2d.wait_event(self.ev_comp[b])
+            for name, t in self.in_dev[b].items():
+                t.copy_(host_in[name], non_blocking=True)
+            self.cot_dev[b].copy_(host_in["dL_dcolor"], non_blocking=True)
+            self.ev_in[b].record(self.s_h2d)
+        # compute on the staged inputs, gradients into slab b (free once its previous download is done)
+        with torch.cuda.stream(self.s_comp):
+            self.s_comp.wait_event(self.ev_in[b])
+            if k >= self.depth:
+                self.s_comp.wait_event(self.ev_out[b])
+            for name, p in vp.params.items():
+                p.data = self.in_dev[b][name]
+            vp.slab = self.slabs[b]
+            vp.step(self.cot_dev[b], keep=True)
+            color, radii, depth = vp.last
+            self.ev_comp[b].record(self.s_comp)
+        with torch.cuda.stream(self.s_d2h):
+            self.s_d2h.wait_event(self.ev_comp[b])
+            for t in (color, depth, radii, self.slabs[b]):
+                t.record_stream(self.s_d2h)      # allocated on the compute stream, read on this one
+            host_out["color"].copy_(color, non_blocking=True)
+            host_out["depth"].copy_(depth, non_blocking=True)
+            host_out["radii"].copy_(radii, non_blocking=True)
+            host_out["grads"].copy_(self.slabs[b], non_blocking=True)
+            self.ev_out[b].record(self.s_d2h)
+        self.live[b] = (color, radii, depth)
+        self.n += 1
+        return k
+
+    def wait(self, ticket: int) -> None:
+        """Returns when the host_out buffers given to submit(ticket) are valid."""
+        self.ev_out[ticket % self.depth].synchronize()
+
+    def drain(self) -> None:
+        for s in (self.s_h2d, self.s_comp, self.s_d2h):
+            s.synchronize()
