@@ -48,6 +48,8 @@ const char* sfb_last_error(void);
  *                     exactly one of (scales [P][3], rotations [P][4]) / cov3D_precomp ([P][6]) is non-NULL
  *   opacities [P]     bg [3]   viewmatrix, projmatrix [16]   campos [3]
  *   out_color [3][H][W]   out_depth [1][H][W]   radii [P] (int32)      — caller-allocated outputs
+ *   out_alpha [1][H][W] or NULL — optional fused coverage image sum(alpha*T): what the reference computes with
+ *                     a second full pass (colours = 1, bg = 0; gaussian_renderer/__init__.py:104-115)
  *   geom/binning/img  scratch allocators; the returned base pointers + *num_rendered must be handed to
  *                     sfb_rasterize_backward unchanged.
  * One blocking 4-byte device->host read (num_rendered) per call, like the reference. */
@@ -57,14 +59,14 @@ int sfb_rasterize_forward(
     const float* opacities, const float* scales, float scale_modifier, const float* rotations,
     const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix, const float* campos,
     float tan_fovx, float tan_fovy, int prefiltered,
-    float* out_color, float* out_depth, int* radii,
+    float* out_color, float* out_depth, float* out_alpha, int* radii,
     sfb_alloc_fn geom_alloc, void* geom_user,
     sfb_alloc_fn binning_alloc, void* binning_user,
     sfb_alloc_fn img_alloc, void* img_user,
     int* num_rendered, int debug, void* stream);
 
 /* Backward.  Replaces _C.rasterize_gaussians_backward.  dL_dout_color [3][H][W] is the
- * cotangent of out_color.  Outputs (all caller-allocated, fully written by the call — no pre-zeroing
+ * cotangent of out_color; dL_dout_alpha [1][H][W] (or NULL) the cotangent of the fused out_alpha.  Outputs (all caller-allocated, fully written by the call — no pre-zeroing
  * needed): dL_dmeans2D [P][3] (xy = gradient w.r.t. the NDC-scaled screen mean, z = 0; this is what
  * lands in viewspace_points.grad, scene/gaussian_model.py:429), dL_dcolors [P][3], dL_dopacity [P][1],
  * dL_dmeans3D [P][3], dL_dcov3D [P][6], dL_dsh [P][M][3] (may be NULL when shs is NULL),
@@ -76,7 +78,7 @@ int sfb_rasterize_backward(
     const float* viewmatrix, const float* projmatrix, const float* campos,
     float tan_fovx, float tan_fovy, const int* radii,
     void* geom_buffer, void* binning_buffer, void* img_buffer,
-    const float* dL_dout_color,
+    const float* dL_dout_color, const float* dL_dout_alpha,
     float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D, float* dL_dcov3D,
     float* dL_dsh, float* dL_dscales, float* dL_drotations,
     int debug, void* stream);

@@ -60,11 +60,35 @@ def main():
     torch.cuda.synchronize()
     pf, pb = dict(_lib.profile_read(0)), dict(_lib.profile_read(1))
     _lib.profile_enable(False)
+    # render(): the reference's two rasterizer passes vs the fused alpha channel
+    from splatfields_b200 import render
+    gd = dict(means3D=t["means3D"], active_sh_degree=deg, gaussian_opacity=t["opacities"], gaussian_scales=t["scales"],
+              gaussian_rotations=t["rotations"])
+    if "shs" in t:
+        gd["gaussian_features"] = t["shs"]
+    else:
+        gd["gaussian_rgb"] = t["colors_precomp"]
+    Ga = torch.randn(1, H, W, device=dev)
+    rtimes = {}
+    for fused in (False, True):
+        ts = []
+        for i in range(a.warmup + a.iters):
+            for v in t.values():
+                v.grad = None
+            ef[0].record()
+            o = render(cam, gd, None, torch.ones(3, device=dev), return_opacity=True, fused_alpha=fused)
+            ((o["render"] * G).sum() + (o["opacity"] * Ga).sum()).backward()
+            ef[2].record()
+            torch.cuda.synchronize()
+            if i >= a.warmup:
+                ts.append(ef[0].elapsed_time(ef[2]))
+        rtimes["fused" if fused else "two_pass"] = float(np.median(ts))
     med = lambda x: float(np.median(x))
     T = ((W + 15) // 16) * ((H + 15) // 16)
     res = dict(config=a.config, P=cfg["P"], H=H, W=W, R=R, visible=int((radii > 0).sum()), mean_list=R / T,
                fwd_ms=med(tf), bwd_ms=med(tb), total_ms=med(tf) + med(tb),
-               msplats_s=cfg["P"] / (med(tf) + med(tb)) / 1e3, fwd_stages=pf, bwd_stages=pb)
+               msplats_s=cfg["P"] / (med(tf) + med(tb)) / 1e3, render_with_opacity_ms=rtimes, fwd_stages=pf,
+               bwd_stages=pb)
     print(json.dumps(res))
 
 

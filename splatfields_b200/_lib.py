@@ -46,7 +46,7 @@ def load():
         ci, ci, ci, ci, ci,                       # P, sh_degree, M, W, H
         vp, vp, vp, vp, vp, vp, cf, vp, vp,       # bg, means3D, shs, colors, opacities, scales, mod, rot, cov3D
         vp, vp, vp, cf, cf, ci,                   # view, proj, campos, tanfovx, tanfovy, prefiltered
-        vp, vp, vp,                               # out_color, out_depth, radii
+        vp, vp, vp, vp,                           # out_color, out_depth, out_alpha (nullable), radii
         ALLOC_FN, vp, ALLOC_FN, vp, ALLOC_FN, vp,
         C.POINTER(ci), ci, vp]
     lib.sfb_rasterize_backward.restype = ci
@@ -54,7 +54,7 @@ def load():
         ci, ci, ci, ci, ci, ci,                   # P, sh_degree, M, R, W, H
         vp, vp, vp, vp, vp, cf, vp, vp,           # bg, means3D, shs, colors, scales, mod, rot, cov3D
         vp, vp, vp, cf, cf, vp,                   # view, proj, campos, tanfovx, tanfovy, radii
-        vp, vp, vp, vp,                           # geom, binning, img, dL_dout_color
+        vp, vp, vp, vp, vp,                       # geom, binning, img, dL_dout_color, dL_dout_alpha (nullable)
         vp, vp, vp, vp, vp, vp, vp, vp,           # 8 gradient outputs
         ci, vp]
     lib.sfb_mark_visible.restype = ci
@@ -73,7 +73,7 @@ def load():
     lib.sfb_profile_count.argtypes = [ci]
     lib.sfb_profile_name.restype = C.c_char_p
     lib.sfb_profile_name.argtypes = [ci, ci]
-    if lib.sfb_abi_version() != 1:
+    if lib.sfb_abi_version() != 2:
         raise SplatB200Error("libsplat_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -82,7 +82,7 @@ void prof_end(cudaStream_t s) {
 
 extern "C" {
 
-int sfb_abi_version(void) { return 1; }
+int sfb_abi_version(void) { return 2; }
 const char* sfb_last_error(void) { return g_err.c_str(); }
 int sfb_last_launch_count(void) { return g_launches; }
 
@@ -91,7 +91,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
                           const float* scales, float scale_modifier, const float* rotations,
                           const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
                           const float* campos, float tan_fovx, float tan_fovy, int prefiltered,
-                          float* out_color, float* out_depth, int* radii, sfb_alloc_fn geom_alloc,
+                          float* out_color, float* out_depth, float* out_alpha, int* radii, sfb_alloc_fn geom_alloc,
                           void* geom_user, sfb_alloc_fn binning_alloc, void* binning_user, sfb_alloc_fn img_alloc,
                           void* img_user, int* num_rendered, int debug, void* stream) {
   using namespace sfb;
@@ -106,6 +106,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   if (P == 0) {  // like the reference: nothing is launched, outputs are zero-filled
     CK(cudaMemsetAsync(out_color, 0, 3 * HW * sizeof(float), s));
     CK(cudaMemsetAsync(out_depth, 0, HW * sizeof(float), s));
+    if (out_alpha) CK(cudaMemsetAsync(out_alpha, 0, HW * sizeof(float), s));
     return SFB_OK;
   }
   if (!means3D || !opacities || !viewmatrix || !projmatrix || !campos || !radii)
@@ -184,8 +185,8 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   CK_LAUNCH("tile ranges", debug, s);
 
   prof_begin("render_forward", s);
-  launch_render_forward(W, H, b.ranges, b.inst_idx[tfinal], g.rec, bg, out_color, out_depth, img.final_T,
-                        img.n_contrib, s);
+  launch_render_forward(W, H, b.ranges, b.inst_idx[tfinal], g.rec, bg, out_color, out_depth, out_alpha,
+                        img.final_T, img.n_contrib, s);
   prof_end(s);
   g_launches++;
   CK_LAUNCH("render forward", debug, s);
@@ -198,7 +199,8 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
                            const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
                            const float* campos, float tan_fovx, float tan_fovy, const int* radii,
                            void* geom_buffer, void* binning_buffer, void* img_buffer,
-                           const float* dL_dout_color, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                           const float* dL_dout_color, const float* dL_dout_alpha, float* dL_dmeans2D,
+                           float* dL_dcolors, float* dL_dopacity,
                            float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscales,
                            float* dL_drotations, int debug, void* stream) {
   using namespace sfb;
@@ -229,7 +231,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   prof_end(s);
   prof_begin("render_backward", s);
   launch_render_backward(W, H, b.ranges, b.inst_idx[tfinal], g.rec, bg, img.final_T, img.n_contrib,
-                         dL_dout_color, g.grad, s);
+                         dL_dout_color, dL_dout_alpha, g.grad, s);
   prof_end(s);
   g_launches++;
   CK_LAUNCH("render backward", debug, s);

@@ -381,7 +381,9 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
                                      cudaStream_t s, int* launches, const char* const* names) {
   const int npass = (nbits + 7) / 8;
   const bool small = sort_blocks(n) < 4 * NUM_SMS_B200;       // < 4 tiles per SM with 4096-item tiles
-  const int tile = small ? SORT_THREADS * 4 : SORT_TILE;
+  static int ipt_big = -1;                                    // experiment knob: SFB_SORT_IPT=8 -> 2048-item tiles
+  if (ipt_big < 0) { const char* e = getenv("SFB_SORT_IPT"); ipt_big = (e && e[0] == '8') ? 8 : 16; }
+  const int tile = small ? SORT_THREADS * 4 : SORT_THREADS * ipt_big;
   const int nblocks = (n + tile - 1) / tile;
   // scratch layout: [hist_all: 4*256][tickets: 8][tile_state: npass * nblocks * bins]
   uint32_t* hist_all = scratch;
@@ -410,6 +412,10 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
     prof_begin(names[2], s);
     if (small)
       onesweep_pass_kernel<4><<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
+                                                                shifts[pass], nbins[pass],
+                                                                hist_all + pass * SORT_MAX_BINS, state, tickets + pass);
+    else if (ipt_big == 8)
+      onesweep_pass_kernel<8><<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
                                                                 shifts[pass], nbins[pass],
                                                                 hist_all + pass * SORT_MAX_BINS, state, tickets + pass);
     else

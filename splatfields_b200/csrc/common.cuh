@@ -106,7 +106,7 @@ __host__ __device__ inline size_t sort_scratch_words(size_t n) {
   // (small inputs use 1024-item tiles: at most 4 * 4 * NUM_SMS_B200 of them)
   const size_t blocks = (size_t)sort_blocks((int)n) + 1;
   const size_t blocks_small = (n + 1023) / 1024 + 1;
-  const size_t nb = blocks < (size_t)4 * NUM_SMS_B200 ? blocks_small : blocks;
+  const size_t nb = blocks < (size_t)4 * NUM_SMS_B200 ? blocks_small : 2 * blocks;   // 2x: 2048-item tile variant
   return (size_t)4 * SORT_MAX_BINS + 8 + (size_t)4 * SORT_MAX_BINS * nb + 16;
 }
 
@@ -230,13 +230,13 @@ void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_
 
 // render_fwd.cu
 void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
-                           const float* bg, float* out_color, float* out_depth, float* final_T,
+                           const float* bg, float* out_color, float* out_depth, float* out_alpha, float* final_T,
                            uint32_t* n_contrib, cudaStream_t s);
 
 // render_bwd.cu
 void launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
                             const float* bg, const float* final_T, const uint32_t* n_contrib,
-                            const float* dL_dpixels, GradRec* grad, cudaStream_t s);
+                            const float* dL_dpixels, const float* dL_dalpha_img, GradRec* grad, cudaStream_t s);
 
 // geom_bwd.cu
 struct BwdParams {

@@ -25,13 +25,16 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 // CULL: same per-warp footprint culling as the forward render (SplatRec::hx/hy): a warp skips splats that
 // cannot reach alpha >= 1/255 on any of its 32 pixels — pairs whose contribution is exactly zero.
-template <bool CULL>
+// ALPHA: the cotangent of the fused coverage image (see render_fwd.cu) enters as a fourth channel with
+// colour 1 and background 0: it only adds to dL/dalpha, exactly the sum the reference gets from the backward
+// of its second (alpha) pass.
+template <bool CULL, bool ALPHA>
 __global__ void __launch_bounds__(BB)
 render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
                        const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ rec,
                        const float* __restrict__ bg, const float* __restrict__ final_T,
                        const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
-                       GradRec* __restrict__ grad) {
+                       const float* __restrict__ dL_dalpha_img, GradRec* __restrict__ grad) {
   __shared__ float4 s_q0[BB];
   __shared__ float4 s_q1[BB];
   __shared__ float2 s_q2[BB];
@@ -58,6 +61,8 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
   float T = T_final;
   float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f;
   if (inside) { dLp0 = dL_dpixels[pix]; dLp1 = dL_dpixels[HW + pix]; dLp2 = dL_dpixels[2 * HW + pix]; }
+  float dLpa = 0.f, acca = 0.f;          // alpha channel: cotangent, accumulated "colour" (= 1) behind
+  if (ALPHA && inside) dLpa = dL_dalpha_img[pix];
   const float bg_dot = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
   const float Tf_bg = T_final * bg_dot;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
@@ -126,7 +131,8 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
           if (alpha >= 1.0f / 255.0f) {
             contrib = true;
             const float2 q2 = s_q2[j];
-            const float inv = __fdividef(1.f, 1.f - alpha);
+            float inv;   // 1 - alpha is in [0.01, 1]: the bare approximate reciprocal (1 ulp) is safe
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - alpha));
             T *= inv;
             wgt = alpha * T;
             acc0 = fmaf(last_alpha, lc0 - acc0, acc0);
@@ -136,6 +142,10 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
             float dL_dalpha = (lc0 - acc0) * dLp0;
             dL_dalpha = fmaf(lc1 - acc1, dLp1, dL_dalpha);
             dL_dalpha = fmaf(lc2 - acc2, dLp2, dL_dalpha);
+            if (ALPHA) {
+              acca = fmaf(last_alpha, 1.f - acca, acca);   // every splat's "colour" is 1 (last_alpha = 0 at the first)
+              dL_dalpha = fmaf(1.f - acca, dLpa, dL_dalpha);
+            }
             dL_dalpha = fmaf(dL_dalpha, T, -Tf_bg * inv);
             last_alpha = alpha;
             sG = q1.y * dL_dalpha * G;
@@ -209,16 +219,16 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
 
 void launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
                             const float* bg, const float* final_T, const uint32_t* n_contrib,
-                            const float* dL_dpixels, GradRec* grad, cudaStream_t s) {
+                            const float* dL_dpixels, const float* dL_dalpha_img, GradRec* grad, cudaStream_t s) {
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
   static int cull = -1;
   if (cull < 0) { const char* e = getenv("SFB_NO_CULL"); cull = (e && e[0] == '1') ? 0 : 1; }
-  if (cull)
-    render_backward_kernel<true><<<gx * gy, BB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib,
-                                                         dL_dpixels, grad);
-  else
-    render_backward_kernel<false><<<gx * gy, BB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T,
-                                                          n_contrib, dL_dpixels, grad);
+#define SFB_RB(C, A)                                                                                          \
+  render_backward_kernel<C, A><<<gx * gy, BB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib, \
+                                                      dL_dpixels, dL_dalpha_img, grad)
+  if (cull) { if (dL_dalpha_img) SFB_RB(true, true); else SFB_RB(true, false); }
+  else      { if (dL_dalpha_img) SFB_RB(false, true); else SFB_RB(false, false); }
+#undef SFB_RB
 }
 
 }  // namespace sfb

@@ -19,13 +19,16 @@ constexpr int RB = 256;  // batch = block size
 // can touch (SplatRec::hx/hy, computed conservatively in preprocess); every warp then sweeps only its own
 // compacted sub-list.  Skipped (splat, patch) pairs are pairs the reference's own `alpha < 1/255` test would
 // reject for all 32 pixels, so the output is bit-identical; the sweep shrinks ~3x on dense scenes.
-template <bool CULL>
+// ALPHA: also accumulate the coverage image A = sum(alpha * T) — the image the reference obtains from a SECOND
+// full rasterizer pass with colours = 1 and bg = 0 (gaussian_renderer/__init__.py:104-115); it shares every
+// skip / stop decision with the colour pass, so one extra FADD per contribution replaces that whole pass.
+template <bool CULL, bool ALPHA>
 __global__ void __launch_bounds__(RB)
 render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
                       const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ rec,
                       const float* __restrict__ bg, float* __restrict__ out_color,
-                      float* __restrict__ out_depth, float* __restrict__ final_T,
-                      uint32_t* __restrict__ n_contrib) {
+                      float* __restrict__ out_depth, float* __restrict__ out_alpha,
+                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
   __shared__ float4 s_q0[RB];  // x, y, conA, conB
   __shared__ float4 s_q1[RB];  // conC, opacity, depth, r
   __shared__ float2 s_q2[RB];  // g, b
@@ -45,7 +48,7 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
   int todo = (int)(range.y - range.x);
   bool done = !inside;
 
-  float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
+  float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, Ac = 0.f;
   uint32_t last_contributor = 0;
 
   for (int base = 0; todo > 0; base += RB, todo -= RB) {
@@ -96,6 +99,7 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
       C1 = __fmaf_rn(q2.x, w, C1);
       C2 = __fmaf_rn(q2.y, w, C2);
       Dp = __fmaf_rn(q1.z, w, Dp);
+      if (ALPHA) Ac = __fmaf_rn(1.0f, w, Ac);
       T = test_T;
       last_contributor = (uint32_t)(base + j + 1);   // 1-based position in the tile list
     }
@@ -109,6 +113,7 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
     out_color[HW + pix] = __fmaf_rn(T, bg[1], C1);
     out_color[2 * HW + pix] = __fmaf_rn(T, bg[2], C2);
     out_depth[pix] = Dp;
+    if (ALPHA) out_alpha[pix] = Ac;     // bg = 0 in the reference's alpha pass
   }
 }
 
@@ -119,15 +124,15 @@ static bool cull_enabled() {
 }
 
 void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
-                           const float* bg, float* out_color, float* out_depth, float* final_T,
+                           const float* bg, float* out_color, float* out_depth, float* out_alpha, float* final_T,
                            uint32_t* n_contrib, cudaStream_t s) {
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
-  if (cull_enabled())
-    render_forward_kernel<true><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, out_color, out_depth,
-                                                        final_T, n_contrib);
-  else
-    render_forward_kernel<false><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, out_color,
-                                                         out_depth, final_T, n_contrib);
+#define SFB_RF(C, A)                                                                                          \
+  render_forward_kernel<C, A><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, out_color, out_depth, \
+                                                     out_alpha, final_T, n_contrib)
+  if (cull_enabled()) { if (out_alpha) SFB_RF(true, true); else SFB_RF(true, false); }
+  else                { if (out_alpha) SFB_RF(false, true); else SFB_RF(false, false); }
+#undef SFB_RF
 }
 
 }  // namespace sfb

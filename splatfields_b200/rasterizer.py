@@ -108,12 +108,13 @@ class _Scratch:
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings):
-    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings)
+                        raster_settings, with_alpha=False):
+    out = _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                    cov3Ds_precomp, raster_settings, with_alpha)
+    return out if with_alpha else out[:3]
 
 
-def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs):
+def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, with_alpha=False):
     lib = _lib.load()
     if means3D.dim() != 2 or means3D.shape[1] != 3:
         raise Exception("means3D must have dimensions (num_points, 3)")
@@ -130,6 +131,7 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
     color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
     depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
+    alpha = torch.empty((1, H, W), dtype=torch.float32, device=dev) if with_alpha else None
     scratch = _Scratch(dev)
     import ctypes as C
     nr = C.c_int(0)
@@ -139,32 +141,33 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
             P, int(rs.sh_degree), int(M), W, H,
             _ptr(bg), _ptr(means3D_c), _ptr(sh_c), _ptr(col_c), _ptr(op_c), _ptr(sc_c), float(rs.scale_modifier),
             _ptr(rot_c), _ptr(cov_c), _ptr(vm), _ptr(pm), _ptr(cp), float(rs.tanfovx), float(rs.tanfovy),
-            int(bool(rs.prefiltered)), _ptr(color), _ptr(depth), _ptr(radii),
+            int(bool(rs.prefiltered)), _ptr(color), _ptr(depth), _ptr(alpha), _ptr(radii),
             scratch.cb("geom"), None, scratch.cb("binning"), None, scratch.cb("img"), None,
             C.byref(nr), int(bool(rs.debug)), stream)
     _lib.check(rc)
     empty = torch.empty(0, dtype=torch.uint8, device=dev)
     geom, binning, img = (scratch.bufs.get(k, empty) for k in ("geom", "binning", "img"))
     saved = (means3D_c, sh_c, col_c, sc_c, rot_c, cov_c, bg, vm, pm, cp)
-    return int(nr.value), color, depth, radii, geom, binning, img, M, saved
+    return int(nr.value), color, depth, radii, geom, binning, img, M, saved, alpha
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings):
+                raster_settings, with_alpha=False):
         rs = raster_settings
         args = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs)
         if rs.debug:
             try:
-                out = _forward_impl(*args)
+                out = _forward_impl(*args, with_alpha=with_alpha)
             except Exception as ex:
                 torch.save(tuple(a.detach().cpu() if torch.is_tensor(a) else a for a in args[:-1]), "snapshot_fw.dump")
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise ex
         else:
-            out = _forward_impl(*args)
-        num_rendered, color, depth, radii, geom, binning, img, M, saved = out
+            out = _forward_impl(*args, with_alpha=with_alpha)
+        num_rendered, color, depth, radii, geom, binning, img, M, saved, alpha = out
+        ctx.with_alpha = bool(with_alpha)
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.M = M
@@ -173,10 +176,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.saved_inputs = saved
         ctx.save_for_backward(radii, geom, binning, img)
         ctx.mark_non_differentiable(radii)
-        return color, radii, depth
+        if with_alpha:
+            return color, radii, depth, alpha
+        # always four outputs so that backward has a fixed arity; the wrapper drops the placeholder
+        return color, radii, depth, color.new_empty(0)
 
     @staticmethod
-    def backward(ctx, grad_out_color, _grad_radii, _grad_depth):
+    def backward(ctx, grad_out_color, _grad_radii, _grad_depth, grad_out_alpha=None):
         # Like the pinned reference build, depth is a forward-only output: its cotangent is not
         # propagated (every shipped recipe keeps lambda_depth = 0).
         lib = _lib.load()
@@ -198,6 +204,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         dL_dscales = _arena_out("scales", P, (P, 3), **f32) if cov is None else None
         dL_drot = _arena_out("rotations", P, (P, 4), **f32) if cov is None else None
         g = _prep(grad_out_color)
+        ga = _prep(grad_out_alpha) if (ctx.with_alpha and grad_out_alpha is not None) else None
+        if g is None:      # only the alpha image was used downstream
+            g = torch.zeros((3, H, W), **f32)
         if P > 0:
             with torch.cuda.device(dev):
                 stream = torch.cuda.current_stream(dev).cuda_stream
@@ -205,7 +214,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     P, int(rs.sh_degree), int(M), int(ctx.num_rendered), W, H,
                     _ptr(bg), _ptr(means3D), _ptr(sh), _ptr(col), _ptr(sc), float(rs.scale_modifier), _ptr(rot),
                     _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cp), float(rs.tanfovx), float(rs.tanfovy), _ptr(radii),
-                    _ptr(geom), _ptr(binning), _ptr(img), _ptr(g),
+                    _ptr(geom), _ptr(binning), _ptr(img), _ptr(g), _ptr(ga),
                     _ptr(dL_dmeans2D), _ptr(dL_dcolors), _ptr(dL_dopacity), _ptr(dL_dmeans3D), _ptr(dL_dcov3D),
                     _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drot), int(bool(rs.debug)), stream)
             _lib.check(rc)
@@ -221,6 +230,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             shaped(dL_dscales, sh_sc),
             shaped(dL_drot, sh_rot),
             shaped(dL_dcov3D, sh_cov) if cov is not None else None,
+            None,
             None,
         )
         return grads
@@ -246,7 +256,10 @@ class GaussianRasterizer(nn.Module):
             return out.bool()
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None):
+                cov3D_precomp=None, with_alpha=False):
+        """Reference signature plus one extension: `with_alpha=True` appends a fused coverage image
+        alpha[1,H,W] = sum(alpha_i * T_i) to the outputs — the image the reference's render() obtains from
+        a second full rasterizer call with colours = 1 and bg = 0 (gaussian_renderer/__init__.py:104-115)."""
         rs = self.raster_settings
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
             raise Exception('Please provide excatly one of either SHs or precomputed colors!')
@@ -254,4 +267,4 @@ class GaussianRasterizer(nn.Module):
                 ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                   cov3D_precomp, rs)
+                                   cov3D_precomp, rs, with_alpha=with_alpha)

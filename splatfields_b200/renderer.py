@@ -19,7 +19,9 @@ class _Pipe:
 
 
 def render(viewpoint_camera, gaussian_dict: dict, pipe=None, bg_color: torch.Tensor = None,
-           scaling_modifier: float = 1.0, return_opacity: bool = True):
+           scaling_modifier: float = 1.0, return_opacity: bool = True, fused_alpha: bool = False):
+    """fused_alpha=False reproduces the reference call for call (two rasterizer passes when
+    return_opacity); fused_alpha=True obtains the opacity image from the SAME pass."""
     pipe = pipe or _Pipe()
     means3D = gaussian_dict["means3D"]
     active_sh_degree = gaussian_dict["active_sh_degree"]
@@ -52,10 +54,16 @@ def render(viewpoint_camera, gaussian_dict: dict, pipe=None, bg_color: torch.Ten
             debug=pipe.debug)
 
     rasterizer = GaussianRasterizer(raster_settings=settings(bg_color))
+    opacity_image = None
+    if return_opacity and fused_alpha:
+        rendered_image, radii, depth, opacity_image = rasterizer(
+            means3D=means3D, means2D=screenspace_points, shs=features, colors_precomp=rgb, opacities=opacity,
+            scales=scales, rotations=rotations, cov3D_precomp=None, with_alpha=True)
+        return {"render": rendered_image, "viewspace_points": screenspace_points,
+                "visibility_filter": radii > 0, "radii": radii, "opacity": opacity_image, "depth": depth}
     rendered_image, radii, depth = rasterizer(
         means3D=means3D, means2D=screenspace_points, shs=features, colors_precomp=rgb, opacities=opacity,
         scales=scales, rotations=rotations, cov3D_precomp=None)
-    opacity_image = None
     if return_opacity:                                                # reference :104-115
         rasterizer_mask = GaussianRasterizer(raster_settings=settings(bg_color * 0.0))
         opacity_image = rasterizer_mask(

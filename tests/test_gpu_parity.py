@@ -114,3 +114,65 @@ def test_scale_modifier_and_background(oracle, cuda_lib):
     assert np.array_equal(radii.cpu().numpy(), f["radii"])
     assert np.abs(color.cpu().numpy() - f["color"])[:, ok].max() <= IMG_ATOL
     assert depth.shape == (1, H, W) and radii.dtype == torch.int32
+
+
+def test_fused_alpha_matches_two_reference_passes(oracle, cuda_lib):
+    """render() runs the whole rasterizer twice when return_opacity (colour pass, then colours = 1
+    / bg = 0).  The fused path must give the second pass's image and the SUM of both passes' gradients."""
+    import math
+    from splatfields_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    from tests.helpers import cam_kwargs
+    P, H, W, deg = 6_000, 144, 176, 3
+    sc, cam = scene_and_camera(P, H, W, 51, scale_mult=2.5)
+    bg = (1.0, 0.5, 0.2)
+    gen = torch.Generator().manual_seed(78)
+    dLc = torch.randn(3, H, W, generator=gen).numpy()
+    dLa = torch.randn(1, H, W, generator=gen).numpy()
+    n = lambda k: sc[k].numpy()
+    kw = cam_kwargs(cam, H, W, bg)
+    f1 = oracle.forward(n("means3D"), n("opacities"), n("scales"), n("rotations"), shs=n("shs"), sh_degree=deg,
+                        want_margin=True, **kw)
+    ok = f1["margin"] > 1e-4
+    dLc[:, ~ok] = 0
+    dLa[:, ~ok] = 0
+    kw0 = dict(kw)
+    kw0["bg"] = np.zeros(3, np.float32)
+    ones = np.ones((P, 3), np.float32)
+    f2 = oracle.forward(n("means3D"), n("opacities"), n("scales"), n("rotations"), colors_precomp=ones,
+                        sh_degree=0, **kw0)
+    bk = dict(viewmatrix=kw["viewmatrix"], projmatrix=kw["projmatrix"], campos=kw["campos"], tanfovx=kw["tanfovx"],
+              tanfovy=kw["tanfovy"])
+    b1 = oracle.backward(f1, dLc, n("means3D"), n("scales"), n("rotations"), shs=n("shs"), sh_degree=deg, **bk)
+    dLa3 = np.concatenate([dLa, np.zeros((2, H, W), np.float32)], 0)   # reference uses channel 0 of the alpha pass
+    b2 = oracle.backward(f2, dLa3, n("means3D"), n("scales"), n("rotations"), sh_degree=0, **bk)
+
+    dev = torch.device("cuda")
+    camd = cam.to(dev)
+    rs = GaussianRasterizationSettings(H, W, math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2),
+                                       torch.tensor(bg, device=dev), 1.0, camd.world_view_transform,
+                                       camd.full_proj_transform, deg, camd.camera_center, False, False)
+    t = {k: v.to(dev).clone().requires_grad_(True) for k, v in sc.items()}
+    m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
+    color, radii, depth, alpha = GaussianRasterizer(rs)(
+        means3D=t["means3D"], means2D=m2d, opacities=t["opacities"], shs=t["shs"], scales=t["scales"],
+        rotations=t["rotations"], with_alpha=True)
+    assert alpha.shape == (1, H, W)
+    assert np.abs(color.detach().cpu().numpy() - f1["color"])[:, ok].max() <= IMG_ATOL
+    assert np.abs(alpha.detach().cpu().numpy()[0] - f2["color"][0])[ok].max() <= IMG_ATOL
+    # coverage = 1 - final transmittance (telescoping sum), to rounding
+    assert np.abs(alpha.detach().cpu().numpy()[0] - (1.0 - f1["final_T"]))[ok].max() <= 1e-5
+    ((color * torch.as_tensor(dLc, device=dev)).sum() + (alpha * torch.as_tensor(dLa, device=dev)).sum()).backward()
+    got = dict(dL_dmeans3D=t["means3D"].grad, dL_dmeans2D=m2d.grad, dL_dopacity=t["opacities"].grad,
+               dL_dsh=t["shs"].grad, dL_dscales=t["scales"].grad, dL_drotations=t["rotations"].grad)
+    for k, v in got.items():
+        ref = b1[k].astype(np.float64) + (b2[k].astype(np.float64) if k != "dL_dsh" else 0.0)
+        grad_close(k, v.detach().cpu().numpy(), ref.reshape(v.shape))
+    # and the mirror of render(): fused == two-pass
+    from splatfields_b200 import render
+    gd = dict(means3D=t["means3D"].detach(), active_sh_degree=deg, gaussian_opacity=t["opacities"].detach(),
+              gaussian_scales=t["scales"].detach(), gaussian_rotations=t["rotations"].detach(),
+              gaussian_features=t["shs"].detach())
+    o2 = render(camd, gd, None, torch.tensor(bg, device=dev), return_opacity=True, fused_alpha=False)
+    o1 = render(camd, gd, None, torch.tensor(bg, device=dev), return_opacity=True, fused_alpha=True)
+    assert torch.equal(o1["render"], o2["render"]) and torch.equal(o1["radii"], o2["radii"])
+    assert float((o1["opacity"] - o2["opacity"]).abs().max()) <= 1e-6
