@@ -50,6 +50,24 @@ ProfRec g_rec[2][MAX_REC];
 int g_nrec[2] = {0, 0};
 bool g_rec_made = false;
 
+// ---- red-zone verification (debug=True only) ----
+int redzones_fill(const sfb::RedzoneList& rz, cudaStream_t s) {
+  for (int i = 0; i < rz.n; i++)
+    if (cudaMemsetAsync(rz.ptr[i], 0xA5, sfb::REDZONE_BYTES, s) != cudaSuccess) return -1;
+  return 0;
+}
+// returns the index of the first clobbered red zone, -1 if all intact, -2 on a CUDA error
+int redzones_check(const sfb::RedzoneList& rz, cudaStream_t s) {
+  unsigned char host[sfb::REDZONE_BYTES];
+  for (int i = 0; i < rz.n; i++) {
+    if (cudaMemcpyAsync(host, rz.ptr[i], sfb::REDZONE_BYTES, cudaMemcpyDeviceToHost, s) != cudaSuccess) return -2;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return -2;
+    for (size_t k = 0; k < sfb::REDZONE_BYTES; k++)
+      if (host[k] != 0xA5) return i;
+  }
+  return -1;
+}
+
 int tile_sort_final(int T) {
   int bits = sfb::tile_bits(T);
   int npass = (bits + 7) / 8;
@@ -124,12 +142,18 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   if (!g_pinned) CK(cudaHostAlloc((void**)&g_pinned, 64, cudaHostAllocDefault));
   if (!g_evt) CK(cudaEventCreateWithFlags(&g_evt, cudaEventDisableTiming));
 
+  RedzoneList rz;
   char* gchunk = (char*)geom_alloc(geom_user, GeomState::required((size_t)P));
   if (!gchunk) return fail(SFB_ERR_ALLOC, "geometry buffer allocation failed");
+  if (debug) redzone_collector() = &rz;
   GeomState g = GeomState::from_chunk(gchunk, (size_t)P);
+  redzone_collector() = nullptr;
   char* ichunk = (char*)img_alloc(img_user, ImgState::required(HW));
   if (!ichunk) return fail(SFB_ERR_ALLOC, "image buffer allocation failed");
+  if (debug) redzone_collector() = &rz;
   ImgState img = ImgState::from_chunk(ichunk, HW);
+  redzone_collector() = nullptr;
+  if (debug && redzones_fill(rz, s)) return fail(SFB_ERR_CUDA, "red-zone fill");
 
   FwdParams fp;
   fp.P = P; fp.D = sh_degree; fp.M = M; fp.W = W; fp.H = H;
@@ -165,7 +189,11 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
 
   char* bchunk = (char*)binning_alloc(binning_user, BinState::required((size_t)R, (size_t)T));
   if (!bchunk) return fail(SFB_ERR_ALLOC, "binning buffer allocation failed");
+  RedzoneList rzb;
+  if (debug) redzone_collector() = &rzb;
   BinState b = BinState::from_chunk(bchunk, (size_t)R, (size_t)T);
+  redzone_collector() = nullptr;
+  if (debug && redzones_fill(rzb, s)) return fail(SFB_ERR_CUDA, "red-zone fill");
 
   int tfinal = 0;
   if (R > 0) {
@@ -190,6 +218,15 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   prof_end(s);
   g_launches++;
   CK_LAUNCH("render forward", debug, s);
+  if (debug) {
+    int bad = redzones_check(rz, s);
+    if (bad == -1) { bad = redzones_check(rzb, s); if (bad >= 0) bad += 100; }
+    if (bad != -1) {
+      char msg[128];
+      snprintf(msg, sizeof(msg), "forward wrote past a scratch array (red zone %d clobbered)", bad);
+      return fail(SFB_ERR_CUDA, msg);
+    }
+  }
   return SFB_OK;
 }
 
@@ -217,12 +254,15 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
     return fail(SFB_ERR_ARG, "dL_dscales / dL_drotations required with scales / rotations");
   const size_t HW = (size_t)H * W;
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y, T = gx * gy;
+  RedzoneList rz;
+  if (debug) redzone_collector() = &rz;
   char* gchunk = (char*)geom_buffer;
   GeomState g = GeomState::from_chunk(gchunk, (size_t)P);
   char* bchunk = (char*)binning_buffer;
   BinState b = BinState::from_chunk(bchunk, (size_t)num_rendered, (size_t)T);
   char* ichunk = (char*)img_buffer;
   ImgState img = ImgState::from_chunk(ichunk, HW);
+  redzone_collector() = nullptr;
   const int tfinal = num_rendered > 0 ? tile_sort_final(T) : 0;
 
   g_which = 1; g_nrec[1] = 0;
@@ -250,6 +290,14 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   prof_end(s);
   g_launches++;
   CK_LAUNCH("geometry backward", debug, s);
+  if (debug) {   // the forward (run with debug) left the pattern in place; nothing may have touched it since
+    int bad = redzones_check(rz, s);
+    if (bad != -1) {
+      char msg[128];
+      snprintf(msg, sizeof(msg), "backward wrote past a scratch array (red zone %d clobbered)", bad);
+      return fail(SFB_ERR_CUDA, msg);
+    }
+  }
   return SFB_OK;
 }
 

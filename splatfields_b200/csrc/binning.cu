@@ -440,8 +440,7 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n
 }
 
 // ------------------------------------------------------------------ instance emission in depth order
-constexpr int DUP_THREADS = 256;
-constexpr int DUP_GPB = 1024;  // Gaussians (depth ranks) per block
+constexpr int DUP_THREADS = 256;   // DUP_GPB (Gaussians / depth ranks per block) lives in common.cuh: it sizes block_sums
 
 __global__ void __launch_bounds__(DUP_THREADS)
 instance_block_sums_kernel(int P, const uint32_t* __restrict__ sorted_idx,
@@ -549,7 +548,7 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
       // the Gaussian that spills in: largest s with s_pref[s] <= cb (it has a non-zero count)
       int lo = 0, hi = DUP_GPB;
 #pragma unroll
-      for (int it = 0; it < 10; it++) {
+      for (int it = 0; (1 << it) < DUP_GPB; it++) {
         int mid = (lo + hi) >> 1;
         if (s_pref[mid] <= cb) lo = mid; else hi = mid;
       }

@@ -84,13 +84,23 @@ struct __align__(16) GradRec {
 };
 static_assert(sizeof(GradRec) == 48, "GradRec must be 48 bytes");
 
-__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Every carved array is followed by a 256-byte red zone.  With debug=True the API fills the red zones with a
+// pattern before the kernels run and verifies them afterwards (forward and backward), which catches writes that
+// run past an array but stay inside the caller's single allocation — invisible to compute-sanitizer.
+constexpr size_t REDZONE_BYTES = 256;
+struct RedzoneList { char* ptr[64]; int n = 0; };
+inline RedzoneList*& redzone_collector() { static thread_local RedzoneList* c = nullptr; return c; }
 
 template <typename T>
-__host__ __device__ inline T* carve(char*& p, size_t n) {
+inline T* carve(char*& p, size_t n) {
   size_t off = align_up(reinterpret_cast<size_t>(p), 256);
   T* r = reinterpret_cast<T*>(off);
-  p = reinterpret_cast<char*>(r + n);
+  char* end = reinterpret_cast<char*>(r + n);
+  char* rz = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(end), 16));
+  if (RedzoneList* c = redzone_collector()) { if (c->n < 64) c->ptr[c->n++] = rz; }
+  p = rz + REDZONE_BYTES;
   return r;
 }
 
@@ -110,6 +120,11 @@ __host__ __device__ inline size_t sort_scratch_words(size_t n) {
   return (size_t)4 * SORT_MAX_BINS + 8 + (size_t)4 * SORT_MAX_BINS * nb + 16;
 }
 
+// Depth ranks expanded per block of the instance-emission kernels (binning.cu); also the granularity of the
+// block_sums array.  256 keeps >= 4 CTAs per SM in flight even for 500k-splat scenes with ~140 tiles per splat.
+constexpr int DUP_GPB = 256;
+__host__ __device__ inline size_t dup_blocks(size_t P) { return (P + DUP_GPB - 1) / DUP_GPB; }
+
 // ---- P-sized scratch ("geomBuffer") ----
 struct GeomState {
   SplatRec* rec;            // [P]
@@ -120,7 +135,7 @@ struct GeomState {
   uint32_t* depth_key[2];   // [P]    ping-pong keys of the depth sort (0xFFFFFFFF = culled)
   uint32_t* depth_idx[2];   // [P]    ping-pong values (Gaussian index)
   uint32_t* sort_hist;      // [SORT_MAX_BINS * sort_blocks(P)]
-  uint32_t* block_sums;     // [sort_blocks(P) + 1]   per-block instance counts in depth order, then scanned
+  uint32_t* block_sums;     // [dup_blocks(P) + 2]    per-block instance counts in depth order, then scanned
   uint32_t* counters;       // [8]    [0] = num_rendered, [1] = num_visible
   GradRec* grad;            // [P]    backward accumulators
 
@@ -134,7 +149,7 @@ struct GeomState {
     for (int i = 0; i < 2; i++) g.depth_key[i] = carve<uint32_t>(chunk, P);
     for (int i = 0; i < 2; i++) g.depth_idx[i] = carve<uint32_t>(chunk, P);
     g.sort_hist = carve<uint32_t>(chunk, sort_scratch_words(P));
-    g.block_sums = carve<uint32_t>(chunk, (size_t)sort_blocks((int)P) + 2);
+    g.block_sums = carve<uint32_t>(chunk, dup_blocks(P) + 2);
     g.counters = carve<uint32_t>(chunk, 8);
     g.grad = carve<GradRec>(chunk, P);
     return g;
