@@ -35,14 +35,26 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
                        const float* __restrict__ bg, const float* __restrict__ final_T,
                        const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
                        const float* __restrict__ dL_dalpha_img, GradRec* __restrict__ grad) {
-  __shared__ float4 s_q0[BB];
-  __shared__ float4 s_q1[BB];
-  __shared__ float2 s_q2[BB];
-  __shared__ uint32_t s_id[BB];
-  __shared__ float s_acc[BB * 9];
-  __shared__ uint32_t s_max[BB / 32];
-  __shared__ uint8_t s_mask[CULL ? BB : 1];
-  __shared__ uint8_t s_list[CULL ? BB / 32 : 1][CULL ? BB : 1];
+  // one struct = one base register: every access below is base + immediate (+ j * stride)
+  struct Smem {
+    float4 q0[BB];
+    float4 q1[BB];
+    float2 q2[BB];
+    uint32_t id[BB];
+    float acc[BB * 9];
+    uint32_t maxc[BB / 32];
+    uint8_t mask[CULL ? BB : 1];
+    uint8_t list[CULL ? BB / 32 : 1][CULL ? BB : 1];
+  };
+  __shared__ Smem sm;
+  float4* const s_q0 = sm.q0;
+  float4* const s_q1 = sm.q1;
+  float2* const s_q2 = sm.q2;
+  uint32_t* const s_id = sm.id;
+  float* const s_acc = sm.acc;
+  uint32_t* const s_max = sm.maxc;
+  uint8_t* const s_mask = sm.mask;
+  uint8_t (*const s_list)[CULL ? BB : 1] = sm.list;
   const float tx0 = (float)((blockIdx.x % grid_x) * TILE_X), ty0 = (float)((blockIdx.x / grid_x) * TILE_Y);
 
   const int tile = blockIdx.x;

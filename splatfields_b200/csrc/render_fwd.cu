@@ -29,11 +29,20 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
                       const float* __restrict__ bg, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ out_alpha,
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
-  __shared__ float4 s_q0[RB];  // x, y, conA, conB
-  __shared__ float4 s_q1[RB];  // conC, opacity, depth, r
-  __shared__ float2 s_q2[RB];  // g, b
-  __shared__ uint8_t s_mask[CULL ? RB : 1];
-  __shared__ uint8_t s_list[CULL ? RB / 32 : 1][CULL ? RB : 1];
+  // one struct = one base register: every access below is base + immediate (+ j * stride)
+  struct Smem {
+    float4 q0[RB];   // x, y, conA, conB
+    float4 q1[RB];   // conC, opacity, depth, r
+    float2 q2[RB];   // g, b
+    uint8_t mask[CULL ? RB : 1];
+    uint8_t list[CULL ? RB / 32 : 1][CULL ? RB : 1];
+  };
+  __shared__ Smem sm;
+  float4* const s_q0 = sm.q0;
+  float4* const s_q1 = sm.q1;
+  float2* const s_q2 = sm.q2;
+  uint8_t* const s_mask = sm.mask;
+  uint8_t (*const s_list)[CULL ? RB : 1] = sm.list;
 
   const int tile = blockIdx.x;
   const int tile_x = tile % grid_x, tile_y = tile / grid_x;
