@@ -175,7 +175,8 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   CK(cudaEventRecord(g_evt, s));
 
   // stage 1: stable sort of the Gaussians by depth bits (culled ones carry 0xFFFFFFFF and sink)
-  int dfinal = radix_sort_pairs(g.depth_key, g.depth_idx, g.sort_hist, P, 32, s, &g_launches, kDepthSortNames);
+  int dfinal = radix_sort_pairs(g.depth_key, g.depth_idx, g.sort_hist, P, 32, s, &g_launches, kDepthSortNames,
+                                g.counters + 2);
   CK_LAUNCH("depth sort", debug, s);
   const uint32_t* sorted_idx = g.depth_idx[dfinal];
   launch_instance_block_sums(P, sorted_idx, g.tiles_touched, g.block_sums, s);

@@ -200,9 +200,14 @@ constexpr uint32_t OS_FLAG_AGG = 1u << 30, OS_FLAG_INC = 2u << 30, OS_VAL_MASK =
 constexpr int OS_MAX_PASSES = 4;
 constexpr int OS_LB = 8;   // look-back probes in flight per digit
 
+// bias_c (optional): pointer to ~kmin, the complement of the smallest valid key (preprocess reduces it with
+// atomicMax).  Keys are then rewritten IN PLACE as key - kmin (0xFFFFFFFF = culled -> 0: culled splats emit no
+// instances, so their place in the order is irrelevant).  Depth keys of a bounded scene span < 2^24 after the
+// shift, which makes the most significant digit pass an identity permutation (see onesweep_pass_kernel).
 __global__ void __launch_bounds__(SORT_THREADS)
-radix_hist_all_kernel(const uint32_t* __restrict__ keys, int n, int npass, int4 shifts, int4 nbins,
-                      uint32_t* __restrict__ hist_all /* [npass][SORT_MAX_BINS] */) {
+radix_hist_all_kernel(uint32_t* __restrict__ keys, int n, int npass, int4 shifts, int4 nbins,
+                      uint32_t* __restrict__ hist_all /* [npass][SORT_MAX_BINS] */,
+                      const uint32_t* __restrict__ bias_c) {
   // one private histogram per warp: 8x fewer same-address collisions on the shared-memory atomics
   constexpr int NW = SORT_THREADS / 32;
   __shared__ uint32_t s_h[NW][OS_MAX_PASSES][SORT_MAX_BINS];
@@ -212,8 +217,13 @@ radix_hist_all_kernel(const uint32_t* __restrict__ keys, int n, int npass, int4 
   const int sh[4] = {shifts.x, shifts.y, shifts.z, shifts.w};
   const int nb[4] = {nbins.x, nbins.y, nbins.z, nbins.w};
   const int stride = gridDim.x * SORT_THREADS;
+  const uint32_t kmin = bias_c ? ~(*bias_c) : 0u;
   for (int k = blockIdx.x * SORT_THREADS + threadIdx.x; k < n; k += stride) {
-    const uint32_t key = keys[k];
+    uint32_t key = keys[k];
+    if (bias_c) {
+      key = (key == 0xFFFFFFFFu || key < kmin) ? 0u : key - kmin;
+      keys[k] = key;
+    }
 #pragma unroll
     for (int p = 0; p < OS_MAX_PASSES; p++)
       if (p < npass) atomicAdd(&s_h[warp][p][(key >> sh[p]) & (uint32_t)(nb[p] - 1)], 1u);
@@ -247,6 +257,16 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   __shared__ uint32_t s_ticket;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t mask = (uint32_t)bins - 1;
+  if (digit_totals[0] == (uint32_t)n) {
+    // every key has digit 0 in this pass: the stable sort is the identity permutation -> plain coalesced copy
+    const int base = blockIdx.x * OS_TILE;
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+      const int k = base + i * SORT_THREADS + threadIdx.x;
+      if (k < n) { keys_out[k] = keys_in[k]; vals_out[k] = vals_in[k]; }
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < NW * SORT_MAX_BINS; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
   if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
   __syncthreads();
@@ -378,7 +398,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 }
 
 static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint32_t* scratch, int n, int nbits,
-                                     cudaStream_t s, int* launches, const char* const* names) {
+                                     cudaStream_t s, int* launches, const char* const* names,
+                                     const uint32_t* bias_c) {
   const int npass = (nbits + 7) / 8;
   const bool small = sort_blocks(n) < 4 * NUM_SMS_B200;       // < 4 tiles per SM with 4096-item tiles
   static int ipt_big = -1;                                    // experiment knob: SFB_SORT_IPT=8 -> 2048-item tiles
@@ -403,7 +424,7 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
   prof_begin(names[0], s);
   const int hblocks = min(sort_blocks(n), 4 * NUM_SMS_B200);
   radix_hist_all_kernel<<<hblocks, SORT_THREADS, 0, s>>>(keys[0], n, npass, make_int4(shifts[0], shifts[1], shifts[2], shifts[3]),
-                                                          make_int4(nbins[0], nbins[1], nbins[2], nbins[3]), hist_all);
+                                                          make_int4(nbins[0], nbins[1], nbins[2], nbins[3]), hist_all, bias_c);
   prof_end(s);
   if (launches) *launches += 1;
   int cur = 0;
@@ -431,12 +452,12 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
 }
 
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
-                     int* launches, const char* const* names) {
+                     int* launches, const char* const* names, const uint32_t* bias_c) {
   if (n <= 0 || nbits <= 0) return 0;
   static int legacy = -1;
   if (legacy < 0) { const char* e = getenv("SFB_SORT"); legacy = (e && e[0] == 'l') ? 1 : 0; }
-  if (legacy) return radix_sort_pairs_legacy(keys, vals, hist, n, nbits, s, launches, names);
-  return radix_sort_pairs_onesweep(keys, vals, hist, n, nbits, s, launches, names);
+  if (legacy) return radix_sort_pairs_legacy(keys, vals, hist, n, nbits, s, launches, names);   // (ignores bias_c)
+  return radix_sort_pairs_onesweep(keys, vals, hist, n, nbits, s, launches, names, bias_c);
 }
 
 // ------------------------------------------------------------------ instance emission in depth order

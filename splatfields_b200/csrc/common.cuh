@@ -136,7 +136,7 @@ struct GeomState {
   uint32_t* depth_idx[2];   // [P]    ping-pong values (Gaussian index)
   uint32_t* sort_hist;      // [SORT_MAX_BINS * sort_blocks(P)]
   uint32_t* block_sums;     // [dup_blocks(P) + 2]    per-block instance counts in depth order, then scanned
-  uint32_t* counters;       // [8]    [0] = num_rendered, [1] = num_visible
+  uint32_t* counters;       // [8]    [0] = num_rendered, [2] = ~(smallest depth key of a visible splat)
   GradRec* grad;            // [P]    backward accumulators
 
   static GeomState from_chunk(char*& chunk, size_t P) {
@@ -233,7 +233,8 @@ void launch_export_geom(int P, const GeomState& g, float* means2D, float* depths
 // Stable LSD radix sort of (key, value) pairs on key bits [0, nbits); returns the index (0/1) of the
 // ping-pong half that holds the result.  hist must hold sort_scratch_words(n) words.
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
-                     int* launches, const char* const* names /* {hist, scan, scatter} */);
+                     int* launches, const char* const* names /* {hist, scan, scatter} */,
+                     const uint32_t* bias_c = nullptr /* device: ~min key; keys are rebased in place */);
 void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
                                 uint32_t* block_sums, cudaStream_t s);
 void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,

@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(256)
 preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
   __shared__ Cam cam;
   __shared__ uint32_t s_tiles[8];
+  __shared__ uint32_t s_nkey[8];
   __shared__ uint64_t s_bar;
   extern __shared__ __align__(128) float s_shrows[];
   if (TMA_SH) {
@@ -130,7 +131,7 @@ preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
   __syncthreads();
 
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t my_tiles = 0;
+  uint32_t my_tiles = 0, my_key = 0xFFFFFFFFu;
   if (idx < p.P) {
     int out_radius = 0;
     uint32_t key = 0xFFFFFFFFu;
@@ -287,19 +288,26 @@ preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
     g.clamped[idx] = clamp_mask;
     g.depth_key[0][idx] = key;
     g.depth_idx[0][idx] = (uint32_t)idx;
+    my_key = key;
   }
   if (TMA_SH) mbar_wait(&s_bar, 0);   // never retire the CTA with the bulk copy still landing in its smem
   // num_rendered = sum of tiles_touched: order-independent, so one atomic per block is exact.
+  // ... and counters[2] = max(~key) = ~(smallest depth key of a visible splat): lets the depth sort rebase
+  // its keys so that the top digit pass degenerates to a copy for bounded scenes.
   uint32_t v = my_tiles;
+  uint32_t nk = my_tiles ? ~my_key : 0u;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) s_tiles[threadIdx.x >> 5] = v;
+  for (int o = 16; o > 0; o >>= 1) {
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+    nk = max(nk, __shfl_xor_sync(0xffffffffu, nk, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_tiles[threadIdx.x >> 5] = v; s_nkey[threadIdx.x >> 5] = nk; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t t = 0;
+    uint32_t t = 0, m = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) t += s_tiles[w];
-    if (t) atomicAdd(g.counters, t);
+    for (int w = 0; w < 8; w++) { t += s_tiles[w]; m = max(m, s_nkey[w]); }
+    if (t) { atomicAdd(g.counters, t); atomicMax(g.counters + 2, m); }
   }
 }
 

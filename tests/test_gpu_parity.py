@@ -67,6 +67,45 @@ def _compare(O, sc, cam, H, W, deg, bg=(1.0, 1.0, 1.0), check_grads=True):
     return f, c
 
 
+def _mut_aniso(sc):
+    """needle-like splats: lambda1/lambda2 of the screen covariance far above 1e4 -> the never-cull path"""
+    sc["scales"] = sc["scales"] * torch.tensor([0.03, 1.0, 25.0])
+
+
+def _mut_opacity(sc):
+    """opacities below the 1/255 visibility floor (never contribute), exactly 0, and 1 (0.99 clamp, fast saturation)"""
+    o = sc["opacities"]
+    n = o.shape[0]
+    o[: n // 4] = 0.003
+    o[n // 4: n // 3] = 0.0
+    o[n // 3: n // 2] = 1.0
+    o[n // 2: n // 2 + 50] = 1.0 / 255.0
+
+
+def _mut_huge(sc):
+    sc["scales"] = sc["scales"] * 40.0
+
+
+EDGE_CASES = [
+    ("needles",          4_000, 128, 160, 3, dict(seed=61, scale_mult=2.0), _mut_aniso),
+    ("opacity_extremes", 6_000, 128, 160, 3, dict(seed=62, scale_mult=3.0), _mut_opacity),
+    ("huge_splats",        300, 96,  112, 2, dict(seed=63, scale_mult=1.0), _mut_huge),
+    ("tiny_image",         500, 17,  17,  3, dict(seed=64, scale_mult=6.0), None),
+    ("one_pixel_row",      800, 1,   300, 1, dict(seed=65, scale_mult=6.0), None),
+]
+
+
+@pytest.mark.parametrize("name,P,H,W,deg,kw,mut", EDGE_CASES, ids=[c[0] for c in EDGE_CASES])
+def test_parity_edge_cases(oracle, cuda_lib, name, P, H, W, deg, kw, mut):
+    kw = dict(kw)
+    seed = kw.pop("seed")
+    sc, cam = scene_and_camera(P, H, W, seed, sh_degree=deg, **kw)
+    if mut is not None:
+        mut(sc)
+    f, c = _compare(oracle, sc, cam, H, W, deg, bg=(0.2, 0.9, 0.4))
+    assert f["num_rendered"] > 0
+
+
 @pytest.mark.parametrize("name,P,H,W,deg,kw", CASES, ids=[c[0] for c in CASES])
 def test_parity_small(oracle, cuda_lib, name, P, H, W, deg, kw):
     kw = dict(kw)
