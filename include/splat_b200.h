@@ -89,9 +89,12 @@ int sfb_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 
 /* Inspection of the opaque scratch buffers (parity tests compare these with the oracle bit-for-bit).
  * Each output may be NULL.  means2D [P][2], depths [P], cov3D [P][6], conic_opacity [P][4], rgb [P][3],
- * clamped [P][3] (uint8), tiles_touched [P] (uint32).  */
-int sfb_export_geom(int P, const void* geom_buffer, float* means2D, float* depths, float* cov3D,
-                    float* conic_opacity, float* rgb, uint8_t* clamped, uint32_t* tiles_touched, void* stream);
+ * clamped [P][3] (uint8), tiles_touched [P] (uint32).  The 3D covariance is not kept in the scratch (the
+ * backward recomputes it): it is re-derived here from the forward's scales / rotations (or cov3D_precomp). */
+int sfb_export_geom(int P, const void* geom_buffer, const float* scales, float scale_modifier,
+                    const float* rotations, const float* cov3D_precomp, float* means2D, float* depths,
+                    float* cov3D, float* conic_opacity, float* rgb, uint8_t* clamped, uint32_t* tiles_touched,
+                    void* stream);
 /* point_list_keys [R] (uint64: tile<<32 | depth bits), point_list [R] (uint32), ranges [T][2] (uint32). */
 int sfb_export_binning(int P, int num_rendered, int W, int H, const void* geom_buffer,
                        const void* binning_buffer, uint64_t* point_list_keys, uint32_t* point_list,

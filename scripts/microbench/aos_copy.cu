@@ -14,6 +14,27 @@ __global__ void row_copy(const float4* __restrict__ in, float4* __restrict__ out
   for (int k = 0; k < 12; k++) { v[k].x += 1.f; out[(size_t)i * 12 + k] = v[k]; }
 }
 
+// thread-per-row with 256-bit accesses (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a): one full 32-byte sector per lane
+__global__ void row_copy_v8(const float* __restrict__ in, float* __restrict__ out, int P) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  float v[6][8];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const float* p = in + (size_t)i * 48 + 8 * k;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[k][0]), "=f"(v[k][1]), "=f"(v[k][2]), "=f"(v[k][3]), "=f"(v[k][4]), "=f"(v[k][5]), "=f"(v[k][6]), "=f"(v[k][7])
+                 : "l"(p));
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    float* q = out + (size_t)i * 48 + 8 * k;
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(q), "f"(v[k][0] + 1.f), "f"(v[k][1]), "f"(v[k][2]),
+                 "f"(v[k][3]), "f"(v[k][4]), "f"(v[k][5]), "f"(v[k][6]), "f"(v[k][7])
+                 : "memory");
+  }
+}
+
 // same, but 4 lanes cooperate on one row: lane j of a quad moves float4 j, j+4, j+8 (3 x 64-byte segments / row)
 __global__ void quad_copy(const float4* __restrict__ in, float4* __restrict__ out, int P) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -55,6 +76,10 @@ int main() {
   printf("{\"kernel\": \"row_copy_256\", \"ms\": %.4f, \"GBps\": %.0f}\n", t, gb / (t * 1e-3));
   t = time_it([&] { row_copy<<<(P + 127) / 128, 128>>>(in, out, P); });
   printf("{\"kernel\": \"row_copy_128\", \"ms\": %.4f, \"GBps\": %.0f}\n", t, gb / (t * 1e-3));
+  t = time_it([&] { row_copy_v8<<<(P + 255) / 256, 256>>>((const float*)in, (float*)out, P); });
+  printf("{\"kernel\": \"row_copy_v8_256\", \"ms\": %.4f, \"GBps\": %.0f}\n", t, gb / (t * 1e-3));
+  t = time_it([&] { row_copy_v8<<<(P + 127) / 128, 128>>>((const float*)in, (float*)out, P); });
+  printf("{\"kernel\": \"row_copy_v8_128\", \"ms\": %.4f, \"GBps\": %.0f}\n", t, gb / (t * 1e-3));
   t = time_it([&] { quad_copy<<<(4 * P + 255) / 256, 256>>>(in, out, P); });
   printf("{\"kernel\": \"quad_copy_256\", \"ms\": %.4f, \"GBps\": %.0f}\n", t, gb / (t * 1e-3));
   t = time_it([&] { flat_copy<<<148 * 8, 256>>>(in, out, n4); });

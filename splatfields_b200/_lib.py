@@ -60,7 +60,7 @@ def load():
     lib.sfb_mark_visible.restype = ci
     lib.sfb_mark_visible.argtypes = [ci, vp, vp, vp, vp, vp]
     lib.sfb_export_geom.restype = ci
-    lib.sfb_export_geom.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.sfb_export_geom.argtypes = [ci, vp, vp, cf, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_export_binning.restype = ci
     lib.sfb_export_binning.argtypes = [ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
     lib.sfb_export_img.restype = ci

@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -66,6 +67,12 @@ int redzones_check(const sfb::RedzoneList& rz, cudaStream_t s) {
       if (host[k] != 0xA5) return i;
   }
   return -1;
+}
+
+bool wide256_enabled() {   // SFB_NO_LD256=1 falls back to 128-bit accesses (A/B knob)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SFB_NO_LD256"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
 }
 
 int tile_sort_final(int T) {
@@ -161,6 +168,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   fp.scales = scales; fp.rotations = rotations; fp.cov3D_precomp = cov3D_precomp;
   fp.viewmatrix = viewmatrix; fp.projmatrix = projmatrix; fp.campos = campos;
   fp.scale_modifier = scale_modifier; fp.tan_fovx = tan_fovx; fp.tan_fovy = tan_fovy; fp.prefiltered = prefiltered;
+  fp.wide256 = wide256_enabled() && shs && ((M * 12) % 32 == 0) && ((reinterpret_cast<size_t>(shs) & 31) == 0);
 
   // K1 (+ num_rendered reduction) ; the 4-byte read-back is issued right behind it so that the host
   // wait overlaps the depth sort instead of draining the whole pipeline.
@@ -179,13 +187,11 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
                                 g.counters + 2);
   CK_LAUNCH("depth sort", debug, s);
   const uint32_t* sorted_idx = g.depth_idx[dfinal];
-  launch_instance_block_sums(P, sorted_idx, g.tiles_touched, g.block_sums, s);
-  g_launches += 2;
-  CK_LAUNCH("instance scan", debug, s);
+  CK(cudaMemsetAsync(g.block_sums, 0, sizeof(uint32_t) * (dup_blocks((size_t)P) + 2), s));
 
   CK(cudaEventSynchronize(g_evt));
   const uint32_t R = *g_pinned;
-  if (R > 0x7FFFFFFFu) return fail(SFB_ERR_ARG, "num_rendered overflows int32");
+  if (R >= (1u << 30)) return fail(SFB_ERR_ARG, "num_rendered >= 2^30 is not supported");
   if (num_rendered) *num_rendered = (int)R;
 
   char* bchunk = (char*)binning_alloc(binning_user, BinState::required((size_t)R, (size_t)T));
@@ -200,7 +206,8 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   if (R > 0) {
     // stage 2: emit (tile, gaussian) instances in depth order; stage 3: stable sort by tile id
     prof_begin("duplicate", s);
-    launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, b.tile_key[0], b.inst_idx[0], s);
+    launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, g.counters + 4, b.tile_key[0],
+                     b.inst_idx[0], s);
     prof_end(s);
     g_launches++;
     CK_LAUNCH("duplicate", debug, s);
@@ -283,6 +290,8 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   bp.rotations = rotations; bp.cov3D_precomp = cov3D_precomp;
   bp.viewmatrix = viewmatrix; bp.projmatrix = projmatrix; bp.campos = campos;
   bp.scale_modifier = scale_modifier; bp.tan_fovx = tan_fovx; bp.tan_fovy = tan_fovy; bp.radii = radii;
+  bp.wide256 = wide256_enabled() && shs && ((M * 12) % 32 == 0) && ((reinterpret_cast<size_t>(shs) & 31) == 0) &&
+               ((reinterpret_cast<size_t>(dL_dsh) & 31) == 0);
   bp.dL_dmeans2D = dL_dmeans2D; bp.dL_dcolors = dL_dcolors; bp.dL_dopacity = dL_dopacity;
   bp.dL_dmeans3D = dL_dmeans3D; bp.dL_dcov3D = dL_dcov3D; bp.dL_dsh = dL_dsh; bp.dL_dscales = dL_dscales;
   bp.dL_drot = dL_drotations;
@@ -334,14 +343,17 @@ int sfb_mark_visible(int P, const float* means3D, const float* viewmatrix, const
   return SFB_OK;
 }
 
-int sfb_export_geom(int P, const void* geom_buffer, float* means2D, float* depths, float* cov3D,
-                    float* conic_opacity, float* rgb, uint8_t* clamped, uint32_t* tiles_touched, void* stream) {
+int sfb_export_geom(int P, const void* geom_buffer, const float* scales, float scale_modifier,
+                    const float* rotations, const float* cov3D_precomp, float* means2D, float* depths,
+                    float* cov3D, float* conic_opacity, float* rgb, uint8_t* clamped, uint32_t* tiles_touched,
+                    void* stream) {
   using namespace sfb;
   g_err.clear();
   if (P <= 0 || !geom_buffer) return fail(SFB_ERR_ARG, "bad arguments");
   char* gchunk = (char*)geom_buffer;
   GeomState g = GeomState::from_chunk(gchunk, (size_t)P);
-  launch_export_geom(P, g, means2D, depths, cov3D, conic_opacity, rgb, clamped, tiles_touched, (cudaStream_t)stream);
+  launch_export_geom(P, g, scales, rotations, scale_modifier, cov3D_precomp, means2D, depths, cov3D, conic_opacity,
+                     rgb, clamped, tiles_touched, (cudaStream_t)stream);
   CK_LAUNCH("export_geom", 0, (cudaStream_t)stream);
   return SFB_OK;
 }

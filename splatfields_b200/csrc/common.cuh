@@ -37,6 +37,20 @@ __device__ __forceinline__ uint32_t patch_mask(float x, float y, float hx, float
   return m;
 }
 
+// 256-bit global accesses (sm_100a: LDG.E.ENL2.256 / STG.E.ENL2.256): one full 32-byte sector per lane, which
+// is what a one-thread-per-row walk over 192-byte SH rows needs — with 128-bit accesses every sector is touched by
+// two separate requests (measured on B200: 4.1 TB/s vs 6+ TB/s for a [1M][48] fp32 row copy).  p must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 // Non-blocking L2 prefetch of the 128-byte line holding p (no register, no scoreboard).
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -128,21 +142,19 @@ __host__ __device__ inline size_t dup_blocks(size_t P) { return (P + DUP_GPB - 1
 // ---- P-sized scratch ("geomBuffer") ----
 struct GeomState {
   SplatRec* rec;            // [P]
-  float* cov3D;             // [6P]   (kept for the backward; also the precomputed-cov path)
   uint32_t* tiles_touched;  // [P]
   uint2* rect;              // [P]    packed tile rectangle: x = xmin | ymin<<16, y = xmax | ymax<<16
   uint8_t* clamped;         // [P]    bit c set: channel c was clamped at 0
   uint32_t* depth_key[2];   // [P]    ping-pong keys of the depth sort (0xFFFFFFFF = culled)
   uint32_t* depth_idx[2];   // [P]    ping-pong values (Gaussian index)
   uint32_t* sort_hist;      // [SORT_MAX_BINS * sort_blocks(P)]
-  uint32_t* block_sums;     // [dup_blocks(P) + 2]    per-block instance counts in depth order, then scanned
-  uint32_t* counters;       // [8]    [0] = num_rendered, [2] = ~(smallest depth key of a visible splat)
+  uint32_t* block_sums;     // [dup_blocks(P) + 2]    look-back words of the instance-emission blocks (zeroed per call)
+  uint32_t* counters;       // [8]    [0] = num_rendered, [2] = ~(smallest depth key of a visible splat), [4] = emission ticket
   GradRec* grad;            // [P]    backward accumulators
 
   static GeomState from_chunk(char*& chunk, size_t P) {
     GeomState g;
     g.rec = carve<SplatRec>(chunk, P);
-    g.cov3D = carve<float>(chunk, 6 * P);
     g.tiles_touched = carve<uint32_t>(chunk, P);
     g.rect = carve<uint2>(chunk, P);
     g.clamped = carve<uint8_t>(chunk, P);
@@ -220,12 +232,14 @@ struct FwdParams {
   const float *viewmatrix, *projmatrix, *campos;
   float scale_modifier, tan_fovx, tan_fovy;
   int prefiltered;
+  int wide256;      // SH rows are 32-byte aligned multiples of 32 bytes: use 256-bit loads
 };
 
 // preprocess.cu
 void launch_preprocess(const FwdParams& p, const GeomState& g, int* radii, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
-void launch_export_geom(int P, const GeomState& g, float* means2D, float* depths, float* cov3D,
+void launch_export_geom(int P, const GeomState& g, const float* scales, const float* rotations, float mod,
+                        const float* cov3D_precomp, float* means2D, float* depths, float* cov3D,
                         float* conic_opacity, float* rgb, uint8_t* clamped, uint32_t* tiles_touched,
                         cudaStream_t s);
 
@@ -235,11 +249,9 @@ void launch_export_geom(int P, const GeomState& g, float* means2D, float* depths
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
                      int* launches, const char* const* names /* {hist, scan, scatter} */,
                      const uint32_t* bias_c = nullptr /* device: ~min key; keys are rebased in place */);
-void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
-                                uint32_t* block_sums, cudaStream_t s);
 void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
-                      const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
-                      uint32_t* inst_idx, cudaStream_t s);
+                      const uint2* rect, uint32_t* block_state /* zeroed, dup_blocks(P) words */,
+                      uint32_t* ticket /* zeroed */, uint32_t* tile_keys, uint32_t* inst_idx, cudaStream_t s);
 void launch_tile_ranges(int R, int T, const uint32_t* sorted_tile_keys, uint2* ranges, cudaStream_t s);
 void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_list, const SplatRec* rec,
                         uint64_t* out_keys, cudaStream_t s);
@@ -260,6 +272,7 @@ struct BwdParams {
   const float *means3D, *shs, *colors_precomp, *scales, *rotations, *cov3D_precomp;
   const float *viewmatrix, *projmatrix, *campos;
   float scale_modifier, tan_fovx, tan_fovy;
+  int wide256;      // SH / dL_dsh rows are 32-byte aligned multiples of 32 bytes: use 256-bit loads and stores
   const int* radii;
   float *dL_dmeans2D, *dL_dcolors, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drot;
 };

@@ -26,7 +26,7 @@ struct CamB {
 // TMA: the block's SH rows arrive through one bulk async copy and its dL_dsh rows leave through one bulk
 // async store (cp.async.bulk both ways, UBLKCP.S.G / UBLKCP.G.S): each thread only touches its own 192-byte
 // row in shared memory (read, then overwritten in place with the gradient row; zeros for culled splats).
-template <int D, bool VEC, bool TMA, int MINB = 1>
+template <int D, bool VEC, bool TMA, int MINB = 1, bool W256 = false>
 __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, GeomState g) {
   __shared__ CamB cam;
   __shared__ uint64_t s_bar;
@@ -78,9 +78,30 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
     gcol[0] = g1.z; gcol[1] = g1.w; gcol[2] = g2.x;
 
     const float mean[3] = {p.means3D[3 * i], p.means3D[3 * i + 1], p.means3D[3 * i + 2]};
+    // Sigma3D: re-derived (scale / rotation) or re-read (precomputed) instead of round-tripping 24 B through HBM
     float c6[6];
+    if (p.cov3D_precomp) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) c6[k] = g.cov3D[6 * i + k];
+      for (int k = 0; k < 6; k++) c6[k] = p.cov3D_precomp[6 * i + k];
+    } else {   // (R and s are re-derived again at the end instead of being kept live: registers, not ALU, are scarce)
+      float Rm[9], sc3[3];
+      const float qr = p.rotations[4 * i], qx = p.rotations[4 * i + 1], qy = p.rotations[4 * i + 2],
+                  qz = p.rotations[4 * i + 3];
+      Rm[0] = 1.f - 2.f * (qy * qy + qz * qz); Rm[1] = 2.f * (qx * qy - qr * qz); Rm[2] = 2.f * (qx * qz + qr * qy);
+      Rm[3] = 2.f * (qx * qy + qr * qz); Rm[4] = 1.f - 2.f * (qx * qx + qz * qz); Rm[5] = 2.f * (qy * qz - qr * qx);
+      Rm[6] = 2.f * (qx * qz - qr * qy); Rm[7] = 2.f * (qy * qz + qr * qx); Rm[8] = 1.f - 2.f * (qx * qx + qy * qy);
+      sc3[0] = p.scale_modifier * p.scales[3 * i]; sc3[1] = p.scale_modifier * p.scales[3 * i + 1];
+      sc3[2] = p.scale_modifier * p.scales[3 * i + 2];
+      float L[9];
+#pragma unroll
+      for (int r = 0; r < 3; r++) { L[3 * r] = Rm[3 * r] * sc3[0]; L[3 * r + 1] = Rm[3 * r + 1] * sc3[1]; L[3 * r + 2] = Rm[3 * r + 2] * sc3[2]; }
+      c6[0] = L[0] * L[0] + L[1] * L[1] + L[2] * L[2];
+      c6[1] = L[0] * L[3] + L[1] * L[4] + L[2] * L[5];
+      c6[2] = L[0] * L[6] + L[1] * L[7] + L[2] * L[8];
+      c6[3] = L[3] * L[3] + L[4] * L[4] + L[5] * L[5];
+      c6[4] = L[3] * L[6] + L[4] * L[7] + L[5] * L[8];
+      c6[5] = L[6] * L[6] + L[7] * L[7] + L[8] * L[8];
+    }
     const float fx = (float)p.W / (2.0f * p.tan_fovx), fy = (float)p.H / (2.0f * p.tan_fovy);
 
     // ---- conic -> cov2D -> (Sigma3D, view-space t) ----
@@ -171,7 +192,10 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
         }
       } else {
         const float* shp = p.shs + i * p.M * 3;
-        if (VEC) {
+        if (VEC && W256 && (3 * NB) % 8 == 0) {
+#pragma unroll
+          for (int k = 0; k < (3 * NB) / 8; k++) ldg256(shp + 8 * k, sh + 8 * k);
+        } else if (VEC) {
 #pragma unroll
           for (int k = 0; k < NF4; k++) {
             const float4 q = __ldg(reinterpret_cast<const float4*>(shp) + k);
@@ -214,7 +238,10 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) dshv[3 * k + ch] = basis[k] * gc[ch];
       }
-      if (VEC) {
+      if (VEC && !TMA && W256 && (3 * NB) % 8 == 0) {   // launcher guarantees M == (D+1)^2 here
+#pragma unroll
+        for (int k = 0; k < (3 * NB) / 8; k++) stg256(dsh + 8 * k, dshv + 8 * k);
+      } else if (VEC) {
         float4* d4 = TMA ? reinterpret_cast<float4*>(my_row) : reinterpret_cast<float4*>(dsh);
 #pragma unroll
         for (int k = 0; k < NF4; k++) d4[k] = make_float4(dshv[4 * k], dshv[4 * k + 1], dshv[4 * k + 2], dshv[4 * k + 3]);
@@ -291,7 +318,10 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
   } else if (p.shs) {
     float* dsh = p.dL_dsh + i * p.M * 3;
     if (TMA) mbar_wait(&s_bar, 0);     // the incoming row must have landed before it is overwritten
-    if (VEC) {
+    if (VEC && !TMA && W256) {
+      const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < (3 * p.M) / 8; k++) stg256(dsh + 8 * k, zero8);
+    } else if (VEC) {
       float4* d4 = TMA ? reinterpret_cast<float4*>(my_row) : reinterpret_cast<float4*>(dsh);
       for (int k = 0; k < (3 * p.M) / 4; k++) d4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
@@ -339,6 +369,8 @@ void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s
       attr_set = true;                                                                                     \
     }                                                                                                      \
     geom_backward_kernel<DD, true, true><<<blocks, 256, smem, s>>>(p, g);                                  \
+  } else if (vec && p.wide256 && p.M == (DD + 1) * (DD + 1) && (3 * (DD + 1) * (DD + 1)) % 8 == 0) {       \
+    geom_backward_kernel<DD, true, false, 2, true><<<blocks, 256, 0, s>>>(p, g);                           \
   } else if (vec && minb3 && DD == 3) geom_backward_kernel<3, true, false, 3><<<blocks, 256, 0, s>>>(p, g); \
   else if (vec) geom_backward_kernel<DD, true, false><<<blocks, 256, 0, s>>>(p, g);                        \
   else            geom_backward_kernel<DD, false, false><<<blocks, 256, 0, s>>>(p, g);

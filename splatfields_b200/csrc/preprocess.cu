@@ -51,10 +51,13 @@ struct Cam {
 };
 
 template <int D, bool VEC>
-__device__ __forceinline__ void load_sh(const float* __restrict__ shs, int idx, int M, float* sh) {
+__device__ __forceinline__ void load_sh(const float* __restrict__ shs, int idx, int M, float* sh, bool wide256) {
   constexpr int NF = 3 * (D + 1) * (D + 1);
   const float* base = shs + (size_t)idx * M * 3;
-  if (VEC) {
+  if (VEC && wide256 && NF % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < NF / 8; i++) ldg256(base + 8 * i, sh + 8 * i);
+  } else if (VEC) {
     constexpr int NV = (NF + 3) / 4;
     const float4* b4 = reinterpret_cast<const float4*>(base);
 #pragma unroll
@@ -213,9 +216,6 @@ preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
       float b = dot3(m1[0], v0[0], m1[1], v0[1], m1[2], v0[2]);
       float c = dot3(m1[0], v1[0], m1[1], v1[1], m1[2], v1[2]) + 0.3f;
       float det = fmaf(a, c, -(b * b));
-      // the 3D covariance is part of the forward state whenever the point passes the near cull
-#pragma unroll
-      for (int k = 0; k < 6; k++) g.cov3D[6 * (size_t)idx + k] = c6[k];
       if (det != 0.0f) {
         float det_inv = 1.f / det;
         float conA = c * det_inv, conB = -b * det_inv, conC = a * det_inv;
@@ -250,7 +250,7 @@ preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
                 sh[4 * i + 0] = v.x; sh[4 * i + 1] = v.y; sh[4 * i + 2] = v.z; sh[4 * i + 3] = v.w;
               }
             } else {
-              load_sh<D, VEC_SH>(p.shs, idx, p.M, sh);
+              load_sh<D, VEC_SH>(p.shs, idx, p.M, sh, p.wide256 != 0);
             }
             sh_to_rgb<D>(sh, mean, cam.campos, rgb, clamp_mask);
           }
@@ -362,7 +362,33 @@ void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, u
   if (P > 0) mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, viewmatrix, present);
 }
 
-__global__ void export_geom_kernel(int P, GeomState g, float* means2D, float* depths, float* cov3D,
+// cov3D is not part of the forward state any more (the backward recomputes it from scale / rotation): the
+// export recomputes it here with the SAME -fmad=false formula sheet the preprocess kernel uses.
+__device__ void cov3d_from_scale_rot(const float* scales, const float* rotations, float mod, size_t idx, float* c6) {
+  float r = rotations[4 * idx], x = rotations[4 * idx + 1], y = rotations[4 * idx + 2], z = rotations[4 * idx + 3];
+  float R[9];
+  R[0] = fmaf(-2.f, fmaf(y, y, z * z), 1.f);
+  R[1] = 2.f * fmaf(x, y, -(r * z));
+  R[2] = 2.f * fmaf(x, z, r * y);
+  R[3] = 2.f * fmaf(x, y, r * z);
+  R[4] = fmaf(-2.f, fmaf(x, x, z * z), 1.f);
+  R[5] = 2.f * fmaf(y, z, -(r * x));
+  R[6] = 2.f * fmaf(x, z, -(r * y));
+  R[7] = 2.f * fmaf(y, z, r * x);
+  R[8] = fmaf(-2.f, fmaf(x, x, y * y), 1.f);
+  float s0 = mod * scales[3 * idx], s1 = mod * scales[3 * idx + 1], s2 = mod * scales[3 * idx + 2];
+  float L[9];
+  for (int i = 0; i < 3; i++) { L[3 * i] = R[3 * i] * s0; L[3 * i + 1] = R[3 * i + 1] * s1; L[3 * i + 2] = R[3 * i + 2] * s2; }
+  c6[0] = dot3(L[0], L[0], L[1], L[1], L[2], L[2]);
+  c6[1] = dot3(L[0], L[3], L[1], L[4], L[2], L[5]);
+  c6[2] = dot3(L[0], L[6], L[1], L[7], L[2], L[8]);
+  c6[3] = dot3(L[3], L[3], L[4], L[4], L[5], L[5]);
+  c6[4] = dot3(L[3], L[6], L[4], L[7], L[5], L[8]);
+  c6[5] = dot3(L[6], L[6], L[7], L[7], L[8], L[8]);
+}
+
+__global__ void export_geom_kernel(int P, GeomState g, const float* scales, const float* rotations, float mod,
+                                   const float* cov3D_precomp, float* means2D, float* depths, float* cov3D,
                                    float* conic_opacity, float* rgb, uint8_t* clamped, uint32_t* tiles_touched) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P) return;
@@ -376,7 +402,14 @@ __global__ void export_geom_kernel(int P, GeomState g, float* means2D, float* de
     conic_opacity[4 * idx + 2] = vis ? r.conC : 0.f; conic_opacity[4 * idx + 3] = vis ? r.opacity : 0.f;
   }
   if (rgb) { rgb[3 * idx] = vis ? r.r : 0.f; rgb[3 * idx + 1] = vis ? r.g : 0.f; rgb[3 * idx + 2] = vis ? r.b : 0.f; }
-  if (cov3D) for (int k = 0; k < 6; k++) cov3D[6 * idx + k] = vis ? g.cov3D[6 * (size_t)idx + k] : 0.f;
+  if (cov3D) {
+    float c6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (vis) {
+      if (cov3D_precomp) for (int k = 0; k < 6; k++) c6[k] = cov3D_precomp[6 * (size_t)idx + k];
+      else if (scales && rotations) cov3d_from_scale_rot(scales, rotations, mod, (size_t)idx, c6);
+    }
+    for (int k = 0; k < 6; k++) cov3D[6 * idx + k] = c6[k];
+  }
   if (clamped) {
     uint8_t m = vis ? g.clamped[idx] : 0;
     clamped[3 * idx] = m & 1; clamped[3 * idx + 1] = (m >> 1) & 1; clamped[3 * idx + 2] = (m >> 2) & 1;
@@ -384,12 +417,13 @@ __global__ void export_geom_kernel(int P, GeomState g, float* means2D, float* de
   if (tiles_touched) tiles_touched[idx] = g.tiles_touched[idx];
 }
 
-void launch_export_geom(int P, const GeomState& g, float* means2D, float* depths, float* cov3D,
+void launch_export_geom(int P, const GeomState& g, const float* scales, const float* rotations, float mod,
+                        const float* cov3D_precomp, float* means2D, float* depths, float* cov3D,
                         float* conic_opacity, float* rgb, uint8_t* clamped, uint32_t* tiles_touched,
                         cudaStream_t s) {
   if (P > 0)
-    export_geom_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g, means2D, depths, cov3D, conic_opacity, rgb, clamped,
-                                                       tiles_touched);
+    export_geom_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g, scales, rotations, mod, cov3D_precomp, means2D, depths,
+                                                       cov3D, conic_opacity, rgb, clamped, tiles_touched);
 }
 
 }  // namespace sfb

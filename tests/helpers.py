@@ -76,7 +76,10 @@ def run_cuda(sc, cam, H, W, bg, sh_degree, dL=None, device="cuda", debug=False):
                  cov3D=torch.zeros(P, 6, device=dev), conic_opacity=torch.zeros(P, 4, device=dev),
                  rgb=torch.zeros(P, 3, device=dev), clamped=torch.zeros(P, 3, dtype=torch.uint8, device=dev),
                  tiles_touched=torch.zeros(P, dtype=torch.int32, device=dev))
-        _lib.check(lib.sfb_export_geom(P, geom.data_ptr(), e["means2D"].data_ptr(), e["depths"].data_ptr(),
+        dp = lambda k: fn.saved_inputs[k].data_ptr() if fn.saved_inputs[k] is not None else None
+        # saved_inputs = (means3D, sh, col, scales, rotations, cov3D_precomp, bg, view, proj, campos)
+        _lib.check(lib.sfb_export_geom(P, geom.data_ptr(), dp(3), 1.0, dp(4), dp(5),
+                                       e["means2D"].data_ptr(), e["depths"].data_ptr(),
                                        e["cov3D"].data_ptr(), e["conic_opacity"].data_ptr(), e["rgb"].data_ptr(),
                                        e["clamped"].data_ptr(), e["tiles_touched"].data_ptr(), None))
         keys = torch.zeros(max(R, 1), dtype=torch.int64, device=dev)
