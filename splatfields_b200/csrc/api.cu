@@ -187,7 +187,9 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
                                 g.counters + 2);
   CK_LAUNCH("depth sort", debug, s);
   const uint32_t* sorted_idx = g.depth_idx[dfinal];
-  CK(cudaMemsetAsync(g.block_sums, 0, sizeof(uint32_t) * (dup_blocks((size_t)P) + 2), s));
+  launch_instance_block_sums(P, sorted_idx, g.tiles_touched, g.block_sums, s);
+  g_launches += 2;
+  CK_LAUNCH("instance scan", debug, s);
 
   CK(cudaEventSynchronize(g_evt));
   const uint32_t R = *g_pinned;
@@ -206,8 +208,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   if (R > 0) {
     // stage 2: emit (tile, gaussian) instances in depth order; stage 3: stable sort by tile id
     prof_begin("duplicate", s);
-    launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, g.counters + 4, b.tile_key[0],
-                     b.inst_idx[0], s);
+    launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, b.tile_key[0], b.inst_idx[0], s);
     prof_end(s);
     g_launches++;
     CK_LAUNCH("duplicate", debug, s);

@@ -463,6 +463,35 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n
 // ------------------------------------------------------------------ instance emission in depth order
 constexpr int DUP_THREADS = 256;   // DUP_GPB (Gaussians / depth ranks per block) lives in common.cuh: it sizes block_sums
 
+__global__ void __launch_bounds__(DUP_THREADS)
+instance_block_sums_kernel(int P, const uint32_t* __restrict__ sorted_idx,
+                           const uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t s_w[DUP_THREADS / 32];
+  uint32_t v = 0;
+  for (int j = blockIdx.x * DUP_GPB + threadIdx.x; j < min(P, (blockIdx.x + 1) * DUP_GPB); j += DUP_THREADS)
+    v += tiles_touched[sorted_idx[j]];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < DUP_THREADS / 32; w++) t += s_w[w];
+    block_sums[blockIdx.x] = t;
+  }
+}
+
+void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
+                                uint32_t* block_sums, cudaStream_t s) {
+  int nb = (P + DUP_GPB - 1) / DUP_GPB;
+  prof_begin("instance_block_sums", s);
+  instance_block_sums_kernel<<<nb, DUP_THREADS, 0, s>>>(P, sorted_idx, tiles_touched, block_sums);
+  prof_end(s);
+  prof_begin("instance_block_scan", s);
+  scan_exclusive_kernel<<<1, 1024, 0, s>>>(block_sums, nb, nullptr);
+  prof_end(s);
+}
+
 // Each block expands DUP_GPB depth-ranked Gaussians into their (tile, gaussian) instances.  Output slot k
 // has to know which Gaussian it belongs to.  Instead of a per-slot binary search, the block works in rounds
 // of DUP_CHUNK slots: every Gaussian that STARTS inside the round marks its first slot with its (local
@@ -475,21 +504,15 @@ constexpr int DUP_SPT = DUP_CHUNK / DUP_THREADS;   // slots per thread in the sc
 __global__ void __launch_bounds__(DUP_THREADS)
 duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
                  const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ rect,
-                 uint32_t* __restrict__ block_state /* [blocks], zeroed: look-back words */,
-                 uint32_t* __restrict__ ticket /* zeroed */, uint32_t* __restrict__ tile_keys,
+                 const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ tile_keys,
                  uint32_t* __restrict__ inst_idx) {
   __shared__ uint32_t s_pref[DUP_GPB + 1];
-  __shared__ uint32_t s_blk, s_out0;
   __shared__ uint32_t s_gidx[DUP_GPB];
   __shared__ uint2 s_rect[DUP_GPB];
   __shared__ uint32_t s_warp[DUP_THREADS / 32];
   __shared__ __align__(16) uint16_t s_own[DUP_CHUNK];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // blocks take tickets so that block t only ever waits for blocks that are already running (t' < t)
-  if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1u);
-  __syncthreads();
-  const int blk = (int)s_blk;
-  const int j0 = blk * DUP_GPB;
+  const int j0 = blockIdx.x * DUP_GPB;
   constexpr int PER = DUP_GPB / DUP_THREADS;  // consecutive ranks per thread
   uint32_t cnt[PER];
   uint32_t tsum = 0;
@@ -529,38 +552,9 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
   }
   __syncthreads();
   const uint32_t total = s_pref[DUP_GPB];
-  // exclusive prefix of the block totals (= first output slot of this block) by decoupled look-back:
-  // warp 0 publishes the block aggregate and inspects a window of 32 predecessors per probe.
-  if (warp == 0) {
-    volatile uint32_t* st = block_state;
-    if (lane == 0) st[blk] = (blk == 0 ? OS_FLAG_INC : OS_FLAG_AGG) | total;
-    uint32_t excl = 0;
-    if (blk > 0) {
-      int base = blk - 1;
-      while (true) {
-        const int p = base - lane;
-        uint32_t v = 2u << 30;                       // virtual block -1: inclusive prefix 0
-        if (p >= 0) v = st[p];
-        const uint32_t f = v & ~OS_VAL_MASK;
-        const uint32_t inc_m = __ballot_sync(0xffffffffu, f == (2u << 30));
-        const uint32_t zero_m = __ballot_sync(0xffffffffu, f == 0u);
-        if (inc_m) {
-          const int first = __ffs(inc_m) - 1;
-          const uint32_t need = first == 31 ? 0xffffffffu : ((2u << first) - 1u);
-          if (zero_m & need) continue;               // a nearer predecessor has not published yet: spin
-          excl += __reduce_add_sync(0xffffffffu, lane <= first ? (v & OS_VAL_MASK) : 0u);
-          break;
-        }
-        if (zero_m) continue;
-        excl += __reduce_add_sync(0xffffffffu, v & OS_VAL_MASK);
-        base -= 32;
-      }
-      if (lane == 0) st[blk] = (2u << 30) | (excl + total);
-    }
-    if (lane == 0) s_out0 = excl;
-  }
-  __syncthreads();
-  const uint32_t out0 = s_out0;
+  // (the block offsets come from a separate per-block sum + scan: fusing that scan into this kernel with a
+  //  decoupled look-back was measured SLOWER on B200 — 57 vs 53 us at 1M splats, 157 vs 132 us on dtu_500k)
+  const uint32_t out0 = block_offsets[blockIdx.x];
 
   for (uint32_t cb = 0; cb < total; cb += DUP_CHUNK) {
     // A: clear the marks (two 16-byte stores per thread)
@@ -635,10 +629,10 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
 }
 
 void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
-                      const uint2* rect, uint32_t* block_state, uint32_t* ticket, uint32_t* tile_keys,
+                      const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
                       uint32_t* inst_idx, cudaStream_t s) {
   int nb = (P + DUP_GPB - 1) / DUP_GPB;
-  duplicate_kernel<<<nb, DUP_THREADS, 0, s>>>(P, grid_x, sorted_idx, tiles_touched, rect, block_state, ticket,
+  duplicate_kernel<<<nb, DUP_THREADS, 0, s>>>(P, grid_x, sorted_idx, tiles_touched, rect, block_offsets,
                                               tile_keys, inst_idx);
 }
 

@@ -148,8 +148,8 @@ struct GeomState {
   uint32_t* depth_key[2];   // [P]    ping-pong keys of the depth sort (0xFFFFFFFF = culled)
   uint32_t* depth_idx[2];   // [P]    ping-pong values (Gaussian index)
   uint32_t* sort_hist;      // [SORT_MAX_BINS * sort_blocks(P)]
-  uint32_t* block_sums;     // [dup_blocks(P) + 2]    look-back words of the instance-emission blocks (zeroed per call)
-  uint32_t* counters;       // [8]    [0] = num_rendered, [2] = ~(smallest depth key of a visible splat), [4] = emission ticket
+  uint32_t* block_sums;     // [dup_blocks(P) + 2]    per-block instance counts in depth order, then scanned
+  uint32_t* counters;       // [8]    [0] = num_rendered, [2] = ~(smallest depth key of a visible splat)
   GradRec* grad;            // [P]    backward accumulators
 
   static GeomState from_chunk(char*& chunk, size_t P) {
@@ -249,9 +249,11 @@ void launch_export_geom(int P, const GeomState& g, const float* scales, const fl
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
                      int* launches, const char* const* names /* {hist, scan, scatter} */,
                      const uint32_t* bias_c = nullptr /* device: ~min key; keys are rebased in place */);
+void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
+                                uint32_t* block_sums, cudaStream_t s);
 void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
-                      const uint2* rect, uint32_t* block_state /* zeroed, dup_blocks(P) words */,
-                      uint32_t* ticket /* zeroed */, uint32_t* tile_keys, uint32_t* inst_idx, cudaStream_t s);
+                      const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
+                      uint32_t* inst_idx, cudaStream_t s);
 void launch_tile_ranges(int R, int T, const uint32_t* sorted_tile_keys, uint2* ranges, cudaStream_t s);
 void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_list, const SplatRec* rec,
                         uint64_t* out_keys, cudaStream_t s);
