@@ -196,11 +196,13 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   if (R >= (1u << 30)) return fail(SFB_ERR_ARG, "num_rendered >= 2^30 is not supported");
   if (num_rendered) *num_rendered = (int)R;
 
-  char* bchunk = (char*)binning_alloc(binning_user, BinState::required((size_t)R, (size_t)T));
+  const InstPacking pk = inst_packing((size_t)P, (size_t)T);
+  const bool packed = pk.idx_bits > 0;
+  char* bchunk = (char*)binning_alloc(binning_user, BinState::required((size_t)R, (size_t)T, packed));
   if (!bchunk) return fail(SFB_ERR_ALLOC, "binning buffer allocation failed");
   RedzoneList rzb;
   if (debug) redzone_collector() = &rzb;
-  BinState b = BinState::from_chunk(bchunk, (size_t)R, (size_t)T);
+  BinState b = BinState::from_chunk(bchunk, (size_t)R, (size_t)T, packed);
   redzone_collector() = nullptr;
   if (debug && redzones_fill(rzb, s)) return fail(SFB_ERR_CUDA, "red-zone fill");
 
@@ -208,21 +210,25 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   if (R > 0) {
     // stage 2: emit (tile, gaussian) instances in depth order; stage 3: stable sort by tile id
     prof_begin("duplicate", s);
-    launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, b.tile_key[0], b.inst_idx[0], s);
+    launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, b.tile_key[0], b.inst_idx[0],
+                     pk.idx_bits, s);
     prof_end(s);
     g_launches++;
     CK_LAUNCH("duplicate", debug, s);
-      tfinal = radix_sort_pairs(b.tile_key, b.inst_idx, b.sort_hist, (int)R, tile_bits(T), s, &g_launches, kTileSortNames);
+    // packed: bare 32-bit words, digits start above the index bits; unpacked: (tile, index) pairs from bit 0
+    tfinal = radix_sort_pairs(b.tile_key, b.inst_idx, b.sort_hist, (int)R, tile_bits(T), s, &g_launches, kTileSortNames,
+                              nullptr, pk.idx_bits);
       CK_LAUNCH("tile sort", debug, s);
   }
   prof_begin("tile_ranges", s);
-  launch_tile_ranges((int)R, T, b.tile_key[tfinal], b.ranges, s);
+  launch_tile_ranges((int)R, T, b.tile_key[tfinal], pk.idx_bits, b.ranges, s);
   prof_end(s);
   g_launches++;
   CK_LAUNCH("tile ranges", debug, s);
 
   prof_begin("render_forward", s);
-  launch_render_forward(W, H, b.ranges, b.inst_idx[tfinal], g.rec, bg, out_color, out_depth, out_alpha,
+  launch_render_forward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, bg, out_color, out_depth,
+                        out_alpha,
                         img.final_T, img.n_contrib, s);
   prof_end(s);
   g_launches++;
@@ -268,7 +274,9 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   char* gchunk = (char*)geom_buffer;
   GeomState g = GeomState::from_chunk(gchunk, (size_t)P);
   char* bchunk = (char*)binning_buffer;
-  BinState b = BinState::from_chunk(bchunk, (size_t)num_rendered, (size_t)T);
+  const InstPacking pk = inst_packing((size_t)P, (size_t)T);
+  const bool packed = pk.idx_bits > 0;
+  BinState b = BinState::from_chunk(bchunk, (size_t)num_rendered, (size_t)T, packed);
   char* ichunk = (char*)img_buffer;
   ImgState img = ImgState::from_chunk(ichunk, HW);
   redzone_collector() = nullptr;
@@ -279,7 +287,8 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   CK(cudaMemsetAsync(g.grad, 0, sizeof(GradRec) * (size_t)P, s));
   prof_end(s);
   prof_begin("render_backward", s);
-  launch_render_backward(W, H, b.ranges, b.inst_idx[tfinal], g.rec, bg, img.final_T, img.n_contrib,
+  launch_render_backward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, bg, img.final_T,
+                         img.n_contrib,
                          dL_dout_color, dL_dout_alpha, g.grad, s);
   prof_end(s);
   g_launches++;
@@ -370,13 +379,13 @@ int sfb_export_binning(int P, int num_rendered, int W, int H, const void* geom_b
   char* gchunk = (char*)geom_buffer;
   GeomState g = GeomState::from_chunk(gchunk, (size_t)P);
   char* bchunk = (char*)binning_buffer;
-  BinState b = BinState::from_chunk(bchunk, (size_t)num_rendered, (size_t)T);
+  const InstPacking pk = inst_packing((size_t)P, (size_t)T);
+  const bool packed = pk.idx_bits > 0;
+  BinState b = BinState::from_chunk(bchunk, (size_t)num_rendered, (size_t)T, packed);
   const int tfinal = num_rendered > 0 ? tile_sort_final(T) : 0;
-  if (point_list_keys)
-    launch_export_keys(num_rendered, b.tile_key[tfinal], b.inst_idx[tfinal], g.rec, point_list_keys, s);
-  if (point_list && num_rendered > 0)
-    CK(cudaMemcpyAsync(point_list, b.inst_idx[tfinal], sizeof(uint32_t) * (size_t)num_rendered,
-                       cudaMemcpyDeviceToDevice, s));
+  if (point_list_keys || point_list)
+    launch_export_keys(num_rendered, b.tile_key[tfinal], packed ? nullptr : b.inst_idx[tfinal], pk.idx_bits, g.rec,
+                       point_list_keys, point_list, s);
   if (ranges) CK(cudaMemcpyAsync(ranges, b.ranges, sizeof(uint2) * (size_t)T, cudaMemcpyDeviceToDevice, s));
   CK_LAUNCH("export_binning", 0, s);
   return SFB_OK;

@@ -239,7 +239,8 @@ radix_hist_all_kernel(uint32_t* __restrict__ keys, int n, int npass, int4 shifts
 
 // IPT items per thread: 16 (4096-item tiles) for large inputs, 4 (1024-item tiles) when 4096-item tiles
 // would leave most SMs idle and every block a long latency chain.
-template <int IPT>
+// HAS_VALS = false sorts bare 32-bit words (the packed tile|index instances): nothing but keys is staged or moved.
+template <int IPT, bool HAS_VALS>
 __global__ void __launch_bounds__(SORT_THREADS, 3)
 onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift, int bins,
@@ -252,7 +253,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   __shared__ uint32_t s_lstart[SORT_MAX_BINS];    // block-local start of each digit run
   __shared__ int32_t s_gofs[SORT_MAX_BINS];       // global position - local position, per digit
   __shared__ uint32_t s_key[OS_TILE];
-  __shared__ uint32_t s_val[OS_TILE];
+  __shared__ uint32_t s_val[HAS_VALS ? OS_TILE : 1];
   __shared__ uint32_t s_wsum[NW];
   __shared__ uint32_t s_ticket;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -263,7 +264,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 #pragma unroll
     for (int i = 0; i < IPT; i++) {
       const int k = base + i * SORT_THREADS + threadIdx.x;
-      if (k < n) { keys_out[k] = keys_in[k]; vals_out[k] = vals_in[k]; }
+      if (k < n) { keys_out[k] = keys_in[k]; if (HAS_VALS) vals_out[k] = vals_in[k]; }
     }
     return;
   }
@@ -274,7 +275,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 
   // ---- stable ranking inside the block (sequential order = warp, item, lane) ----
   const int seg = blk * OS_TILE + warp * (32 * IPT);
-  constexpr bool PRELOAD_VALS = true;         // measured: 88 vs 121 us per 9M-item pass without the early value loads
+  constexpr bool PRELOAD_VALS = HAS_VALS;     // measured: 88 vs 121 us per 9M-item pass without the early value loads
   uint32_t key[IPT], val[PRELOAD_VALS ? IPT : 1], rank[IPT];
   const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
@@ -383,7 +384,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
       const uint32_t dd = (key[i] >> shift) & mask;
       const uint32_t lp = s_lstart[dd] + s_cnt[warp][dd] + rank[i];
       s_key[lp] = key[i];
-      s_val[lp] = PRELOAD_VALS ? val[i] : vals_in[k];
+      if (HAS_VALS) s_val[lp] = val[i];
     }
   }
   __syncthreads();
@@ -393,13 +394,14 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     const uint32_t dd = (kk >> shift) & mask;
     const int32_t dst = (int32_t)q + s_gofs[dd];
     keys_out[dst] = kk;
-    vals_out[dst] = s_val[q];
+    if (HAS_VALS) vals_out[dst] = s_val[q];
   }
 }
 
 static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint32_t* scratch, int n, int nbits,
                                      cudaStream_t s, int* launches, const char* const* names,
-                                     const uint32_t* bias_c) {
+                                     const uint32_t* bias_c, int first_bit) {
+  const bool has_vals = vals != nullptr && vals[0] != nullptr;
   const int npass = (nbits + 7) / 8;
   const bool small = sort_blocks(n) < 4 * NUM_SMS_B200;       // < 4 tiles per SM with 4096-item tiles
   static int ipt_big = -1;                                    // experiment knob: SFB_SORT_IPT=8 -> 2048-item tiles
@@ -415,7 +417,7 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
   size_t state_words = 0;
   for (int pass = 0; pass < npass; pass++) {
     const int bits = (nbits - shift + (npass - pass) - 1) / (npass - pass);
-    shifts[pass] = shift;
+    shifts[pass] = first_bit + shift;
     nbins[pass] = 1 << bits;
     state_words += (size_t)nblocks * nbins[pass];
     shift += bits;
@@ -431,18 +433,16 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
   uint32_t* state = state0;
   for (int pass = 0; pass < npass; pass++) {
     prof_begin(names[2], s);
-    if (small)
-      onesweep_pass_kernel<4><<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
-                                                                shifts[pass], nbins[pass],
-                                                                hist_all + pass * SORT_MAX_BINS, state, tickets + pass);
-    else if (ipt_big == 8)
-      onesweep_pass_kernel<8><<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
-                                                                shifts[pass], nbins[pass],
-                                                                hist_all + pass * SORT_MAX_BINS, state, tickets + pass);
-    else
-      onesweep_pass_kernel<16><<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
-                                                                 shifts[pass], nbins[pass],
-                                                                 hist_all + pass * SORT_MAX_BINS, state, tickets + pass);
+    uint32_t* vin = has_vals ? vals[cur] : nullptr;
+    uint32_t* vout = has_vals ? vals[cur ^ 1] : nullptr;
+#define SFB_OS(IPTV, HV)                                                                                       \
+  onesweep_pass_kernel<IPTV, HV><<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vin, keys[cur ^ 1], vout, n,       \
+                                                                  shifts[pass], nbins[pass],                   \
+                                                                  hist_all + pass * SORT_MAX_BINS, state, tickets + pass)
+    if (small)             { if (has_vals) SFB_OS(4, true);  else SFB_OS(4, false); }
+    else if (ipt_big == 8) { if (has_vals) SFB_OS(8, true);  else SFB_OS(8, false); }
+    else                   { if (has_vals) SFB_OS(16, true); else SFB_OS(16, false); }
+#undef SFB_OS
     prof_end(s);
     if (launches) *launches += 1;
     state += (size_t)nblocks * nbins[pass];
@@ -452,12 +452,13 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
 }
 
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
-                     int* launches, const char* const* names, const uint32_t* bias_c) {
+                     int* launches, const char* const* names, const uint32_t* bias_c, int first_bit) {
   if (n <= 0 || nbits <= 0) return 0;
   static int legacy = -1;
   if (legacy < 0) { const char* e = getenv("SFB_SORT"); legacy = (e && e[0] == 'l') ? 1 : 0; }
-  if (legacy) return radix_sort_pairs_legacy(keys, vals, hist, n, nbits, s, launches, names);   // (ignores bias_c)
-  return radix_sort_pairs_onesweep(keys, vals, hist, n, nbits, s, launches, names, bias_c);
+  if (legacy && first_bit == 0 && vals && vals[0])   // (the 3-kernel path ignores bias_c; pairs from bit 0 only)
+    return radix_sort_pairs_legacy(keys, vals, hist, n, nbits, s, launches, names);
+  return radix_sort_pairs_onesweep(keys, vals, hist, n, nbits, s, launches, names, bias_c, first_bit);
 }
 
 // ------------------------------------------------------------------ instance emission in depth order
@@ -505,7 +506,8 @@ __global__ void __launch_bounds__(DUP_THREADS)
 duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
                  const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ rect,
                  const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ tile_keys,
-                 uint32_t* __restrict__ inst_idx) {
+                 uint32_t* __restrict__ inst_idx /* nullptr: packed mode, tile_keys[k] = tile << idx_bits | index */,
+                 int idx_bits) {
   __shared__ uint32_t s_pref[DUP_GPB + 1];
   __shared__ uint32_t s_gidx[DUP_GPB];
   __shared__ uint2 s_rect[DUP_GPB];
@@ -621,8 +623,13 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
       const uint32_t x0 = r.x & 0xFFFFu, y0 = r.x >> 16, x1 = r.y & 0xFFFFu;
       const uint32_t w = x1 - x0;
       const uint32_t yy = t / w, xx = t - yy * w;
-      tile_keys[out0 + cb + q] = (y0 + yy) * (uint32_t)grid_x + (x0 + xx);
-      inst_idx[out0 + cb + q] = s_gidx[sidx];
+      const uint32_t tile = (y0 + yy) * (uint32_t)grid_x + (x0 + xx);
+      if (inst_idx) {
+        tile_keys[out0 + cb + q] = tile;
+        inst_idx[out0 + cb + q] = s_gidx[sidx];
+      } else {
+        tile_keys[out0 + cb + q] = (tile << idx_bits) | s_gidx[sidx];
+      }
     }
     __syncthreads();
   }
@@ -630,27 +637,27 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
 
 void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
                       const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
-                      uint32_t* inst_idx, cudaStream_t s) {
+                      uint32_t* inst_idx, int idx_bits, cudaStream_t s) {
   int nb = (P + DUP_GPB - 1) / DUP_GPB;
   duplicate_kernel<<<nb, DUP_THREADS, 0, s>>>(P, grid_x, sorted_idx, tiles_touched, rect, block_offsets,
-                                              tile_keys, inst_idx);
+                                              tile_keys, inst_idx, idx_bits);
 }
 
 // ------------------------------------------------------------------ tile ranges
 // Four consecutive keys per thread (one 16-byte load) + the key before them.
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int R, const uint32_t* __restrict__ keys,
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int R, const uint32_t* __restrict__ keys, int key_shift,
                                                            uint2* __restrict__ ranges) {
   const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i0 >= R) return;
   uint32_t k[4];
   if (i0 + 3 < R) {
     const uint4 v = *reinterpret_cast<const uint4*>(keys + i0);
-    k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+    k[0] = v.x >> key_shift; k[1] = v.y >> key_shift; k[2] = v.z >> key_shift; k[3] = v.w >> key_shift;
   } else {
 #pragma unroll
-    for (int j = 0; j < 4; j++) k[j] = (i0 + j < R) ? keys[i0 + j] : 0u;
+    for (int j = 0; j < 4; j++) k[j] = (i0 + j < R) ? (keys[i0 + j] >> key_shift) : 0u;
   }
-  uint32_t prev = i0 > 0 ? keys[i0 - 1] : 0u;
+  uint32_t prev = i0 > 0 ? (keys[i0 - 1] >> key_shift) : 0u;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     const int i = i0 + j;
@@ -664,23 +671,29 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int R, const uint32_t*
   }
 }
 
-void launch_tile_ranges(int R, int T, const uint32_t* sorted_tile_keys, uint2* ranges, cudaStream_t s) {
+void launch_tile_ranges(int R, int T, const uint32_t* sorted_tile_keys, int key_shift, uint2* ranges, cudaStream_t s) {
   cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)T, s);
-  if (R > 0) tile_ranges_kernel<<<((R + 3) / 4 + 255) / 256, 256, 0, s>>>(R, sorted_tile_keys, ranges);
+  if (R > 0) tile_ranges_kernel<<<((R + 3) / 4 + 255) / 256, 256, 0, s>>>(R, sorted_tile_keys, key_shift, ranges);
 }
 
+// point_list == nullptr: packed mode (tile_keys[i] = tile << idx_bits | index)
 __global__ void export_keys_kernel(int R, const uint32_t* __restrict__ tile_keys,
-                                   const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ rec,
-                                   uint64_t* __restrict__ out) {
+                                   const uint32_t* __restrict__ point_list, int idx_bits,
+                                   const SplatRec* __restrict__ rec, uint64_t* __restrict__ out_keys,
+                                   uint32_t* __restrict__ out_list) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R) return;
-  uint32_t d = __float_as_uint(rec[point_list[i]].depth);
-  out[i] = ((uint64_t)tile_keys[i] << 32) | d;
+  uint32_t tile, idx;
+  if (point_list) { tile = tile_keys[i]; idx = point_list[i]; }
+  else { const uint32_t w = tile_keys[i]; tile = w >> idx_bits; idx = w & ((1u << idx_bits) - 1u); }
+  if (out_keys) out_keys[i] = ((uint64_t)tile << 32) | __float_as_uint(rec[idx].depth);
+  if (out_list) out_list[i] = idx;
 }
 
-void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_list, const SplatRec* rec,
-                        uint64_t* out_keys, cudaStream_t s) {
-  if (R > 0) export_keys_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, tile_keys, point_list, rec, out_keys);
+void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_list, int idx_bits,
+                        const SplatRec* rec, uint64_t* out_keys, uint32_t* out_list, cudaStream_t s) {
+  if (R > 0)
+    export_keys_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, tile_keys, point_list, idx_bits, rec, out_keys, out_list);
 }
 
 }  // namespace sfb

@@ -173,28 +173,44 @@ struct GeomState {
   }
 };
 
+// Instance packing: when ceil(log2 P) + ceil(log2 T) <= 32 an instance is ONE 32-bit word,
+// tile << idx_bits | gaussian index, and the tile sort moves bare keys (half the bytes of (key, value) pairs).
+struct InstPacking {
+  int idx_bits;     // bits of the Gaussian index inside the word (0 = unpacked: separate key / value arrays)
+  uint32_t idx_mask;
+};
+inline int ceil_log2(size_t n) { int b = 0; while (((size_t)1 << b) < n) b++; return b; }
+inline int tile_bits_for(size_t T) { int b = 1; while (((size_t)1 << b) < T) b++; return b; }
+inline InstPacking inst_packing(size_t P, size_t T) {
+  InstPacking k;
+  const int ib = ceil_log2(P < 2 ? 2 : P);
+  if (ib + tile_bits_for(T) <= 32) { k.idx_bits = ib; k.idx_mask = ib >= 32 ? 0xFFFFFFFFu : ((1u << ib) - 1u); }
+  else { k.idx_bits = 0; k.idx_mask = 0xFFFFFFFFu; }
+  return k;
+}
+
 // ---- R-sized scratch ("binningBuffer") ----
 struct BinState {
-  uint32_t* tile_key[2];    // [R]  ping-pong tile ids
-  uint32_t* inst_idx[2];    // [R]  ping-pong Gaussian indices; inst_idx[final] is the point list
-  uint32_t* sort_hist;      // [SORT_MAX_BINS * sort_blocks(R)]
+  uint32_t* tile_key[2];    // [R]  ping-pong tile ids (unpacked) or packed tile|index words
+  uint32_t* inst_idx[2];    // [R]  ping-pong Gaussian indices (unpacked mode only; nullptr when packed)
+  uint32_t* sort_hist;      // sort scratch
   uint2* ranges;            // [T]
-  int final_buf;            // which ping-pong half holds the sorted result (set by the host)
 
-  static BinState from_chunk(char*& chunk, size_t R, size_t T) {
+  static BinState from_chunk(char*& chunk, size_t R, size_t T, bool packed) {
     BinState b;
     for (int i = 0; i < 2; i++) b.tile_key[i] = carve<uint32_t>(chunk, R);
-    for (int i = 0; i < 2; i++) b.inst_idx[i] = carve<uint32_t>(chunk, R);
+    for (int i = 0; i < 2; i++) b.inst_idx[i] = packed ? nullptr : carve<uint32_t>(chunk, R);
     b.sort_hist = carve<uint32_t>(chunk, sort_scratch_words(R));
     b.ranges = carve<uint2>(chunk, T);
-    b.final_buf = 0;
     return b;
   }
-  static size_t required(size_t R, size_t T) {
+  static size_t required(size_t R, size_t T, bool packed) {
     char* p = nullptr;
-    from_chunk(p, R, T);
+    from_chunk(p, R, T, packed);
     return reinterpret_cast<size_t>(p) + 256;
   }
+  // the sorted instance list the render kernels walk: entries are `word & idx_mask`
+  const uint32_t* point_list(int final_buf, bool packed) const { return packed ? tile_key[final_buf] : inst_idx[final_buf]; }
 };
 
 // ---- pixel-sized scratch ("imgBuffer") ----
@@ -248,23 +264,26 @@ void launch_export_geom(int P, const GeomState& g, const float* scales, const fl
 // ping-pong half that holds the result.  hist must hold sort_scratch_words(n) words.
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
                      int* launches, const char* const* names /* {hist, scan, scatter} */,
-                     const uint32_t* bias_c = nullptr /* device: ~min key; keys are rebased in place */);
+                     const uint32_t* bias_c = nullptr /* device: ~min key; keys are rebased in place */,
+                     int first_bit = 0 /* digits start at this bit; vals[0] == nullptr sorts bare keys */);
 void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
                                 uint32_t* block_sums, cudaStream_t s);
 void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
                       const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
-                      uint32_t* inst_idx, cudaStream_t s);
-void launch_tile_ranges(int R, int T, const uint32_t* sorted_tile_keys, uint2* ranges, cudaStream_t s);
-void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_list, const SplatRec* rec,
-                        uint64_t* out_keys, cudaStream_t s);
+                      uint32_t* inst_idx /* nullptr: packed */, int idx_bits, cudaStream_t s);
+void launch_tile_ranges(int R, int T, const uint32_t* sorted_tile_keys, int key_shift, uint2* ranges, cudaStream_t s);
+void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_list /* nullptr: packed */,
+                        int idx_bits, const SplatRec* rec, uint64_t* out_keys, uint32_t* out_list, cudaStream_t s);
 
 // render_fwd.cu
-void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
+void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
+                           const SplatRec* rec,
                            const float* bg, float* out_color, float* out_depth, float* out_alpha, float* final_T,
                            uint32_t* n_contrib, cudaStream_t s);
 
 // render_bwd.cu
-void launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
+void launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
+                            const SplatRec* rec,
                             const float* bg, const float* final_T, const uint32_t* n_contrib,
                             const float* dL_dpixels, const float* dL_dalpha_img, GradRec* grad, cudaStream_t s);
 

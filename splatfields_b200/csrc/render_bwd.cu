@@ -31,7 +31,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 template <bool CULL, bool ALPHA>
 __global__ void __launch_bounds__(BB)
 render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
-                       const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ rec,
+                       const uint32_t* __restrict__ point_list, uint32_t idx_mask,
+                      const SplatRec* __restrict__ rec,
                        const float* __restrict__ bg, const float* __restrict__ final_T,
                        const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
                        const float* __restrict__ dL_dalpha_img, GradRec* __restrict__ grad) {
@@ -94,7 +95,7 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
     __syncthreads();
     uint32_t mask = 0u;
     if ((int)threadIdx.x < n) {
-      uint32_t id = point_list[range.x + (uint32_t)(top - 1 - (int)threadIdx.x)];
+      uint32_t id = point_list[range.x + (uint32_t)(top - 1 - (int)threadIdx.x)] & idx_mask;
       const float4* rp = reinterpret_cast<const float4*>(rec + id);
       float4 a = __ldg(rp), b = __ldg(rp + 1), c = __ldg(rp + 2);
       s_q0[threadIdx.x] = a;
@@ -229,14 +230,15 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
   }
 }
 
-void launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
+void launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
+                            const SplatRec* rec,
                             const float* bg, const float* final_T, const uint32_t* n_contrib,
                             const float* dL_dpixels, const float* dL_dalpha_img, GradRec* grad, cudaStream_t s) {
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
   static int cull = -1;
   if (cull < 0) { const char* e = getenv("SFB_NO_CULL"); cull = (e && e[0] == '1') ? 0 : 1; }
 #define SFB_RB(C, A)                                                                                          \
-  render_backward_kernel<C, A><<<gx * gy, BB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib, \
+  render_backward_kernel<C, A><<<gx * gy, BB, 0, s>>>(W, H, gx, ranges, point_list, idx_mask, rec, bg, final_T, n_contrib, \
                                                       dL_dpixels, dL_dalpha_img, grad)
   if (cull) { if (dL_dalpha_img) SFB_RB(true, true); else SFB_RB(true, false); }
   else      { if (dL_dalpha_img) SFB_RB(false, true); else SFB_RB(false, false); }

@@ -25,7 +25,8 @@ constexpr int RB = 256;  // batch = block size
 template <bool CULL, bool ALPHA>
 __global__ void __launch_bounds__(RB)
 render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
-                      const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ rec,
+                      const uint32_t* __restrict__ point_list, uint32_t idx_mask,
+                      const SplatRec* __restrict__ rec,
                       const float* __restrict__ bg, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ out_alpha,
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
@@ -64,7 +65,7 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
     if (__syncthreads_count(done) == RB) break;
     uint32_t mask = 0u;
     if ((int)threadIdx.x < todo) {
-      uint32_t id = point_list[range.x + base + threadIdx.x];
+      uint32_t id = point_list[range.x + base + threadIdx.x] & idx_mask;
       const float4* rp = reinterpret_cast<const float4*>(rec + id);
       float4 a = __ldg(rp), b = __ldg(rp + 1), c = __ldg(rp + 2);
       s_q0[threadIdx.x] = a;
@@ -132,12 +133,13 @@ static bool cull_enabled() {
   return v == 1;
 }
 
-void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
+void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
+                           const SplatRec* rec,
                            const float* bg, float* out_color, float* out_depth, float* out_alpha, float* final_T,
                            uint32_t* n_contrib, cudaStream_t s) {
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
 #define SFB_RF(C, A)                                                                                          \
-  render_forward_kernel<C, A><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, out_color, out_depth, \
+  render_forward_kernel<C, A><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, idx_mask, rec, bg, out_color, out_depth, \
                                                      out_alpha, final_T, n_contrib)
   if (cull_enabled()) { if (out_alpha) SFB_RF(true, true); else SFB_RF(true, false); }
   else                { if (out_alpha) SFB_RF(false, true); else SFB_RF(false, false); }
