@@ -70,7 +70,9 @@ int sfb_rasterize_forward(
  * needed): dL_dmeans2D [P][3] (xy = gradient w.r.t. the NDC-scaled screen mean, z = 0; this is what
  * lands in viewspace_points.grad, scene/gaussian_model.py:429), dL_dcolors [P][3], dL_dopacity [P][1],
  * dL_dmeans3D [P][3], dL_dcov3D [P][6], dL_dsh [P][M][3] (may be NULL when shs is NULL),
- * dL_dscales [P][3], dL_drotations [P][4] (may be NULL when cov3D_precomp is given). */
+ * dL_dscales [P][3], dL_drotations [P][4] (may be NULL when cov3D_precomp is given).  dL_dcolors may be NULL when
+ * shs is given and dL_dcov3D may be NULL when scales / rotations are given (the reference returns those two
+ * gradients only for the corresponding precomputed inputs); a NULL output is simply not written. */
 int sfb_rasterize_backward(
     int P, int sh_degree, int M, int num_rendered, int W, int H,
     const float* bg, const float* means3D, const float* shs, const float* colors_precomp,

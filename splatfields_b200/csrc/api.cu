@@ -262,8 +262,10 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   if (P == 0) return SFB_OK;
   if (P < 0 || W <= 0 || H <= 0 || num_rendered < 0) return fail(SFB_ERR_ARG, "bad sizes");
   if (!geom_buffer || !binning_buffer || !img_buffer) return fail(SFB_ERR_ARG, "null scratch buffer");
-  if (!dL_dout_color || !dL_dmeans2D || !dL_dcolors || !dL_dopacity || !dL_dmeans3D || !dL_dcov3D)
+  if (!dL_dout_color || !dL_dmeans2D || !dL_dopacity || !dL_dmeans3D)
     return fail(SFB_ERR_ARG, "null gradient buffer");
+  if (colors_precomp && !dL_dcolors) return fail(SFB_ERR_ARG, "dL_dcolors required with colors_precomp");
+  if (cov3D_precomp && !dL_dcov3D) return fail(SFB_ERR_ARG, "dL_dcov3D required with cov3D_precomp");
   if (shs && !dL_dsh) return fail(SFB_ERR_ARG, "dL_dsh required with shs");
   if (!cov3D_precomp && (!dL_dscales || !dL_drotations || !scales || !rotations))
     return fail(SFB_ERR_ARG, "dL_dscales / dL_drotations required with scales / rotations");

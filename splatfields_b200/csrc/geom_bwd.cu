@@ -340,10 +340,12 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
   }
   p.dL_dmeans3D[3 * i] = dmean[0]; p.dL_dmeans3D[3 * i + 1] = dmean[1]; p.dL_dmeans3D[3 * i + 2] = dmean[2];
   p.dL_dmeans2D[3 * i] = gm2[0]; p.dL_dmeans2D[3 * i + 1] = gm2[1]; p.dL_dmeans2D[3 * i + 2] = 0.f;
-  p.dL_dcolors[3 * i] = gcol[0]; p.dL_dcolors[3 * i + 1] = gcol[1]; p.dL_dcolors[3 * i + 2] = gcol[2];
+  if (p.dL_dcolors) { p.dL_dcolors[3 * i] = gcol[0]; p.dL_dcolors[3 * i + 1] = gcol[1]; p.dL_dcolors[3 * i + 2] = gcol[2]; }
   p.dL_dopacity[i] = gop;
+  if (p.dL_dcov3D) {
 #pragma unroll
-  for (int k = 0; k < 6; k++) p.dL_dcov3D[6 * i + k] = dcov[k];
+    for (int k = 0; k < 6; k++) p.dL_dcov3D[6 * i + k] = dcov[k];
+  }
   if (p.dL_dscales) { p.dL_dscales[3 * i] = dscale[0]; p.dL_dscales[3 * i + 1] = dscale[1]; p.dL_dscales[3 * i + 2] = dscale[2]; }
   if (p.dL_drot) { p.dL_drot[4 * i] = drot[0]; p.dL_drot[4 * i + 1] = drot[1]; p.dL_drot[4 * i + 2] = drot[2]; p.dL_drot[4 * i + 3] = drot[3]; }
 }

@@ -197,9 +197,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         dL_dmeans3D = _arena_out("means3D", P, (P, 3), **f32)
         dL_dmeans2D = torch.empty((P, 3), **f32)
-        dL_dcolors = _arena_out("colors_precomp", P, (P, 3), **f32)
+        dL_dcolors = _arena_out("colors_precomp", P, (P, 3), **f32) if col is not None else None
         dL_dopacity = _arena_out("opacities", P, (P, 1), **f32)
-        dL_dcov3D = _arena_out("cov3D_precomp", P, (P, 6), **f32)
+        dL_dcov3D = _arena_out("cov3D_precomp", P, (P, 6), **f32) if cov is not None else None
         dL_dsh = _arena_out("shs", P, (P, M, 3), **f32) if sh is not None else None
         dL_dscales = _arena_out("scales", P, (P, 3), **f32) if cov is None else None
         dL_drot = _arena_out("rotations", P, (P, 4), **f32) if cov is None else None
