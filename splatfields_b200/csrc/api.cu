@@ -69,6 +69,12 @@ int redzones_check(const sfb::RedzoneList& rz, cudaStream_t s) {
   return -1;
 }
 
+bool hits_enabled() {      // SFB_NO_HITS=1: backward falls back to the footprint-box culling (A/B knob)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SFB_NO_HITS"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 bool wide256_enabled() {   // SFB_NO_LD256=1 falls back to 128-bit accesses (A/B knob)
   static int v = -1;
   if (v < 0) { const char* e = getenv("SFB_NO_LD256"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -229,7 +235,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   prof_begin("render_forward", s);
   launch_render_forward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, bg, out_color, out_depth,
                         out_alpha,
-                        img.final_T, img.n_contrib, s);
+                        img.final_T, img.n_contrib, hits_enabled() ? b.hit : nullptr, s);
   prof_end(s);
   g_launches++;
   CK_LAUNCH("render forward", debug, s);
@@ -291,7 +297,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   prof_begin("render_backward", s);
   launch_render_backward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, bg, img.final_T,
                          img.n_contrib,
-                         dL_dout_color, dL_dout_alpha, g.grad, s);
+                         dL_dout_color, dL_dout_alpha, hits_enabled() ? b.hit : nullptr, g.grad, s);
   prof_end(s);
   g_launches++;
   CK_LAUNCH("render backward", debug, s);

@@ -195,6 +195,7 @@ struct BinState {
   uint32_t* inst_idx[2];    // [R]  ping-pong Gaussian indices (unpacked mode only; nullptr when packed)
   uint32_t* sort_hist;      // sort scratch
   uint2* ranges;            // [T]
+  uint8_t* hit;             // [R]  per sorted instance: bit w = warp (8x4 patch) w accumulated it in the forward
 
   static BinState from_chunk(char*& chunk, size_t R, size_t T, bool packed) {
     BinState b;
@@ -202,6 +203,7 @@ struct BinState {
     for (int i = 0; i < 2; i++) b.inst_idx[i] = packed ? nullptr : carve<uint32_t>(chunk, R);
     b.sort_hist = carve<uint32_t>(chunk, sort_scratch_words(R));
     b.ranges = carve<uint2>(chunk, T);
+    b.hit = carve<uint8_t>(chunk, R + 256);
     return b;
   }
   static size_t required(size_t R, size_t T, bool packed) {
@@ -279,13 +281,14 @@ void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_
 void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
                            const SplatRec* rec,
                            const float* bg, float* out_color, float* out_depth, float* out_alpha, float* final_T,
-                           uint32_t* n_contrib, cudaStream_t s);
+                           uint32_t* n_contrib, uint8_t* hit /* [R] or nullptr: do not record */, cudaStream_t s);
 
 // render_bwd.cu
 void launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
                             const SplatRec* rec,
                             const float* bg, const float* final_T, const uint32_t* n_contrib,
-                            const float* dL_dpixels, const float* dL_dalpha_img, GradRec* grad, cudaStream_t s);
+                            const float* dL_dpixels, const float* dL_dalpha_img, const uint8_t* hit /* or nullptr */,
+                            GradRec* grad, cudaStream_t s);
 
 // geom_bwd.cu
 struct BwdParams {

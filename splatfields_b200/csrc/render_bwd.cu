@@ -35,7 +35,8 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
                       const SplatRec* __restrict__ rec,
                        const float* __restrict__ bg, const float* __restrict__ final_T,
                        const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
-                       const float* __restrict__ dL_dalpha_img, GradRec* __restrict__ grad) {
+                       const float* __restrict__ dL_dalpha_img, const uint8_t* __restrict__ hit,
+                       GradRec* __restrict__ grad) {
   // one struct = one base register: every access below is base + immediate (+ j * stride)
   struct Smem {
     float4 q0[BB];
@@ -102,7 +103,9 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
       s_q1[threadIdx.x] = b;
       s_q2[threadIdx.x] = make_float2(c.x, c.y);
       s_id[threadIdx.x] = id;
-      if (CULL) mask = patch_mask(a.x, a.y, c.z, c.w, tx0, ty0);
+      // the forward recorded which warps accumulated this entry: exact, and cheaper than the footprint box
+      if (CULL) mask = hit ? (uint32_t)hit[range.x + (uint32_t)(top - 1 - (int)threadIdx.x)]
+                           : patch_mask(a.x, a.y, c.z, c.w, tx0, ty0);
     }
     if (CULL) s_mask[threadIdx.x] = (uint8_t)mask;
 #pragma unroll
@@ -233,13 +236,14 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
 void launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
                             const SplatRec* rec,
                             const float* bg, const float* final_T, const uint32_t* n_contrib,
-                            const float* dL_dpixels, const float* dL_dalpha_img, GradRec* grad, cudaStream_t s) {
+                            const float* dL_dpixels, const float* dL_dalpha_img, const uint8_t* hit, GradRec* grad,
+                            cudaStream_t s) {
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
   static int cull = -1;
   if (cull < 0) { const char* e = getenv("SFB_NO_CULL"); cull = (e && e[0] == '1') ? 0 : 1; }
 #define SFB_RB(C, A)                                                                                          \
   render_backward_kernel<C, A><<<gx * gy, BB, 0, s>>>(W, H, gx, ranges, point_list, idx_mask, rec, bg, final_T, n_contrib, \
-                                                      dL_dpixels, dL_dalpha_img, grad)
+                                                      dL_dpixels, dL_dalpha_img, hit, grad)
   if (cull) { if (dL_dalpha_img) SFB_RB(true, true); else SFB_RB(true, false); }
   else      { if (dL_dalpha_img) SFB_RB(false, true); else SFB_RB(false, false); }
 #undef SFB_RB
