@@ -285,15 +285,23 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     if (PRELOAD_VALS) val[i] = k < n ? vals_in[k] : 0u;
   }
   // Round i ranks item i of every lane: lanes with equal digits find each other with match.any; the lowest
-  // of them bumps the warp's private digit counter and broadcasts the old value.  (A returning shared-memory
-  // atomic instead of the load/store pair was measured slower on B200: 117 vs 85 us per 9M-item pass.)
+  // of them bumps the warp's private digit counter and broadcasts the old value.  All match.any of the tile
+  // are issued first (they are independent and slow: ncu shows the dependent LOP3 behind each MATCH as the top
+  // stall of this kernel), the counter updates then run back to back.
+  // (A returning shared-memory atomic instead of the load/store pair was measured slower on B200.)
+  uint32_t peers_of[IPT];
+#pragma unroll
+  for (int i = 0; i < IPT; i++) {
+    const int k = seg + i * 32 + lane;
+    const uint32_t d = (key[i] >> shift) & mask;
+    peers_of[i] = __match_any_sync(0xffffffffu, k < n ? d : 0xFFFFu);   // invalid lanes: unmatched digit
+  }
 #pragma unroll
   for (int i = 0; i < IPT; i++) {
     const int k = seg + i * 32 + lane;
     const bool valid = k < n;
     const uint32_t d = (key[i] >> shift) & mask;
-    const uint32_t md = valid ? d : 0xFFFFu;   // invalid lanes: a digit no valid lane can match
-    const uint32_t peers = __match_any_sync(0xffffffffu, md);
+    const uint32_t peers = peers_of[i];
     const uint32_t before = __popc(peers & lt_mask);
     uint32_t prev = 0;
     if (valid && before == 0) {
