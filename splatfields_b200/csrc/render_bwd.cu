@@ -105,7 +105,8 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
       s_id[threadIdx.x] = id;
       // the forward recorded which warps accumulated this entry: exact, and cheaper than the footprint box
       if (CULL) mask = hit ? (uint32_t)hit[range.x + (uint32_t)(top - 1 - (int)threadIdx.x)]
-                           : patch_mask(a.x, a.y, c.z, c.w, tx0, ty0);
+                           : refine_patch_mask(patch_mask(a.x, a.y, c.z, c.w, tx0, ty0), a.x, a.y, a.z, a.w, b.x, b.y, c.z,
+                                               tx0, ty0);
     }
     if (CULL) s_mask[threadIdx.x] = (uint8_t)mask;
 #pragma unroll

@@ -31,7 +31,8 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
                       const SplatRec* __restrict__ rec,
                       const float* __restrict__ bg, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ out_alpha,
-                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, uint8_t* __restrict__ hit) {
+                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, uint8_t* __restrict__ hit,
+                      bool refine_enabled) {
   // one struct = one base register: every access below is base + immediate (+ j * stride)
   struct Smem {
     float4 q0[RB];   // x, y, conA, conB
@@ -74,7 +75,10 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
       s_q0[threadIdx.x] = a;
       s_q1[threadIdx.x] = b;
       s_q2[threadIdx.x] = make_float2(c.x, c.y);
-      if (CULL) mask = patch_mask(a.x, a.y, c.z, c.w, tx0, ty0);
+      if (CULL) {
+        mask = patch_mask(a.x, a.y, c.z, c.w, tx0, ty0);
+        if (refine_enabled) mask = refine_patch_mask(mask, a.x, a.y, a.z, a.w, b.x, b.y, c.z, tx0, ty0);
+      }
     }
     if (CULL) s_mask[threadIdx.x] = (uint8_t)mask;
     if (REC) reinterpret_cast<uint2*>(&sm.hitw[0][0])[threadIdx.x] = make_uint2(0u, 0u);   // 8 warps x 256 B
@@ -155,8 +159,11 @@ void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* po
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
 #define SFB_RF(C, A, R)                                                                                       \
   render_forward_kernel<C, A, R><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, idx_mask, rec, bg, out_color, \
-                                                        out_depth, out_alpha, final_T, n_contrib, hit)
+                                                        out_depth, out_alpha, final_T, n_contrib, hit, refine)
   const bool cull = cull_enabled();
+  static int refine_i = -1;   // SFB_NO_REFINE=1: footprint boxes only (A/B knob)
+  if (refine_i < 0) { const char* e = getenv("SFB_NO_REFINE"); refine_i = (e && e[0] == '1') ? 0 : 1; }
+  const bool refine = refine_i == 1;
   if (hit) {
     if (cull) { if (out_alpha) SFB_RF(true, true, true); else SFB_RF(true, false, true); }
     else      { if (out_alpha) SFB_RF(false, true, true); else SFB_RF(false, false, true); }
