@@ -25,7 +25,7 @@ constexpr int RB = 256;  // batch = block size
 // REC: record, per list entry, which warps (8x4 patches) accumulated it.  The backward sweeps exactly those
 // (warp, entry) pairs instead of every pair whose footprint box touches the patch (3.1 M -> 1.9 M per view).
 template <bool CULL, bool ALPHA, bool REC>
-__global__ void __launch_bounds__(RB)
+__global__ void __launch_bounds__(RB, 6)   // <= 42 registers: the sweep loop needs ~40; the fetch-phase culling math may spill
 render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
                       const uint32_t* __restrict__ point_list, uint32_t idx_mask,
                       const SplatRec* __restrict__ rec,
