@@ -58,7 +58,12 @@ def main():
     color, radii = step()
     color.backward(G)
     torch.cuda.synchronize()
-    pf, pb = dict(_lib.profile_read(0)), dict(_lib.profile_read(1))
+    def agg(rows):      # several launches share a name (the sort passes): report the per-step sum
+        d = {}
+        for k, v in rows:
+            d[k] = d.get(k, 0.0) + v
+        return d
+    pf, pb = agg(_lib.profile_read(0)), agg(_lib.profile_read(1))
     _lib.profile_enable(False)
     # render(): the reference's two rasterizer passes vs the fused alpha channel
     from splatfields_b200 import render

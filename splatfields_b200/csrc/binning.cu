@@ -198,7 +198,7 @@ static int radix_sort_pairs_legacy(uint32_t* keys[2], uint32_t* vals[2], uint32_
 // read once and written once per pass; the digit histograms of ALL passes come from one up-front sweep.
 constexpr uint32_t OS_FLAG_AGG = 1u << 30, OS_FLAG_INC = 2u << 30, OS_VAL_MASK = (1u << 30) - 1u;
 constexpr int OS_MAX_PASSES = 4;
-constexpr int OS_LB = 8;   // look-back probes in flight per digit
+constexpr int OS_LB = 8;   // look-back probes in flight per digit (16 and 32 measured slower: 91 -> 103 -> 118 us depth sort)
 
 // bias_c (optional): pointer to ~kmin, the complement of the smallest valid key (preprocess reduces it with
 // atomicMax).  Keys are then rewritten IN PLACE as key - kmin (0xFFFFFFFF = culled -> 0: culled splats emit no
@@ -240,7 +240,12 @@ radix_hist_all_kernel(uint32_t* __restrict__ keys, int n, int npass, int4 shifts
 // IPT items per thread: 16 (4096-item tiles) for large inputs, 4 (1024-item tiles) when 4096-item tiles
 // would leave most SMs idle and every block a long latency chain.
 // HAS_VALS = false sorts bare 32-bit words (the packed tile|index instances): nothing but keys is staged or moved.
-template <int IPT, bool HAS_VALS>
+// NB = digit bits the ranking resolves with ballots (6, 7 or 8 >= log2(bins)); NB = 0 ranks with match.any.
+// For 4096-item tiles the IPT ranking rounds of a warp are split into CH independent chains (CH * bins <= SORT_MAX_BINS;
+// chain c = items [c*IPT/CH, (c+1)*IPT/CH) of every lane) with their own digit counters, so the load -> add -> store ->
+// shuffle dependency that serialises the rounds is IPT/CH long; the counters of the chains are stitched together by
+// the per-digit exclusive prefix that already runs over the warps.
+template <int IPT, bool HAS_VALS, int NB>
 __global__ void __launch_bounds__(SORT_THREADS, 3)
 onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift, int bins,
@@ -249,7 +254,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
                      uint32_t* __restrict__ ticket /* zeroed */) {
   constexpr int NW = SORT_THREADS / 32;
   constexpr int OS_TILE = SORT_THREADS * IPT;
-  __shared__ uint32_t s_cnt[NW][SORT_MAX_BINS];   // per-warp digit counts -> exclusive-over-warps prefixes
+  constexpr int CH = IPT == 16 ? (NB == 6 ? 4 : (NB == 7 ? 2 : 1)) : 1;
+  __shared__ uint32_t s_cnt[NW][SORT_MAX_BINS];   // per-warp (x chain) digit counts -> exclusive prefixes
   __shared__ uint32_t s_lstart[SORT_MAX_BINS];    // block-local start of each digit run
   __shared__ int32_t s_gofs[SORT_MAX_BINS];       // global position - local position, per digit
   __shared__ uint32_t s_key[OS_TILE];
@@ -294,22 +300,51 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   for (int i = 0; i < IPT; i++) {
     const int k = seg + i * 32 + lane;
     const uint32_t d = (key[i] >> shift) & mask;
-    peers_of[i] = __match_any_sync(0xffffffffu, k < n ? d : 0xFFFFu);   // invalid lanes: unmatched digit
-  }
+    if (NB == 0) {
+      peers_of[i] = __match_any_sync(0xffffffffu, k < n ? d : 0xFFFFu);   // invalid lanes: unmatched digit
+    } else {
+      // MATCH.ANY costs ~300 cycles per warp here (its latency grows with the number of distinct digits among the
+      // lanes and it does not pipeline: ~110 Gkeys/s per pass whatever n).  One ballot per digit bit builds the same
+      // peer mask from 4 pipelined instructions per bit: m &= ballot(bit) ^ (my bit ? 0 : ~0).
+      uint32_t m = __ballot_sync(0xffffffffu, k < n);
 #pragma unroll
-  for (int i = 0; i < IPT; i++) {
-    const int k = seg + i * 32 + lane;
-    const bool valid = k < n;
-    const uint32_t d = (key[i] >> shift) & mask;
-    const uint32_t peers = peers_of[i];
-    const uint32_t before = __popc(peers & lt_mask);
-    uint32_t prev = 0;
-    if (valid && before == 0) {
-      prev = s_cnt[warp][d];
-      s_cnt[warp][d] = prev + __popc(peers);
+      for (int b = 0; b < NB; b++) {
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 t, v, x;\n\t"
+            "and.b32 t, %1, %2;\n\t"
+            "setp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
+            "selp.b32 x, 0, 0xffffffff, p;\n\t"
+            "lop3.b32 %0, %0, v, x, 0x60;\n\t}"          // m & (v ^ x)
+            : "+r"(m) : "r"(d), "r"(1u << b));
+      }
+      peers_of[i] = k < n ? m : (1u << lane);
     }
-    prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
-    rank[i] = prev + before;
+  }
+  constexpr int RPC = IPT / CH;   // rounds per chain
+#pragma unroll
+  for (int r = 0; r < RPC; r++) {
+    uint32_t prevv[CH], before[CH];
+    bool leader[CH];
+#pragma unroll
+    for (int c = 0; c < CH; c++) {    // CH independent counter reads in flight
+      const int i = c * RPC + r;
+      const int k = seg + i * 32 + lane;
+      const uint32_t d = (key[i] >> shift) & mask;
+      before[c] = __popc(peers_of[i] & lt_mask);
+      leader[c] = k < n && before[c] == 0;
+      prevv[c] = leader[c] ? s_cnt[warp][c * bins + d] : 0u;
+    }
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+      const int i = c * RPC + r;
+      const uint32_t d = (key[i] >> shift) & mask;
+      if (leader[c]) s_cnt[warp][c * bins + d] = prevv[c] + __popc(peers_of[i]);
+    }
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+      const int i = c * RPC + r;
+      rank[i] = __shfl_sync(0xffffffffu, prevv[c], __ffs(peers_of[i]) - 1) + before[c];
+    }
     __syncwarp();
   }
   __syncthreads();
@@ -322,9 +357,11 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   const int d = threadIdx.x;
   volatile uint32_t* st = tile_state;
   if (d < bins) {
-    uint32_t run = 0;
+    uint32_t run = 0;    // exclusive prefix in sequence order: warp-major, chain-minor
 #pragma unroll
-    for (int w = 0; w < NW; w++) { const uint32_t c = s_cnt[w][d]; s_cnt[w][d] = run; run += c; }
+    for (int w = 0; w < NW; w++)
+#pragma unroll
+      for (int c = 0; c < CH; c++) { const uint32_t v = s_cnt[w][c * bins + d]; s_cnt[w][c * bins + d] = run; run += v; }
     my_count = run;
     s_count[d] = run;
     dtotal = digit_totals[d];
@@ -390,7 +427,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     const int k = seg + i * 32 + lane;
     if (k < n) {
       const uint32_t dd = (key[i] >> shift) & mask;
-      const uint32_t lp = s_lstart[dd] + s_cnt[warp][dd] + rank[i];
+      const uint32_t lp = s_lstart[dd] + s_cnt[warp][(i / RPC) * bins + dd] + rank[i];
       s_key[lp] = key[i];
       if (HAS_VALS) s_val[lp] = val[i];
     }
@@ -412,9 +449,9 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
   const bool has_vals = vals != nullptr && vals[0] != nullptr;
   const int npass = (nbits + 7) / 8;
   const bool small = sort_blocks(n) < 4 * NUM_SMS_B200;       // < 4 tiles per SM with 4096-item tiles
-  static int ipt_big = -1;                                    // experiment knob: SFB_SORT_IPT=8 -> 2048-item tiles
-  if (ipt_big < 0) { const char* e = getenv("SFB_SORT_IPT"); ipt_big = (e && e[0] == '8') ? 8 : 16; }
-  const int tile = small ? SORT_THREADS * 4 : SORT_THREADS * ipt_big;
+  static int use_match = -1;                                  // A/B knob: SFB_SORT_MATCH=1 -> match.any ranking
+  if (use_match < 0) { const char* e = getenv("SFB_SORT_MATCH"); use_match = (e && e[0] == '1') ? 1 : 0; }
+  const int tile = small ? SORT_THREADS * 4 : SORT_THREADS * 16;
   const int nblocks = (n + tile - 1) / tile;
   // scratch layout: [hist_all: 4*256][tickets: 8][tile_state: npass * nblocks * bins]
   uint32_t* hist_all = scratch;
@@ -443,13 +480,17 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
     prof_begin(names[2], s);
     uint32_t* vin = has_vals ? vals[cur] : nullptr;
     uint32_t* vout = has_vals ? vals[cur ^ 1] : nullptr;
+#define SFB_OS2(IPTV, HV, NBV)                                                                                 \
+  onesweep_pass_kernel<IPTV, HV, NBV><<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vin, keys[cur ^ 1], vout, n,   \
+                                                                        shifts[pass], nbins[pass],                \
+                                                                        hist_all + pass * SORT_MAX_BINS, state, tickets + pass)
 #define SFB_OS(IPTV, HV)                                                                                       \
-  onesweep_pass_kernel<IPTV, HV><<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vin, keys[cur ^ 1], vout, n,       \
-                                                                  shifts[pass], nbins[pass],                   \
-                                                                  hist_all + pass * SORT_MAX_BINS, state, tickets + pass)
-    if (small)             { if (has_vals) SFB_OS(4, true);  else SFB_OS(4, false); }
-    else if (ipt_big == 8) { if (has_vals) SFB_OS(8, true);  else SFB_OS(8, false); }
-    else                   { if (has_vals) SFB_OS(16, true); else SFB_OS(16, false); }
+  do { if (nb == 0) SFB_OS2(IPTV, HV, 0); else if (nb == 6) SFB_OS2(IPTV, HV, 6); else if (nb == 7) SFB_OS2(IPTV, HV, 7); \
+       else SFB_OS2(IPTV, HV, 8); } while (0)
+    const int nb = use_match ? 0 : (nbins[pass] <= 64 ? 6 : (nbins[pass] <= 128 ? 7 : 8));
+    if (small) { if (has_vals) SFB_OS(4, true);  else SFB_OS(4, false); }
+    else       { if (has_vals) SFB_OS(16, true); else SFB_OS(16, false); }
+#undef SFB_OS2
 #undef SFB_OS
     prof_end(s);
     if (launches) *launches += 1;
