@@ -448,7 +448,11 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
                                      const uint32_t* bias_c, int first_bit) {
   const bool has_vals = vals != nullptr && vals[0] != nullptr;
   const int npass = (nbits + 7) / 8;
-  const bool small = sort_blocks(n) < 4 * NUM_SMS_B200;       // < 4 tiles per SM with 4096-item tiles
+  // 1024-item tiles only for really small inputs: with the ballot ranking 4096-item tiles win from ~0.3 M items
+  // (measured: 1 M pairs 87 -> 65 us, 0.5 M 63 -> 54 us, 0.1 M 43 -> 51 us), although they fill < 2 CTAs per SM
+  static int small_on = -1;                                   // A/B knob: SFB_SORT_SMALL=0 -> 4096-item tiles always
+  if (small_on < 0) { const char* e = getenv("SFB_SORT_SMALL"); small_on = (e && e[0] == '0') ? 0 : 1; }
+  const bool small = small_on && sort_blocks(n) < 64;
   static int use_match = -1;                                  // A/B knob: SFB_SORT_MATCH=1 -> match.any ranking
   if (use_match < 0) { const char* e = getenv("SFB_SORT_MATCH"); use_match = (e && e[0] == '1') ? 1 : 0; }
   const int tile = small ? SORT_THREADS * 4 : SORT_THREADS * 16;
