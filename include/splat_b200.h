@@ -116,6 +116,52 @@ const char* sfb_profile_name(int which, int i);
 /* Number of kernel launches issued by the last forward / backward on the calling thread. */
 int sfb_last_launch_count(void);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * SURVEY.md §8f rows adjacent to the rasterizer (the steps right after it in the reference's training iteration).
+ * --------------------------------------------------------------------------------------------------------------- */
+
+/* Fused photometric loss and its gradient.  Replaces utils/loss_utils.py:18-19 (l1_loss) and :33-76 (gaussian,
+ * create_window, ssim, _ssim: 11x11 Gaussian window, sigma 1.5, zero padding 5, C1 = 0.01^2, C2 = 0.03^2,
+ * size_average=True) as combined at train.py:183-184, plus the optional mask term of train.py:189-193:
+ *     loss = (1 - lambda_dssim) * mean|img - gt| + lambda_dssim * (1 - ssim(img, gt))
+ *            [+ lambda_mask * mean|clamp(opacity, 0, 1) - gt_mask|]
+ *   img, gt [C][H][W];  opacity, gt_mask [H][W] or both NULL
+ *   out_scalars [4] (device): {l1, ssim, mask_l1, loss}   (ssim = 0 when lambda_dssim == 0: it is not evaluated)
+ *   dL_dimg [C][H][W] or NULL (forward only), dL_dopacity [H][W] or NULL: gradients of `loss`, times grad_scale
+ *                     (the upstream cotangent, e.g. 1 / #views for train.py:242's mean), fully written
+ *   scratch           device buffer of sfb_loss_scratch_bytes(C, H, W) bytes, 256-byte aligned, caller-owned
+ * The scalars are reduced in a fixed order (bit-reproducible run to run). */
+size_t sfb_loss_scratch_bytes(int C, int H, int W);
+/* host-side: the 11 fp32 weights of the 1-D window (= loss_utils.gaussian(11, 1.5), bit for bit) */
+void sfb_loss_window(float* out11);
+int sfb_l1_ssim_loss(int C, int H, int W, const float* img, const float* gt, float lambda_dssim,
+                     const float* opacity, const float* gt_mask, float lambda_mask, float grad_scale,
+                     float* out_scalars, float* dL_dimg, float* dL_dopacity, void* scratch, void* stream);
+
+/* Densification statistics of one view.  Replaces GaussianModel.add_densification_stats
+ * (scene/gaussian_model.py:427-430) and the max_radii2D update of train.py:280-282.  For every i with
+ * update_filter[i] != 0 (update_filter == NULL: radii[i] > 0, the reference's visibility_filter):
+ *     xyz_gradient_accum[i] += hypot(dL_dmeans2D[i][0], dL_dmeans2D[i][1]);  denom[i] += 1;
+ *     max_radii2D[i] = max(max_radii2D[i], radii[i])          (when max_radii2D and radii are non-NULL)
+ * dL_dmeans2D [P][3] is viewspace_points.grad (the rasterizer backward's dL_dmeans2D); radii [P] int32. */
+int sfb_densify_stats(int P, const float* dL_dmeans2D, const int* radii, const uint8_t* update_filter,
+                      float* xyz_gradient_accum, float* denom, float* max_radii2D, void* stream);
+
+/* Selection predicates of GaussianModel.densify_and_prune / densify_and_clone / densify_and_split
+ * (scene/gaussian_model.py:355-425) for the P existing Gaussians:
+ *     g = xyz_gradient_accum / denom (NaN -> 0);  smax = max(scale)
+ *     clone = |g| >= grad_threshold && smax <= dense_extent          dense_extent = percent_dense * scene_extent
+ *     split =  g  >= grad_threshold && smax >  dense_extent
+ *     prune = opacity < min_opacity || (max_screen_size > 0 && (max_radii2D > max_screen_size || smax > big_extent))
+ *                                                                    big_extent = 0.1 * scene_extent
+ * scales [P][3], opacity [P]: activated values, or the raw parameters when raw_params != 0 (exp / sigmoid applied
+ * here, scene/gaussian_model.py:53-58).  Masks are uint8 [P]; counts [3] (device, may be NULL) = #clone, #split,
+ * #prune.  The optimizer-state surgery that consumes the masks stays with the caller. */
+int sfb_densify_masks(int P, const float* xyz_gradient_accum, const float* denom, const float* scales,
+                      const float* opacity, const float* max_radii2D, int raw_params, float grad_threshold,
+                      float dense_extent, float big_extent, float min_opacity, float max_screen_size,
+                      uint8_t* clone_mask, uint8_t* split_mask, uint8_t* prune_mask, uint32_t* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,5 +3,8 @@
 See DESIGN.md for the path, the boundary and the kernels."""
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians  # noqa: F401
 from .renderer import render  # noqa: F401
+from .losses import l1_loss, ssim, photometric_loss  # noqa: F401
+from .densify import add_densification_stats, densify_masks  # noqa: F401
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "render"]
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "render",
+           "l1_loss", "ssim", "photometric_loss", "add_densification_stats", "densify_masks"]

@@ -20,6 +20,7 @@ SYMBOLS = (
     "sfb_abi_version", "sfb_last_error", "sfb_rasterize_forward", "sfb_rasterize_backward", "sfb_mark_visible",
     "sfb_export_geom", "sfb_export_binning", "sfb_export_img", "sfb_last_launch_count",
     "sfb_profile_enable", "sfb_profile_count", "sfb_profile_read", "sfb_profile_name",
+    "sfb_loss_scratch_bytes", "sfb_loss_window", "sfb_l1_ssim_loss", "sfb_densify_stats", "sfb_densify_masks",
 )
 
 
@@ -73,7 +74,17 @@ def load():
     lib.sfb_profile_count.argtypes = [ci]
     lib.sfb_profile_name.restype = C.c_char_p
     lib.sfb_profile_name.argtypes = [ci, ci]
-    if lib.sfb_abi_version() != 2:
+    lib.sfb_loss_scratch_bytes.restype = C.c_size_t
+    lib.sfb_loss_scratch_bytes.argtypes = [ci, ci, ci]
+    lib.sfb_loss_window.restype = None
+    lib.sfb_loss_window.argtypes = [C.POINTER(cf)]
+    lib.sfb_l1_ssim_loss.restype = ci
+    lib.sfb_l1_ssim_loss.argtypes = [ci, ci, ci, vp, vp, cf, vp, vp, cf, cf, vp, vp, vp, vp, vp]
+    lib.sfb_densify_stats.restype = ci
+    lib.sfb_densify_stats.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp]
+    lib.sfb_densify_masks.restype = ci
+    lib.sfb_densify_masks.argtypes = [ci, vp, vp, vp, vp, vp, ci, cf, cf, cf, cf, cf, vp, vp, vp, vp, vp]
+    if lib.sfb_abi_version() != 3:
         raise SplatB200Error("libsplat_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

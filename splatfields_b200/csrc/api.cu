@@ -90,6 +90,7 @@ int tile_sort_final(int T) {
 }  // namespace
 
 namespace sfb {
+void set_error(const char* msg) { g_err = msg ? msg : ""; }
 void prof_begin(const char* name, cudaStream_t s) {
   if (!g_prof) return;
   if (!g_rec_made) {
@@ -113,7 +114,7 @@ void prof_end(cudaStream_t s) {
 
 extern "C" {
 
-int sfb_abi_version(void) { return 2; }
+int sfb_abi_version(void) { return 3; }
 const char* sfb_last_error(void) { return g_err.c_str(); }
 int sfb_last_launch_count(void) { return g_launches; }
 

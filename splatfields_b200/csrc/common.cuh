@@ -282,6 +282,8 @@ inline int tile_bits(int num_tiles) {
 // per-kernel profiling brackets (api.cu); no-ops unless sfb_profile_enable(1)
 void prof_begin(const char* name, cudaStream_t s);
 void prof_end(cudaStream_t s);
+// text returned by sfb_last_error() on the calling thread (api.cu)
+void set_error(const char* msg);
 
 // ------------------------------------------------------------------ launchers (one per .cu file)
 struct FwdParams {

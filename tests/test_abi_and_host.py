@@ -24,8 +24,34 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_lib.SYMBOLS) == declared
-    assert lib.sfb_abi_version() == 2
+    assert lib.sfb_abi_version() == 3
     assert lib.sfb_last_error() == b""
+
+
+def test_loss_window_is_the_reference_window_bit_for_bit():
+    """Host-side piece of the fused loss: the 11 weights equal loss_utils.gaussian(11, 1.5) as the reference computed
+    them (golden file), and the scratch size follows the documented layout (3 maps + block partials)."""
+    import ctypes as C
+    import numpy as np
+    _built()
+    from splatfields_b200 import _lib
+    lib = _lib.load()
+    buf = (C.c_float * 11)()
+    lib.sfb_loss_window(buf)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "next_rows.npz"))
+    assert np.array_equal(np.array(list(buf), dtype=np.float32), gold["window_1d"])
+    n = lib.sfb_loss_scratch_bytes(3, 800, 800)
+    assert 3 * 3 * 800 * 800 * 4 <= n <= 3 * 3 * 800 * 800 * 4 + (1 << 20)
+    assert lib.sfb_loss_scratch_bytes(0, 800, 800) == 0
+
+
+def test_next_row_mirrors_refuse_cpu_tensors():
+    from splatfields_b200 import losses, densify
+    from splatfields_b200._lib import SplatB200Error
+    with pytest.raises(SplatB200Error, match="no CPU fallback"):
+        losses.photometric_loss(torch.zeros(3, 8, 8), torch.zeros(3, 8, 8), 0.2)
+    with pytest.raises(Exception, match="CUDA tensor"):
+        densify.add_densification_stats(torch.zeros(4, 1), torch.zeros(4, 1), torch.zeros(4, 3), radii=torch.ones(4))
 
 
 def test_library_is_sm100a_only():
