@@ -72,7 +72,11 @@ int sfb_rasterize_forward(
  * dL_dmeans3D [P][3], dL_dcov3D [P][6], dL_dsh [P][M][3] (may be NULL when shs is NULL),
  * dL_dscales [P][3], dL_drotations [P][4] (may be NULL when cov3D_precomp is given).  dL_dcolors may be NULL when
  * shs is given and dL_dcov3D may be NULL when scales / rotations are given (the reference returns those two
- * gradients only for the corresponding precomputed inputs); a NULL output is simply not written. */
+ * gradients only for the corresponding precomputed inputs); a NULL output is simply not written.
+ * flags: SFB_BWD_ACC_FRESH = this is the FIRST backward on these scratch buffers since the forward that filled them
+ * (the forward leaves the per-splat gradient accumulators inside geom_buffer cleared, so the backward can skip its
+ * 48 B/Gaussian memset); pass 0 when in doubt or when running backward again on the same buffers (retain_graph). */
+#define SFB_BWD_ACC_FRESH 1
 int sfb_rasterize_backward(
     int P, int sh_degree, int M, int num_rendered, int W, int H,
     const float* bg, const float* means3D, const float* shs, const float* colors_precomp,
@@ -83,7 +87,7 @@ int sfb_rasterize_backward(
     const float* dL_dout_color, const float* dL_dout_alpha,
     float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D, float* dL_dcov3D,
     float* dL_dsh, float* dL_dscales, float* dL_drotations,
-    int debug, void* stream);
+    int debug, int flags, void* stream);
 
 /* Replaces _C.mark_visible: present[i] = 1 iff the view-space z of means3D[i] is > 0.2. */
 int sfb_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsplat_b200.so")
+# SFB_LIB_VARIANT selects an experimental build variant of the same library (build.py VARIANTS); default: the product
+_VARIANT = os.environ.get("SFB_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, "libsplat_b200" + ("_" + _VARIANT if _VARIANT else "") + ".so")
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
@@ -22,6 +24,9 @@ SYMBOLS = (
     "sfb_profile_enable", "sfb_profile_count", "sfb_profile_read", "sfb_profile_name",
     "sfb_loss_scratch_bytes", "sfb_loss_window", "sfb_l1_ssim_loss", "sfb_densify_stats", "sfb_densify_masks",
 )
+
+
+BWD_ACC_FRESH = 1   # include/splat_b200.h: SFB_BWD_ACC_FRESH
 
 
 class SplatB200Error(RuntimeError):
@@ -57,7 +62,7 @@ def load():
         vp, vp, vp, cf, cf, vp,                   # view, proj, campos, tanfovx, tanfovy, radii
         vp, vp, vp, vp, vp,                       # geom, binning, img, dL_dout_color, dL_dout_alpha (nullable)
         vp, vp, vp, vp, vp, vp, vp, vp,           # 8 gradient outputs
-        ci, vp]
+        ci, ci, vp]                               # debug, flags (SFB_BWD_ACC_FRESH), stream
     lib.sfb_mark_visible.restype = ci
     lib.sfb_mark_visible.argtypes = [ci, vp, vp, vp, vp, vp]
     lib.sfb_export_geom.restype = ci

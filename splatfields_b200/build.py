@@ -38,7 +38,16 @@ def _stale(out: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+# Build variants (A/B experiments; the default library is the product): name -> (extra nvcc flags, library path)
+VARIANTS = {
+    "": ([], LIB),
+    "fastexp": (["-DSFB_FAST_EXP"], os.path.join(HERE, "libsplat_b200_fastexp.so")),
+}
+
+
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
+    vflags, LIB = VARIANTS[variant]
+    BUILD = os.path.join(CSRC, "build" + ("_" + variant if variant else ""))
     os.makedirs(BUILD, exist_ok=True)
     hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "splat_b200.h"), __file__]
     objs = []
@@ -47,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         op = os.path.join(BUILD, src.replace(".cu", ".o"))
         objs.append(op)
         if force or _stale(op, [sp] + hdrs):
-            cmd = [nvcc()] + ARCH + COMMON + EXTRA.get(src, []) + ["-c", sp, "-o", op]
+            cmd = [nvcc()] + ARCH + COMMON + EXTRA.get(src, []) + vflags + ["-c", sp, "-o", op]
             r = subprocess.run(cmd, capture_output=True, text=True)
             log = os.path.join(BUILD, src + ".ptxas.log")
             with open(log, "w") as f:
@@ -63,4 +72,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    var = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), "")
+    print(build(force="--force" in sys.argv, verbose="--quiet" not in sys.argv, variant=var))

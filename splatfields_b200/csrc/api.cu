@@ -75,6 +75,12 @@ bool hits_enabled() {      // SFB_NO_HITS=1: backward falls back to the footprin
   return v == 1;
 }
 
+bool zero_in_fwd_enabled() {   // SFB_ZERO_IN_FWD=0: the backward clears its accumulators with a memset (A/B knob)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SFB_ZERO_IN_FWD"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 bool wide256_enabled() {   // SFB_NO_LD256=1 falls back to 128-bit accesses (A/B knob)
   static int v = -1;
   if (v < 0) { const char* e = getenv("SFB_NO_LD256"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -236,7 +242,8 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   prof_begin("render_forward", s);
   launch_render_forward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, bg, out_color, out_depth,
                         out_alpha,
-                        img.final_T, img.n_contrib, hits_enabled() ? b.hit : nullptr, s);
+                        img.final_T, img.n_contrib, hits_enabled() ? b.hit : nullptr,
+                        zero_in_fwd_enabled() ? g.grad : nullptr, (size_t)P, s);
   prof_end(s);
   g_launches++;
   CK_LAUNCH("render forward", debug, s);
@@ -261,7 +268,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
                            const float* dL_dout_color, const float* dL_dout_alpha, float* dL_dmeans2D,
                            float* dL_dcolors, float* dL_dopacity,
                            float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscales,
-                           float* dL_drotations, int debug, void* stream) {
+                           float* dL_drotations, int debug, int flags, void* stream) {
   using namespace sfb;
   g_err.clear();
   g_launches = 0;
@@ -292,9 +299,13 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   const int tfinal = num_rendered > 0 ? tile_sort_final(T) : 0;
 
   g_which = 1; g_nrec[1] = 0;
-  prof_begin("zero_grad_acc", s);
-  CK(cudaMemsetAsync(g.grad, 0, sizeof(GradRec) * (size_t)P, s));
-  prof_end(s);
+  // the forward render cleared the accumulators as a prologue (render_fwd.cu) unless told otherwise
+  const bool acc_fresh = (flags & SFB_BWD_ACC_FRESH) && zero_in_fwd_enabled() && (size_t)P < ((size_t)1 << 30);
+  if (!acc_fresh) {
+    prof_begin("zero_grad_acc", s);
+    CK(cudaMemsetAsync(g.grad, 0, sizeof(GradRec) * (size_t)P, s));
+    prof_end(s);
+  }
   prof_begin("render_backward", s);
   launch_render_backward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, bg, img.final_T,
                          img.n_contrib,

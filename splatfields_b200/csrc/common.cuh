@@ -51,6 +51,19 @@ __device__ __forceinline__ void stg256(float* p, const float* v) {
                : "memory");
 }
 
+// exp() of the compositing kernels.  Default: libdevice expf, the function the reference's kernels call.
+// -DSFB_FAST_EXP (the libsplat_b200_fastexp.so build variant, an A/B experiment): one MUFU.EX2 on power * log2(e);
+// alpha then differs from the expf value by <= ~7e-7 relative, i.e. <= 1e-6 on an RGB pixel and <= 4e-6 on depth.
+__device__ __forceinline__ float splat_exp(float power) {
+#ifdef SFB_FAST_EXP
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(power * 1.4426950408889634f));
+  return r;
+#else
+  return expf(power);
+#endif
+}
+
 // Non-blocking L2 prefetch of the 128-byte line holding p (no register, no scoreboard).
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -323,7 +336,9 @@ void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_
 void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
                            const SplatRec* rec,
                            const float* bg, float* out_color, float* out_depth, float* out_alpha, float* final_T,
-                           uint32_t* n_contrib, uint8_t* hit /* [R] or nullptr: do not record */, cudaStream_t s);
+                           uint32_t* n_contrib, uint8_t* hit /* [R] or nullptr: do not record */,
+                           GradRec* zero_grad /* [P] or nullptr: cleared by the CTAs as a prologue */, size_t P,
+                           cudaStream_t s);
 
 // render_bwd.cu
 void launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,

@@ -143,7 +143,7 @@ render_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ range
         const float s = __fmaf_rn(__fmul_rn(q0.z, dx), dx, __fmul_rn(__fmul_rn(q1.x, dy), dy));
         const float power = __fmaf_rn(s, -0.5f, -__fmul_rn(__fmul_rn(q0.w, dx), dy));
         if (power <= 0.0f) {
-          const float G = expf(power);
+          const float G = splat_exp(power);
           const float alpha = fminf(0.99f, __fmul_rn(q1.y, G));
           if (alpha >= 1.0f / 255.0f) {
             contrib = true;
@@ -270,7 +270,7 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 struct SmemBwdMma {
   float4 q0[BB];
   float4 q1[BB];
-  float2 q2[BB];
+  float4 q2[BB];            // g, b, -, - (16-byte stride like q0 / q1: one address register + immediates)
   uint32_t id[BB];
   float acc[BB * 9];
   uint32_t maxc[BB / 32];
@@ -367,7 +367,7 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
       float4 a = __ldg(rp), b = __ldg(rp + 1), c = __ldg(rp + 2);
       sm.q0[threadIdx.x] = a;
       sm.q1[threadIdx.x] = b;
-      sm.q2[threadIdx.x] = make_float2(c.x, c.y);
+      sm.q2[threadIdx.x] = c;
       sm.id[threadIdx.x] = id;
       mask = hit ? (uint32_t)hit[range.x + (uint32_t)(top - 1 - (int)threadIdx.x)]
                  : refine_patch_mask(patch_mask(a.x, a.y, c.z, c.w, tx0, ty0), a.x, a.y, a.z, a.w, b.x, b.y, c.z,
@@ -391,24 +391,25 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
       __syncwarp();
     }
 
+    // list position of slot j is top-1-j; it is in front of this pixel's last contributor iff j >= top - my_last
+    const int jmin = top - (int)my_last;
     for (int g0 = 0; g0 < nsweep; g0 += MG) {
       const int gn = nsweep - g0 < MG ? nsweep - g0 : MG;
       // ---- phase A: per-pixel chain over up to 16 entries; (sG, w) of every pixel go to the staging rows
       for (int i = 0; i < gn; i++) {
         const int j = (int)sm.list[warp][g0 + i];
-        const uint32_t pos = (uint32_t)(top - 1 - j);
         float sG = 0.f, wgt = 0.f;
-        if (pos < my_last) {
+        if (j >= jmin) {
           const float4 q0 = sm.q0[j];
           const float4 q1 = sm.q1[j];
           const float dx = q0.x - pixfx, dy = q0.y - pixfy;
           const float s = __fmaf_rn(__fmul_rn(q0.z, dx), dx, __fmul_rn(__fmul_rn(q1.x, dy), dy));
           const float power = __fmaf_rn(s, -0.5f, -__fmul_rn(__fmul_rn(q0.w, dx), dy));
           if (power <= 0.0f) {
-            const float G = expf(power);
+            const float G = splat_exp(power);
             const float alpha = fminf(0.99f, __fmul_rn(q1.y, G));
             if (alpha >= 1.0f / 255.0f) {
-              const float2 q2 = sm.q2[j];
+              const float2 q2 = make_float2(sm.q2[j].x, sm.q2[j].y);
               float inv;
               asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - alpha));
               T *= inv;

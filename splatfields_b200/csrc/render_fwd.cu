@@ -32,12 +32,12 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
                       const float* __restrict__ bg, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ out_alpha,
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, uint8_t* __restrict__ hit,
-                      bool refine_enabled) {
+                      bool refine_enabled, float4* __restrict__ zero16, uint32_t zero_per_cta, uint32_t zero_total) {
   // one struct = one base register: every access below is base + immediate (+ j * stride)
   struct Smem {
     float4 q0[RB];   // x, y, conA, conB
     float4 q1[RB];   // conC, opacity, depth, r
-    float2 q2[RB];   // g, b
+    float4 q2[RB];   // g, b, -, -   (16-byte stride like q0 / q1: one address register + immediates)
     uint8_t mask[CULL ? RB : 1];
     uint8_t list[CULL ? RB / 32 : 1][CULL ? RB : 1];
     uint8_t hitw[REC ? RB / 32 : 1][REC ? RB : 1];   // [warp][entry]: 1 = some pixel of the warp accumulated it
@@ -45,11 +45,19 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
   __shared__ Smem sm;
   float4* const s_q0 = sm.q0;
   float4* const s_q1 = sm.q1;
-  float2* const s_q2 = sm.q2;
+  float4* const s_q2 = sm.q2;
   uint8_t* const s_mask = sm.mask;
   uint8_t (*const s_list)[CULL ? RB : 1] = sm.list;
 
   const int tile = blockIdx.x;
+  // Prologue: clear this CTA's slice of the backward's per-splat gradient accumulators (GradRec[P]).  The kernel is
+  // issue-bound with an idle memory system, so these fire-and-forget stores replace a 48 B/splat memset in front of
+  // the backward render for free.
+  if (zero16) {
+    const uint32_t z0 = (uint32_t)tile * zero_per_cta;
+    const uint32_t z1 = min(z0 + zero_per_cta, zero_total);
+    for (uint32_t i = z0 + threadIdx.x; i < z1; i += RB) zero16[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const int tile_x = tile % grid_x, tile_y = tile / grid_x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int px = tile_x * TILE_X + (warp & 1) * 8 + (lane & 7);
@@ -74,7 +82,7 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
       float4 a = __ldg(rp), b = __ldg(rp + 1), c = __ldg(rp + 2);
       s_q0[threadIdx.x] = a;
       s_q1[threadIdx.x] = b;
-      s_q2[threadIdx.x] = make_float2(c.x, c.y);
+      s_q2[threadIdx.x] = c;
       if (CULL) {
         mask = patch_mask(a.x, a.y, c.z, c.w, tx0, ty0);
         if (refine_enabled) mask = refine_patch_mask(mask, a.x, a.y, a.z, a.w, b.x, b.y, c.z, tx0, ty0);
@@ -98,29 +106,35 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
       __syncwarp();
       n = cnt;
     }
-    for (int k = 0; !done && k < n; k++) {
-      const int j = CULL ? (int)s_list[warp][k] : k;
-      const float4 q0 = s_q0[j];
-      const float dx = q0.x - pixfx, dy = q0.y - pixfy;
-      const float4 q1 = s_q1[j];
-      // -0.5f*(A*dx*dx + C*dy*dy) - B*dx*dy, in the op order nvcc gives that expression
-      const float s = __fmaf_rn(__fmul_rn(q0.z, dx), dx, __fmul_rn(__fmul_rn(q1.x, dy), dy));
-      const float power = __fmaf_rn(s, -0.5f, -__fmul_rn(__fmul_rn(q0.w, dx), dy));
-      if (power > 0.0f) continue;
-      const float alpha = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
-      if (alpha < 1.0f / 255.0f) continue;
-      const float test_T = __fmul_rn(T, 1.0f - alpha);
-      if (test_T < 0.0001f) { done = true; continue; }
-      const float w = __fmul_rn(alpha, T);
-      const float2 q2 = s_q2[j];
-      C0 = __fmaf_rn(q1.w, w, C0);
-      C1 = __fmaf_rn(q2.x, w, C1);
-      C2 = __fmaf_rn(q2.y, w, C2);
-      Dp = __fmaf_rn(q1.z, w, Dp);
-      if (ALPHA) Ac = __fmaf_rn(1.0f, w, Ac);
-      T = test_T;
-      last_contributor = (uint32_t)(base + j + 1);   // 1-based position in the tile list
-      if (REC) sm.hitw[warp][j] = 1;                 // same value from every contributing lane: benign
+    // Sweep.  `done` pixels skip the whole batch; a pixel that saturates leaves the loop (no per-iteration flag
+    // bookkeeping: the loop body is the kernel, every instruction in it is paid ~150 M times per view).
+    if (!done) {
+      int lastj = -1;
+      for (int k = 0; k < n; k++) {
+        const int j = CULL ? (int)s_list[warp][k] : k;
+        const float4 q0 = s_q0[j];
+        const float dx = q0.x - pixfx, dy = q0.y - pixfy;
+        const float4 q1 = s_q1[j];
+        // -0.5f*(A*dx*dx + C*dy*dy) - B*dx*dy, in the op order nvcc gives that expression
+        const float s = __fmaf_rn(__fmul_rn(q0.z, dx), dx, __fmul_rn(__fmul_rn(q1.x, dy), dy));
+        const float power = __fmaf_rn(s, -0.5f, -__fmul_rn(__fmul_rn(q0.w, dx), dy));
+        if (power > 0.0f) continue;
+        const float alpha = fminf(0.99f, __fmul_rn(q1.y, splat_exp(power)));
+        if (alpha < 1.0f / 255.0f) continue;
+        const float test_T = __fmul_rn(T, 1.0f - alpha);
+        if (test_T < 0.0001f) { done = true; break; }
+        const float w = __fmul_rn(alpha, T);
+        const float2 q2 = make_float2(s_q2[j].x, s_q2[j].y);
+        C0 = __fmaf_rn(q1.w, w, C0);
+        C1 = __fmaf_rn(q2.x, w, C1);
+        C2 = __fmaf_rn(q2.y, w, C2);
+        Dp = __fmaf_rn(q1.z, w, Dp);
+        if (ALPHA) Ac = __fmaf_rn(1.0f, w, Ac);
+        T = test_T;
+        lastj = j;                                     // list order is kept by the compaction: the last one wins
+        if (REC) sm.hitw[warp][j] = 1;                 // same value from every contributing lane: benign
+      }
+      if (lastj >= 0) last_contributor = (uint32_t)(base + lastj + 1);   // 1-based position in the tile list
     }
     if (REC) {
       __syncthreads();
@@ -155,11 +169,16 @@ static bool cull_enabled() {
 void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
                            const SplatRec* rec,
                            const float* bg, float* out_color, float* out_depth, float* out_alpha, float* final_T,
-                           uint32_t* n_contrib, uint8_t* hit, cudaStream_t s) {
+                           uint32_t* n_contrib, uint8_t* hit, GradRec* zero_grad, size_t P, cudaStream_t s) {
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+  // GradRec = 3 x 16 bytes; 32-bit word counts cover P < 2^30 (checked by the caller for num_rendered anyway)
+  float4* const zero16 = (zero_grad && P > 0 && P < ((size_t)1 << 30)) ? reinterpret_cast<float4*>(zero_grad) : nullptr;
+  const uint32_t zero_total = zero16 ? (uint32_t)(P * 3) : 0u;
+  const uint32_t zero_per_cta = zero16 ? (zero_total + (uint32_t)(gx * gy) - 1u) / (uint32_t)(gx * gy) : 0u;
 #define SFB_RF(C, A, R)                                                                                       \
   render_forward_kernel<C, A, R><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, idx_mask, rec, bg, out_color, \
-                                                        out_depth, out_alpha, final_T, n_contrib, hit, refine)
+                                                        out_depth, out_alpha, final_T, n_contrib, hit, refine,  \
+                                                        zero16, zero_per_cta, zero_total)
   const bool cull = cull_enabled();
   static int refine_i = -1;   // SFB_NO_REFINE=1: footprint boxes only (A/B knob)
   if (refine_i < 0) { const char* e = getenv("SFB_NO_REFINE"); refine_i = (e && e[0] == '1') ? 0 : 1; }

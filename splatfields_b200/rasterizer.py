@@ -174,6 +174,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.shapes = tuple(None if t is None else t.shape for t in
                            (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
         ctx.saved_inputs = saved
+        ctx.acc_fresh = [True]      # the forward left the gradient accumulators cleared; true for ONE backward
         ctx.save_for_backward(radii, geom, binning, img)
         ctx.mark_non_differentiable(radii)
         if with_alpha:
@@ -207,6 +208,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         ga = _prep(grad_out_alpha) if (ctx.with_alpha and grad_out_alpha is not None) else None
         if g is None:      # only the alpha image was used downstream
             g = torch.zeros((3, H, W), **f32)
+        flags = _lib.BWD_ACC_FRESH if ctx.acc_fresh[0] else 0
+        ctx.acc_fresh[0] = False    # a second backward on the same buffers (retain_graph) must clear them itself
         if P > 0:
             with torch.cuda.device(dev):
                 stream = torch.cuda.current_stream(dev).cuda_stream
@@ -216,7 +219,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cp), float(rs.tanfovx), float(rs.tanfovy), _ptr(radii),
                     _ptr(geom), _ptr(binning), _ptr(img), _ptr(g), _ptr(ga),
                     _ptr(dL_dmeans2D), _ptr(dL_dcolors), _ptr(dL_dopacity), _ptr(dL_dmeans3D), _ptr(dL_dcov3D),
-                    _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drot), int(bool(rs.debug)), stream)
+                    _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drot), int(bool(rs.debug)), flags, stream)
             _lib.check(rc)
 
         def shaped(t, shape):

@@ -207,3 +207,27 @@ def test_c_abi_argument_errors(cuda_lib):
     with pytest.raises(Exception, match="must have dimensions"):
         GaussianRasterizer(rs)(means3D=z(8, 2), means2D=z(8, 2), opacities=z(8, 1), colors_precomp=z(8, 3),
                                scales=z(8, 3), rotations=z(8, 4))
+
+
+def test_second_backward_on_the_same_buffers(cuda_lib):
+    """The forward render leaves the per-splat gradient accumulators cleared and the FIRST backward relies on it
+    (SFB_BWD_ACC_FRESH); a second backward on the same saved buffers (retain_graph) must clear them itself and give
+    the same gradients — not the sum of both runs."""
+    from splatfields_b200 import render
+    dev = torch.device("cuda:0")
+    P, H, W = 30_000, 160, 208
+    sc = {k: v.to(dev) for k, v in synth.make_scene(P, 21, scale_mult=2.0).items()}
+    cam = synth.orbit_camera(2, H, W).to(dev)
+    leaves = {k: sc[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    gd = dict(means3D=leaves["means3D"], active_sh_degree=3, gaussian_opacity=leaves["opacities"],
+              gaussian_features=leaves["shs"], gaussian_scales=leaves["scales"], gaussian_rotations=leaves["rotations"])
+    out = render(cam, gd, None, torch.ones(3, device=dev), return_opacity=False)
+    G = torch.randn(3, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    loss = (out["render"] * G).sum()
+    g1 = torch.autograd.grad(loss, list(leaves.values()), retain_graph=True)
+    g2 = torch.autograd.grad(loss, list(leaves.values()), retain_graph=False)
+    for name, a, b in zip(leaves, g1, g2):
+        scale = a.abs().max().item()
+        assert scale > 0, name
+        # float atomics reorder between runs: equal up to summation noise, nowhere near a factor of two
+        assert (a - b).abs().max().item() <= 1e-4 * scale, name
