@@ -314,7 +314,7 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
   if (ALPHA && inside) dLpa = dL_dalpha_img[pix];
   const float bg_dot = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
   const float Tf_bg = T_final * bg_dot;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
   // B operand of the colour product: this warp's dL/dC per pixel (row k = lane), split for tf32
@@ -396,8 +396,7 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
     for (int g0 = 0; g0 < nsweep; g0 += MG) {
       const int gn = nsweep - g0 < MG ? nsweep - g0 : MG;
       // ---- phase A: per-pixel chain over up to 16 entries; (sG, w) of every pixel go to the staging rows
-      for (int i = 0; i < gn; i++) {
-        const int j = (int)sm.list[warp][g0 + i];
+      auto entry = [&](const int i, const int j) {
         float sG = 0.f, wgt = 0.f;
         if (j >= jmin) {
           const float4 q0 = sm.q0[j];
@@ -414,24 +413,36 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
               asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - alpha));
               T *= inv;
               wgt = alpha * T;
-              acc0 = fmaf(last_alpha, lc0 - acc0, acc0);
-              acc1 = fmaf(last_alpha, lc1 - acc1, acc1);
-              acc2 = fmaf(last_alpha, lc2 - acc2, acc2);
-              lc0 = q1.w; lc1 = q2.x; lc2 = q2.y;
-              float dL_dalpha = (lc0 - acc0) * dLp0;
-              dL_dalpha = fmaf(lc1 - acc1, dLp1, dL_dalpha);
-              dL_dalpha = fmaf(lc2 - acc2, dLp2, dL_dalpha);
+              // colour accumulated BEHIND this splat: acc <- alpha c + (1 - alpha) acc, applied after its use below
+              // (the reference carries last_alpha / last_color to the next iteration; same values, fewer registers)
+              const float d0 = q1.w - acc0, d1 = q2.x - acc1, d2 = q2.y - acc2;
+              float dL_dalpha = d0 * dLp0;
+              dL_dalpha = fmaf(d1, dLp1, dL_dalpha);
+              dL_dalpha = fmaf(d2, dLp2, dL_dalpha);
+              acc0 = fmaf(alpha, d0, acc0);
+              acc1 = fmaf(alpha, d1, acc1);
+              acc2 = fmaf(alpha, d2, acc2);
               if (ALPHA) {
-                acca = fmaf(last_alpha, 1.f - acca, acca);
-                dL_dalpha = fmaf(1.f - acca, dLpa, dL_dalpha);
+                const float da = 1.f - acca;
+                dL_dalpha = fmaf(da, dLpa, dL_dalpha);
+                acca = fmaf(alpha, da, acca);
               }
               dL_dalpha = fmaf(dL_dalpha, T, -Tf_bg * inv);
-              last_alpha = alpha;
               sG = q1.y * dL_dalpha * G;
             }
           }
         }
         st[i * 32 + (lane ^ ((i & 3) << 2))] = make_float2(sG, wgt);
+      };
+      if (gn == MG) {
+        // full group (the common case): straight-line code, the 16 list bytes come with one 16-byte load and every
+        // staging address is base + immediate
+        const uint4 lw = *reinterpret_cast<const uint4*>(&sm.list[warp][g0]);
+        const uint32_t lws[4] = {lw.x, lw.y, lw.z, lw.w};
+#pragma unroll
+        for (int i = 0; i < MG; i++) entry(i, (int)((lws[i >> 2] >> (8 * (i & 3))) & 0xffu));
+      } else {
+        for (int i = 0; i < gn; i++) entry(i, (int)sm.list[warp][g0 + i]);
       }
       for (int i = gn; i < MG; i++) st[i * 32 + lane] = make_float2(0.f, 0.f);   // rows without an entry (last group)
       __syncwarp();

@@ -170,5 +170,7 @@ def test_densify_stats_vs_torch_statements_200k(cuda_lib):
     for _ in range(2):
         densify.add_densification_stats(acc_a, den_a, grad, radii=radii, max_radii2D=mr_a)
         TR.add_densification_stats(acc_b, den_b, mr_b, grad, radii)
-    assert torch.equal(acc_a, acc_b) and torch.equal(den_a, den_b) and torch.equal(mr_a, mr_b)
+    assert torch.equal(den_a, den_b) and torch.equal(mr_a, mr_b)
+    # the norm: same formula, rounded at most one ulp apart (torch.norm's CUDA reduction may round differently)
+    assert (acc_a - acc_b).abs().max().item() <= 2.5e-7 * acc_b.abs().max().item()
     assert int(den_a.sum().item()) == 2 * int((radii > 0).sum().item()) > 0
