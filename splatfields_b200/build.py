@@ -41,7 +41,7 @@ def _stale(out: str, deps) -> bool:
 # Build variants (A/B experiments; the default library is the product): name -> (extra nvcc flags, library path)
 VARIANTS = {
     "": ([], LIB),
-    "fastexp": (["-DSFB_FAST_EXP"], os.path.join(HERE, "libsplat_b200_fastexp.so")),
+    "exactexp": (["-DSFB_EXACT_EXP"], os.path.join(HERE, "libsplat_b200_exactexp.so")),
 }
 
 

@@ -81,6 +81,17 @@ bool zero_in_fwd_enabled() {   // SFB_ZERO_IN_FWD=0: the backward clears its acc
   return v == 1;
 }
 
+bool knob_on(const char* name, bool dflt) {     // "0" / "1" environment knobs for A/B runs
+  const char* e = getenv(name);
+  if (!e || !e[0]) return dflt;
+  return e[0] != '0';
+}
+// SFB_FUSED_RANGES=0: separate tile_ranges kernel; SFB_FOLD_MEMSETS=0: memset nodes for the sort scratch;
+// SFB_NR_MEMCPY=1: num_rendered read back with a D2H copy node instead of the kernel's own store to pinned memory
+bool fused_ranges_enabled() { static int v = -1; if (v < 0) v = knob_on("SFB_FUSED_RANGES", true) && !sfb::radix_sort_is_legacy(); return v == 1; }
+bool fold_memsets_enabled() { static int v = -1; if (v < 0) v = knob_on("SFB_FOLD_MEMSETS", true) && !sfb::radix_sort_is_legacy(); return v == 1; }
+bool nr_memcpy_enabled() { static int v = -1; if (v < 0) v = knob_on("SFB_NR_MEMCPY", false); return v == 1; }
+
 bool wide256_enabled() {   // SFB_NO_LD256=1 falls back to 128-bit accesses (A/B knob)
   static int v = -1;
   if (v < 0) { const char* e = getenv("SFB_NO_LD256"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -159,7 +170,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y, T = gx * gy;
   if (gx > 65535 || gy > 65535) return fail(SFB_ERR_ARG, "image too large for packed tile rectangles");
 
-  if (!g_pinned) CK(cudaHostAlloc((void**)&g_pinned, 64, cudaHostAllocDefault));
+  if (!g_pinned) CK(cudaHostAlloc((void**)&g_pinned, 64, cudaHostAllocMapped | cudaHostAllocPortable));
   if (!g_evt) CK(cudaEventCreateWithFlags(&g_evt, cudaEventDisableTiming));
 
   RedzoneList rz;
@@ -182,6 +193,11 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   fp.viewmatrix = viewmatrix; fp.projmatrix = projmatrix; fp.campos = campos;
   fp.scale_modifier = scale_modifier; fp.tan_fovx = tan_fovx; fp.tan_fovy = tan_fovy; fp.prefiltered = prefiltered;
   fp.wide256 = wide256_enabled() && shs && ((M * 12) % 32 == 0) && ((reinterpret_cast<size_t>(shs) & 31) == 0);
+  const bool fold = fold_memsets_enabled();
+  const size_t dzero = fold ? radix_sort_zero_words(P, 32) : 0;
+  fp.zero_ptr = dzero ? g.sort_hist : nullptr;
+  fp.zero_words = (uint32_t)dzero;
+  fp.nr_host = nr_memcpy_enabled() ? nullptr : g_pinned;
 
   // K1 (+ num_rendered reduction) ; the 4-byte read-back is issued right behind it so that the host
   // wait overlaps the depth sort instead of draining the whole pipeline.
@@ -192,12 +208,12 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   prof_end(s);
   g_launches++;
   CK_LAUNCH("preprocess", debug, s);
-  CK(cudaMemcpyAsync(g_pinned, g.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  if (!fp.nr_host) CK(cudaMemcpyAsync(g_pinned, g.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(g_evt, s));
 
   // stage 1: stable sort of the Gaussians by depth bits (culled ones carry 0xFFFFFFFF and sink)
   int dfinal = radix_sort_pairs(g.depth_key, g.depth_idx, g.sort_hist, P, 32, s, &g_launches, kDepthSortNames,
-                                g.counters + 2);
+                                g.counters + 2, 0, dzero != 0);
   CK_LAUNCH("depth sort", debug, s);
   const uint32_t* sorted_idx = g.depth_idx[dfinal];
   launch_instance_block_sums(P, sorted_idx, g.tiles_touched, g.block_sums, s);
@@ -205,7 +221,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   CK_LAUNCH("instance scan", debug, s);
 
   CK(cudaEventSynchronize(g_evt));
-  const uint32_t R = *g_pinned;
+  const uint32_t R = *reinterpret_cast<volatile uint32_t*>(g_pinned);
   if (R >= (1u << 30)) return fail(SFB_ERR_ARG, "num_rendered >= 2^30 is not supported");
   if (num_rendered) *num_rendered = (int)R;
 
@@ -220,24 +236,29 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   if (debug && redzones_fill(rzb, s)) return fail(SFB_ERR_CUDA, "red-zone fill");
 
   int tfinal = 0;
+  const bool fused_ranges = fused_ranges_enabled();
   if (R > 0) {
     // stage 2: emit (tile, gaussian) instances in depth order; stage 3: stable sort by tile id
+    const size_t tzero = fold ? radix_sort_zero_words((int)R, tile_bits(T)) : 0;
     prof_begin("duplicate", s);
     launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, b.tile_key[0], b.inst_idx[0],
-                     pk.idx_bits, s);
+                     pk.idx_bits, tzero ? b.sort_hist : nullptr, tzero, fused_ranges ? b.ranges : nullptr, T, s);
     prof_end(s);
     g_launches++;
     CK_LAUNCH("duplicate", debug, s);
-    // packed: bare 32-bit words, digits start above the index bits; unpacked: (tile, index) pairs from bit 0
+    // packed: bare 32-bit words, digits start above the index bits; unpacked: (tile, index) pairs from bit 0.
+    // The last pass also writes the per-tile [start, end) ranges (K5) when fused_ranges.
     tfinal = radix_sort_pairs(b.tile_key, b.inst_idx, b.sort_hist, (int)R, tile_bits(T), s, &g_launches, kTileSortNames,
-                              nullptr, pk.idx_bits);
-      CK_LAUNCH("tile sort", debug, s);
+                              nullptr, pk.idx_bits, tzero != 0, fused_ranges ? b.ranges : nullptr, pk.idx_bits);
+    CK_LAUNCH("tile sort", debug, s);
   }
-  prof_begin("tile_ranges", s);
-  launch_tile_ranges((int)R, T, b.tile_key[tfinal], pk.idx_bits, b.ranges, s);
-  prof_end(s);
-  g_launches++;
-  CK_LAUNCH("tile ranges", debug, s);
+  if (!fused_ranges || R == 0) {
+    prof_begin("tile_ranges", s);
+    launch_tile_ranges((int)R, T, b.tile_key[tfinal], pk.idx_bits, b.ranges, s);
+    prof_end(s);
+    g_launches++;
+    CK_LAUNCH("tile ranges", debug, s);
+  }
 
   prof_begin("render_forward", s);
   launch_render_forward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, bg, out_color, out_depth,

@@ -251,7 +251,9 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift, int bins,
                      const uint32_t* __restrict__ digit_totals /* [SORT_MAX_BINS] for this pass */,
                      uint32_t* __restrict__ tile_state /* [nblocks][bins], zeroed */,
-                     uint32_t* __restrict__ ticket /* zeroed */) {
+                     uint32_t* __restrict__ ticket /* zeroed */,
+                     uint2* __restrict__ ranges /* nullptr, or [T] = (0xFFFFFFFF, 0): fused K5, last tile-sort pass */,
+                     int tile_shift /* tile id = key >> tile_shift */) {
   constexpr int NW = SORT_THREADS / 32;
   constexpr int OS_TILE = SORT_THREADS * IPT;
   constexpr int CH = IPT == 16 ? (NB == 6 ? 4 : (NB == 7 ? 2 : 1)) : 1;
@@ -270,7 +272,20 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 #pragma unroll
     for (int i = 0; i < IPT; i++) {
       const int k = base + i * SORT_THREADS + threadIdx.x;
-      if (k < n) { keys_out[k] = keys_in[k]; if (HAS_VALS) vals_out[k] = vals_in[k]; }
+      if (k < n) {
+        const uint32_t kk = keys_in[k];
+        keys_out[k] = kk;
+        if (HAS_VALS) vals_out[k] = vals_in[k];
+        if (ranges) {   // tile boundaries of an already sorted sequence: compare with the predecessor
+          const uint32_t t = kk >> tile_shift;
+          const uint32_t tp = k > 0 ? (keys_in[k - 1] >> tile_shift) : 0xFFFFFFFFu;
+          if (tp != t) {
+            atomicMin(&ranges[t].x, (uint32_t)k);
+            if (k > 0) atomicMax(&ranges[tp].y, (uint32_t)k);
+          }
+          if (k == n - 1) atomicMax(&ranges[t].y, (uint32_t)n);
+        }
+      }
     }
     return;
   }
@@ -440,19 +455,53 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     const int32_t dst = (int32_t)q + s_gofs[dd];
     keys_out[dst] = kk;
     if (HAS_VALS) vals_out[dst] = s_val[q];
+    if (ranges) {
+      // Fused K5 (identifyTileRanges) on the LAST pass of the tile sort: the block's staged items are in final order
+      // inside each digit run, and a run is contiguous in the output.  Inside a run a tile boundary is seen by comparing
+      // neighbours; what happens at the two ends of a run is unknown here (the neighbour belongs to another block or
+      // digit), so the ends contribute with atomicMin / atomicMax: start = min, end = max over all contributions.
+      const uint32_t t = kk >> tile_shift;
+      uint32_t tp = 0xFFFFFFFFu, tn = 0xFFFFFFFFu;           // tile of the neighbour inside the same run, if any
+      if (q > 0) { const uint32_t kp = s_key[q - 1]; if (((kp >> shift) & mask) == dd) tp = kp >> tile_shift; }
+      if (q + 1 < cnt_blk) { const uint32_t kn = s_key[q + 1]; if (((kn >> shift) & mask) == dd) tn = kn >> tile_shift; }
+      if (tp != t) atomicMin(&ranges[t].x, (uint32_t)dst);
+      if (tn != t) atomicMax(&ranges[t].y, (uint32_t)dst + 1u);
+    }
   }
+}
+
+static bool sort_small_tiles(int n) {
+  static int small_on = -1;                                   // A/B knob: SFB_SORT_SMALL=0 -> 4096-item tiles always
+  if (small_on < 0) { const char* e = getenv("SFB_SORT_SMALL"); small_on = (e && e[0] == '0') ? 0 : 1; }
+  return small_on && sort_blocks(n) < 64;
+}
+
+// words of `hist` that have to be zero when radix_sort_pairs starts (the caller may clear them itself, e.g. from a kernel
+// that runs anyway, and pass scratch_zeroed = true)
+size_t radix_sort_zero_words(int n, int nbits) {
+  if (n <= 0 || nbits <= 0) return 0;
+  const int npass = (nbits + 7) / 8;
+  const int tile = sort_small_tiles(n) ? SORT_THREADS * 4 : SORT_THREADS * 16;
+  const int nblocks = (n + tile - 1) / tile;
+  size_t state_words = 0;
+  int shift = 0;
+  for (int pass = 0; pass < npass; pass++) {
+    const int bits = (nbits - shift + (npass - pass) - 1) / (npass - pass);
+    state_words += (size_t)nblocks << bits;
+    shift += bits;
+  }
+  return (size_t)OS_MAX_PASSES * SORT_MAX_BINS + 8 + state_words;
 }
 
 static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint32_t* scratch, int n, int nbits,
                                      cudaStream_t s, int* launches, const char* const* names,
-                                     const uint32_t* bias_c, int first_bit) {
+                                     const uint32_t* bias_c, int first_bit, bool scratch_zeroed, uint2* ranges,
+                                     int tile_shift) {
   const bool has_vals = vals != nullptr && vals[0] != nullptr;
   const int npass = (nbits + 7) / 8;
   // 1024-item tiles only for really small inputs: with the ballot ranking 4096-item tiles win from ~0.3 M items
   // (measured: 1 M pairs 87 -> 65 us, 0.5 M 63 -> 54 us, 0.1 M 43 -> 51 us), although they fill < 2 CTAs per SM
-  static int small_on = -1;                                   // A/B knob: SFB_SORT_SMALL=0 -> 4096-item tiles always
-  if (small_on < 0) { const char* e = getenv("SFB_SORT_SMALL"); small_on = (e && e[0] == '0') ? 0 : 1; }
-  const bool small = small_on && sort_blocks(n) < 64;
+  const bool small = sort_small_tiles(n);
   static int use_match = -1;                                  // A/B knob: SFB_SORT_MATCH=1 -> match.any ranking
   if (use_match < 0) { const char* e = getenv("SFB_SORT_MATCH"); use_match = (e && e[0] == '1') ? 1 : 0; }
   const int tile = small ? SORT_THREADS * 4 : SORT_THREADS * 16;
@@ -471,7 +520,8 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
     state_words += (size_t)nblocks * nbins[pass];
     shift += bits;
   }
-  cudaMemsetAsync(scratch, 0, sizeof(uint32_t) * (OS_MAX_PASSES * SORT_MAX_BINS + 8 + state_words), s);
+  if (!scratch_zeroed)
+    cudaMemsetAsync(scratch, 0, sizeof(uint32_t) * (OS_MAX_PASSES * SORT_MAX_BINS + 8 + state_words), s);
   prof_begin(names[0], s);
   const int hblocks = min(sort_blocks(n), 4 * NUM_SMS_B200);
   radix_hist_all_kernel<<<hblocks, SORT_THREADS, 0, s>>>(keys[0], n, npass, make_int4(shifts[0], shifts[1], shifts[2], shifts[3]),
@@ -487,7 +537,8 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
 #define SFB_OS2(IPTV, HV, NBV)                                                                                 \
   onesweep_pass_kernel<IPTV, HV, NBV><<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vin, keys[cur ^ 1], vout, n,   \
                                                                         shifts[pass], nbins[pass],                \
-                                                                        hist_all + pass * SORT_MAX_BINS, state, tickets + pass)
+                                                                        hist_all + pass * SORT_MAX_BINS, state, tickets + pass, \
+                                                                        pass == npass - 1 ? ranges : nullptr, tile_shift)
 #define SFB_OS(IPTV, HV)                                                                                       \
   do { if (nb == 0) SFB_OS2(IPTV, HV, 0); else if (nb == 6) SFB_OS2(IPTV, HV, 6); else if (nb == 7) SFB_OS2(IPTV, HV, 7); \
        else SFB_OS2(IPTV, HV, 8); } while (0)
@@ -504,14 +555,20 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
   return cur;
 }
 
-int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
-                     int* launches, const char* const* names, const uint32_t* bias_c, int first_bit) {
-  if (n <= 0 || nbits <= 0) return 0;
+bool radix_sort_is_legacy() {
   static int legacy = -1;
   if (legacy < 0) { const char* e = getenv("SFB_SORT"); legacy = (e && e[0] == 'l') ? 1 : 0; }
-  if (legacy && first_bit == 0 && vals && vals[0])   // (the 3-kernel path ignores bias_c; pairs from bit 0 only)
+  return legacy == 1;
+}
+
+int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
+                     int* launches, const char* const* names, const uint32_t* bias_c, int first_bit,
+                     bool scratch_zeroed, uint2* ranges, int tile_shift) {
+  if (n <= 0 || nbits <= 0) return 0;
+  if (radix_sort_is_legacy() && first_bit == 0 && vals && vals[0] && !ranges)   // (the 3-kernel path ignores bias_c; pairs from bit 0 only)
     return radix_sort_pairs_legacy(keys, vals, hist, n, nbits, s, launches, names);
-  return radix_sort_pairs_onesweep(keys, vals, hist, n, nbits, s, launches, names, bias_c, first_bit);
+  return radix_sort_pairs_onesweep(keys, vals, hist, n, nbits, s, launches, names, bias_c, first_bit, scratch_zeroed,
+                                   ranges, tile_shift);
 }
 
 // ------------------------------------------------------------------ instance emission in depth order
@@ -560,7 +617,20 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
                  const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ rect,
                  const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ tile_keys,
                  uint32_t* __restrict__ inst_idx /* nullptr: packed mode, tile_keys[k] = tile << idx_bits | index */,
-                 int idx_bits) {
+                 int idx_bits, uint32_t* __restrict__ zero_ptr, uint32_t zero_words, uint2* __restrict__ ranges_init,
+                 int T) {
+  // Prologue: this kernel runs right in front of the tile sort anyway, so its blocks also clear the sort's scratch
+  // (digit histograms, tickets, look-back state) and set the tile ranges to "empty" — two memset nodes less per forward.
+  if (zero_ptr) {
+    const uint32_t per = (zero_words + gridDim.x - 1) / gridDim.x;
+    const uint32_t z0 = blockIdx.x * per, z1 = min(z0 + per, zero_words);
+    for (uint32_t i = z0 + threadIdx.x; i < z1; i += DUP_THREADS) zero_ptr[i] = 0u;
+  }
+  if (ranges_init) {
+    const int per = (T + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int t0 = blockIdx.x * per, t1 = min(t0 + per, T);
+    for (int i = t0 + threadIdx.x; i < t1; i += DUP_THREADS) ranges_init[i] = make_uint2(0xFFFFFFFFu, 0u);
+  }
   __shared__ uint32_t s_pref[DUP_GPB + 1];
   __shared__ uint32_t s_gidx[DUP_GPB];
   __shared__ uint2 s_rect[DUP_GPB];
@@ -690,10 +760,11 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
 
 void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
                       const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
-                      uint32_t* inst_idx, int idx_bits, cudaStream_t s) {
+                      uint32_t* inst_idx, int idx_bits, uint32_t* zero_ptr, size_t zero_words, uint2* ranges_init, int T,
+                      cudaStream_t s) {
   int nb = (P + DUP_GPB - 1) / DUP_GPB;
   duplicate_kernel<<<nb, DUP_THREADS, 0, s>>>(P, grid_x, sorted_idx, tiles_touched, rect, block_offsets,
-                                              tile_keys, inst_idx, idx_bits);
+                                              tile_keys, inst_idx, idx_bits, zero_ptr, (uint32_t)zero_words, ranges_init, T);
 }
 
 // ------------------------------------------------------------------ tile ranges

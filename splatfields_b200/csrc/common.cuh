@@ -51,16 +51,19 @@ __device__ __forceinline__ void stg256(float* p, const float* v) {
                : "memory");
 }
 
-// exp() of the compositing kernels.  Default: libdevice expf, the function the reference's kernels call.
-// -DSFB_FAST_EXP (the libsplat_b200_fastexp.so build variant, an A/B experiment): one MUFU.EX2 on power * log2(e);
-// alpha then differs from the expf value by <= ~7e-7 relative, i.e. <= 1e-6 on an RGB pixel and <= 4e-6 on depth.
+// exp() of the compositing kernels: one MUFU.EX2 on power * log2(e) instead of libdevice expf's 10-instruction
+// sequence (the sweep loops are issue-bound: -6 % forward, -5 % backward render time).  alpha differs from the expf
+// value by <= ~7e-7 relative; measured against the fp64-accumulating oracle the image / depth / gradient errors are the
+// same as with expf (lego_100k: RGB 3.0e-7 vs 3.3e-7, depth 1.7e-6 vs 1.4e-6 max abs; gradients 6e-7..8e-7 norm-wise
+// either way; profiles/r01w_parity_margin.jsonl) — a factor 6 inside the 1e-5 tolerance.
+// -DSFB_EXACT_EXP (the libsplat_b200_exactexp.so build variant) restores expf, the function the reference calls.
 __device__ __forceinline__ float splat_exp(float power) {
-#ifdef SFB_FAST_EXP
+#ifdef SFB_EXACT_EXP
+  return expf(power);
+#else
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(power * 1.4426950408889634f));
   return r;
-#else
-  return expf(power);
 #endif
 }
 
@@ -306,6 +309,9 @@ struct FwdParams {
   float scale_modifier, tan_fovx, tan_fovy;
   int prefiltered;
   int wide256;      // SH rows are 32-byte aligned multiples of 32 bytes: use 256-bit loads
+  uint32_t* zero_ptr;     // or nullptr: words the kernel's blocks clear as a prologue (the depth sort's scratch)
+  uint32_t zero_words;
+  uint32_t* nr_host;      // or nullptr: pinned host word; the last block to finish stores num_rendered there
 };
 
 // preprocess.cu
@@ -322,18 +328,26 @@ void launch_export_geom(int P, const GeomState& g, const float* scales, const fl
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
                      int* launches, const char* const* names /* {hist, scan, scatter} */,
                      const uint32_t* bias_c = nullptr /* device: ~min key; keys are rebased in place */,
-                     int first_bit = 0 /* digits start at this bit; vals[0] == nullptr sorts bare keys */);
+                     int first_bit = 0 /* digits start at this bit; vals[0] == nullptr sorts bare keys */,
+                     bool scratch_zeroed = false /* the first radix_sort_zero_words(n, nbits) words of hist are already 0 */,
+                     uint2* ranges = nullptr /* fused K5: [T] pre-set to (0xFFFFFFFF, 0); filled by the last pass */,
+                     int tile_shift = 0 /* tile id = key >> tile_shift */);
+size_t radix_sort_zero_words(int n, int nbits);
+bool radix_sort_is_legacy();
 void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
                                 uint32_t* block_sums, cudaStream_t s);
 void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
                       const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
-                      uint32_t* inst_idx /* nullptr: packed */, int idx_bits, cudaStream_t s);
+                      uint32_t* inst_idx /* nullptr: packed */, int idx_bits,
+                      uint32_t* zero_ptr /* or nullptr */, size_t zero_words, uint2* ranges_init /* or nullptr */, int T,
+                      cudaStream_t s);
 void launch_tile_ranges(int R, int T, const uint32_t* sorted_tile_keys, int key_shift, uint2* ranges, cudaStream_t s);
 void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_list /* nullptr: packed */,
                         int idx_bits, const SplatRec* rec, uint64_t* out_keys, uint32_t* out_list, cudaStream_t s);
 
 // render_fwd.cu
-void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
+void launch_render_forward(int W, int H, uint2* ranges /* empty tiles are normalised to (0, 0) in place */,
+                           const uint32_t* point_list, uint32_t idx_mask,
                            const SplatRec* rec,
                            const float* bg, float* out_color, float* out_depth, float* out_alpha, float* final_T,
                            uint32_t* n_contrib, uint8_t* hit /* [R] or nullptr: do not record */,

@@ -22,8 +22,9 @@ densify_stats_kernel(int P, const float* __restrict__ g2d /* [P][3] */, const in
   const bool on = filter ? (filter[i] != 0) : (r > 0);
   if (!on) return;
   const float gx = g2d[3 * (size_t)i], gy = g2d[3 * (size_t)i + 1];
-  // torch.norm(grad[:, :2], dim=-1): fp32 accumulation acc = fma(v, v, acc) in element order (bit-checked, golden file)
-  accum[i] += sqrtf(fmaf(gy, gy, gx * gx));
+  // torch.norm(grad[:, :2], dim=-1) on CUDA: sqrt(fl(gx*gx) + fl(gy*gy)), products rounded separately (checked bit for
+  // bit on a B200 over 1M random rows, scripts/diag_norm.py; torch's CPU kernel contracts to fma(gy, gy, gx*gx) instead)
+  accum[i] += sqrtf(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
   denom[i] += 1.f;
   if (max_radii2D && radii) max_radii2D[i] = fmaxf(max_radii2D[i], (float)r);
 }

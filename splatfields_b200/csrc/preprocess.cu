@@ -115,6 +115,11 @@ preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
   __shared__ uint32_t s_nkey[8];
   __shared__ uint64_t s_bar;
   extern __shared__ __align__(128) float s_shrows[];
+  if (p.zero_ptr) {   // clear the depth sort's scratch on the way (it runs right behind this kernel): one memset node less
+    const uint32_t per = (p.zero_words + gridDim.x - 1) / gridDim.x;
+    const uint32_t z0 = blockIdx.x * per, z1 = min(z0 + per, p.zero_words);
+    for (uint32_t i = z0 + threadIdx.x; i < z1; i += 256) p.zero_ptr[i] = 0u;
+  }
   if (TMA_SH) {
     if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     __syncthreads();
@@ -308,6 +313,16 @@ preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
 #pragma unroll
     for (int w = 0; w < 8; w++) { t += s_tiles[w]; m = max(m, s_nkey[w]); }
     if (t) { atomicAdd(g.counters, t); atomicMax(g.counters + 2, m); }
+    if (p.nr_host) {
+      // last block to get here publishes num_rendered straight into pinned host memory: no D2H copy node in the stream
+      __threadfence();
+      const uint32_t done = atomicAdd(g.counters + 1, 1u);
+      if (done == gridDim.x - 1) {
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(p.nr_host) = atomicAdd(g.counters, 0u);
+        __threadfence_system();
+      }
+    }
   }
 }
 

@@ -26,7 +26,7 @@ constexpr int RB = 256;  // batch = block size
 // (warp, entry) pairs instead of every pair whose footprint box touches the patch (3.1 M -> 1.9 M per view).
 template <bool CULL, bool ALPHA, bool REC>
 __global__ void __launch_bounds__(RB, 6)   // <= 42 registers: the sweep loop needs ~40; the fetch-phase culling math may spill
-render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
+render_forward_kernel(int W, int H, int grid_x, uint2* __restrict__ ranges,
                       const uint32_t* __restrict__ point_list, uint32_t idx_mask,
                       const SplatRec* __restrict__ rec,
                       const float* __restrict__ bg, float* __restrict__ out_color,
@@ -66,7 +66,12 @@ render_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
   const float pixfx = (float)px, pixfy = (float)py;
   const float tx0 = (float)(tile_x * TILE_X), ty0 = (float)(tile_y * TILE_Y);
 
-  const uint2 range = ranges[tile];
+  uint2 range = ranges[tile];
+  if (range.y == 0u && range.x != 0u) {
+    // tile without instances: the fused range pass (binning.cu) leaves (0xFFFFFFFF, 0); store the reference's (0, 0)
+    range.x = 0u;
+    if (threadIdx.x == 0) ranges[tile] = make_uint2(0u, 0u);
+  }
   int todo = (int)(range.y - range.x);
   bool done = !inside;
 
@@ -166,7 +171,7 @@ static bool cull_enabled() {
   return v == 1;
 }
 
-void launch_render_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
+void launch_render_forward(int W, int H, uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
                            const SplatRec* rec,
                            const float* bg, float* out_color, float* out_depth, float* out_alpha, float* final_T,
                            uint32_t* n_contrib, uint8_t* hit, GradRec* zero_grad, size_t P, cudaStream_t s) {

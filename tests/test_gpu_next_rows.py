@@ -134,10 +134,16 @@ def test_densify_matches_reference_golden(key, cuda_lib):
             densify.add_densification_stats(acc, den, grad, update_filter=radii > 0, radii=radii, max_radii2D=mr)
         else:
             densify.add_densification_stats(acc, den, grad, radii=radii, max_radii2D=mr)
-        assert np.array_equal(acc.cpu().numpy(), GOLD[f"{key}.view{v}.accum"])
+        # CPU-torch golden: the norm may round one ulp differently from the GPU formula (fma vs separate products)
+        ga = GOLD[f"{key}.view{v}.accum"]
+        assert np.abs(acc.cpu().numpy() - ga).max() <= 2.5e-7 * np.abs(ga).max()
         assert np.array_equal(den.cpu().numpy(), GOLD[f"{key}.view{v}.denom"])
         assert np.array_equal(mr.cpu().numpy(), GOLD[f"{key}.view{v}.max_radii2D"])
     thr, pd, ext, mino, mss = (float(x) for x in GOLD[f"{key}.params"])
+    # the predicates are compared on the golden statistics themselves (a one-ulp difference in accum could flip a
+    # Gaussian sitting exactly on the gradient threshold)
+    acc = torch.from_numpy(GOLD[f"{key}.view2.accum"]).to(dev)
+    den = torch.from_numpy(GOLD[f"{key}.view2.denom"]).to(dev)
     raw_s, raw_o = torch.from_numpy(GOLD[f"{key}.raw_scaling"]).to(dev), torch.from_numpy(GOLD[f"{key}.raw_opacity"]).to(dev)
     for raw in (True, False):
         s = raw_s if raw else torch.exp(raw_s)
@@ -170,7 +176,6 @@ def test_densify_stats_vs_torch_statements_200k(cuda_lib):
     for _ in range(2):
         densify.add_densification_stats(acc_a, den_a, grad, radii=radii, max_radii2D=mr_a)
         TR.add_densification_stats(acc_b, den_b, mr_b, grad, radii)
-    assert torch.equal(den_a, den_b) and torch.equal(mr_a, mr_b)
-    # the norm: same formula, rounded at most one ulp apart (torch.norm's CUDA reduction may round differently)
-    assert (acc_a - acc_b).abs().max().item() <= 2.5e-7 * acc_b.abs().max().item()
+    # bit for bit what the reference's statements give on this GPU (torch.norm on CUDA rounds the products separately)
+    assert torch.equal(acc_a, acc_b) and torch.equal(den_a, den_b) and torch.equal(mr_a, mr_b)
     assert int(den_a.sum().item()) == 2 * int((radii > 0).sum().item()) > 0
