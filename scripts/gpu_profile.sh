@@ -11,7 +11,7 @@ KERNELS='preprocess_kernel|radix_hist_all_kernel|onesweep_pass_kernel|instance_b
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
 echo "launch list rows: $(wc -l < $OUT/launches.csv)"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$KERNELS" -s 48 -c 16 -f -o $OUT/prof \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$KERNELS" -s 45 -c 15 -f -o $OUT/prof \
     python scripts/quick_perf.py --config lego_1m --iters 1 --warmup 3 > $OUT/ncu_full.log 2>&1
 tail -2 $OUT/ncu_full.log | cut -c1-200
 ncu -i $OUT/prof.ncu-rep --page raw --csv > $OUT/ncu_raw.csv 2>/dev/null
