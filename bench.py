@@ -6,8 +6,10 @@
 
 One "step" = one forward + backward pass of the rasterizer over the workload BASELINE.json's metric is
 quoted on: 1 000 000 synthetic Gaussians, 800x800, SH degree 3 (configs[2], "lego_1m"), one camera per
-rank (view-parallel, splats replicated), followed for N > 1 by ONE NCCL all-reduce (sum) of the flat
-per-splat gradient slab [P, 59].  metric = Msplats/s = N * P / t_step.
+rank (view-parallel, splats replicated), followed for N > 1 by the exchange that sums the per-splat gradient
+slab [P, 59] over the ranks (default: all-gather of the [P, 3] colour gradients + all-reduce of the [P, 11]
+geometry gradients, SH rows rebuilt on every rank; SFB_EXCHANGE=allreduce: one all-reduce of the whole slab).
+metric = Msplats/s = N * P / t_step.
 
 Printed by rank 0 as one JSON line.  Extra objects: roofline (dominant kernel, live CUDA-event timing on
 the launching stream), cpu_baseline (the oracle port timed on the host cores, N=1 only), e2e (same metric
@@ -287,6 +289,7 @@ def run_ours(args):
     # only rank 0 records and reads the per-kernel events.
     if rank == 0:
         _lib.profile_enable(True)
+    vp.time_exchange = True
     for _ in range(nprof):
         vp.step(Gd)
         torch.cuda.synchronize()
@@ -294,6 +297,8 @@ def run_ours(args):
             for which in (0, 1):
                 for name, ms in _lib.profile_read(which):
                     acc.setdefault(name, []).append(ms)
+    vp.time_exchange = False
+    exch_ms = vp.exchange_ms()
     if rank == 0:
         _lib.profile_enable(False)
     sync_all()
@@ -348,11 +353,19 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "P": P, "H": H, "W": W, "sh_degree": SH_DEGREE,
-                       "parallelism": f"view-parallel x{world} (one camera per GPU, splats replicated, "
-                                      f"1 all-reduce of [P,59] fp32 grads)" if world > 1 else "single view",
+                       "parallelism": (f"view-parallel x{world} (one camera per GPU, splats replicated; gradient "
+                                       f"exchange: " + ("all-gather of [P,3] colour gradients + all-reduce of [P,11] "
+                                                        "geometry gradients, SH rows rebuilt per rank"
+                                                        if vp.exchange == "factored" else
+                                                        "1 all-reduce of [P,59] fp32 grads") + ")")
+                       if world > 1 else "single view",
                        "l2": "inputs larger than L2 (236 MB of splat parameters + 0.5 GB of scratch per step "
                              "vs 126 MB L2)"},
             "views_per_s": world / (ms_step * 1e-3), "host_enqueue_ms_per_step": host_enqueue_ms,
+            "exchange": None if world == 1 else {
+                "mode": vp.exchange, "ms_per_step": float(np.mean(exch_ms)) if exch_ms else None,
+                "wire_bytes_per_splat_per_rank": vp.bytes_on_wire_per_splat(),
+                "note": "device time from the first collective to the end of the exchange on rank 0 (profiled steps)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "stages": stages,
         }

@@ -77,6 +77,11 @@ int sfb_rasterize_forward(
  * (the forward leaves the per-splat gradient accumulators inside geom_buffer cleared, so the backward can skip its
  * 48 B/Gaussian memset); pass 0 when in doubt or when running backward again on the same buffers (retain_graph). */
 #define SFB_BWD_ACC_FRESH 1
+/* SFB_BWD_SH_FACTORED (with shs): dL_dcolors (required) receives the gradient w.r.t. the SH-evaluated colour BEFORE its
+ * max(0, .) clamp — i.e. the render backward's colour gradient with the clamped channels zeroed — and dL_dsh may be
+ * NULL (not written).  dL_dsh[i][k][c] = basis_k(normalize(means3D[i] - campos)) * dL_dcolors[i][c]: the view-parallel
+ * trainer exchanges these 3 floats per Gaussian and view instead of the 3*M-float rows (sfb_sh_grad_combine). */
+#define SFB_BWD_SH_FACTORED 2
 int sfb_rasterize_backward(
     int P, int sh_degree, int M, int num_rendered, int W, int H,
     const float* bg, const float* means3D, const float* shs, const float* colors_precomp,
@@ -88,6 +93,15 @@ int sfb_rasterize_backward(
     float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D, float* dL_dcov3D,
     float* dL_dsh, float* dL_dscales, float* dL_drotations,
     int debug, int flags, void* stream);
+
+/* Multi-view sum of SH gradients from their factored form (view-parallel training; the serial loop
+ * it replaces is train.py:169-242, whose loss.backward() accumulates the V per-view dL_dsh into features.grad):
+ *     dL_dsh[i][k][c] = sum_{v < V} basis_k(normalize(means3D[i] - campos[v])) * dL_dcolor_views[v][i][c]
+ * basis = the real SH basis of utils/sh_utils.py:57-112 up to sh_degree; coefficients k >= (sh_degree+1)^2 of the
+ * [P][M][3] output are written as 0.  campos [V][3] (device), dL_dcolor_views [V][P][3] = the dL_dcolors outputs of
+ * V backward calls run with SFB_BWD_SH_FACTORED.  1 <= V <= 64.  Views are summed in index order (reproducible). */
+int sfb_sh_grad_combine(int P, int V, int sh_degree, int M, const float* means3D, const float* campos,
+                        const float* dL_dcolor_views, float* dL_dsh, void* stream);
 
 /* Replaces _C.mark_visible: present[i] = 1 iff the view-space z of means3D[i] is > 0.2. */
 int sfb_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -38,6 +38,25 @@ def sh_basis(deg: int, d: torch.Tensor) -> torch.Tensor:
     return torch.stack(b, dim=1)
 
 
+def sh_grad_combine_ref(means3D, campos_views, dcolor_views, deg: int, M: int) -> torch.Tensor:
+    """fp64 restatement of sfb_sh_grad_combine: the multi-view sum of SH gradients from their factored form,
+        dL_dsh[i, k, :] = sum_v basis_k(normalize(means3D[i] - campos_views[v])) * dcolor_views[v, i, :],
+    i.e. what loss.backward() over the serial per-view loop of train.py:169-242 accumulates in features.grad when
+    the colour of view v is eval_sh(deg, shs, dir_v) (utils/sh_utils.py:57-112; extract_geo.py:40-44) and
+    dcolor_views[v] is its gradient before the max(0, .) clamp.  Returns [P, M, 3] (zeros above the active degree)."""
+    means3D = torch.as_tensor(means3D, dtype=torch.float64)
+    campos_views = torch.as_tensor(campos_views, dtype=torch.float64).reshape(-1, 3)
+    dcolor_views = torch.as_tensor(dcolor_views, dtype=torch.float64).reshape(campos_views.shape[0], -1, 3)
+    P = means3D.shape[0]
+    out = torch.zeros(P, M, 3, dtype=torch.float64)
+    nb = (deg + 1) ** 2
+    for v in range(campos_views.shape[0]):
+        d = means3D - campos_views[v]
+        d = d / d.norm(dim=1, keepdim=True)
+        out[:, :nb, :] += sh_basis(deg, d)[:, :, None] * dcolor_views[v][:, None, :]
+    return out
+
+
 def quat_to_rot(q: torch.Tensor) -> torch.Tensor:
     r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
     R = torch.stack([

@@ -23,10 +23,12 @@ SYMBOLS = (
     "sfb_export_geom", "sfb_export_binning", "sfb_export_img", "sfb_last_launch_count",
     "sfb_profile_enable", "sfb_profile_count", "sfb_profile_read", "sfb_profile_name",
     "sfb_loss_scratch_bytes", "sfb_loss_window", "sfb_l1_ssim_loss", "sfb_densify_stats", "sfb_densify_masks",
+    "sfb_sh_grad_combine",
 )
 
 
-BWD_ACC_FRESH = 1   # include/splat_b200.h: SFB_BWD_ACC_FRESH
+BWD_ACC_FRESH = 1     # include/splat_b200.h: SFB_BWD_ACC_FRESH
+BWD_SH_FACTORED = 2   # include/splat_b200.h: SFB_BWD_SH_FACTORED
 
 
 class SplatB200Error(RuntimeError):
@@ -89,7 +91,9 @@ def load():
     lib.sfb_densify_stats.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_densify_masks.restype = ci
     lib.sfb_densify_masks.argtypes = [ci, vp, vp, vp, vp, vp, ci, cf, cf, cf, cf, cf, vp, vp, vp, vp, vp]
-    if lib.sfb_abi_version() != 3:
+    lib.sfb_sh_grad_combine.restype = ci
+    lib.sfb_sh_grad_combine.argtypes = [ci, ci, ci, ci, vp, vp, vp, vp, vp]
+    if lib.sfb_abi_version() != 4:
         raise SplatB200Error("libsplat_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

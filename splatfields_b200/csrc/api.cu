@@ -131,7 +131,7 @@ void prof_end(cudaStream_t s) {
 
 extern "C" {
 
-int sfb_abi_version(void) { return 3; }
+int sfb_abi_version(void) { return 4; }
 const char* sfb_last_error(void) { return g_err.c_str(); }
 int sfb_last_launch_count(void) { return g_launches; }
 
@@ -301,7 +301,9 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
     return fail(SFB_ERR_ARG, "null gradient buffer");
   if (colors_precomp && !dL_dcolors) return fail(SFB_ERR_ARG, "dL_dcolors required with colors_precomp");
   if (cov3D_precomp && !dL_dcov3D) return fail(SFB_ERR_ARG, "dL_dcov3D required with cov3D_precomp");
-  if (shs && !dL_dsh) return fail(SFB_ERR_ARG, "dL_dsh required with shs");
+  const bool sh_factored = (flags & SFB_BWD_SH_FACTORED) != 0;
+  if (sh_factored && (!shs || !dL_dcolors)) return fail(SFB_ERR_ARG, "SFB_BWD_SH_FACTORED needs shs and dL_dcolors");
+  if (shs && !dL_dsh && !sh_factored) return fail(SFB_ERR_ARG, "dL_dsh required with shs");
   if (!cov3D_precomp && (!dL_dscales || !dL_drotations || !scales || !rotations))
     return fail(SFB_ERR_ARG, "dL_dscales / dL_drotations required with scales / rotations");
   const size_t HW = (size_t)H * W;
@@ -343,6 +345,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   bp.scale_modifier = scale_modifier; bp.tan_fovx = tan_fovx; bp.tan_fovy = tan_fovy; bp.radii = radii;
   bp.wide256 = wide256_enabled() && shs && ((M * 12) % 32 == 0) && ((reinterpret_cast<size_t>(shs) & 31) == 0) &&
                ((reinterpret_cast<size_t>(dL_dsh) & 31) == 0);
+  bp.sh_factored = sh_factored ? 1 : 0;
   bp.dL_dmeans2D = dL_dmeans2D; bp.dL_dcolors = dL_dcolors; bp.dL_dopacity = dL_dopacity;
   bp.dL_dmeans3D = dL_dmeans3D; bp.dL_dcov3D = dL_dcov3D; bp.dL_dsh = dL_dsh; bp.dL_dscales = dL_dscales;
   bp.dL_drot = dL_drotations;
@@ -359,6 +362,21 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
       return fail(SFB_ERR_CUDA, msg);
     }
   }
+  return SFB_OK;
+}
+
+int sfb_sh_grad_combine(int P, int V, int sh_degree, int M, const float* means3D, const float* campos,
+                        const float* dL_dcolor_views, float* dL_dsh, void* stream) {
+  using namespace sfb;
+  g_err.clear();
+  if (P == 0) return SFB_OK;
+  if (P < 0 || V < 1 || V > 64 || sh_degree < 0 || sh_degree > 3 || M < (sh_degree + 1) * (sh_degree + 1))
+    return fail(SFB_ERR_ARG, "sfb_sh_grad_combine: bad sizes (1 <= V <= 64, 0 <= sh_degree <= 3, M >= (sh_degree+1)^2)");
+  if (!means3D || !campos || !dL_dcolor_views || !dL_dsh) return fail(SFB_ERR_ARG, "sfb_sh_grad_combine: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  launch_sh_grad_combine(P, V, sh_degree, M, means3D, campos, dL_dcolor_views, dL_dsh, wide256_enabled(), s);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SFB_ERR_CUDA, "sh grad combine", e);
   return SFB_OK;
 }
 

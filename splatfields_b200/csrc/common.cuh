@@ -368,9 +368,14 @@ struct BwdParams {
   const float *viewmatrix, *projmatrix, *campos;
   float scale_modifier, tan_fovx, tan_fovy;
   int wide256;      // SH / dL_dsh rows are 32-byte aligned multiples of 32 bytes: use 256-bit loads and stores
+  int sh_factored;  // SFB_BWD_SH_FACTORED: dL_dcolors receives the clamp-masked colour gradient, dL_dsh may be nullptr
   const int* radii;
   float *dL_dmeans2D, *dL_dcolors, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drot;
 };
 void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s);
+// dL_dsh[i] = sum over V views of basis(normalize(means3D[i] - campos[v])) (x) dcolor[v][i]   (view-parallel exchange)
+void launch_sh_grad_combine(int P, int V, int D, int M, const float* means3D, const float* campos /* [V][3] */,
+                            const float* dcolor /* [V][P][3] */, float* dL_dsh /* [P][M][3] */, bool wide256,
+                            cudaStream_t s);
 
 }  // namespace sfb

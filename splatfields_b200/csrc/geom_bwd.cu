@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
           for (int k = 0; k < 3 * NB; k++) sh[k] = __ldg(shp + k);
         }
       }
-      float* dsh = p.dL_dsh + i * p.M * 3;
+      float* dsh = p.dL_dsh ? p.dL_dsh + i * p.M * 3 : nullptr;   // nullptr: factored mode (see sh_grad_combine_kernel)
       const float vx = mean[0] - cam.campos[0], vy = mean[1] - cam.campos[1], vz = mean[2] - cam.campos[2];
       const float sum2 = vx * vx + vy * vy + vz * vz;
       const float ilen = rsqrtf(sum2);
@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
       float gc[3];
 #pragma unroll
       for (int ch = 0; ch < 3; ch++) gc[ch] = ((cm >> ch) & 1) ? 0.f : gcol[ch];
+      if (p.sh_factored) { gcol[0] = gc[0]; gcol[1] = gc[1]; gcol[2] = gc[2]; }   // dL_dcolors <- clamp-masked gradient
       float ddx = 0.f, ddy = 0.f, ddz = 0.f;
       float basis[NB];
       basis[0] = SH_C0;
@@ -238,7 +239,9 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) dshv[3 * k + ch] = basis[k] * gc[ch];
       }
-      if (VEC && !TMA && W256 && (3 * NB) % 8 == 0) {   // launcher guarantees M == (D+1)^2 here
+      if (!TMA && !dsh) {
+        // factored mode: the 3*M-float row is rebuilt later from the masked colour gradients of all views
+      } else if (VEC && !TMA && W256 && (3 * NB) % 8 == 0) {   // launcher guarantees M == (D+1)^2 here
 #pragma unroll
         for (int k = 0; k < (3 * NB) / 8; k++) stg256(dsh + 8 * k, dshv + 8 * k);
       } else if (VEC) {
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
       drot[2] = 2.f * (qx * (Dr[1] + Dr[3]) + qr * (Dr[2] - Dr[6]) + qz * (Dr[5] + Dr[7])) - 4.f * qy * (Dr[0] + Dr[8]);
       drot[3] = 2.f * (qr * (Dr[3] - Dr[1]) + qx * (Dr[2] + Dr[6]) + qy * (Dr[5] + Dr[7])) - 4.f * qz * (Dr[0] + Dr[4]);
     }
-  } else if (p.shs) {
+  } else if (p.shs && (TMA || p.dL_dsh)) {
     float* dsh = p.dL_dsh + i * p.M * 3;
     if (TMA) mbar_wait(&s_bar, 0);     // the incoming row must have landed before it is overwritten
     if (VEC && !TMA && W256) {
@@ -350,6 +353,90 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
   if (p.dL_drot) { p.dL_drot[4 * i] = drot[0]; p.dL_drot[4 * i + 1] = drot[1]; p.dL_drot[4 * i + 2] = drot[2]; p.dL_drot[4 * i + 3] = drot[3]; }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// View-parallel exchange of the SH gradient in factored form.
+//
+// Per view v and Gaussian i the SH gradient is a rank-1 block: dL_dsh[i][k][c] = basis_k(dir(v, i)) * gc[v][i][c], with
+// dir = normalize(mean_i - campos_v) known to every rank (splats are replicated, cameras are 3 floats each) and
+// gc = the clamp-masked colour gradient (3 floats).  So the ranks exchange gc (12 B per Gaussian and view) instead of
+// all-reducing the 3*M-float rows (192 B at degree 3), and every rank rebuilds the summed rows here — with the same
+// basis arithmetic as geom_backward_kernel above and a fixed v = 0..V-1 summation order (bit-reproducible, unlike
+// a ring all-reduce).  One thread per Gaussian, 12 + 12*V bytes in, 12*M out: HBM-bound streaming work.
+template <int D, bool W256>
+__global__ void __launch_bounds__(256)
+sh_grad_combine_kernel(int P, int V, int M, const float* __restrict__ means3D, const float* __restrict__ campos,
+                       const float* __restrict__ dcolor, float* __restrict__ dL_dsh) {
+  constexpr int NB = (D + 1) * (D + 1);
+  constexpr int NF8 = (3 * NB + 7) / 8;
+  __shared__ float s_cam[3 * 64];
+  for (int k = threadIdx.x; k < 3 * V; k += blockDim.x) s_cam[k] = campos[k];
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const size_t i = (size_t)idx;
+  const float mx = means3D[3 * i], my = means3D[3 * i + 1], mz = means3D[3 * i + 2];
+  float acc[NF8 * 8];
+#pragma unroll
+  for (int k = 0; k < NF8 * 8; k++) acc[k] = 0.f;
+  for (int v = 0; v < V; v++) {
+    const float* gp = dcolor + ((size_t)v * P + i) * 3;
+    const float g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
+    if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;     // culled in this view (or no gradient reached it)
+    const float vx = mx - s_cam[3 * v], vy = my - s_cam[3 * v + 1], vz = mz - s_cam[3 * v + 2];
+    const float ilen = rsqrtf(vx * vx + vy * vy + vz * vz);
+    const float x = vx * ilen, y = vy * ilen, z = vz * ilen;
+    float basis[NB];
+    basis[0] = SH_C0;
+    if (D > 0) { basis[1] = -SH_C1 * y; basis[2] = SH_C1 * z; basis[3] = -SH_C1 * x; }
+    if (D > 1) {
+      const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+      basis[4] = SHB_C2[0] * xy; basis[5] = SHB_C2[1] * yz; basis[6] = SHB_C2[2] * (2.f * zz - xx - yy);
+      basis[7] = SHB_C2[3] * xz; basis[8] = SHB_C2[4] * (xx - yy);
+      if (D > 2) {
+        basis[9] = SHB_C3[0] * y * (3.f * xx - yy); basis[10] = SHB_C3[1] * xy * z;
+        basis[11] = SHB_C3[2] * y * (4.f * zz - xx - yy); basis[12] = SHB_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+        basis[13] = SHB_C3[4] * x * (4.f * zz - xx - yy); basis[14] = SHB_C3[5] * z * (xx - yy);
+        basis[15] = SHB_C3[6] * x * (xx - 3.f * yy);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+      // the product is rounded on its own (as geom_backward_kernel stores it) before it enters the sum over views
+      acc[3 * k] = __fadd_rn(acc[3 * k], __fmul_rn(basis[k], g0));
+      acc[3 * k + 1] = __fadd_rn(acc[3 * k + 1], __fmul_rn(basis[k], g1));
+      acc[3 * k + 2] = __fadd_rn(acc[3 * k + 2], __fmul_rn(basis[k], g2));
+    }
+  }
+  float* dsh = dL_dsh + i * M * 3;
+  if (W256) {      // launcher: M == NB, rows are 32-byte aligned multiples of 32 bytes
+#pragma unroll
+    for (int k = 0; k < (3 * NB) / 8; k++) stg256(dsh + 8 * k, acc + 8 * k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3 * NB; k++) dsh[k] = acc[k];
+    for (int k = 3 * NB; k < 3 * M; k++) dsh[k] = 0.f;      // coefficients above the active degree
+  }
+}
+
+void launch_sh_grad_combine(int P, int V, int D, int M, const float* means3D, const float* campos,
+                            const float* dcolor, float* dL_dsh, bool wide256, cudaStream_t s) {
+  if (P <= 0) return;
+  const int blocks = (P + 255) / 256;
+  const bool w256 = wide256 && (M * 12) % 32 == 0 && (reinterpret_cast<size_t>(dL_dsh) & 31) == 0;
+#define SFB_SC(DD)                                                                                              \
+  if (w256 && M == (DD + 1) * (DD + 1) && (3 * (DD + 1) * (DD + 1)) % 8 == 0)                                   \
+    sh_grad_combine_kernel<DD, true><<<blocks, 256, 0, s>>>(P, V, M, means3D, campos, dcolor, dL_dsh);          \
+  else                                                                                                          \
+    sh_grad_combine_kernel<DD, false><<<blocks, 256, 0, s>>>(P, V, M, means3D, campos, dcolor, dL_dsh);
+  switch (D) {
+    case 0: SFB_SC(0) break;
+    case 1: SFB_SC(1) break;
+    case 2: SFB_SC(2) break;
+    default: SFB_SC(3) break;
+  }
+#undef SFB_SC
+}
+
 void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s) {
   if (p.P <= 0) return;
   const int blocks = (p.P + 255) / 256;
@@ -363,7 +450,7 @@ void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s
   static int minb3 = -1;   // experiment: trade a few spills for 3 resident CTAs per SM
   if (minb3 < 0) { const char* e = getenv("SFB_GEOM_MINB3"); minb3 = (e && e[0] == '1') ? 1 : 0; }
 #define SFB_GB(DD)                                                                                         \
-  if (vec && !no_tma && p.M == (DD + 1) * (DD + 1) && smem <= 96 * 1024) {                                 \
+  if (vec && !no_tma && p.dL_dsh && p.M == (DD + 1) * (DD + 1) && smem <= 96 * 1024) {                                \
     static bool attr_set = false;                                                                          \
     if (!attr_set) {                                                                                       \
       cudaFuncSetAttribute(geom_backward_kernel<DD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

@@ -3,8 +3,14 @@
 * ViewParallelRasterizer — the multi-GPU unit of BASELINE.json's metric: one process per GPU, splats
   replicated, each rank renders ITS camera (the reference renders the views of one iteration serially in
   the loop at train.py:169 and averages the losses at train.py:242); the per-splat gradients of all
-  ranks are summed by ONE NCCL all-reduce over a flat fp32 slab [59, P] that the backward kernel writes
-  directly (no gather / flatten copy).
+  ranks are summed over a flat fp32 slab [59, P] that the backward kernel writes directly (no gather /
+  flatten copy).  Exchange "factored" (default with SH colours): the SH gradient of one view is the rank-1
+  block basis(dir) (x) dL_dcolour, and dir is known to every rank, so the ranks all-gather the 3 floats of
+  dL_dcolour per splat instead of all-reducing the 48 SH floats; only the 11 geometry floats go through
+  the all-reduce, and every rank rebuilds the summed SH rows with one kernel (sfb_sh_grad_combine) while
+  that all-reduce is in flight: 161 instead of 413 bytes per splat on the wire at 8 ranks.  Exchange
+  "allreduce": ONE NCCL all-reduce of the whole slab (the plain formulation, kept for A/B and for
+  precomputed colours).
 * forward_backward_host — the same step for callers that hold HOST buffers: pinned host -> device copies
   of every input, forward + backward, device -> pinned host copies of image, depth, radii and gradients.
 
@@ -13,6 +19,7 @@ torch is plumbing here (device memory, streams, torch.distributed); the compute 
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -26,9 +33,15 @@ SLAB_FIELDS_RGB = (("means3D", 3), ("opacities", 1), ("scales", 3), ("rotations"
 
 class ViewParallelRasterizer:
     def __init__(self, scene: dict, camera, H: int, W: int, sh_degree: int, device, world_size: int = 1,
-                 bg=(1.0, 1.0, 1.0)):
+                 bg=(1.0, 1.0, 1.0), exchange: str | None = None):
         self.device = torch.device(device)
         self.world = int(world_size)
+        self.sh_degree = int(sh_degree)
+        exchange = exchange or os.environ.get("SFB_EXCHANGE", "factored")
+        if exchange not in ("factored", "allreduce"):
+            raise Exception("exchange must be 'factored' or 'allreduce'")
+        # the factored form exists for SH colours only; a single rank has nothing to exchange
+        self.exchange = exchange if (self.world > 1 and "shs" in scene) else "allreduce"
         self.H, self.W = H, W
         self.P = scene["means3D"].shape[0]
         self.params = {k: v.detach().to(self.device, copy=True).contiguous().requires_grad_(True)
@@ -46,8 +59,22 @@ class ViewParallelRasterizer:
         # the flat gradient slab: field-major [sum(n), P] so every field is one contiguous run
         self.slab = torch.empty(self.floats_per_splat * self.P, dtype=torch.float32, device=self.device)
         self.last = None
+        self._combine = rasterizer.sh_grad_combine
+        self.time_exchange = False       # bench: record CUDA events around the gradient exchange of every step
+        self.exchange_events = []
+        if self.exchange == "factored":
+            import torch.distributed as dist
+            assert self.fields[-1][0] == "shs"          # the SH rows are the tail of the slab
+            self.geo_floats = self.floats_per_splat - self.fields[-1][1]
+            self.dcolor_mine = torch.empty(self.P * 3, dtype=torch.float32, device=self.device)
+            self.dcolor_views = torch.empty(self.world * self.P * 3, dtype=torch.float32, device=self.device)
+            # every rank needs every camera centre (3 floats per view): gathered once
+            mine = cam.camera_center.detach().to(self.device, torch.float32).reshape(3).contiguous()
+            allc = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allc, mine)
+            self.campos_views = torch.stack(allc).contiguous()
 
-    # -- one fwd + bwd (+ all-reduce); returns the number of kernel launches issued
+    # -- one fwd + bwd (+ gradient exchange); returns the number of library kernel launches issued
     def step(self, cotangent: torch.Tensor, keep: bool = False) -> int:
         p = self.params
         for v in p.values():
@@ -58,7 +85,8 @@ class ViewParallelRasterizer:
                                         shs=p.get("shs"), colors_precomp=p.get("colors_precomp"),
                                         scales=p["scales"], rotations=p["rotations"])
         n = lib.sfb_last_launch_count()
-        rasterizer.set_grad_arena(self.slab, self.fields)
+        factored = self.exchange == "factored"
+        rasterizer.set_grad_arena(self.slab, self.fields, self.dcolor_mine.view(self.P, 3) if factored else None)
         try:
             # mean over views (train.py:242) folded into the cotangent: backward is linear in it
             color.backward(cotangent if self.world == 1 else cotangent * (1.0 / self.world))
@@ -68,18 +96,54 @@ class ViewParallelRasterizer:
         # normally a no-op: the backward kernel already wrote into the slab slices (the .grad tensors ARE
         # those slices); copy only if autograd handed back separate storage.
         for name, dst in self.grads().items():
+            if factored and name == "shs":
+                continue                     # rebuilt below from the gathered colour gradients
             g = p[name].grad
             if g is None:
                 dst.zero_()
             elif g.data_ptr() != dst.data_ptr():
                 dst.copy_(g.reshape(-1))
-        if self.world > 1:
+        ev = None
+        if self.time_exchange and self.world > 1 and self.device.type == "cuda":
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        if factored:
+            import torch.distributed as dist
+            # all-gather 3 floats / splat / view, all-reduce the 11 geometry floats; the SH rows are rebuilt
+            # locally while the all-reduce is still in flight (it only depends on the all-gather)
+            h_ag = dist.all_gather_into_tensor(self.dcolor_views, self.dcolor_mine, async_op=True)
+            h_ar = dist.all_reduce(self.slab[:self.geo_floats * self.P], op=dist.ReduceOp.SUM, async_op=True)
+            h_ag.wait()
+            sh_out = self.slab[self.geo_floats * self.P:]
+            self._combine(p["means3D"].detach(), self.campos_views, self.dcolor_views, self.sh_degree, sh_out)
+            h_ar.wait()
+            n += 1                           # the rebuild kernel (the NCCL kernels are not counted as ours)
+        elif self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.slab, op=dist.ReduceOp.SUM)
-            n += 1
+        if ev is not None:
+            ev[1].record()
+            self.exchange_events.append(ev)
         if keep:
             self.last = (color.detach(), radii, depth.detach())
         return n
+
+    def exchange_ms(self) -> list:
+        """Device time of the gradient exchange (collectives + SH rebuild) of the steps run with time_exchange."""
+        torch.cuda.synchronize(self.device)
+        out = [a.elapsed_time(b) for a, b in self.exchange_events]
+        self.exchange_events = []
+        return out
+
+    def bytes_on_wire_per_splat(self) -> float:
+        """Bytes each rank sends (= receives) per splat and step for the gradient exchange (ring / NVSwitch model:
+        all-reduce 2(N-1)/N * size, all-gather (N-1) * size)."""
+        N = self.world
+        if N <= 1:
+            return 0.0
+        if self.exchange == "factored":
+            return 2.0 * (N - 1) / N * 4 * self.geo_floats + (N - 1) * 12.0
+        return 2.0 * (N - 1) / N * 4 * self.floats_per_splat
 
     def grads(self) -> dict:
         out, off = {}, 0

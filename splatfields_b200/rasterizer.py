@@ -40,11 +40,39 @@ class GaussianRasterizationSettings(NamedTuple):
 # caller-owned flat fp32 slab (the buffer a view-parallel trainer hands to NCCL all-reduce) instead of
 # allocating separate tensors.  fields = ((input name, floats per splat), ...) in slab order.
 _ARENA = None
+# Factored SH gradient (view-parallel exchange, host_api.ViewParallelRasterizer): when a [P, 3] tensor is set here,
+# backward writes the clamp-masked colour gradient into it instead of the [P, M, 3] SH gradient rows
+# (SFB_BWD_SH_FACTORED); `shs` then gets no .grad from autograd — the caller rebuilds the multi-view sum with
+# sh_grad_combine().
+_SH_COLOR_OUT = None
 
 
-def set_grad_arena(slab, fields):
-    global _ARENA
+def set_grad_arena(slab, fields, sh_color_out=None):
+    global _ARENA, _SH_COLOR_OUT
     _ARENA = None if slab is None else (slab, tuple(fields))
+    _SH_COLOR_OUT = sh_color_out
+
+
+def sh_grad_combine(means3D, campos_views, dcolor_views, sh_degree, out):
+    """out[P, M, 3] = sum over views v of basis(normalize(means3D - campos_views[v])) (x) dcolor_views[v]
+    (include/splat_b200.h: sfb_sh_grad_combine).  campos_views [V, 3], dcolor_views [V, P, 3]: the factored
+    per-view SH gradients; out: a contiguous fp32 CUDA tensor (e.g. the `shs` slice of the gradient slab)."""
+    lib = _lib.load()
+    if not means3D.is_cuda:
+        raise _lib.SplatB200Error("sh_grad_combine runs on CUDA tensors only (no CPU fallback)")
+    P = means3D.shape[0]
+    V = campos_views.shape[0]
+    if dcolor_views.numel() != V * P * 3 or out.numel() % (3 * max(P, 1)) != 0:
+        raise Exception("dcolor_views must hold [V, P, 3] floats and out [P, M, 3]")
+    M = out.numel() // (3 * P) if P > 0 else 0
+    for t, name in ((means3D, "means3D"), (campos_views, "campos_views"), (dcolor_views, "dcolor_views"), (out, "out")):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise Exception(f"{name} must be a contiguous fp32 tensor")
+    with torch.cuda.device(means3D.device):
+        stream = torch.cuda.current_stream(means3D.device).cuda_stream
+        _lib.check(lib.sfb_sh_grad_combine(P, V, int(sh_degree), int(M), _ptr(means3D), _ptr(campos_views),
+                                           _ptr(dcolor_views), _ptr(out), stream))
+    return out
 
 
 def _arena_out(name, P, shape, **f32):
@@ -201,14 +229,20 @@ class _RasterizeGaussians(torch.autograd.Function):
         dL_dcolors = _arena_out("colors_precomp", P, (P, 3), **f32) if col is not None else None
         dL_dopacity = _arena_out("opacities", P, (P, 1), **f32)
         dL_dcov3D = _arena_out("cov3D_precomp", P, (P, 6), **f32) if cov is not None else None
-        dL_dsh = _arena_out("shs", P, (P, M, 3), **f32) if sh is not None else None
+        factored = sh is not None and _SH_COLOR_OUT is not None
+        if factored:
+            dL_dcolors, dL_dsh = _SH_COLOR_OUT, None
+            if dL_dcolors.numel() != 3 * P or dL_dcolors.dtype != torch.float32 or not dL_dcolors.is_contiguous():
+                raise Exception("sh_color_out must be a contiguous fp32 tensor of P * 3 elements")
+        else:
+            dL_dsh = _arena_out("shs", P, (P, M, 3), **f32) if sh is not None else None
         dL_dscales = _arena_out("scales", P, (P, 3), **f32) if cov is None else None
         dL_drot = _arena_out("rotations", P, (P, 4), **f32) if cov is None else None
         g = _prep(grad_out_color)
         ga = _prep(grad_out_alpha) if (ctx.with_alpha and grad_out_alpha is not None) else None
         if g is None:      # only the alpha image was used downstream
             g = torch.zeros((3, H, W), **f32)
-        flags = _lib.BWD_ACC_FRESH if ctx.acc_fresh[0] else 0
+        flags = (_lib.BWD_ACC_FRESH if ctx.acc_fresh[0] else 0) | (_lib.BWD_SH_FACTORED if factored else 0)
         ctx.acc_fresh[0] = False    # a second backward on the same buffers (retain_graph) must clear them itself
         if P > 0:
             with torch.cuda.device(dev):

@@ -38,7 +38,7 @@ def _worker(rank, world, port, ret):
         P, H, W = 40, 8, 12
         sc = synth.make_scene(P, 5)
         cam = synth.orbit_camera(rank, H, W)
-        vp = ViewParallelRasterizer(sc, cam, H, W, 3, device="cpu", world_size=world)
+        vp = ViewParallelRasterizer(sc, cam, H, W, 3, device="cpu", world_size=world, exchange="allreduce")
         vp.rast = _StubRast(cam, H, W)
         G = torch.randn(3, H, W, generator=torch.Generator().manual_seed(100 + rank))
         vp.step(G)
@@ -60,20 +60,97 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_view_parallel_allreduce_matches_serial_mean():
+class _StubRastSH(torch.nn.Module):
+    """Stand-in whose colour is the SH polynomial of the view direction (no clamp), like the rasterizer's; in
+    factored mode it behaves like the CUDA backward with SFB_BWD_SH_FACTORED: the colour gradient goes to the
+    buffer set with set_grad_arena(..., sh_color_out) and `shs` receives no gradient from autograd."""
+
+    def __init__(self, cam, H, W, deg):
+        super().__init__()
+        self.cam, self.H, self.W, self.deg = cam, H, W, deg
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        from oracle import torch_naive as TN
+        from splatfields_b200 import rasterizer
+        P = means3D.shape[0]
+        d = means3D.detach() - self.cam.camera_center
+        basis = TN.sh_basis(self.deg, d / d.norm(dim=1, keepdim=True))             # [P, nb]
+        nb = basis.shape[1]
+        if rasterizer._SH_COLOR_OUT is not None or getattr(self, "factored", False):
+            col = (basis[:, :, None] * shs.detach()[:, :nb]).sum(1).requires_grad_(True)
+
+            def hook(g):
+                rasterizer._SH_COLOR_OUT.copy_(g)
+            col.register_hook(hook)
+        else:
+            col = (basis[:, :, None] * shs[:, :nb]).sum(1)
+        w = opacities * scales.sum(1, keepdim=True) * (rotations ** 2).sum(1, keepdim=True) * (1 + means3D[:, :1])
+        pix = torch.sin(torch.arange(P * self.H * self.W, dtype=torch.float32).reshape(P, self.H * self.W) * 0.01)
+        color = ((w * col).t() @ pix).reshape(3, self.H, self.W) + 0.0 * means2D.sum()
+        return color, torch.ones(P, dtype=torch.int32), color[:1]
+
+
+def _worker_factored(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import torch_naive as TN
+        P, H, W, deg = 40, 8, 12, 2
+        sc = synth.make_scene(P, 5)
+        cam = synth.orbit_camera(rank, H, W)
+        vp = ViewParallelRasterizer(sc, cam, H, W, deg, device="cpu", world_size=world, exchange="factored")
+        assert vp.exchange == "factored" and vp.campos_views.shape == (world, 3)
+        vp.rast = _StubRastSH(cam, H, W, deg)
+        vp.rast.factored = True
+        # CPU stand-in of sfb_sh_grad_combine (the CUDA kernel is covered by tests/test_sh_factored.py -m gpu)
+        vp._combine = lambda means, campos, dcol, d, out: out.copy_(
+            TN.sh_grad_combine_ref(means, campos, dcol.reshape(campos.shape[0], -1, 3), d, 16).float().reshape(-1))
+        G = torch.randn(3, H, W, generator=torch.Generator().manual_seed(100 + rank))
+        vp.step(G)
+        got = {k: v.clone() for k, v in vp.grads().items()}
+        if rank == 0:
+            leaves = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+            losses = []
+            for r in range(world):
+                c = synth.orbit_camera(r, H, W)
+                Gr = torch.randn(3, H, W, generator=torch.Generator().manual_seed(100 + r))
+                col, _, _ = _StubRastSH(c, H, W, deg)(leaves["means3D"], torch.zeros(P, 3), leaves["opacities"],
+                                                     shs=leaves["shs"], scales=leaves["scales"],
+                                                     rotations=leaves["rotations"])
+                losses.append((col * Gr).sum())
+            (sum(losses) / world).backward()
+            ok = all(torch.allclose(got[n], leaves[n].grad.reshape(-1), rtol=1e-4, atol=1e-5) for n, _ in SLAB_FIELDS_SH)
+            ok = ok and float(got["shs"].abs().max()) > 0
+            ret.put(bool(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def _spawn2(worker):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, 2, port, ret)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=5) is True
+
+
+def test_view_parallel_allreduce_matches_serial_mean():
+    _spawn2(_worker)
+
+
+def test_view_parallel_factored_exchange_matches_serial_mean():
+    """all-gather of the per-view colour gradients + all-reduce of the 11 geometry floats + local rebuild of the SH
+    rows == the serial multi-view accumulation, SH rows included."""
+    _spawn2(_worker_factored)
 
 
 def test_slab_layout():
