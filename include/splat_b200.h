@@ -180,6 +180,35 @@ int sfb_densify_masks(int P, const float* xyz_gradient_accum, const float* denom
                       float dense_extent, float big_extent, float min_opacity, float max_screen_size,
                       uint8_t* clone_mask, uint8_t* split_mask, uint8_t* prune_mask, uint32_t* counts, void* stream);
 
+/* Fused parameter activations — the step right before the rasterizer: the static branch of
+ * get_gaussian_dict (train.py:42-50), i.e. the GaussianModel getters of scene/gaussian_model.py:64-86:
+ *     scales    = exp(raw_scaling) [+ scale_offset]      raw_scaling [P][3], or [P][1] when isotropic != 0 (:64-68);
+ *                                                        scale_offset [P][3] or NULL = ret['scales'] of train.py:73
+ *     rotations = raw_rotation / max(||raw_rotation||_2, 1e-12)                    [P][4]   (:70-72, F.normalize)
+ *     opacity   = sigmoid(raw_opacity)                                             [P]      (:83-85)
+ *     features  = cat(f_dc [P][1][3], f_rest [P][M-1][3], dim=1)                   [P][M][3] (:78-82); NULL: skipped
+ * One kernel.  rotations / features (in and out) must be 16-byte aligned. */
+int sfb_activate_forward(int P, int M, int isotropic, const float* raw_scaling, const float* raw_rotation,
+                         const float* raw_opacity, const float* f_dc, const float* f_rest, const float* scale_offset,
+                         float* scales, float* rotations, float* opacity, float* features, void* stream);
+/* Its backward (what autograd runs through ExpBackward / DivBackward+NormBackward / SigmoidBackward / CatBackward):
+ * each dL_draw_* / dL_df_* output may be NULL (skipped); every non-NULL output is fully written.  The gradient
+ * w.r.t. scale_offset is dL_dscales itself. */
+int sfb_activate_backward(int P, int M, int isotropic, const float* raw_scaling, const float* raw_rotation,
+                          const float* raw_opacity, const float* dL_dscales, const float* dL_drotations,
+                          const float* dL_dopacity, const float* dL_dfeatures, float* dL_draw_scaling,
+                          float* dL_draw_rotation, float* dL_draw_opacity, float* dL_df_dc, float* dL_df_rest,
+                          void* stream);
+
+/* Initial scales from the point cloud.  Replaces simple_knn's distCUDA2 (un-vendored dependency,
+ * README.md:29; only call site scene/gaussian_model.py:105): mean_dist2[i] = mean of the squared Euclidean distances
+ * from points[i] to its 3 nearest OTHER points (self excluded by index, so duplicates count with distance 0;
+ * missing neighbours when P < 4 enter as FLT_MAX, as in simple_knn).  points [P][3]; scratch: device buffer of
+ * sfb_knn_scratch_bytes(P) bytes, 256-byte aligned, caller-owned.  Exact (not approximate) and asynchronous: no host
+ * round trip.  Distances are fp32: fma(dz, dz, fma(dy, dy, dx * dx)). */
+size_t sfb_knn_scratch_bytes(int P);
+int sfb_knn3_mean_dist2(int P, const float* points, float* mean_dist2, void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

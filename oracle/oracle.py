@@ -48,6 +48,14 @@ def set_num_threads(n: int) -> None:
     lib().so_set_num_threads(C.c_int(int(n)))
 
 
+def knn3_mean_dist2(points):
+    """Brute-force restatement of simple_knn.distCUDA2 (see so_knn3_mean_dist2)."""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    out = np.zeros(pts.shape[0], np.float32)
+    lib().so_knn3_mean_dist2(C.c_int(pts.shape[0]), _p(pts), _p(out))
+    return out
+
+
 def _f32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
 

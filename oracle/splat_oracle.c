@@ -694,3 +694,30 @@ void so_preprocess_backward(int P, int D, int M, const float* means3D, const int
     }
   }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * simple_knn's distCUDA2 (un-vendored dependency pinned at reference README.md:29,
+ * gitlab.inria.fr/bkerbl/simple-knn @ 44f7642; only call site scene/gaussian_model.py:105).
+ * PARITY UNPINNED (no source, tests or vectors in the reference tree); published behaviour restated:
+ * for every point the mean of the squared distances to its 3 nearest OTHER points (self excluded by
+ * index; the running best-3 list starts at FLT_MAX, so P < 4 leaves FLT_MAX terms in the mean).
+ * Brute force O(P^2); the squared distance is evaluated as fma(dz,dz, fma(dy,dy, dx*dx)) in fp32 —
+ * the contraction nvcc applies to simple_knn's `d.x*d.x + d.y*d.y + d.z*d.z` — so the CUDA kernel,
+ * which prunes exactly, must agree bit for bit. */
+#include <float.h>
+void so_knn3_mean_dist2(int P, const float* pts, float* out) {
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < P; i++) {
+    float best[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+    const float px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
+    for (int j = 0; j < P; j++) {
+      if (j == i) continue;
+      const float dx = pts[3 * j] - px, dy = pts[3 * j + 1] - py, dz = pts[3 * j + 2] - pz;
+      float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      for (int k = 0; k < 3; k++) {
+        if (best[k] > d) { const float t = best[k]; best[k] = d; d = t; }
+      }
+    }
+    out[i] = (best[0] + best[1] + best[2]) / 3.0f;
+  }
+}

@@ -5,6 +5,7 @@ times it as the "what the reference executes" baseline.  Nothing under splatfiel
 
   l1_loss / gaussian / create_window / ssim / _ssim     utils/loss_utils.py:18-19, :33-76
   add_densification_stats / max_radii2D update          scene/gaussian_model.py:427-430, train.py:280-282
+  gaussian_dict_static (the GaussianModel getters)      scene/gaussian_model.py:53-86, train.py:42-50, :73
 """
 from math import exp
 
@@ -58,3 +59,21 @@ def add_densification_stats(xyz_gradient_accum, denom, max_radii2D, viewspace_gr
     max_radii2D[visibility_filter] = torch.max(max_radii2D[visibility_filter], radii[visibility_filter])
     xyz_gradient_accum[visibility_filter] += torch.norm(viewspace_grad[visibility_filter, :2], dim=-1, keepdim=True)
     denom[visibility_filter] += 1
+
+
+def gaussian_dict_static(xyz, raw_scaling, raw_rotation, raw_opacity, features_dc, features_rest, scale_offset=None,
+                         use_isotropic=False):
+    """train.py:42-50 through the getters of scene/gaussian_model.py:64-86 (activations set at :53-61), plus the
+    `ret['scales'] + scaling` epilogue of the dynamic branch (train.py:73) when scale_offset is given."""
+    scaling = torch.exp(raw_scaling)                                   # :53, :64-68
+    if use_isotropic:
+        scaling = scaling.repeat(1, 3)
+    if scale_offset is not None:
+        scaling = scale_offset + scaling                               # train.py:73
+    return {
+        "means3D": xyz,
+        "gaussian_opacity": torch.sigmoid(raw_opacity),                # :58, :83-85
+        "gaussian_features": torch.cat((features_dc, features_rest), dim=1),   # :78-82
+        "gaussian_scales": scaling,
+        "gaussian_rotations": F.normalize(raw_rotation),               # :61, :70-72
+    }

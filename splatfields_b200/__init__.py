@@ -5,6 +5,9 @@ from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, raste
 from .renderer import render  # noqa: F401
 from .losses import l1_loss, ssim, photometric_loss  # noqa: F401
 from .densify import add_densification_stats, densify_masks  # noqa: F401
+from .activations import activate_parameters  # noqa: F401
+from .knn import distCUDA2  # noqa: F401
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "render",
-           "l1_loss", "ssim", "photometric_loss", "add_densification_stats", "densify_masks"]
+           "l1_loss", "ssim", "photometric_loss", "add_densification_stats", "densify_masks",
+           "activate_parameters", "distCUDA2"]

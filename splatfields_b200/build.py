@@ -21,7 +21,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 # bit-reproducible against the CPU oracle -> no implicit FMA contraction there.
 EXTRA = {"preprocess.cu": ["-fmad=false"]}
 SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "render_fwd.cu", "render_bwd.cu", "geom_bwd.cu",
-           "loss.cu", "densify.cu"]
+           "loss.cu", "densify.cu", "activate.cu", "knn.cu"]
 
 
 def nvcc() -> str:
