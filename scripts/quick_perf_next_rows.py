@@ -113,6 +113,72 @@ def densify_case(P, iters, warmup, flush):
                 masks_GBps=round(31.0 * P / (t3 * 1e-3) / 1e9, 1))
 
 
+def activations_case(P, iters, warmup, flush):
+    """§8f-3: GaussianModel getters (exp / normalize / sigmoid / cat) + their autograd, fused vs torch eager."""
+    from splatfields_b200 import activate_parameters
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(3)
+    mk = lambda *s: torch.randn(*s, device=dev, generator=g).requires_grad_(True)
+    xyz, rs, rr, ro, dc, rest = mk(P, 3), mk(P, 3), mk(P, 4), mk(P, 1), mk(P, 1, 3), mk(P, 15, 3)
+    keys = ("gaussian_opacity", "gaussian_features", "gaussian_scales", "gaussian_rotations")
+    cot = None
+
+    def run(fn):
+        def f():
+            nonlocal cot
+            d = fn(xyz, rs, rr, ro, dc, rest)
+            if cot is None:
+                cot = {k: torch.randn_like(d[k]) for k in keys}
+            torch.autograd.grad([d[k] for k in keys], (rs, rr, ro, dc, rest), [cot[k] for k in keys])
+        return f
+    t_ours = timed(run(activate_parameters), iters, warmup, flush)
+    t_ref = timed(run(TR.gaussian_dict_static), iters, warmup, flush)
+    alg = P * (8 + 48) * 4 * 2 * 2            # (8 + 3M) floats in and out, forward and backward
+    return dict(case="activations", P=P, fused_fwd_bwd_ms=round(t_ours, 4), torch_eager_fwd_bwd_ms=round(t_ref, 4),
+                speedup=round(t_ref / t_ours, 2), algorithmic_bytes=alg,
+                GBps=round(alg / (t_ours * 1e-3) / 1e9, 1), frac_of_measured_hbm=round(alg / (t_ours * 1e-3) / 1e9 / peak_gbs(), 3))
+
+
+def knn_case(P, iters, warmup, flush, clustered=False):
+    """§8f-5: distCUDA2 replacement on an init-like cloud (uniform in the +-1.3 cube, dataset_readers.py:598)."""
+    from splatfields_b200 import distCUDA2
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(4)
+    pts = (torch.rand(P, 3, device=dev, generator=g) * 2 - 1) * 1.3
+    if clustered:       # half of the points in 64 tight blobs: strongly non-uniform density
+        c = (torch.rand(64, 3, device=dev, generator=g) * 2 - 1) * 1.3
+        pts[: P // 2] = c[torch.randint(0, 64, (P // 2,), device=dev, generator=g)] + \
+            torch.randn(P // 2, 3, device=dev, generator=g) * 0.004
+    t = timed(lambda: distCUDA2(pts), iters, warmup, flush)
+    n0 = _lib.load().sfb_profile_count(0)
+    _lib.profile_enable(True)
+    distCUDA2(pts)
+    torch.cuda.synchronize()
+    rows = [r for r in _lib.profile_read(0)[n0:] if r[0].startswith("knn.")]
+    _lib.profile_enable(False)
+    kern = {}
+    for k, v in rows:
+        kern[k] = round(kern.get(k, 0.0) + v * 1e3, 2)
+    return dict(case="distCUDA2", P=P, clustered=clustered, ms=round(t, 4), Mpoints_s=round(P / (t * 1e-3) / 1e6, 1),
+                kernels_us=kern)
+
+
+def combine_case(P, V, iters, warmup, flush):
+    """View-parallel SH-gradient rebuild (sfb_sh_grad_combine): 12 + 12 V bytes in, 192 out per splat."""
+    from splatfields_b200 import rasterizer
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    means = (torch.rand(P, 3, device=dev, generator=g) * 2 - 1) * 1.3
+    campos = torch.randn(V, 3, device=dev, generator=g) * 3.0
+    dcol = torch.randn(V, P, 3, device=dev, generator=g)
+    dcol[:, ::5] = 0.0                       # ~20% of the splats culled in every view
+    out = torch.empty(P, 16, 3, device=dev)
+    t = timed(lambda: rasterizer.sh_grad_combine(means, campos, dcol, 3, out), iters, warmup, flush)
+    alg = P * (12 + 12 * V + 192)
+    return dict(case="sh_grad_combine", P=P, V=V, ms=round(t, 4), algorithmic_bytes=alg,
+                GBps=round(alg / (t * 1e-3) / 1e9, 1), frac_of_measured_hbm=round(alg / (t * 1e-3) / 1e9 / peak_gbs(), 3))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
@@ -123,6 +189,12 @@ def main():
         print(json.dumps(loss_case(C, H, W, a.iters, a.warmup, flush, m)), flush=True)
     for P in (1_000_000, 2_000_000):
         print(json.dumps(densify_case(P, a.iters, a.warmup, flush)), flush=True)
+    for P in (1_000_000, 2_000_000):
+        print(json.dumps(activations_case(P, a.iters, a.warmup, flush)), flush=True)
+    for P, cl in ((100_000, False), (1_000_000, False), (1_000_000, True), (2_000_000, False)):
+        print(json.dumps(knn_case(P, a.iters, a.warmup, flush, cl)), flush=True)
+    for V in (2, 4, 8):
+        print(json.dumps(combine_case(1_000_000, V, a.iters, a.warmup, flush)), flush=True)
 
 
 if __name__ == "__main__":
