@@ -125,7 +125,9 @@ int sfb_export_img(int W, int H, const void* img_buffer, float* final_T, uint32_
 /* Per-kernel device timing with CUDA events recorded on the launching stream (bench.py's roofline leg).
  * While enabled, every kernel of a forward (which = 0) / backward (which = 1) call is bracketed by an event
  * pair; sfb_profile_read waits for the records of the last such call and writes their durations (ms),
- * returning the record count; sfb_profile_name(which, i) names record i ("tile_sort.scatter", ...). */
+ * returning the record count; sfb_profile_name(which, i) names record i ("tile_sort.scatter", ...).  The other entry
+ * points (loss, densify, activate, knn) append their records to the list of the last forward / backward call;
+ * sfb_profile_enable(1) starts empty lists (which = 0 current).  At most 48 records per list. */
 void sfb_profile_enable(int on);
 int sfb_profile_count(int which);
 int sfb_profile_read(int which, float* ms, int max_records);

@@ -62,11 +62,10 @@ def loss_case(C, H, W, iters, warmup, flush, with_mask):
     t_ours = timed(ours, iters, warmup, flush)
     t_ref = timed(ref, iters, warmup, flush)
     # per-kernel device times: the loss kernels append their event pairs to the library's current record list
-    n0 = _lib.load().sfb_profile_count(0)
-    _lib.profile_enable(True)
+    _lib.profile_enable(True)           # (starts a fresh record list)
     ours()
     torch.cuda.synchronize()
-    rows = [r for r in _lib.profile_read(0)[n0:] if r[0].startswith("loss.")]
+    rows = [r for r in _lib.profile_read(0) if r[0].startswith("loss.")]
     _lib.profile_enable(False)
     kern = {k: round(v * 1e3, 2) for k, v in rows}
     N = C * H * W
@@ -150,11 +149,10 @@ def knn_case(P, iters, warmup, flush, clustered=False):
         pts[: P // 2] = c[torch.randint(0, 64, (P // 2,), device=dev, generator=g)] + \
             torch.randn(P // 2, 3, device=dev, generator=g) * 0.004
     t = timed(lambda: distCUDA2(pts), iters, warmup, flush)
-    n0 = _lib.load().sfb_profile_count(0)
     _lib.profile_enable(True)
     distCUDA2(pts)
     torch.cuda.synchronize()
-    rows = [r for r in _lib.profile_read(0)[n0:] if r[0].startswith("knn.")]
+    rows = [r for r in _lib.profile_read(0) if r[0].startswith("knn.")]
     _lib.profile_enable(False)
     kern = {}
     for k, v in rows:

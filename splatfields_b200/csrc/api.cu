@@ -380,7 +380,10 @@ int sfb_sh_grad_combine(int P, int V, int sh_degree, int M, const float* means3D
   return SFB_OK;
 }
 
-void sfb_profile_enable(int on) { g_prof = on != 0; }
+void sfb_profile_enable(int on) {
+  g_prof = on != 0;
+  if (g_prof) { g_nrec[0] = g_nrec[1] = 0; g_which = 0; }   // a fresh record list per profiling session (MAX_REC records each)
+}
 
 int sfb_profile_count(int which) { return (which == 0 || which == 1) ? g_nrec[which] : 0; }
 
