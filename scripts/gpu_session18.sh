@@ -1,7 +1,7 @@
 #!/bin/bash
-# Session 17: factored SH-gradient mode + sfb_sh_grad_combine, fused activations (8f-3), distCUDA2 (8f-5): GPU tests,
+# Session 18: factored SH-gradient mode + sfb_sh_grad_combine, fused activations (8f-3), distCUDA2 (8f-5): GPU tests,
 # quick perf of the main path (geom_backward must not regress) and of the new rows.
-TAG=${1:-s17}
+TAG=${1:-s18}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log; tail -25 $OUT/pytest_gpu.log | cut -c1-400

@@ -42,13 +42,15 @@ __global__ void __launch_bounds__(256) activate_forward_kernel(ActParams p) {
     const size_t row = 3 * (size_t)p.M, total = (size_t)p.P * row, e0 = 4 * t;
     if (e0 < total) {
       float v[4];
+      // one division per thread (32-bit whenever the element index fits), then the (Gaussian, column) pair of the
+      // next three elements by carry
+      size_t i = total <= 0xFFFFFFFFull ? (size_t)((uint32_t)e0 / (uint32_t)row) : e0 / row;
+      uint32_t c = (uint32_t)(e0 - i * row);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const size_t e = e0 + k;
-        if (e < total) {
-          const size_t i = e / row, c = e - i * row;
-          v[k] = c < 3 ? __ldg(p.f_dc + 3 * i + c) : __ldg(p.f_rest + i * (row - 3) + (c - 3));
-        } else v[k] = 0.f;
+        v[k] = 0.f;
+        if (e0 + k < total) v[k] = c < 3 ? __ldg(p.f_dc + 3 * i + c) : __ldg(p.f_rest + i * (row - 3) + (c - 3));
+        if (++c == (uint32_t)row) { c = 0; i++; }
       }
       if (e0 + 4 <= total) reinterpret_cast<float4*>(p.features)[t] = make_float4(v[0], v[1], v[2], v[3]);
       else {
@@ -109,14 +111,15 @@ __global__ void __launch_bounds__(256) activate_backward_kernel(ActBwdParams p) 
 #pragma unroll
         for (int k = 0; k < 4; k++) if (e0 + k < total) v[k] = p.dL_dfeatures[e0 + k];
       }
+      size_t i = total <= 0xFFFFFFFFull ? (size_t)((uint32_t)e0 / (uint32_t)row) : e0 / row;
+      uint32_t c = (uint32_t)(e0 - i * row);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const size_t e = e0 + k;
-        if (e < total) {
-          const size_t i = e / row, c = e - i * row;
+        if (e0 + k < total) {
           if (c < 3) { if (p.d_f_dc) p.d_f_dc[3 * i + c] = v[k]; }
           else if (p.d_f_rest) p.d_f_rest[i * (row - 3) + (c - 3)] = v[k];
         }
+        if (++c == (uint32_t)row) { c = 0; i++; }
       }
     }
   }

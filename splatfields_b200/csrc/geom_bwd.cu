@@ -26,7 +26,10 @@ struct CamB {
 // TMA: the block's SH rows arrive through one bulk async copy and its dL_dsh rows leave through one bulk
 // async store (cp.async.bulk both ways, UBLKCP.S.G / UBLKCP.G.S): each thread only touches its own 192-byte
 // row in shared memory (read, then overwritten in place with the gradient row; zeros for culled splats).
-template <int D, bool VEC, bool TMA, int MINB = 1, bool W256 = false>
+// FACT: factored SH gradient (SFB_BWD_SH_FACTORED) — dL_dcolors receives the clamp-masked colour gradient and the
+// dL_dsh rows are not written (sh_grad_combine_kernel below rebuilds their multi-view sum).  A template flag, so
+// that the default instantiations carry no trace of it (a run-time branch cost 4 registers and 10 us at 1M splats).
+template <int D, bool VEC, bool TMA, int MINB = 1, bool W256 = false, bool FACT = false>
 __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, GeomState g) {
   __shared__ CamB cam;
   __shared__ uint64_t s_bar;
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
           for (int k = 0; k < 3 * NB; k++) sh[k] = __ldg(shp + k);
         }
       }
-      float* dsh = p.dL_dsh ? p.dL_dsh + i * p.M * 3 : nullptr;   // nullptr: factored mode (see sh_grad_combine_kernel)
+      float* dsh = p.dL_dsh + i * p.M * 3;
       const float vx = mean[0] - cam.campos[0], vy = mean[1] - cam.campos[1], vz = mean[2] - cam.campos[2];
       const float sum2 = vx * vx + vy * vy + vz * vz;
       const float ilen = rsqrtf(sum2);
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
       float gc[3];
 #pragma unroll
       for (int ch = 0; ch < 3; ch++) gc[ch] = ((cm >> ch) & 1) ? 0.f : gcol[ch];
-      if (p.sh_factored) { gcol[0] = gc[0]; gcol[1] = gc[1]; gcol[2] = gc[2]; }   // dL_dcolors <- clamp-masked gradient
+      if (FACT) { gcol[0] = gc[0]; gcol[1] = gc[1]; gcol[2] = gc[2]; }   // dL_dcolors <- clamp-masked gradient
       float ddx = 0.f, ddy = 0.f, ddz = 0.f;
       float basis[NB];
       basis[0] = SH_C0;
@@ -239,8 +242,8 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) dshv[3 * k + ch] = basis[k] * gc[ch];
       }
-      if (!TMA && !dsh) {
-        // factored mode: the 3*M-float row is rebuilt later from the masked colour gradients of all views
+      if (FACT) {
+        // the 3*M-float row is rebuilt later from the masked colour gradients of all views
       } else if (VEC && !TMA && W256 && (3 * NB) % 8 == 0) {   // launcher guarantees M == (D+1)^2 here
 #pragma unroll
         for (int k = 0; k < (3 * NB) / 8; k++) stg256(dsh + 8 * k, dshv + 8 * k);
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
       drot[2] = 2.f * (qx * (Dr[1] + Dr[3]) + qr * (Dr[2] - Dr[6]) + qz * (Dr[5] + Dr[7])) - 4.f * qy * (Dr[0] + Dr[8]);
       drot[3] = 2.f * (qr * (Dr[3] - Dr[1]) + qx * (Dr[2] + Dr[6]) + qy * (Dr[5] + Dr[7])) - 4.f * qz * (Dr[0] + Dr[4]);
     }
-  } else if (p.shs && (TMA || p.dL_dsh)) {
+  } else if (p.shs && !FACT) {
     float* dsh = p.dL_dsh + i * p.M * 3;
     if (TMA) mbar_wait(&s_bar, 0);     // the incoming row must have landed before it is overwritten
     if (VEC && !TMA && W256) {
@@ -450,7 +453,12 @@ void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s
   static int minb3 = -1;   // experiment: trade a few spills for 3 resident CTAs per SM
   if (minb3 < 0) { const char* e = getenv("SFB_GEOM_MINB3"); minb3 = (e && e[0] == '1') ? 1 : 0; }
 #define SFB_GB(DD)                                                                                         \
-  if (vec && !no_tma && p.dL_dsh && p.M == (DD + 1) * (DD + 1) && smem <= 96 * 1024) {                                \
+  if (p.sh_factored) {                                                                                     \
+    if (vec && p.wide256 && p.M == (DD + 1) * (DD + 1) && (3 * (DD + 1) * (DD + 1)) % 8 == 0)             \
+      geom_backward_kernel<DD, true, false, 2, true, true><<<blocks, 256, 0, s>>>(p, g);                   \
+    else if (vec) geom_backward_kernel<DD, true, false, 1, false, true><<<blocks, 256, 0, s>>>(p, g);      \
+    else geom_backward_kernel<DD, false, false, 1, false, true><<<blocks, 256, 0, s>>>(p, g);              \
+  } else if (vec && !no_tma && p.M == (DD + 1) * (DD + 1) && smem <= 96 * 1024) {                                \
     static bool attr_set = false;                                                                          \
     if (!attr_set) {                                                                                       \
       cudaFuncSetAttribute(geom_backward_kernel<DD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

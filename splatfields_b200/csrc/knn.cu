@@ -148,38 +148,47 @@ __device__ __forceinline__ void knn_insert(float best[3], float d) {   // simple
   }
 }
 
+// One warp per leaf: its 32 lanes are the 32 queries of that leaf, which are neighbours in space, so they want nearly
+// the same boxes.  The warp walks the hierarchy together — a box is opened when ANY lane cannot reject it (ballot) —
+// which keeps control flow uniform, turns every box read into a broadcast and every leaf read into one coalesced 512-byte
+// load whose points then go round by shuffle.  A lane that did not need a box just sees extra candidates; a candidate
+// can never make a best-3 list wrong.
 __global__ void __launch_bounds__(128)
 knn_query_kernel(int P, const float4* __restrict__ sp, const KnnBox* __restrict__ L0, int n0,
                  const KnnBox* __restrict__ L1, int n1, const KnnBox* __restrict__ L2, int n2,
                  float* __restrict__ mean_dist2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  const float4 p = __ldg(sp + i);
+  const int leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (leaf >= n0) return;                                    // whole warps only
+  const int i = leaf * KNN_FAN + lane;
+  const bool live = i < P;
+  const float4 p = live ? __ldg(sp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int cnt_own = min(KNN_FAN, P - leaf * KNN_FAN);
   float best[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
-  // upper bound of the 3rd-neighbour distance from the query's own leaf (its Morton neighbours)
-  const int leaf = i / KNN_FAN;
-  for (int j = leaf * KNN_FAN; j < min(P, (leaf + 1) * KNN_FAN); j++) {
-    if (j == i) continue;
-    const float4 q = __ldg(sp + j);
-    knn_insert(best, dist2_expr(q.x - p.x, q.y - p.y, q.z - p.z));
+  // upper bound of the 3rd-neighbour distance from the query's own leaf: its points are held by the other lanes
+  for (int t = 0; t < cnt_own; t++) {
+    const float qx = __shfl_sync(0xffffffffu, p.x, t), qy = __shfl_sync(0xffffffffu, p.y, t),
+                qz = __shfl_sync(0xffffffffu, p.z, t);
+    if (t != lane) knn_insert(best, dist2_expr(qx - p.x, qy - p.y, qz - p.z));
   }
   const float reject = best[2];
   best[0] = best[1] = best[2] = FLT_MAX;
   for (int a = 0; a < n2; a++) {
-    if (box_dist2(L2[a], p.x, p.y, p.z) > fminf(reject, best[2])) continue;
+    if (!__any_sync(0xffffffffu, live && box_dist2(L2[a], p.x, p.y, p.z) <= fminf(reject, best[2]))) continue;
     for (int b = a * KNN_FAN; b < min(n1, (a + 1) * KNN_FAN); b++) {
-      if (box_dist2(L1[b], p.x, p.y, p.z) > fminf(reject, best[2])) continue;
+      if (!__any_sync(0xffffffffu, live && box_dist2(L1[b], p.x, p.y, p.z) <= fminf(reject, best[2]))) continue;
       for (int c = b * KNN_FAN; c < min(n0, (b + 1) * KNN_FAN); c++) {
-        if (box_dist2(L0[c], p.x, p.y, p.z) > fminf(reject, best[2])) continue;
-        for (int j = c * KNN_FAN; j < min(P, (c + 1) * KNN_FAN); j++) {
-          if (j == i) continue;
-          const float4 q = __ldg(sp + j);
-          knn_insert(best, dist2_expr(q.x - p.x, q.y - p.y, q.z - p.z));
+        if (!__any_sync(0xffffffffu, live && box_dist2(L0[c], p.x, p.y, p.z) <= fminf(reject, best[2]))) continue;
+        const int j0 = c * KNN_FAN, cnt = min(KNN_FAN, P - j0);
+        const float4 mine = lane < cnt ? __ldg(sp + j0 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 0; t < cnt; t++) {
+          const float qx = __shfl_sync(0xffffffffu, mine.x, t), qy = __shfl_sync(0xffffffffu, mine.y, t),
+                      qz = __shfl_sync(0xffffffffu, mine.z, t);
+          if (j0 + t != i) knn_insert(best, dist2_expr(qx - p.x, qy - p.y, qz - p.z));
         }
       }
     }
   }
-  mean_dist2[__float_as_uint(p.w)] = (best[0] + best[1] + best[2]) / 3.0f;
+  if (live) mean_dist2[__float_as_uint(p.w)] = (best[0] + best[1] + best[2]) / 3.0f;
 }
 
 struct KnnScratch {
@@ -247,7 +256,7 @@ int sfb_knn3_mean_dist2(int P, const float* points, float* mean_dist2, void* scr
   knn_boxes_kernel<false><<<(k.n2 * 32 + 255) / 256, 256, 0, s>>>(k.n2, k.n1, nullptr, k.L1, k.L2);
   prof_end(s);
   prof_begin("knn.query", s);
-  knn_query_kernel<<<(P + 127) / 128, 128, 0, s>>>(P, k.sp, k.L0, k.n0, k.L1, k.n1, k.L2, k.n2, mean_dist2);
+  knn_query_kernel<<<(k.n0 * 32 + 127) / 128, 128, 0, s>>>(P, k.sp, k.L0, k.n0, k.L1, k.n1, k.L2, k.n2, mean_dist2);
   prof_end(s);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e)), SFB_ERR_CUDA;
