@@ -103,6 +103,13 @@ int sfb_rasterize_backward(
 int sfb_sh_grad_combine(int P, int V, int sh_degree, int M, const float* means3D, const float* campos,
                         const float* dL_dcolor_views, float* dL_dsh, void* stream);
 
+/* Early hand-off of the factored colour gradient.  The NEXT sfb_rasterize_backward call made with SFB_BWD_SH_FACTORED
+ * (from any thread: PyTorch runs backward on an autograd worker) writes dL_dcolors with a small kernel of its own right
+ * after the render backward, records `cuda_event` (a cudaEvent_t) on its stream, and only then launches the geometry
+ * kernel — so a stream that waits on the event can start the all-gather of dL_dcolors while the geometry kernel
+ * runs.  One-shot: the call consumes the event; pass NULL to cancel. */
+int sfb_backward_midpoint_event(void* cuda_event);
+
 /* Replaces _C.mark_visible: present[i] = 1 iff the view-space z of means3D[i] is > 0.2. */
 int sfb_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      uint8_t* present, void* stream);

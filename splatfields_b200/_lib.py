@@ -23,7 +23,7 @@ SYMBOLS = (
     "sfb_export_geom", "sfb_export_binning", "sfb_export_img", "sfb_last_launch_count",
     "sfb_profile_enable", "sfb_profile_count", "sfb_profile_read", "sfb_profile_name",
     "sfb_loss_scratch_bytes", "sfb_loss_window", "sfb_l1_ssim_loss", "sfb_densify_stats", "sfb_densify_masks",
-    "sfb_sh_grad_combine", "sfb_activate_forward", "sfb_activate_backward", "sfb_knn_scratch_bytes",
+    "sfb_sh_grad_combine", "sfb_backward_midpoint_event", "sfb_activate_forward", "sfb_activate_backward", "sfb_knn_scratch_bytes",
     "sfb_knn3_mean_dist2",
 )
 
@@ -94,6 +94,8 @@ def load():
     lib.sfb_densify_masks.argtypes = [ci, vp, vp, vp, vp, vp, ci, cf, cf, cf, cf, cf, vp, vp, vp, vp, vp]
     lib.sfb_sh_grad_combine.restype = ci
     lib.sfb_sh_grad_combine.argtypes = [ci, ci, ci, ci, vp, vp, vp, vp, vp]
+    lib.sfb_backward_midpoint_event.restype = ci
+    lib.sfb_backward_midpoint_event.argtypes = [vp]
     lib.sfb_activate_forward.restype = ci
     lib.sfb_activate_forward.argtypes = [ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_activate_backward.restype = ci

@@ -7,12 +7,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
 
 namespace {
 
 thread_local std::string g_err;
 int g_launches = 0;   // process-wide: autograd runs backward on its own thread
+std::atomic<void*> g_mid_event{nullptr};   // sfb_backward_midpoint_event: consumed by the next factored backward (any thread)
 thread_local uint32_t* g_pinned = nullptr;  // pinned word the num_rendered counter is copied into
 thread_local cudaEvent_t g_evt = nullptr;
 
@@ -337,6 +339,19 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   g_launches++;
   CK_LAUNCH("render backward", debug, s);
 
+  // Optional early hand-off of the colour gradient (view-parallel exchange): produce it now, record the caller's
+  // event, and let the geometry kernel run while the caller's all-gather is already on the wire.
+  void* mid_evt = sh_factored ? g_mid_event.exchange(nullptr) : nullptr;
+  if (mid_evt) {
+    prof_begin("extract_dcolor", s);
+    launch_extract_dcolor(P, g, radii, dL_dcolors, s);
+    prof_end(s);
+    g_launches++;
+    CK_LAUNCH("colour gradient extraction", debug, s);
+    CK(cudaEventRecord((cudaEvent_t)mid_evt, s));
+    dL_dcolors = nullptr;                       // already written; the geometry kernel must not write it again
+  }
+
   BwdParams bp;
   bp.P = P; bp.D = sh_degree; bp.M = M; bp.W = W; bp.H = H;
   bp.means3D = means3D; bp.shs = shs; bp.colors_precomp = colors_precomp; bp.scales = scales;
@@ -362,6 +377,11 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
       return fail(SFB_ERR_CUDA, msg);
     }
   }
+  return SFB_OK;
+}
+
+int sfb_backward_midpoint_event(void* cuda_event) {
+  g_mid_event.store(cuda_event);
   return SFB_OK;
 }
 

@@ -373,6 +373,7 @@ struct BwdParams {
   float *dL_dmeans2D, *dL_dcolors, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drot;
 };
 void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s);
+void launch_extract_dcolor(int P, const GeomState& g, const int* radii, float* out /* [P][3] */, cudaStream_t s);
 // dL_dsh[i] = sum over V views of basis(normalize(means3D[i] - campos[v])) (x) dcolor[v][i]   (view-parallel exchange)
 void launch_sh_grad_combine(int P, int V, int D, int M, const float* means3D, const float* campos /* [V][3] */,
                             const float* dcolor /* [V][P][3] */, float* dL_dsh /* [P][M][3] */, bool wide256,

@@ -421,6 +421,28 @@ sh_grad_combine_kernel(int P, int V, int M, const float* __restrict__ means3D, c
   }
 }
 
+// The clamp-masked colour gradient on its own, straight from the render backward's accumulators: 12 of the 48 bytes
+// of a GradRec + 1 byte of clamp flags in, 12 bytes out.  Lets the view-parallel exchange start its all-gather
+// BEFORE the geometry kernel runs (sfb_backward_midpoint_event).
+__global__ void __launch_bounds__(256)
+extract_dcolor_kernel(int P, const GradRec* __restrict__ grad, const uint8_t* __restrict__ clamped,
+                      const int* __restrict__ radii, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  float g[3] = {0.f, 0.f, 0.f};
+  if (radii[i] > 0) {
+    const float4* gp = reinterpret_cast<const float4*>(grad + i);
+    const float4 g1 = gp[1], g2 = gp[2];
+    const uint8_t cm = clamped[i];
+    g[0] = (cm & 1) ? 0.f : g1.z; g[1] = (cm & 2) ? 0.f : g1.w; g[2] = (cm & 4) ? 0.f : g2.x;
+  }
+  out[3 * (size_t)i] = g[0]; out[3 * (size_t)i + 1] = g[1]; out[3 * (size_t)i + 2] = g[2];
+}
+
+void launch_extract_dcolor(int P, const GeomState& g, const int* radii, float* out, cudaStream_t s) {
+  if (P > 0) extract_dcolor_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.grad, g.clamped, radii, out);
+}
+
 void launch_sh_grad_combine(int P, int V, int D, int M, const float* means3D, const float* campos,
                             const float* dcolor, float* dL_dsh, bool wide256, cudaStream_t s) {
   if (P <= 0) return;

@@ -62,6 +62,14 @@ class ViewParallelRasterizer:
         self._combine = rasterizer.sh_grad_combine
         self.time_exchange = False       # bench: record CUDA events around the gradient exchange of every step
         self.exchange_events = []
+        # opt-in (SFB_EARLY_GATHER=1): start the all-gather of the colour gradients before the geometry kernel
+        # (sfb_backward_midpoint_event); CUDA only
+        self.early_gather = (self.exchange == "factored" and self.device.type == "cuda"
+                             and os.environ.get("SFB_EARLY_GATHER", "0") == "1")
+        if self.early_gather:
+            self._mid_event = torch.cuda.Event()
+            self._mid_event.record(torch.cuda.current_stream(self.device))     # materialises the cudaEvent_t handle
+            self._side = torch.cuda.Stream(self.device)
         if self.exchange == "factored":
             import torch.distributed as dist
             assert self.fields[-1][0] == "shs"          # the SH rows are the tail of the slab
@@ -87,6 +95,8 @@ class ViewParallelRasterizer:
         n = lib.sfb_last_launch_count()
         factored = self.exchange == "factored"
         rasterizer.set_grad_arena(self.slab, self.fields, self.dcolor_mine.view(self.P, 3) if factored else None)
+        if self.early_gather:
+            _lib.check(lib.sfb_backward_midpoint_event(self._mid_event.cuda_event))
         try:
             # mean over views (train.py:242) folded into the cotangent: backward is linear in it
             color.backward(cotangent if self.world == 1 else cotangent * (1.0 / self.world))
@@ -111,7 +121,14 @@ class ViewParallelRasterizer:
             import torch.distributed as dist
             # all-gather 3 floats / splat / view, all-reduce the 11 geometry floats; the SH rows are rebuilt
             # locally while the all-reduce is still in flight (it only depends on the all-gather)
-            h_ag = dist.all_gather_into_tensor(self.dcolor_views, self.dcolor_mine, async_op=True)
+            if self.early_gather:
+                # the library recorded _mid_event between the colour-gradient kernel and the geometry kernel: the
+                # collective is enqueued behind that event only, so it overlaps the geometry kernel
+                self._side.wait_event(self._mid_event)
+                with torch.cuda.stream(self._side):
+                    h_ag = dist.all_gather_into_tensor(self.dcolor_views, self.dcolor_mine, async_op=True)
+            else:
+                h_ag = dist.all_gather_into_tensor(self.dcolor_views, self.dcolor_mine, async_op=True)
             h_ar = dist.all_reduce(self.slab[:self.geo_floats * self.P], op=dist.ReduceOp.SUM, async_op=True)
             h_ag.wait()
             sh_out = self.slab[self.geo_floats * self.P:]
