@@ -52,7 +52,8 @@ class ViewParallelRasterizer:
             bg=torch.tensor(bg, dtype=torch.float32, device=self.device), scale_modifier=1.0,
             viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, sh_degree=sh_degree,
             campos=cam.camera_center, prefiltered=False, debug=False)
-        self.rast = GaussianRasterizer(self.settings)
+        self.rast_factory = lambda settings, cam: GaussianRasterizer(settings)   # (the CPU tests plug a stand-in in)
+        self.rast = self.rast_factory(self.settings, cam)
         self.means2D = torch.zeros(self.P, 3, device=self.device, requires_grad=True)
         self.fields = SLAB_FIELDS_SH if "shs" in scene else SLAB_FIELDS_RGB
         self.floats_per_splat = sum(n for _, n in self.fields)
@@ -81,6 +82,39 @@ class ViewParallelRasterizer:
             allc = [torch.empty_like(mine) for _ in range(self.world)]
             dist.all_gather(allc, mine)
             self.campos_views = torch.stack(allc).contiguous()
+
+    # -- per-job state for (view, time)-sharded runs (BASELINE.json configs[4]): a new camera and / or new means
+    def set_camera(self, camera) -> None:
+        """Render another camera from now on.  In factored mode every rank must call this in the same step (the
+        camera centres are re-gathered)."""
+        cam = camera.to(self.device)
+        self.settings = self.settings._replace(
+            tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5), viewmatrix=cam.world_view_transform,
+            projmatrix=cam.full_proj_transform, campos=cam.camera_center)
+        self.rast = self.rast_factory(self.settings, cam)
+        if self.exchange == "factored":
+            import torch.distributed as dist
+            mine = cam.camera_center.detach().to(self.device, torch.float32).reshape(3).contiguous()
+            allc = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allc, mine)
+            self.campos_views = torch.stack(allc).contiguous()
+
+    def set_means(self, means3D: torch.Tensor, same_on_all_ranks: bool = False) -> None:
+        """Replace the means, e.g. canonical means + this job's per-frame offset.  The factored exchange rebuilds the
+        SH rows from the means THIS rank holds, so it needs identical means on every rank; ranks that render
+        different time steps must use exchange="allreduce" (precomputed colours, the 4D recipe's input, always do)."""
+        if self.exchange == "factored" and not same_on_all_ranks:
+            raise Exception("per-rank means with the factored SH exchange: construct with exchange='allreduce', "
+                            "or pass same_on_all_ranks=True if every rank sets the same means")
+        with torch.no_grad():
+            self.params["means3D"].copy_(means3D.to(self.device))
+
+    def idle_step(self) -> int:
+        """A round in which this rank has no job: contribute zeros to the exchange (collectives stay symmetric)."""
+        self.slab.zero_()
+        if self.exchange == "factored":
+            self.dcolor_mine.zero_()
+        return self._exchange(0, early=False)
 
     # -- one fwd + bwd (+ gradient exchange); returns the number of library kernel launches issued
     def step(self, cotangent: torch.Tensor, keep: bool = False) -> int:
@@ -113,6 +147,16 @@ class ViewParallelRasterizer:
                 dst.zero_()
             elif g.data_ptr() != dst.data_ptr():
                 dst.copy_(g.reshape(-1))
+        n = self._exchange(n, early=self.early_gather)
+        if keep:
+            self.last = (color.detach(), radii, depth.detach())
+        return n
+
+    def _exchange(self, n: int, early: bool = False) -> int:
+        """Sum the gradient slab over the ranks (module docstring); n = launch counter to continue; early = this
+        step's backward recorded _mid_event behind the colour-gradient kernel."""
+        p = self.params
+        factored = self.exchange == "factored"
         ev = None
         if self.time_exchange and self.world > 1 and self.device.type == "cuda":
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -121,7 +165,7 @@ class ViewParallelRasterizer:
             import torch.distributed as dist
             # all-gather 3 floats / splat / view, all-reduce the 11 geometry floats; the SH rows are rebuilt
             # locally while the all-reduce is still in flight (it only depends on the all-gather)
-            if self.early_gather:
+            if early:
                 # the library recorded _mid_event between the colour-gradient kernel and the geometry kernel: the
                 # collective is enqueued behind that event only, so it overlaps the geometry kernel
                 self._side.wait_event(self._mid_event)
@@ -141,8 +185,6 @@ class ViewParallelRasterizer:
         if ev is not None:
             ev[1].record()
             self.exchange_events.append(ev)
-        if keep:
-            self.last = (color.detach(), radii, depth.detach())
         return n
 
     def exchange_ms(self) -> list:

@@ -144,3 +144,25 @@ def config_camera(name: str, k: int = 0) -> SynthCamera:
         fovy = focal2fov(2892.0, 1200)
         return orbit_camera(k, c["H"], c["W"], camera_angle_x=fovx, fovy=fovy)
     return orbit_camera(k, c["H"], c["W"])
+
+
+def frame_offset(P: int, t: float, seed: int = 4, amplitude: float = 0.05) -> torch.Tensor:
+    """Deterministic per-frame displacement of the means for the 4D configuration (BASELINE.json configs[4],
+    SURVEY.md §8d): offset_i(t) = amplitude * sin(2 pi t + phi_i), phi_i ~ U(0, 2 pi) per coordinate (seeded).
+    Stands in for the deformation network of scene/deform_model.py, which is the reference's model, not this path."""
+    g = torch.Generator().manual_seed(10_000 + seed)
+    phi = torch.rand(P, 3, generator=g) * (2.0 * math.pi)
+    return amplitude * torch.sin(2.0 * math.pi * float(t) + phi)
+
+
+def view_time_jobs(n_frames: int, n_views: int, rank: int = 0, world: int = 1) -> list:
+    """(frame, view) jobs of one rank: job j = frame * n_views + view goes to rank j % world (round-robin).
+    With world ranks the jobs of round r are j = r * world .. r * world + world - 1; a rank without a job in the
+    last round gets None there (it still takes part in that round's gradient exchange, contributing zeros)."""
+    total = n_frames * n_views
+    rounds = (total + world - 1) // world
+    out = []
+    for r in range(rounds):
+        j = r * world + rank
+        out.append((j // n_views, j % n_views) if j < total else None)
+    return out

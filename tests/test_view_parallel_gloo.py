@@ -164,3 +164,78 @@ def test_slab_layout():
     for v in g.values():
         assert v.data_ptr() == vp.slab.data_ptr() + 4 * off
         off += v.numel()
+
+
+def test_view_time_jobs_cover_every_job_once():
+    for n_frames, n_views, world in ((300, 6, 8), (3, 2, 2), (5, 3, 4), (1, 1, 8)):
+        seen = []
+        rounds = None
+        for r in range(world):
+            jobs = synth.view_time_jobs(n_frames, n_views, r, world)
+            rounds = len(jobs) if rounds is None else rounds
+            assert len(jobs) == rounds                       # every rank takes part in every round
+            seen += [j for j in jobs if j is not None]
+        assert sorted(seen) == [(f, v) for f in range(n_frames) for v in range(n_views)]
+    off0, off1 = synth.frame_offset(50, 0.0), synth.frame_offset(50, 1.0)
+    assert off0.shape == (50, 3) and float(off0.abs().max()) <= 0.05 + 1e-7
+    assert torch.allclose(off0, off1, atol=1e-6)             # period 1 in t
+    assert not torch.allclose(off0, synth.frame_offset(50, 0.25), atol=1e-3)
+
+
+def _worker_view_time(rank, world, port, ret):
+    """BASELINE config 4 in miniature: 3 frames x 1 view = 3 jobs over 2 ranks (the last round has an idle rank);
+    per-job camera and per-frame means; gradients summed per round == the serial loop over the round's jobs."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P, H, W = 30, 8, 12
+        n_frames, n_views = 3, 1
+        sc = synth.make_scene(P, 6)
+        base = sc["means3D"].clone()
+        vp = ViewParallelRasterizer(sc, synth.orbit_camera(0, H, W), H, W, 3, device="cpu", world_size=world,
+                                    exchange="allreduce")
+        vp.rast_factory = lambda settings, cam: _StubRast(cam, H, W)
+        jobs = synth.view_time_jobs(n_frames, n_views, rank, world)
+        ok = True
+        for rnd, job in enumerate(jobs):
+            if job is None:
+                vp.idle_step()
+            else:
+                f, v = job
+                vp.set_camera(synth.orbit_camera(v + f, H, W))
+                vp.set_means(base + synth.frame_offset(P, f / n_frames))
+                G = torch.randn(3, H, W, generator=torch.Generator().manual_seed(7 * f + v))
+                vp.step(G)
+            got = {k: t.clone() for k, t in vp.grads().items()}
+            if rank == 0:
+                leaves = {k: t.clone().requires_grad_(True) for k, t in sc.items()}
+                losses = []
+                for r in range(world):
+                    jr = synth.view_time_jobs(n_frames, n_views, r, world)[rnd]
+                    if jr is None:
+                        continue
+                    f, v = jr
+                    G = torch.randn(3, H, W, generator=torch.Generator().manual_seed(7 * f + v))
+                    m = leaves["means3D"] + synth.frame_offset(P, f / n_frames)
+                    col, _, _ = _StubRast(synth.orbit_camera(v + f, H, W), H, W)(
+                        m, torch.zeros(P, 3), leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"],
+                        rotations=leaves["rotations"])
+                    losses.append((col * G).sum())
+                (sum(losses) / world).backward()
+                ok = ok and all(torch.allclose(got[n], leaves[n].grad.reshape(-1), rtol=1e-4, atol=1e-5)
+                                for n, _ in SLAB_FIELDS_SH)
+        with_factored_guard = False
+        try:
+            vpf = ViewParallelRasterizer(sc, synth.orbit_camera(0, H, W), H, W, 3, device="cpu", world_size=world,
+                                         exchange="factored")
+            vpf.set_means(base)
+        except Exception:
+            with_factored_guard = True
+        if rank == 0:
+            ret.put(bool(ok and with_factored_guard))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_view_time_sharded_rounds_match_serial_loop():
+    _spawn2(_worker_view_time)
