@@ -316,12 +316,18 @@ def run_ours(args):
             traffic_tbl = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         except Exception:
             pass
+        ncu_stats = {}
+        try:     # issue-slot utilisation / DRAM % of the same capture: what actually bounds each kernel
+            ncu_stats = json.load(open(os.path.join(ROOT, "profiles", "ncu_kernel_stats.json")))
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic_tbl.get(dom), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": int(ab), "kernel_ms_per_launch": per_launch[dom],
                     "kernel_share_of_step": per_step[dom] / max(sum(per_step.values()), 1e-9),
-                    "note": "the two render kernels are issue-bound, not HBM-bound (ncu: ~82% issue-active, "
-                            "<1% DRAM; their splat records stay L2-resident), so their HBM fraction is low by "
+                    "ncu": ncu_stats.get(dom),
+                    "note": "the two render kernels are issue-bound, not HBM-bound (ncu: 60-79% issue-active, "
+                            "<3% DRAM; their splat records stay L2-resident), so their HBM fraction is low by "
                             "construction; see roofline_by_kernel for the HBM-bound kernels"}
         roofline_by_kernel = {}
         for kname in per_launch:
@@ -330,7 +336,9 @@ def run_ours(args):
                 a_k = abk / (per_launch[kname] * 1e-3) / 1e9
                 roofline_by_kernel[kname] = {"achieved_GBps": round(a_k, 1), "frac": round(a_k / peak, 4),
                                              "ms_per_launch": round(per_launch[kname], 4),
-                                             "traffic": traffic_tbl.get(kname)}
+                                             "traffic": traffic_tbl.get(kname),
+                                             "ncu_issue_active_pct": (ncu_stats.get(kname) or {}).get("issue_active_pct"),
+                                             "ncu_dram_pct_of_peak": (ncu_stats.get(kname) or {}).get("dram_pct_of_peak")}
         total_bytes = P * 878 + stats["R"] * 200 + H * W * 44     # SURVEY §8d whole-path figure
         stages = {"roofline_by_kernel": roofline_by_kernel, "ms_per_step_by_kernel": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
                   "num_rendered": stats["R"], "visible": stats["visible"], "mean_tile_list": stats["mean_list"],

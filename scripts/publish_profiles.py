@@ -63,6 +63,36 @@ def traffic(raw_csv, src):
     return out
 
 
+def kernel_stats(raw_csv, src):
+    """Per stage (average over its launches): issue-slot utilisation, DRAM / SM throughput (% of peak), registers,
+    warp instructions — the numbers that say what bounds a kernel whose HBM fraction is low by construction."""
+    rows = list(csv.reader(open(raw_csv)))
+    hdr, data = rows[0], rows[2:]
+    kn = hdr.index("Kernel Name")
+    cols = {"issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "dram_pct_of_peak": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm_pct_of_peak": "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "registers": "launch__registers_per_thread", "warp_instructions": "smsp__inst_executed.sum",
+            "duration_us_under_ncu": "gpu__time_duration.sum"}
+    idx = {k: hdr.index(v) for k, v in cols.items() if v in hdr}
+    per = collections.defaultdict(list)
+    seen_hist = 0
+    for r in data:
+        name = r[kn]
+        vals = {k: float(r[i].replace(",", "")) for k, i in idx.items()}
+        if "radix_hist_all_kernel" in name:
+            per["depth_sort.hist" if seen_hist == 0 else "tile_sort.hist"].append(vals)
+            seen_hist += 1
+            continue
+        for pat, stage in STAGES:
+            if pat in name and "radix_hist" not in pat:
+                per[stage].append(vals)
+                break
+    out = {st: {k: round(sum(v[k] for v in lst) / len(lst), 2) for k in lst[0]} for st, lst in per.items()}
+    out["_source"] = src
+    return out
+
+
 def main(sess, tag):
     os.makedirs("profiles", exist_ok=True)
     for f, dst in [("bench_n1.json", f"{tag}_bench_n1.json"), ("launches.csv", f"{tag}_launches.csv"),
@@ -78,6 +108,8 @@ def main(sess, tag):
                          "forward+backward, average per launch of the kernels that run several times per step; "
                          "dram__bytes_read.sum + dram__bytes_write.sum)")
         json.dump(t, open("profiles/ncu_traffic.json", "w"), indent=1)
+        json.dump(kernel_stats(raw, f"profiles/{tag}_ncu_full_summary.txt (same capture as ncu_traffic.json)"),
+                  open("profiles/ncu_kernel_stats.json", "w"), indent=1)
     if os.path.exists(os.path.join(sess, "launches.csv")):
         open(f"profiles/{tag}_launch_shares.txt", "w").write(launch_shares(os.path.join(sess, "launches.csv")))
 
