@@ -55,7 +55,10 @@ class ViewParallelRasterizer:
         self.rast_factory = lambda settings, cam: GaussianRasterizer(settings)   # (the CPU tests plug a stand-in in)
         self.rast = self.rast_factory(self.settings, cam)
         self.means2D = torch.zeros(self.P, 3, device=self.device, requires_grad=True)
-        self.fields = SLAB_FIELDS_SH if "shs" in scene else SLAB_FIELDS_RGB
+        if "shs" in scene:       # 3 * M floats of SH per splat (M = 16 for the reference's max_sh_degree = 3)
+            self.fields = SLAB_FIELDS_SH[:-1] + (("shs", 3 * int(scene["shs"].shape[1])),)
+        else:
+            self.fields = SLAB_FIELDS_RGB
         self.floats_per_splat = sum(n for _, n in self.fields)
         # the flat gradient slab: field-major [sum(n), P] so every field is one contiguous run
         self.slab = torch.empty(self.floats_per_splat * self.P, dtype=torch.float32, device=self.device)

@@ -239,3 +239,13 @@ def _worker_view_time(rank, world, port, ret):
 
 def test_view_time_sharded_rounds_match_serial_loop():
     _spawn2(_worker_view_time)
+
+
+def test_slab_layout_follows_sh_coefficient_count():
+    sc = synth.make_scene(16, 1, sh_coeffs=9)          # max_sh_degree = 2
+    vp = ViewParallelRasterizer(sc, synth.orbit_camera(0, 16, 16), 16, 16, 2, device="cpu")
+    assert vp.floats_per_splat == 11 + 27 and vp.grads()["shs"].numel() == 27 * 16
+    rgb = synth.make_scene(16, 1, precomp_rgb=True)
+    vp = ViewParallelRasterizer(rgb, synth.orbit_camera(0, 16, 16), 16, 16, 0, device="cpu")
+    assert [k for k in vp.grads()] == ["means3D", "opacities", "scales", "rotations", "colors_precomp"]
+    assert vp.floats_per_splat == 14 and vp.exchange == "allreduce"
