@@ -3,7 +3,8 @@
 #   1. the GPU suite, then the experimental tests (SFB_EARLY_GATHER hand-off)
 #   2. bench at N = 1 (must still read ~1234 Msplats/s)
 #   3. ncu --set full of the kernels that have no capture yet (activate, knn, sh_grad_combine, loss, densify)
-#   4. config 4 in one process (view x time jobs, precomputed RGB)
+#   4. A/B of the opt-in tight tile rectangles (SFB_TIGHT_RECT=1)
+#   5. config 4 in one process (view x time jobs, precomputed RGB)
 TAG=${1:-r2a}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
@@ -15,4 +16,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$K"
     python scripts/quick_perf_next_rows.py --iters 1 --warmup 0 > $OUT/ncu_next_rows.log 2>&1
 ncu -i $OUT/prof_next_rows.ncu-rep --page raw --csv > $OUT/ncu_next_rows_raw.csv 2>/dev/null
 python scripts/ncu_summary.py $OUT/ncu_next_rows_raw.csv > $OUT/ncu_next_rows_summary.txt 2>&1; grep -c "^==" $OUT/ncu_next_rows_summary.txt
+for c in lego_100k lego_1m dtu_500k; do timeout 300 python scripts/ab_tight_rect.py --config $c >> $OUT/ab_tight_rect.jsonl 2>> $OUT/ab_tight_rect.err; done; cat $OUT/ab_tight_rect.jsonl
 timeout 300 python scripts/run_view_time.py --rounds 24 > $OUT/view_time_n1.json 2> $OUT/view_time_n1.err; cat $OUT/view_time_n1.json; tail -2 $OUT/view_time_n1.err

@@ -94,6 +94,8 @@ bool fused_ranges_enabled() { static int v = -1; if (v < 0) v = knob_on("SFB_FUS
 bool fold_memsets_enabled() { static int v = -1; if (v < 0) v = knob_on("SFB_FOLD_MEMSETS", true) && !sfb::radix_sort_is_legacy(); return v == 1; }
 bool nr_memcpy_enabled() { static int v = -1; if (v < 0) v = knob_on("SFB_NR_MEMCPY", false); return v == 1; }
 
+bool tight_rect_enabled() { static int v = -1; if (v < 0) v = knob_on("SFB_TIGHT_RECT", false); return v == 1; }
+
 bool wide256_enabled() {   // SFB_NO_LD256=1 falls back to 128-bit accesses (A/B knob)
   static int v = -1;
   if (v < 0) { const char* e = getenv("SFB_NO_LD256"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -194,6 +196,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   fp.scales = scales; fp.rotations = rotations; fp.cov3D_precomp = cov3D_precomp;
   fp.viewmatrix = viewmatrix; fp.projmatrix = projmatrix; fp.campos = campos;
   fp.scale_modifier = scale_modifier; fp.tan_fovx = tan_fovx; fp.tan_fovy = tan_fovy; fp.prefiltered = prefiltered;
+  fp.tight_rect = tight_rect_enabled() ? 1 : 0;
   fp.wide256 = wide256_enabled() && shs && ((M * 12) % 32 == 0) && ((reinterpret_cast<size_t>(shs) & 31) == 0);
   const bool fold = fold_memsets_enabled();
   const size_t dzero = fold ? radix_sort_zero_words(P, 32) : 0;

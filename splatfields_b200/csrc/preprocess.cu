@@ -107,7 +107,11 @@ __device__ __forceinline__ void sh_to_rgb(const float* sh, float3 mean, const fl
 // into shared memory by ONE bulk async copy (cp.async.bulk -> UBLKCP) issued at kernel start and awaited on an
 // mbarrier only where the colours are needed, so the 192 B/Gaussian stream overlaps the projection math and
 // reaches DRAM as full sequential bursts instead of 32 strided 16-byte requests per load instruction.
-template <int D, bool VEC_SH, bool TMA_SH>
+// TIGHT (opt-in, SFB_TIGHT_RECT=1; NOT reference-identical lists): the tile rectangle is intersected with the
+// footprint box below, so tiles in which the splat provably fails the alpha >= 1/255 test on every pixel are never
+// emitted.  The image and the gradients do not change (those tiles' instances are no-ops), but tiles_touched / R / the
+// key and index buffers shrink, which is why it is a separate instantiation and off by default.
+template <int D, bool VEC_SH, bool TMA_SH, bool TIGHT = false>
 __global__ void __launch_bounds__(256)
 preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
   __shared__ Cam cam;
@@ -276,6 +280,17 @@ preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
             hx = ill ? 3.0e38f : 1.02f * sqrtf(tau * a) + 0.5f;
             hy = ill ? 3.0e38f : 1.02f * sqrtf(tau * c) + 0.5f;
           }
+          if (TIGHT && hx < 1.0e30f) {
+            if (hx < 0.f) { area = 0; }
+            else {   // pixel centres sit on integers: pixel px can be touched only if |px - pix| <= hx
+              x0 = max(x0, clampi((int)floorf((pix - hx) / (float)TILE_X), 0, gx));
+              y0 = max(y0, clampi((int)floorf((piy - hy) / (float)TILE_Y), 0, gy));
+              x1 = min(x1, clampi((int)floorf((pix + hx) / (float)TILE_X) + 1, 0, gx));
+              y1 = min(y1, clampi((int)floorf((piy + hy) / (float)TILE_Y) + 1, 0, gy));
+              area = max(x1 - x0, 0) * max(y1 - y0, 0);
+            }
+            if (area == 0) { x0 = x1 = y0 = y1 = 0; }
+          }
           float4* rp = reinterpret_cast<float4*>(g.rec + idx);
           rp[0] = make_float4(pix, piy, conA, conB);
           rp[1] = make_float4(conC, opac, p_view.z, rgb[0]);
@@ -339,7 +354,7 @@ static void launch_pre_d(const FwdParams& p, const GeomState& g, int* radii, cud
   int blocks = (p.P + 255) / 256;
   bool vec = p.shs && ((p.M * 3) % 4 == 0) && ((reinterpret_cast<size_t>(p.shs) & 15) == 0);
   // the bulk-copy path moves whole rows: use it when every coefficient of the row is active
-  bool tma = vec && tma_enabled() && p.M == (D + 1) * (D + 1) && (size_t)256 * p.M * 12 <= 96 * 1024;
+  bool tma = vec && !p.tight_rect && tma_enabled() && p.M == (D + 1) * (D + 1) && (size_t)256 * p.M * 12 <= 96 * 1024;
   if (tma) {
     const size_t smem = (size_t)256 * p.M * 12;
     static bool attr_set = false;
@@ -348,6 +363,9 @@ static void launch_pre_d(const FwdParams& p, const GeomState& g, int* radii, cud
       attr_set = true;
     }
     preprocess_kernel<D, true, true><<<blocks, 256, smem, s>>>(p, g, radii);
+  } else if (p.tight_rect) {
+    if (vec) preprocess_kernel<D, true, false, true><<<blocks, 256, 0, s>>>(p, g, radii);
+    else     preprocess_kernel<D, false, false, true><<<blocks, 256, 0, s>>>(p, g, radii);
   } else if (vec) {
     preprocess_kernel<D, true, false><<<blocks, 256, 0, s>>>(p, g, radii);
   } else {
