@@ -216,7 +216,6 @@ class ViewParallelRasterizer:
 
     # -- tile-list statistics of this rank's view (for the bench's roofline accounting)
     def list_stats(self) -> dict:
-        import ctypes as C  # noqa: F401
         lib = _lib.load()
         p = self.params
         color, radii, depth = self.rast(means3D=p["means3D"], means2D=self.means2D, opacities=p["opacities"],

@@ -63,3 +63,54 @@ def test_patch_culling_never_drops_a_contributing_pair(seed, smax, off):
     # and it is tight: of the pairs it keeps (well-conditioned splats), at most a few percent never contribute
     kept_ok = keep & ~ill
     assert (kept_ok & ~contrib).sum() <= 0.05 * max(kept_ok.sum(), 1)
+
+
+@pytest.mark.parametrize("seed,smax", [(3, 40), (4, 150), (5, 6)])
+def test_tight_tile_rect_never_drops_a_contributing_tile(seed, smax):
+    """The opt-in SFB_TIGHT_RECT path (preprocess.cu, TIGHT instantiation) clips the reference's tile rectangle to the
+    footprint box.  Restated in float32 numpy (same expressions: floorf, +1 on the exclusive edge, clamps to the grid)
+    and checked by brute force: no pixel of a dropped tile passes the reference's alpha >= 1/255 test."""
+    N, gx, gy = 4000, 50, 50                     # 800x800 image
+    rng = np.random.default_rng(seed)
+    a, cc, A, B, C, op, ill, _, _ = _cases(seed, N, smax, 60)
+    op = np.where(rng.random(N) < 0.1, f32(0.002), op)            # some splats below 1/255 everywhere
+    pix = rng.uniform(-40, 840, N).astype(f32)
+    piy = rng.uniform(-40, 840, N).astype(f32)
+    mid = f32(0.5) * (a + cc)
+    det = a * cc - (B / (A * C - B * B)) ** 2                      # b^2 recovered from the conic (b = -B * det)
+    lam1 = mid + np.sqrt(np.maximum(f32(0.1), mid * mid - det)).astype(f32)
+    rad = np.ceil(f32(3.0) * np.sqrt(lam1)).astype(f32)
+    clampi = lambda v, hi: np.clip(v, 0, hi)
+    x0 = clampi(((pix - rad) / f32(16)).astype(np.int32), gx); y0 = clampi(((piy - rad) / f32(16)).astype(np.int32), gy)
+    x1 = clampi(((pix + rad + f32(15)) / f32(16)).astype(np.int32), gx)
+    y1 = clampi(((piy + rad + f32(15)) / f32(16)).astype(np.int32), gy)
+    tau = np.maximum(f32(0), (f32(2) * np.log(f32(255) * op)).astype(f32))
+    hx = np.where(ill, f32(3e38), f32(1.02) * np.sqrt(tau * a) + f32(0.5)).astype(f32)
+    hy = np.where(ill, f32(3e38), f32(1.02) * np.sqrt(tau * cc) + f32(0.5)).astype(f32)
+    below = op < f32(1 / 255.0)
+    with np.errstate(over="ignore", invalid="ignore"):
+        tx0 = np.maximum(x0, clampi(np.floor((pix - hx) / f32(16)).astype(np.int64), gx))
+        ty0 = np.maximum(y0, clampi(np.floor((piy - hy) / f32(16)).astype(np.int64), gy))
+        tx1 = np.minimum(x1, clampi(np.floor((pix + hx) / f32(16)).astype(np.int64) + 1, gx))
+        ty1 = np.minimum(y1, clampi(np.floor((piy + hy) / f32(16)).astype(np.int64) + 1, gy))
+    big = hx >= f32(1e30)
+    tx0, ty0, tx1, ty1 = (np.where(big, o, t) for o, t in ((x0, tx0), (y0, ty0), (x1, tx1), (y1, ty1)))
+    tx1 = np.where(below, tx0, tx1)                                 # area 0
+    ox, oy = np.meshgrid(np.arange(16, dtype=np.float32), np.arange(16, dtype=np.float32))
+    dropped = kept = contributing_dropped = 0
+    for i in range(N):
+        for ty in range(y0[i], y1[i]):
+            for tx in range(x0[i], x1[i]):
+                if tx0[i] <= tx < tx1[i] and ty0[i] <= ty < ty1[i]:
+                    kept += 1
+                    continue
+                dropped += 1
+                dx = pix[i] - (f32(16 * tx) + ox)
+                dy = piy[i] - (f32(16 * ty) + oy)
+                power = ((A[i] * dx) * dx + (C[i] * dy) * dy) * f32(-0.5) - (B[i] * dx) * dy
+                with np.errstate(over="ignore"):
+                    alpha = np.minimum(f32(0.99), op[i] * np.exp(power.astype(f32)))
+                if ((power <= 0) & (alpha >= f32(1 / 255.0))).any():
+                    contributing_dropped += 1
+    assert dropped > 0.05 * (dropped + kept), "the clip should remove a visible share of the tiles"
+    assert contributing_dropped == 0
