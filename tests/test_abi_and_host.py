@@ -52,6 +52,14 @@ def test_next_row_mirrors_refuse_cpu_tensors():
         losses.photometric_loss(torch.zeros(3, 8, 8), torch.zeros(3, 8, 8), 0.2)
     with pytest.raises(Exception, match="CUDA tensor"):
         densify.add_densification_stats(torch.zeros(4, 1), torch.zeros(4, 1), torch.zeros(4, 3), radii=torch.ones(4))
+    from splatfields_b200 import activate_parameters, distCUDA2, rasterizer
+    with pytest.raises(SplatB200Error, match="no CPU fallback"):
+        activate_parameters(torch.zeros(4, 3), torch.zeros(4, 3), torch.zeros(4, 4), torch.zeros(4, 1),
+                            torch.zeros(4, 1, 3), torch.zeros(4, 15, 3))
+    with pytest.raises(SplatB200Error, match="no CPU fallback"):
+        distCUDA2(torch.zeros(8, 3))
+    with pytest.raises(SplatB200Error, match="no CPU fallback"):
+        rasterizer.sh_grad_combine(torch.zeros(4, 3), torch.zeros(1, 3), torch.zeros(1, 4, 3), 3, torch.zeros(4, 16, 3))
 
 
 def test_library_is_sm100a_only():
