@@ -94,6 +94,19 @@ def test_oracle_binning_invariants(oracle):
         assert rg[t, 0] == idx[0] and rg[t, 1] == idx[-1] + 1
     empty = np.setdiff1d(np.arange(rg.shape[0]), np.unique(tiles))
     assert np.all(rg[empty] == 0)
+    # independent construction: every (Gaussian, tile of its rectangle) instance, ordered by (tile, depth bits, index)
+    gx, gy = (160 + 15) // 16, (128 + 15) // 16
+    inst = []
+    for i in np.nonzero(f["radii"] > 0)[0]:
+        x, y, r = f["means2D"][i, 0], f["means2D"][i, 1], np.float32(f["radii"][i])
+        x0, y0 = min(gx, max(0, int((x - r) / 16))), min(gy, max(0, int((y - r) / 16)))
+        x1, y1 = min(gx, max(0, int((x + r + 15) / 16))), min(gy, max(0, int((y + r + 15) / 16)))
+        d = int(f["depths"][i:i + 1].view(np.uint32)[0])
+        inst += [((ty * gx + tx) << 32 | d, i) for ty in range(y0, y1) for tx in range(x0, x1)]
+    inst.sort()
+    assert len(inst) == R
+    assert np.array_equal(np.array([k for k, _ in inst], np.uint64), keys)
+    assert np.array_equal(np.array([i for _, i in inst], np.uint32), pl)
 
 
 def test_empty_and_invisible_inputs(oracle):
@@ -105,3 +118,32 @@ def test_empty_and_invisible_inputs(oracle):
     assert f["num_rendered"] == 0 and np.all(f["radii"] == 0)
     assert np.allclose(f["color"], np.array([0.2, 0.4, 0.6], np.float32)[:, None, None])
     assert all(np.all(v == 0) for v in b.values())
+
+
+def test_oracle_parallel_sort_matches_numpy_stable_sort(oracle):
+    """The multi-threaded path of the oracle's radix sort (>= 65536 instances, >= 2 threads): same list as numpy's
+    stable sort of the emission-order keys."""
+    from tests.helpers import run_oracle
+    oracle.set_num_threads(4)
+    H, W = 256, 320
+    sc = synth.make_scene(20000, 13, scale_mult=2.5)
+    f, _ = run_oracle(oracle, sc, synth.orbit_camera(2, H, W), H, W, [1, 1, 1], 3, want_margin=False)
+    R = f["num_rendered"]
+    assert R >= (1 << 16)
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    vis = np.nonzero(f["radii"] > 0)[0]
+    x, y, r = f["means2D"][vis, 0], f["means2D"][vis, 1], f["radii"][vis].astype(np.float32)
+    cl = lambda v, hi: np.clip(v.astype(np.int64), 0, hi)
+    x0, y0 = cl((x - r) / np.float32(16), gx), cl((y - r) / np.float32(16), gy)
+    x1, y1 = cl((x + r + np.float32(15)) / np.float32(16), gx), cl((y + r + np.float32(15)) / np.float32(16), gy)
+    d = f["depths"][vis].view(np.uint32).astype(np.uint64)
+    keys, vals = [], []
+    for k, i in enumerate(vis):                 # emission order: Gaussian index, then rows, then columns
+        ty, tx = np.meshgrid(np.arange(y0[k], y1[k]), np.arange(x0[k], x1[k]), indexing="ij")
+        t = (ty * gx + tx).reshape(-1).astype(np.uint64)
+        keys.append((t << np.uint64(32)) | d[k])
+        vals.append(np.full(t.size, i, np.uint32))
+    keys, vals = np.concatenate(keys), np.concatenate(vals)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(keys[order], f["point_list_keys"])
+    assert np.array_equal(vals[order], f["point_list"])
