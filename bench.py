@@ -187,6 +187,53 @@ def algorithmic_bytes(kernel, P, R, R_fwd, R_bwd, HW, n_visible):
     return 0
 
 
+def roofline_report(acc, nprof, stats, P, HW, ms_step):
+    """(roofline, stages) objects of the bench line from the per-kernel event timings of the profiled steps.
+    acc: {kernel name: [ms of every launch over nprof steps]}; stats: ViewParallelRasterizer.list_stats()."""
+    # a kernel name can occur several times per step (radix passes): per-launch average duration
+    per_step = {k: sum(v) / nprof for k, v in acc.items()}
+    per_launch = {k: sum(v) / len(v) for k, v in acc.items()}
+    dom = max(per_step, key=per_step.get)
+    peak, peak_src = measured_peak_hbm()
+    ab = algorithmic_bytes(dom, P, stats["R"], stats["R_fwd"], stats["R_bwd"], HW, stats["visible"])
+    ach = ab / (per_launch[dom] * 1e-3) / 1e9
+    traffic_tbl = {}
+    try:     # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/)
+        traffic_tbl = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+    ncu_stats = {}
+    try:     # issue-slot utilisation / DRAM % of the same capture: what actually bounds each kernel
+        ncu_stats = json.load(open(os.path.join(ROOT, "profiles", "ncu_kernel_stats.json")))
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": traffic_tbl.get(dom), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(ab), "kernel_ms_per_launch": per_launch[dom],
+                "kernel_share_of_step": per_step[dom] / max(sum(per_step.values()), 1e-9),
+                "ncu": ncu_stats.get(dom),
+                "note": "the two render kernels are issue-bound, not HBM-bound (ncu: 60-79% issue-active, "
+                        "<3% DRAM; their splat records stay L2-resident), so their HBM fraction is low by "
+                        "construction; see roofline_by_kernel for the HBM-bound kernels"}
+    roofline_by_kernel = {}
+    for kname in per_launch:
+        abk = algorithmic_bytes(kname, P, stats["R"], stats["R_fwd"], stats["R_bwd"], HW, stats["visible"])
+        if abk:
+            a_k = abk / (per_launch[kname] * 1e-3) / 1e9
+            roofline_by_kernel[kname] = {
+                "achieved_GBps": round(a_k, 1), "frac": round(a_k / peak, 4),
+                "ms_per_launch": round(per_launch[kname], 4), "traffic": traffic_tbl.get(kname),
+                "ncu_issue_active_pct": (ncu_stats.get(kname) or {}).get("issue_active_pct"),
+                "ncu_dram_pct_of_peak": (ncu_stats.get(kname) or {}).get("dram_pct_of_peak")}
+    total_bytes = P * 878 + stats["R"] * 200 + HW * 44     # SURVEY §8d whole-path figure
+    stages = {"roofline_by_kernel": roofline_by_kernel,
+              "ms_per_step_by_kernel": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+              "num_rendered": stats["R"], "visible": stats["visible"], "mean_tile_list": stats["mean_list"],
+              "max_tile_list": stats["max_list"],
+              "whole_path_frac_of_hbm_roofline": total_bytes / (ms_step * 1e-3) / 1e9 / peak}
+    return roofline, stages
+
+
 def run_ours(args):
     rank, world, local = _dist_env()
     if not torch.cuda.is_available():
@@ -302,47 +349,8 @@ def run_ours(args):
         _lib.profile_enable(False)
     sync_all()
     if rank == 0:
-        # a kernel name can occur several times per step (radix passes): per-launch average duration
-        per_step = {k: sum(v) / nprof for k, v in acc.items()}
-        per_launch = {k: sum(v) / len(v) for k, v in acc.items()}
         stats = vp.list_stats()
-        dom = max(per_step, key=per_step.get)
-        peak, peak_src = measured_peak_hbm()
-        ab = algorithmic_bytes(dom, P, stats["R"], stats["R_fwd"], stats["R_bwd"], H * W, stats["visible"])
-        ach = ab / (per_launch[dom] * 1e-3) / 1e9
-        traffic_tbl = {}
-        try:     # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/)
-            traffic_tbl = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        except Exception:
-            pass
-        ncu_stats = {}
-        try:     # issue-slot utilisation / DRAM % of the same capture: what actually bounds each kernel
-            ncu_stats = json.load(open(os.path.join(ROOT, "profiles", "ncu_kernel_stats.json")))
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": traffic_tbl.get(dom), "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": int(ab), "kernel_ms_per_launch": per_launch[dom],
-                    "kernel_share_of_step": per_step[dom] / max(sum(per_step.values()), 1e-9),
-                    "ncu": ncu_stats.get(dom),
-                    "note": "the two render kernels are issue-bound, not HBM-bound (ncu: 60-79% issue-active, "
-                            "<3% DRAM; their splat records stay L2-resident), so their HBM fraction is low by "
-                            "construction; see roofline_by_kernel for the HBM-bound kernels"}
-        roofline_by_kernel = {}
-        for kname in per_launch:
-            abk = algorithmic_bytes(kname, P, stats["R"], stats["R_fwd"], stats["R_bwd"], H * W, stats["visible"])
-            if abk:
-                a_k = abk / (per_launch[kname] * 1e-3) / 1e9
-                roofline_by_kernel[kname] = {"achieved_GBps": round(a_k, 1), "frac": round(a_k / peak, 4),
-                                             "ms_per_launch": round(per_launch[kname], 4),
-                                             "traffic": traffic_tbl.get(kname),
-                                             "ncu_issue_active_pct": (ncu_stats.get(kname) or {}).get("issue_active_pct"),
-                                             "ncu_dram_pct_of_peak": (ncu_stats.get(kname) or {}).get("dram_pct_of_peak")}
-        total_bytes = P * 878 + stats["R"] * 200 + H * W * 44     # SURVEY §8d whole-path figure
-        stages = {"roofline_by_kernel": roofline_by_kernel, "ms_per_step_by_kernel": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
-                  "num_rendered": stats["R"], "visible": stats["visible"], "mean_tile_list": stats["mean_list"],
-                  "max_tile_list": stats["max_list"], "whole_path_frac_of_hbm_roofline":
-                      total_bytes / (ms_step * 1e-3) / 1e9 / peak}
+        roofline, stages = roofline_report(acc, nprof, stats, P, H * W, ms_step)
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample (N = 1 only) ----
     cpu_baseline = None
