@@ -16,5 +16,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$K"
     python scripts/quick_perf_next_rows.py --iters 1 --warmup 0 > $OUT/ncu_next_rows.log 2>&1
 ncu -i $OUT/prof_next_rows.ncu-rep --page raw --csv > $OUT/ncu_next_rows_raw.csv 2>/dev/null
 python scripts/ncu_summary.py $OUT/ncu_next_rows_raw.csv > $OUT/ncu_next_rows_summary.txt 2>&1; grep -c "^==" $OUT/ncu_next_rows_summary.txt
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python scripts/sanitize_new_rows.py > $OUT/memcheck_new_rows.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/memcheck_new_rows.log; grep -E "ERROR SUMMARY|Invalid|out of bounds" $OUT/memcheck_new_rows.log | head -5
+timeout 600 compute-sanitizer --tool racecheck --error-exitcode 7 python scripts/sanitize_new_rows.py > $OUT/racecheck_new_rows.log 2>&1; echo "racecheck rc=$?" | tee -a $OUT/racecheck_new_rows.log; grep -E "RACECHECK SUMMARY|hazard" $OUT/racecheck_new_rows.log | head -5
 for c in lego_100k lego_1m dtu_500k; do timeout 300 python scripts/ab_tight_rect.py --config $c >> $OUT/ab_tight_rect.jsonl 2>> $OUT/ab_tight_rect.err; done; cat $OUT/ab_tight_rect.jsonl
 timeout 300 python scripts/run_view_time.py --rounds 24 > $OUT/view_time_n1.json 2> $OUT/view_time_n1.err; cat $OUT/view_time_n1.json; tail -2 $OUT/view_time_n1.err
