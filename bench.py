@@ -141,18 +141,26 @@ def run_reference(args):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     O.set_num_threads(cores)
     cfg, sc, cam, G = make_workload(0)
-    for _ in range(args.warmup):
+    # A CPU step takes about a second: the run is bounded in wall time (REF_ARM_BUDGET_S, default 150 s of timed
+    # steps + at most 3 warm-up steps) so that any --steps K / --warmup W ends within a few minutes; the line says
+    # how many full steps were actually timed.
+    budget_s = float(os.environ.get("REF_ARM_BUDGET_S", "150"))
+    for _ in range(min(args.warmup, 3)):
         oracle_step(O, sc, cam, cfg, G)
     ts = []
     for _ in range(args.steps):
         t, _f = oracle_step(O, sc, cam, cfg, G)
         ts.append(t)
+        if sum(ts) > budget_s:
+            break
     t_step = float(np.mean(ts))
     value = cfg["P"] / t_step / 1e6
-    sample = f"{args.steps} full fwd+bwd steps of {WORKLOAD} (P={cfg['P']}, {cfg['H']}x{cfg['W']}, SH deg 3)"
+    sample = (f"{len(ts)} full fwd+bwd steps of {WORKLOAD} (P={cfg['P']}, {cfg['H']}x{cfg['W']}, SH deg 3) timed"
+              + (f"; stopped at the {budget_s:.0f} s wall-time bound, {args.steps} were asked for" if len(ts) < args.steps else ""))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "timed_steps": len(ts), "ms_per_step": t_step * 1e3,
+        "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "P": cfg["P"], "H": cfg["H"], "W": cfg["W"], "sh_degree": SH_DEGREE,
                    "note": "the reference ships no CPU rasterizer and its CUDA rasterizer is an un-vendored "
