@@ -32,6 +32,10 @@ SLAB_FIELDS_RGB = (("means3D", 3), ("opacities", 1), ("scales", 3), ("rotations"
 
 
 class ViewParallelRasterizer:
+    """One rank of the view-parallel step: holds a replica of the splats, renders this rank's camera, and sums the
+    gradient slab over the ranks (module docstring).  `step(cotangent)` = forward + backward + exchange;
+    `grads()` = views into the summed slab, one per parameter."""
+
     def __init__(self, scene: dict, camera, H: int, W: int, sh_degree: int, device, world_size: int = 1,
                  bg=(1.0, 1.0, 1.0), exchange: str | None = None):
         self.device = torch.device(device)
@@ -75,16 +79,20 @@ class ViewParallelRasterizer:
             self._mid_event.record(torch.cuda.current_stream(self.device))     # materialises the cudaEvent_t handle
             self._side = torch.cuda.Stream(self.device)
         if self.exchange == "factored":
-            import torch.distributed as dist
             assert self.fields[-1][0] == "shs"          # the SH rows are the tail of the slab
             self.geo_floats = self.floats_per_splat - self.fields[-1][1]
             self.dcolor_mine = torch.empty(self.P * 3, dtype=torch.float32, device=self.device)
             self.dcolor_views = torch.empty(self.world * self.P * 3, dtype=torch.float32, device=self.device)
-            # every rank needs every camera centre (3 floats per view): gathered once
-            mine = cam.camera_center.detach().to(self.device, torch.float32).reshape(3).contiguous()
-            allc = [torch.empty_like(mine) for _ in range(self.world)]
-            dist.all_gather(allc, mine)
-            self.campos_views = torch.stack(allc).contiguous()
+            self._gather_campos(cam)
+
+    def _gather_campos(self, cam) -> None:
+        """Every rank needs every camera centre (3 floats per view) to rebuild the SH rows: one tiny all-gather per
+        camera change."""
+        import torch.distributed as dist
+        mine = cam.camera_center.detach().to(self.device, torch.float32).reshape(3).contiguous()
+        allc = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allc, mine)
+        self.campos_views = torch.stack(allc).contiguous()
 
     # -- per-job state for (view, time)-sharded runs (BASELINE.json configs[4]): a new camera and / or new means
     def set_camera(self, camera) -> None:
@@ -96,11 +104,7 @@ class ViewParallelRasterizer:
             projmatrix=cam.full_proj_transform, campos=cam.camera_center)
         self.rast = self.rast_factory(self.settings, cam)
         if self.exchange == "factored":
-            import torch.distributed as dist
-            mine = cam.camera_center.detach().to(self.device, torch.float32).reshape(3).contiguous()
-            allc = [torch.empty_like(mine) for _ in range(self.world)]
-            dist.all_gather(allc, mine)
-            self.campos_views = torch.stack(allc).contiguous()
+            self._gather_campos(cam)
 
     def set_means(self, means3D: torch.Tensor, same_on_all_ranks: bool = False) -> None:
         """Replace the means, e.g. canonical means + this job's per-frame offset.  The factored exchange rebuilds the
