@@ -127,20 +127,25 @@ def _worker_factored(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def _spawn2(worker):
+def _spawn2(worker, world=2):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
-    procs = [ctx.Process(target=worker, args=(r, 2, port, ret)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, world, port, ret)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
-        p.join(120)
+        p.join(180)
         assert p.exitcode == 0
     assert ret.get(timeout=5) is True
+
+
+def test_view_parallel_factored_exchange_world_3():
+    """Odd world size: slot order of the all-gather, 1/world scaling and the rebuild over three views."""
+    _spawn2(_worker_factored, world=3)
 
 
 def test_view_parallel_allreduce_matches_serial_mean():
