@@ -18,5 +18,6 @@ ncu -i $OUT/prof_next_rows.ncu-rep --page raw --csv > $OUT/ncu_next_rows_raw.csv
 python scripts/ncu_summary.py $OUT/ncu_next_rows_raw.csv > $OUT/ncu_next_rows_summary.txt 2>&1; grep -c "^==" $OUT/ncu_next_rows_summary.txt
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python scripts/sanitize_new_rows.py > $OUT/memcheck_new_rows.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/memcheck_new_rows.log; grep -E "ERROR SUMMARY|Invalid|out of bounds" $OUT/memcheck_new_rows.log | head -5
 timeout 600 compute-sanitizer --tool racecheck --error-exitcode 7 python scripts/sanitize_new_rows.py > $OUT/racecheck_new_rows.log 2>&1; echo "racecheck rc=$?" | tee -a $OUT/racecheck_new_rows.log; grep -E "RACECHECK SUMMARY|hazard" $OUT/racecheck_new_rows.log | head -5
+for v in 0 1; do echo "== SFB_PRE_OCC4=$v"; SFB_PRE_OCC4=$v timeout 120 python scripts/quick_perf.py --config lego_1m | tee -a $OUT/quick_perf_pre_occ4_$v.jsonl | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['fwd_ms'], d['fwd_stages']['preprocess'])"; done
 for c in lego_100k lego_1m dtu_500k; do timeout 300 python scripts/ab_tight_rect.py --config $c >> $OUT/ab_tight_rect.jsonl 2>> $OUT/ab_tight_rect.err; done; cat $OUT/ab_tight_rect.jsonl
 timeout 300 python scripts/run_view_time.py --rounds 24 > $OUT/view_time_n1.json 2> $OUT/view_time_n1.err; cat $OUT/view_time_n1.json; tail -2 $OUT/view_time_n1.err

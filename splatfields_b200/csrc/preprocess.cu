@@ -111,9 +111,8 @@ __device__ __forceinline__ void sh_to_rgb(const float* sh, float3 mean, const fl
 // footprint box below, so tiles in which the splat provably fails the alpha >= 1/255 test on every pixel are never
 // emitted.  The image and the gradients do not change (those tiles' instances are no-ops), but tiles_touched / R / the
 // key and index buffers shrink, which is why it is a separate instantiation and off by default.
-template <int D, bool VEC_SH, bool TMA_SH, bool TIGHT = false>
-__global__ void __launch_bounds__(256)
-preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
+template <int D, bool VEC_SH, bool TMA_SH, bool TIGHT>
+__device__ __forceinline__ void preprocess_body(const FwdParams& p, const GeomState& g, int* __restrict__ radii) {
   __shared__ Cam cam;
   __shared__ uint32_t s_tiles[8];
   __shared__ uint32_t s_nkey[8];
@@ -341,11 +340,33 @@ preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
   }
 }
 
+template <int D, bool VEC_SH, bool TMA_SH, bool TIGHT = false>
+__global__ void __launch_bounds__(256)
+preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
+  preprocess_body<D, VEC_SH, TMA_SH, TIGHT>(p, g, radii);
+}
+
+// Opt-in occupancy variant (SFB_PRE_OCC4=1): the same body under __launch_bounds__(256, 4) — 64 registers and ~50 bytes
+// of spills for 4 instead of 3 resident CTAs per SM.  The kernel is load-latency-bound at 33 % occupancy; whether the
+// extra warps pay for the spills is an A/B for the next GPU session.  (A wrapper of its own: putting the bound on the
+// shared template changes the default's register allocation.)
+template <int D>
+__global__ void __launch_bounds__(256, 4)
+preprocess_kernel_occ4(FwdParams p, GeomState g, int* __restrict__ radii) {
+  preprocess_body<D, true, false, false>(p, g, radii);
+}
+
 // The bulk-copy (TMA) staging of the SH slab is opt-in (SFB_TMA=1): on B200 it measured equal to the
 // prefetch + 128-bit-load path for this kernel (85 vs 86 us at 1M splats) while costing 48 KB of smem per CTA.
 static bool tma_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("SFB_TMA"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+static bool pre_occ4_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SFB_PRE_OCC4"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
 
@@ -363,6 +384,8 @@ static void launch_pre_d(const FwdParams& p, const GeomState& g, int* radii, cud
       attr_set = true;
     }
     preprocess_kernel<D, true, true><<<blocks, 256, smem, s>>>(p, g, radii);
+  } else if (vec && !p.tight_rect && pre_occ4_enabled()) {
+    preprocess_kernel_occ4<D><<<blocks, 256, 0, s>>>(p, g, radii);
   } else if (p.tight_rect) {
     if (vec) preprocess_kernel<D, true, false, true><<<blocks, 256, 0, s>>>(p, g, radii);
     else     preprocess_kernel<D, false, false, true><<<blocks, 256, 0, s>>>(p, g, radii);
