@@ -45,26 +45,33 @@ VARIANTS = {
 }
 
 
-def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", force_sources=()) -> str:
     vflags, LIB = VARIANTS[variant]
     BUILD = os.path.join(CSRC, "build" + ("_" + variant if variant else ""))
     os.makedirs(BUILD, exist_ok=True)
     hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "splat_b200.h"), __file__]
-    objs = []
-    for src in SOURCES:
+    objs = [os.path.join(BUILD, src.replace(".cu", ".o")) for src in SOURCES]
+
+    def compile_one(src):
         sp = os.path.join(CSRC, src)
         op = os.path.join(BUILD, src.replace(".cu", ".o"))
-        objs.append(op)
-        if force or _stale(op, [sp] + hdrs):
-            cmd = [nvcc()] + ARCH + COMMON + EXTRA.get(src, []) + vflags + ["-c", sp, "-o", op]
-            r = subprocess.run(cmd, capture_output=True, text=True)
-            log = os.path.join(BUILD, src + ".ptxas.log")
-            with open(log, "w") as f:
-                f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
-            if verbose or r.returncode != 0:
-                sys.stderr.write(r.stdout + r.stderr)
-            if r.returncode != 0:
-                raise RuntimeError(f"nvcc failed on {src}")
+        if not (force or src in force_sources or _stale(op, [sp] + hdrs)):
+            return
+        cmd = [nvcc()] + ARCH + COMMON + EXTRA.get(src, []) + vflags + ["-c", sp, "-o", op]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log = os.path.join(BUILD, src + ".ptxas.log")
+        with open(log, "w") as f:
+            f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+
+    # translation units are independent: compile them side by side
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+        list(ex.map(compile_one, SOURCES))
+    force = force or bool(force_sources)
     if force or _stale(LIB, objs):
         cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
         subprocess.check_call(cmd)

@@ -15,8 +15,9 @@ namespace {
 thread_local std::string g_err;
 int g_launches = 0;   // process-wide: autograd runs backward on its own thread
 std::atomic<void*> g_mid_event{nullptr};   // sfb_backward_midpoint_event: consumed by the next factored backward (any thread)
-thread_local uint32_t* g_pinned = nullptr;  // pinned word the num_rendered counter is copied into
-thread_local cudaEvent_t g_evt = nullptr;
+thread_local uint32_t* g_pinned = nullptr;  // pinned (portable, mapped) word the preprocess kernel stores num_rendered into
+constexpr int MAX_DEVICES = 64;
+thread_local cudaEvent_t g_evt[MAX_DEVICES] = {};   // one per device: an event can only be recorded on its own device's streams
 
 int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
   char buf[512];
@@ -71,36 +72,13 @@ int redzones_check(const sfb::RedzoneList& rz, cudaStream_t s) {
   return -1;
 }
 
-bool hits_enabled() {      // SFB_NO_HITS=1: backward falls back to the footprint-box culling (A/B knob)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SFB_NO_HITS"); v = (e && e[0] == '1') ? 0 : 1; }
-  return v == 1;
-}
-
-bool zero_in_fwd_enabled() {   // SFB_ZERO_IN_FWD=0: the backward clears its accumulators with a memset (A/B knob)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SFB_ZERO_IN_FWD"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
-}
-
-bool knob_on(const char* name, bool dflt) {     // "0" / "1" environment knobs for A/B runs
+bool knob_on(const char* name, bool dflt) {     // "0" / "1" environment knobs
   const char* e = getenv(name);
   if (!e || !e[0]) return dflt;
   return e[0] != '0';
 }
-// SFB_FUSED_RANGES=0: separate tile_ranges kernel; SFB_FOLD_MEMSETS=0: memset nodes for the sort scratch;
-// SFB_NR_MEMCPY=1: num_rendered read back with a D2H copy node instead of the kernel's own store to pinned memory
-bool fused_ranges_enabled() { static int v = -1; if (v < 0) v = knob_on("SFB_FUSED_RANGES", true) && !sfb::radix_sort_is_legacy(); return v == 1; }
-bool fold_memsets_enabled() { static int v = -1; if (v < 0) v = knob_on("SFB_FOLD_MEMSETS", true) && !sfb::radix_sort_is_legacy(); return v == 1; }
-bool nr_memcpy_enabled() { static int v = -1; if (v < 0) v = knob_on("SFB_NR_MEMCPY", false); return v == 1; }
 
 bool tight_rect_enabled() { static int v = -1; if (v < 0) v = knob_on("SFB_TIGHT_RECT", false); return v == 1; }
-
-bool wide256_enabled() {   // SFB_NO_LD256=1 falls back to 128-bit accesses (A/B knob)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SFB_NO_LD256"); v = (e && e[0] == '1') ? 0 : 1; }
-  return v == 1;
-}
 
 int tile_sort_final(int T) {
   int bits = sfb::tile_bits(T);
@@ -175,7 +153,11 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   if (gx > 65535 || gy > 65535) return fail(SFB_ERR_ARG, "image too large for packed tile rectangles");
 
   if (!g_pinned) CK(cudaHostAlloc((void**)&g_pinned, 64, cudaHostAllocMapped | cudaHostAllocPortable));
-  if (!g_evt) CK(cudaEventCreateWithFlags(&g_evt, cudaEventDisableTiming));
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEVICES) return fail(SFB_ERR_ARG, "device ordinal out of range");
+  if (!g_evt[dev]) CK(cudaEventCreateWithFlags(&g_evt[dev], cudaEventDisableTiming));
+  cudaEvent_t evt = g_evt[dev];
 
   RedzoneList rz;
   char* gchunk = (char*)geom_alloc(geom_user, GeomState::required((size_t)P));
@@ -197,12 +179,12 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   fp.viewmatrix = viewmatrix; fp.projmatrix = projmatrix; fp.campos = campos;
   fp.scale_modifier = scale_modifier; fp.tan_fovx = tan_fovx; fp.tan_fovy = tan_fovy; fp.prefiltered = prefiltered;
   fp.tight_rect = tight_rect_enabled() ? 1 : 0;
-  fp.wide256 = wide256_enabled() && shs && ((M * 12) % 32 == 0) && ((reinterpret_cast<size_t>(shs) & 31) == 0);
-  const bool fold = fold_memsets_enabled();
-  const size_t dzero = fold ? radix_sort_zero_words(P, 32) : 0;
+  fp.wide256 = shs && ((M * 12) % 32 == 0) && ((reinterpret_cast<size_t>(shs) & 31) == 0);
+  // the depth sort's scratch is cleared by the preprocess blocks on their way (one memset node less)
+  const size_t dzero = radix_sort_zero_words(P, 32);
   fp.zero_ptr = dzero ? g.sort_hist : nullptr;
   fp.zero_words = (uint32_t)dzero;
-  fp.nr_host = nr_memcpy_enabled() ? nullptr : g_pinned;
+  fp.nr_host = g_pinned;
 
   // K1 (+ num_rendered reduction) ; the 4-byte read-back is issued right behind it so that the host
   // wait overlaps the depth sort instead of draining the whole pipeline.
@@ -213,8 +195,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   prof_end(s);
   g_launches++;
   CK_LAUNCH("preprocess", debug, s);
-  if (!fp.nr_host) CK(cudaMemcpyAsync(g_pinned, g.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  CK(cudaEventRecord(g_evt, s));
+  CK(cudaEventRecord(evt, s));
 
   // stage 1: stable sort of the Gaussians by depth bits (culled ones carry 0xFFFFFFFF and sink)
   int dfinal = radix_sort_pairs(g.depth_key, g.depth_idx, g.sort_hist, P, 32, s, &g_launches, kDepthSortNames,
@@ -225,7 +206,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   g_launches += 2;
   CK_LAUNCH("instance scan", debug, s);
 
-  CK(cudaEventSynchronize(g_evt));
+  CK(cudaEventSynchronize(evt));
   const uint32_t R = *reinterpret_cast<volatile uint32_t*>(g_pinned);
   if (R >= (1u << 30)) return fail(SFB_ERR_ARG, "num_rendered >= 2^30 is not supported");
   if (num_rendered) *num_rendered = (int)R;
@@ -241,35 +222,29 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   if (debug && redzones_fill(rzb, s)) return fail(SFB_ERR_CUDA, "red-zone fill");
 
   int tfinal = 0;
-  const bool fused_ranges = fused_ranges_enabled();
   if (R > 0) {
-    // stage 2: emit (tile, gaussian) instances in depth order; stage 3: stable sort by tile id
-    const size_t tzero = fold ? radix_sort_zero_words((int)R, tile_bits(T)) : 0;
+    // stage 2: emit (tile, gaussian) instances in depth order (the blocks also clear the tile sort's scratch and set
+    // every tile range to "empty"); stage 3: stable sort by tile id
+    const size_t tzero = radix_sort_zero_words((int)R, tile_bits(T));
     prof_begin("duplicate", s);
     launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, b.tile_key[0], b.inst_idx[0],
-                     pk.idx_bits, tzero ? b.sort_hist : nullptr, tzero, fused_ranges ? b.ranges : nullptr, T, s);
+                     pk.idx_bits, tzero ? b.sort_hist : nullptr, tzero, b.ranges, T, s);
     prof_end(s);
     g_launches++;
     CK_LAUNCH("duplicate", debug, s);
     // packed: bare 32-bit words, digits start above the index bits; unpacked: (tile, index) pairs from bit 0.
-    // The last pass also writes the per-tile [start, end) ranges (K5) when fused_ranges.
+    // The last pass also writes the per-tile [start, end) ranges (K5): it sees every sorted key on its way out.
     tfinal = radix_sort_pairs(b.tile_key, b.inst_idx, b.sort_hist, (int)R, tile_bits(T), s, &g_launches, kTileSortNames,
-                              nullptr, pk.idx_bits, tzero != 0, fused_ranges ? b.ranges : nullptr, pk.idx_bits);
+                              nullptr, pk.idx_bits, tzero != 0, b.ranges, pk.idx_bits);
     CK_LAUNCH("tile sort", debug, s);
-  }
-  if (!fused_ranges || R == 0) {
-    prof_begin("tile_ranges", s);
-    launch_tile_ranges((int)R, T, b.tile_key[tfinal], pk.idx_bits, b.ranges, s);
-    prof_end(s);
-    g_launches++;
-    CK_LAUNCH("tile ranges", debug, s);
+  } else {
+    CK(cudaMemsetAsync(b.ranges, 0, sizeof(uint2) * (size_t)T, s));     // nothing to render: every tile is (0, 0)
   }
 
   prof_begin("render_forward", s);
   launch_render_forward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, bg, out_color, out_depth,
                         out_alpha,
-                        img.final_T, img.n_contrib, hits_enabled() ? b.hit : nullptr,
-                        zero_in_fwd_enabled() ? g.grad : nullptr, (size_t)P, s);
+                        img.final_T, img.n_contrib, b.hit, g.grad, (size_t)P, s);
   prof_end(s);
   g_launches++;
   CK_LAUNCH("render forward", debug, s);
@@ -328,7 +303,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
 
   g_which = 1; g_nrec[1] = 0;
   // the forward render cleared the accumulators as a prologue (render_fwd.cu) unless told otherwise
-  const bool acc_fresh = (flags & SFB_BWD_ACC_FRESH) && zero_in_fwd_enabled() && (size_t)P < ((size_t)1 << 30);
+  const bool acc_fresh = (flags & SFB_BWD_ACC_FRESH) && (size_t)P < ((size_t)1 << 30);
   if (!acc_fresh) {
     prof_begin("zero_grad_acc", s);
     CK(cudaMemsetAsync(g.grad, 0, sizeof(GradRec) * (size_t)P, s));
@@ -337,7 +312,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   prof_begin("render_backward", s);
   launch_render_backward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, bg, img.final_T,
                          img.n_contrib,
-                         dL_dout_color, dL_dout_alpha, hits_enabled() ? b.hit : nullptr, g.grad, s);
+                         dL_dout_color, dL_dout_alpha, b.hit, g.grad, s);
   prof_end(s);
   g_launches++;
   CK_LAUNCH("render backward", debug, s);
@@ -361,7 +336,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   bp.rotations = rotations; bp.cov3D_precomp = cov3D_precomp;
   bp.viewmatrix = viewmatrix; bp.projmatrix = projmatrix; bp.campos = campos;
   bp.scale_modifier = scale_modifier; bp.tan_fovx = tan_fovx; bp.tan_fovy = tan_fovy; bp.radii = radii;
-  bp.wide256 = wide256_enabled() && shs && ((M * 12) % 32 == 0) && ((reinterpret_cast<size_t>(shs) & 31) == 0) &&
+  bp.wide256 = shs && ((M * 12) % 32 == 0) && ((reinterpret_cast<size_t>(shs) & 31) == 0) &&
                ((reinterpret_cast<size_t>(dL_dsh) & 31) == 0);
   bp.sh_factored = sh_factored ? 1 : 0;
   bp.dL_dmeans2D = dL_dmeans2D; bp.dL_dcolors = dL_dcolors; bp.dL_dopacity = dL_dopacity;
@@ -397,7 +372,7 @@ int sfb_sh_grad_combine(int P, int V, int sh_degree, int M, const float* means3D
     return fail(SFB_ERR_ARG, "sfb_sh_grad_combine: bad sizes (1 <= V <= 64, 0 <= sh_degree <= 3, M >= (sh_degree+1)^2)");
   if (!means3D || !campos || !dL_dcolor_views || !dL_dsh) return fail(SFB_ERR_ARG, "sfb_sh_grad_combine: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
-  launch_sh_grad_combine(P, V, sh_degree, M, means3D, campos, dL_dcolor_views, dL_dsh, wide256_enabled(), s);
+  launch_sh_grad_combine(P, V, sh_degree, M, means3D, campos, dL_dcolor_views, dL_dsh, true, s);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(SFB_ERR_CUDA, "sh grad combine", e);
   return SFB_OK;

@@ -16,28 +16,6 @@
 
 namespace sfb {
 
-// ------------------------------------------------------------------ radix sort, one pass = 3 kernels
-// Block b owns items [b*SORT_TILE, (b+1)*SORT_TILE).  Within a block, warp w owns a contiguous
-// segment of 32*SORT_IPT items and item i of lane l sits at seg + i*32 + l (coalesced, and the
-// sequential order inside the block is (warp, i, lane)).
-
-__global__ void __launch_bounds__(SORT_THREADS)
-radix_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift, int bins, int nblocks,
-                  uint32_t* __restrict__ hist) {
-  __shared__ uint32_t s_hist[SORT_MAX_BINS];
-  for (int i = threadIdx.x; i < bins; i += SORT_THREADS) s_hist[i] = 0;
-  __syncthreads();
-  const uint32_t mask = (uint32_t)bins - 1;
-  const int base = blockIdx.x * SORT_TILE;
-#pragma unroll 4
-  for (int i = 0; i < SORT_IPT; i++) {
-    int k = base + i * SORT_THREADS + threadIdx.x;
-    if (k < n) atomicAdd(&s_hist[(keys[k] >> shift) & mask], 1u);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < bins; i += SORT_THREADS) hist[(size_t)i * nblocks + blockIdx.x] = s_hist[i];
-}
-
 // Exclusive scan, in place, of gridDim.x independent rows of `n` words (row r at data + r*n), one block
 // of 1024 threads per row; the row total goes to total_out[r] (if non-null).
 __global__ void __launch_bounds__(1024) scan_exclusive_kernel(uint32_t* __restrict__ data_all, int n,
@@ -86,109 +64,6 @@ __global__ void __launch_bounds__(1024) scan_exclusive_kernel(uint32_t* __restri
   }
   if (total_out && threadIdx.x == 0) total_out[blockIdx.x] = s_carry;
 }
-
-__global__ void __launch_bounds__(SORT_THREADS)
-radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift,
-                     int bins, int nblocks, const uint32_t* __restrict__ hist_scanned,
-                     const uint32_t* __restrict__ digit_totals) {
-  constexpr int NW = SORT_THREADS / 32;
-  __shared__ uint32_t s_cnt[NW][SORT_MAX_BINS];  // per-warp digit counters, later per-warp global bases
-  __shared__ uint32_t s_dbase[SORT_MAX_BINS];    // exclusive scan of the digit totals
-  __shared__ uint32_t s_wsum[NW];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t mask = (uint32_t)bins - 1;
-  for (int i = threadIdx.x; i < NW * SORT_MAX_BINS; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
-  {  // block-wide exclusive scan of digit_totals[0..bins) (bins <= SORT_THREADS)
-    uint32_t t = (int)threadIdx.x < bins ? digit_totals[threadIdx.x] : 0u;
-    uint32_t inc = t;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += u;
-    }
-    if (lane == 31) s_wsum[warp] = inc;
-    __syncthreads();
-    uint32_t wb = 0;
-    for (int w = 0; w < warp; w++) wb += s_wsum[w];
-    s_dbase[threadIdx.x] = wb + inc - t;
-  }
-  __syncthreads();
-
-  const int seg = blockIdx.x * SORT_TILE + warp * (32 * SORT_IPT);
-  uint32_t key[SORT_IPT], rank[SORT_IPT];
-  const uint32_t lt_mask = (1u << lane) - 1u;
-#pragma unroll
-  for (int i = 0; i < SORT_IPT; i++) {
-    int k = seg + i * 32 + lane;
-    bool valid = k < n;
-    key[i] = valid ? keys_in[k] : 0xFFFFFFFFu;
-    uint32_t d = (key[i] >> shift) & mask;
-    // invalid lanes use a digit no valid lane can match (bins <= 256)
-    uint32_t md = valid ? d : 0xFFFFu;
-    uint32_t peers = __match_any_sync(0xffffffffu, md);
-    uint32_t before = __popc(peers & lt_mask);
-    uint32_t prev = 0;
-    if (valid && before == 0) {  // leader of its digit group
-      prev = s_cnt[warp][d];
-      s_cnt[warp][d] = prev + __popc(peers);
-    }
-    prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
-    rank[i] = prev + before;
-    __syncwarp();
-  }
-  __syncthreads();
-  // per digit: turn per-warp counts into global bases (exclusive over warps + block's scanned base)
-  for (int d = threadIdx.x; d < bins; d += SORT_THREADS) {
-    uint32_t run = s_dbase[d] + hist_scanned[(size_t)d * nblocks + blockIdx.x];
-#pragma unroll
-    for (int w = 0; w < NW; w++) {
-      uint32_t c = s_cnt[w][d];
-      s_cnt[w][d] = run;
-      run += c;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < SORT_IPT; i++) {
-    int k = seg + i * 32 + lane;
-    if (k < n) {
-      uint32_t d = (key[i] >> shift) & mask;
-      uint32_t dst = s_cnt[warp][d] + rank[i];
-      keys_out[dst] = key[i];
-      vals_out[dst] = vals_in[k];
-    }
-  }
-}
-
-static int radix_sort_pairs_legacy(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
-                     int* launches, const char* const* names) {
-  if (n <= 0 || nbits <= 0) return 0;
-  const int npass = (nbits + 7) / 8;
-  const int nblocks = sort_blocks(n);
-  int cur = 0, shift = 0;
-  for (int pass = 0; pass < npass; pass++) {
-    // spread the bits evenly over the passes (12 -> 6+6, 13 -> 7+6, 32 -> 8x4)
-    int bits = (nbits - shift + (npass - pass) - 1) / (npass - pass);
-    int bins = 1 << bits;
-    prof_begin(names[0], s);
-    radix_hist_kernel<<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], n, shift, bins, nblocks, hist);
-    prof_end(s);
-    uint32_t* totals = hist + (size_t)SORT_MAX_BINS * nblocks;
-    prof_begin(names[1], s);
-    scan_exclusive_kernel<<<bins, 1024, 0, s>>>(hist, nblocks, totals);  // one row (digit) per block
-    prof_end(s);
-    prof_begin(names[2], s);
-    radix_scatter_kernel<<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
-                                                          shift, bins, nblocks, hist, totals);
-    prof_end(s);
-    if (launches) *launches += 3;
-    cur ^= 1;
-    shift += bits;
-  }
-  return cur;
-}
-
 
 // ------------------------------------------------------------------ onesweep radix sort (default)
 // One kernel per digit pass: a block takes a ticket, ranks its 4096 (key, value) pairs stably, publishes
@@ -240,7 +115,7 @@ radix_hist_all_kernel(uint32_t* __restrict__ keys, int n, int npass, int4 shifts
 // IPT items per thread: 16 (4096-item tiles) for large inputs, 4 (1024-item tiles) when 4096-item tiles
 // would leave most SMs idle and every block a long latency chain.
 // HAS_VALS = false sorts bare 32-bit words (the packed tile|index instances): nothing but keys is staged or moved.
-// NB = digit bits the ranking resolves with ballots (6, 7 or 8 >= log2(bins)); NB = 0 ranks with match.any.
+// NB = digit bits the ranking resolves with ballots (6, 7 or 8 >= log2(bins)).
 // For 4096-item tiles the IPT ranking rounds of a warp are split into CH independent chains (CH * bins <= SORT_MAX_BINS;
 // chain c = items [c*IPT/CH, (c+1)*IPT/CH) of every lane) with their own digit counters, so the load -> add -> store ->
 // shuffle dependency that serialises the rounds is IPT/CH long; the counters of the chains are stitched together by
@@ -305,22 +180,20 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     key[i] = k < n ? keys_in[k] : 0xFFFFFFFFu;
     if (PRELOAD_VALS) val[i] = k < n ? vals_in[k] : 0u;
   }
-  // Round i ranks item i of every lane: lanes with equal digits find each other with match.any; the lowest
-  // of them bumps the warp's private digit counter and broadcasts the old value.  All match.any of the tile
-  // are issued first (they are independent and slow: ncu shows the dependent LOP3 behind each MATCH as the top
-  // stall of this kernel), the counter updates then run back to back.
+  // Round i ranks item i of every lane: lanes with equal digits find each other through a peer mask; the lowest
+  // of them bumps the warp's private digit counter and broadcasts the old value.  All peer masks of the tile are
+  // built first (independent work), the counter updates then run back to back.
   // (A returning shared-memory atomic instead of the load/store pair was measured slower on B200.)
   uint32_t peers_of[IPT];
 #pragma unroll
   for (int i = 0; i < IPT; i++) {
     const int k = seg + i * 32 + lane;
     const uint32_t d = (key[i] >> shift) & mask;
-    if (NB == 0) {
-      peers_of[i] = __match_any_sync(0xffffffffu, k < n ? d : 0xFFFFu);   // invalid lanes: unmatched digit
-    } else {
-      // MATCH.ANY costs ~300 cycles per warp here (its latency grows with the number of distinct digits among the
-      // lanes and it does not pipeline: ~110 Gkeys/s per pass whatever n).  One ballot per digit bit builds the same
-      // peer mask from 4 pipelined instructions per bit: m &= ballot(bit) ^ (my bit ? 0 : ~0).
+    {
+      // MATCH.ANY costs ~300 cycles per warp on B200 with random 6-bit digits (its latency grows with the number of
+      // distinct values among the lanes and it does not pipeline: ~110 Gkeys/s per pass whatever n; measured in round 1,
+      // profiles/r01s_*).  One ballot per digit bit builds the same peer mask from 4 pipelined instructions per bit:
+      // m &= ballot(bit) ^ (my bit ? 0 : ~0).
       uint32_t m = __ballot_sync(0xffffffffu, k < n);
 #pragma unroll
       for (int b = 0; b < NB; b++) {
@@ -471,9 +344,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 }
 
 static bool sort_small_tiles(int n) {
-  static int small_on = -1;                                   // A/B knob: SFB_SORT_SMALL=0 -> 4096-item tiles always
-  if (small_on < 0) { const char* e = getenv("SFB_SORT_SMALL"); small_on = (e && e[0] == '0') ? 0 : 1; }
-  return small_on && sort_blocks(n) < 64;
+  return sort_blocks(n) < 64;
 }
 
 // words of `hist` that have to be zero when radix_sort_pairs starts (the caller may clear them itself, e.g. from a kernel
@@ -502,8 +373,6 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
   // 1024-item tiles only for really small inputs: with the ballot ranking 4096-item tiles win from ~0.3 M items
   // (measured: 1 M pairs 87 -> 65 us, 0.5 M 63 -> 54 us, 0.1 M 43 -> 51 us), although they fill < 2 CTAs per SM
   const bool small = sort_small_tiles(n);
-  static int use_match = -1;                                  // A/B knob: SFB_SORT_MATCH=1 -> match.any ranking
-  if (use_match < 0) { const char* e = getenv("SFB_SORT_MATCH"); use_match = (e && e[0] == '1') ? 1 : 0; }
   const int tile = small ? SORT_THREADS * 4 : SORT_THREADS * 16;
   const int nblocks = (n + tile - 1) / tile;
   // scratch layout: [hist_all: 4*256][tickets: 8][tile_state: npass * nblocks * bins]
@@ -540,9 +409,8 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
                                                                         hist_all + pass * SORT_MAX_BINS, state, tickets + pass, \
                                                                         pass == npass - 1 ? ranges : nullptr, tile_shift)
 #define SFB_OS(IPTV, HV)                                                                                       \
-  do { if (nb == 0) SFB_OS2(IPTV, HV, 0); else if (nb == 6) SFB_OS2(IPTV, HV, 6); else if (nb == 7) SFB_OS2(IPTV, HV, 7); \
-       else SFB_OS2(IPTV, HV, 8); } while (0)
-    const int nb = use_match ? 0 : (nbins[pass] <= 64 ? 6 : (nbins[pass] <= 128 ? 7 : 8));
+  do { if (nb == 6) SFB_OS2(IPTV, HV, 6); else if (nb == 7) SFB_OS2(IPTV, HV, 7); else SFB_OS2(IPTV, HV, 8); } while (0)
+    const int nb = nbins[pass] <= 64 ? 6 : (nbins[pass] <= 128 ? 7 : 8);
     if (small) { if (has_vals) SFB_OS(4, true);  else SFB_OS(4, false); }
     else       { if (has_vals) SFB_OS(16, true); else SFB_OS(16, false); }
 #undef SFB_OS2
@@ -555,18 +423,10 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
   return cur;
 }
 
-bool radix_sort_is_legacy() {
-  static int legacy = -1;
-  if (legacy < 0) { const char* e = getenv("SFB_SORT"); legacy = (e && e[0] == 'l') ? 1 : 0; }
-  return legacy == 1;
-}
-
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
                      int* launches, const char* const* names, const uint32_t* bias_c, int first_bit,
                      bool scratch_zeroed, uint2* ranges, int tile_shift) {
   if (n <= 0 || nbits <= 0) return 0;
-  if (radix_sort_is_legacy() && first_bit == 0 && vals && vals[0] && !ranges)   // (the 3-kernel path ignores bias_c; pairs from bit 0 only)
-    return radix_sort_pairs_legacy(keys, vals, hist, n, nbits, s, launches, names);
   return radix_sort_pairs_onesweep(keys, vals, hist, n, nbits, s, launches, names, bias_c, first_bit, scratch_zeroed,
                                    ranges, tile_shift);
 }
@@ -765,39 +625,6 @@ void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint3
   int nb = (P + DUP_GPB - 1) / DUP_GPB;
   duplicate_kernel<<<nb, DUP_THREADS, 0, s>>>(P, grid_x, sorted_idx, tiles_touched, rect, block_offsets,
                                               tile_keys, inst_idx, idx_bits, zero_ptr, (uint32_t)zero_words, ranges_init, T);
-}
-
-// ------------------------------------------------------------------ tile ranges
-// Four consecutive keys per thread (one 16-byte load) + the key before them.
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int R, const uint32_t* __restrict__ keys, int key_shift,
-                                                           uint2* __restrict__ ranges) {
-  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i0 >= R) return;
-  uint32_t k[4];
-  if (i0 + 3 < R) {
-    const uint4 v = *reinterpret_cast<const uint4*>(keys + i0);
-    k[0] = v.x >> key_shift; k[1] = v.y >> key_shift; k[2] = v.z >> key_shift; k[3] = v.w >> key_shift;
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; j++) k[j] = (i0 + j < R) ? (keys[i0 + j] >> key_shift) : 0u;
-  }
-  uint32_t prev = i0 > 0 ? (keys[i0 - 1] >> key_shift) : 0u;
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const int i = i0 + j;
-    if (i < R) {
-      const uint32_t t = k[j];
-      if (i == 0) ranges[t].x = 0;
-      else if (prev != t) { ranges[prev].y = (uint32_t)i; ranges[t].x = (uint32_t)i; }
-      if (i == R - 1) ranges[t].y = (uint32_t)R;
-      prev = t;
-    }
-  }
-}
-
-void launch_tile_ranges(int R, int T, const uint32_t* sorted_tile_keys, int key_shift, uint2* ranges, cudaStream_t s) {
-  cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)T, s);
-  if (R > 0) tile_ranges_kernel<<<((R + 3) / 4 + 255) / 256, 256, 0, s>>>(R, sorted_tile_keys, key_shift, ranges);
 }
 
 // point_list == nullptr: packed mode (tile_keys[i] = tile << idx_bits | index)

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 namespace sfb {
 
@@ -181,7 +182,7 @@ constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;    // items per block
 constexpr int SORT_MAX_BINS = 256;
 __host__ __device__ inline int sort_blocks(int n) { return (n + SORT_TILE - 1) / SORT_TILE; }
 // words of sort scratch for n items: 4 digit histograms + tickets + one look-back state row per pass
-// (worst case 4 passes x 256 bins), which also covers the legacy path's [bins][blocks] histogram + totals.
+// (worst case 4 passes x 256 bins).
 __host__ __device__ inline size_t sort_scratch_words(size_t n) {
   // (small inputs use 1024-item tiles: at most 4 * 4 * NUM_SMS_B200 of them)
   const size_t blocks = (size_t)sort_blocks((int)n) + 1;
@@ -237,10 +238,17 @@ struct InstPacking {
 };
 inline int ceil_log2(size_t n) { int b = 0; while (((size_t)1 << b) < n) b++; return b; }
 inline int tile_bits_for(size_t T) { int b = 1; while (((size_t)1 << b) < T) b++; return b; }
+// SFB_NO_PACK=1 forces the unpacked layout (what scenes with ceil(log2 P) + ceil(log2 T) > 32 get, e.g. 2 M splats at
+// 1080p) so that the parity tests can drive that path with small scenes.
+inline bool inst_packing_allowed() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SFB_NO_PACK"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
 inline InstPacking inst_packing(size_t P, size_t T) {
   InstPacking k;
   const int ib = ceil_log2(P < 2 ? 2 : P);
-  if (ib + tile_bits_for(T) <= 32) { k.idx_bits = ib; k.idx_mask = ib >= 32 ? 0xFFFFFFFFu : ((1u << ib) - 1u); }
+  if (inst_packing_allowed() && ib + tile_bits_for(T) <= 32) { k.idx_bits = ib; k.idx_mask = ib >= 32 ? 0xFFFFFFFFu : ((1u << ib) - 1u); }
   else { k.idx_bits = 0; k.idx_mask = 0xFFFFFFFFu; }
   return k;
 }
@@ -334,7 +342,6 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n
                      uint2* ranges = nullptr /* fused K5: [T] pre-set to (0xFFFFFFFF, 0); filled by the last pass */,
                      int tile_shift = 0 /* tile id = key >> tile_shift */);
 size_t radix_sort_zero_words(int n, int nbits);
-bool radix_sort_is_legacy();
 void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
                                 uint32_t* block_sums, cudaStream_t s);
 void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
@@ -342,7 +349,6 @@ void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint3
                       uint32_t* inst_idx /* nullptr: packed */, int idx_bits,
                       uint32_t* zero_ptr /* or nullptr */, size_t zero_words, uint2* ranges_init /* or nullptr */, int T,
                       cudaStream_t s);
-void launch_tile_ranges(int R, int T, const uint32_t* sorted_tile_keys, int key_shift, uint2* ranges, cudaStream_t s);
 void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_list /* nullptr: packed */,
                         int idx_bits, const SplatRec* rec, uint64_t* out_keys, uint32_t* out_list, cudaStream_t s);
 

@@ -23,28 +23,15 @@ struct CamB {
 };
 
 // VEC: shs / dL_dsh rows are 16-byte aligned and 3*M is a multiple of 4 -> 128-bit loads and stores.
-// TMA: the block's SH rows arrive through one bulk async copy and its dL_dsh rows leave through one bulk
-// async store (cp.async.bulk both ways, UBLKCP.S.G / UBLKCP.G.S): each thread only touches its own 192-byte
-// row in shared memory (read, then overwritten in place with the gradient row; zeros for culled splats).
+// (Bulk-copy staging of the block's SH / dL_dsh slabs through shared memory was measured SLOWER here — 150 vs 134 us at
+// 1M splats, round 1: the whole 48 KB slab has to land before any thread can start and only 2 CTAs fit per SM — and
+// was removed; the rows move as L2-prefetched 256-bit loads and 256-bit stores.)
 // FACT: factored SH gradient (SFB_BWD_SH_FACTORED) — dL_dcolors receives the clamp-masked colour gradient and the
 // dL_dsh rows are not written (sh_grad_combine_kernel below rebuilds their multi-view sum).  A template flag, so
 // that the default instantiations carry no trace of it (a run-time branch cost 4 registers and 10 us at 1M splats).
-template <int D, bool VEC, bool TMA, int MINB = 1, bool W256 = false, bool FACT = false>
+template <int D, bool VEC, int MINB = 1, bool W256 = false, bool FACT = false>
 __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, GeomState g) {
   __shared__ CamB cam;
-  __shared__ uint64_t s_bar;
-  extern __shared__ __align__(128) float s_rows[];
-  const int row0 = blockIdx.x * 256;
-  const int rows_blk = min(256, p.P - row0);
-  if (TMA) {
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const uint32_t bytes = (uint32_t)rows_blk * (uint32_t)p.M * 12u;
-      mbar_expect_tx(&s_bar, bytes);
-      bulk_g2s(s_rows, p.shs + (size_t)row0 * p.M * 3, bytes, &s_bar);
-    }
-  }
   if (threadIdx.x < 16) {
     cam.view[threadIdx.x] = p.viewmatrix[threadIdx.x];
     cam.proj[threadIdx.x] = p.projmatrix[threadIdx.x];
@@ -53,11 +40,10 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
   __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = idx < p.P;
-  if (!TMA && !in_range) return;
-  const size_t i = (size_t)(in_range ? idx : 0);
-  const bool visible = in_range && p.radii[idx] > 0;
-  float* my_row = TMA ? s_rows + (size_t)threadIdx.x * p.M * 3 : nullptr;
-  if (!TMA && visible && p.shs) {   // pull the SH row towards L2 while the covariance math runs
+  if (!in_range) return;
+  const size_t i = (size_t)idx;
+  const bool visible = p.radii[idx] > 0;
+  if (visible && p.shs) {   // pull the SH row towards L2 while the covariance math runs
     const char* row = reinterpret_cast<const char*>(p.shs + i * p.M * 3);
     prefetch_l2(row);
     prefetch_l2(row + 128);
@@ -186,14 +172,7 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
       constexpr int NF4 = (3 * NB + 3) / 4;   // float4s that hold the active coefficients
       float sh[NF4 * 4];
       float dshv[NF4 * 4];
-      if (TMA) {
-        mbar_wait(&s_bar, 0);
-#pragma unroll
-        for (int k = 0; k < NF4; k++) {
-          const float4 q = reinterpret_cast<const float4*>(my_row)[k];
-          sh[4 * k] = q.x; sh[4 * k + 1] = q.y; sh[4 * k + 2] = q.z; sh[4 * k + 3] = q.w;
-        }
-      } else {
+      {
         const float* shp = p.shs + i * p.M * 3;
         if (VEC && W256 && (3 * NB) % 8 == 0) {
 #pragma unroll
@@ -244,11 +223,11 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
       }
       if (FACT) {
         // the 3*M-float row is rebuilt later from the masked colour gradients of all views
-      } else if (VEC && !TMA && W256 && (3 * NB) % 8 == 0) {   // launcher guarantees M == (D+1)^2 here
+      } else if (VEC && W256 && (3 * NB) % 8 == 0) {   // launcher guarantees M == (D+1)^2 here
 #pragma unroll
         for (int k = 0; k < (3 * NB) / 8; k++) stg256(dsh + 8 * k, dshv + 8 * k);
       } else if (VEC) {
-        float4* d4 = TMA ? reinterpret_cast<float4*>(my_row) : reinterpret_cast<float4*>(dsh);
+        float4* d4 = reinterpret_cast<float4*>(dsh);
 #pragma unroll
         for (int k = 0; k < NF4; k++) d4[k] = make_float4(dshv[4 * k], dshv[4 * k + 1], dshv[4 * k + 2], dshv[4 * k + 3]);
         for (int k = NF4; k < (3 * p.M) / 4; k++) d4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -323,27 +302,17 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
     }
   } else if (p.shs && !FACT) {
     float* dsh = p.dL_dsh + i * p.M * 3;
-    if (TMA) mbar_wait(&s_bar, 0);     // the incoming row must have landed before it is overwritten
-    if (VEC && !TMA && W256) {
+    if (VEC && W256) {
       const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int k = 0; k < (3 * p.M) / 8; k++) stg256(dsh + 8 * k, zero8);
     } else if (VEC) {
-      float4* d4 = TMA ? reinterpret_cast<float4*>(my_row) : reinterpret_cast<float4*>(dsh);
+      float4* d4 = reinterpret_cast<float4*>(dsh);
       for (int k = 0; k < (3 * p.M) / 4; k++) d4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
       for (int k = 0; k < 3 * p.M; k++) dsh[k] = 0.f;
     }
   }
 
-  if (TMA) {
-    bulk_store_fence();                // generic-proxy row writes -> visible to the async proxy
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      bulk_s2g(p.dL_dsh + (size_t)row0 * p.M * 3, s_rows, (uint32_t)rows_blk * (uint32_t)p.M * 12u);
-      bulk_store_wait_read();
-    }
-    if (!in_range) return;
-  }
   p.dL_dmeans3D[3 * i] = dmean[0]; p.dL_dmeans3D[3 * i + 1] = dmean[1]; p.dL_dmeans3D[3 * i + 2] = dmean[2];
   p.dL_dmeans2D[3 * i] = gm2[0]; p.dL_dmeans2D[3 * i + 1] = gm2[1]; p.dL_dmeans2D[3 * i + 2] = 0.f;
   if (p.dL_dcolors) { p.dL_dcolors[3 * i] = gcol[0]; p.dL_dcolors[3 * i + 1] = gcol[1]; p.dL_dcolors[3 * i + 2] = gcol[2]; }
@@ -467,32 +436,16 @@ void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s
   const int blocks = (p.P + 255) / 256;
   const bool vec = p.shs && ((p.M * 3) % 4 == 0) && ((reinterpret_cast<size_t>(p.shs) & 15) == 0) &&
                    ((reinterpret_cast<size_t>(p.dL_dsh) & 15) == 0);
-  // bulk-copy (TMA) staging is opt-in (SFB_TMA=1): measured slower here (150 vs 134 us at 1M splats) —
-  // the whole 48 KB slab has to land before any thread of the CTA can start, and only 2 CTAs fit per SM.
-  static int no_tma = -1;
-  if (no_tma < 0) { const char* e = getenv("SFB_TMA"); no_tma = (e && e[0] == '1') ? 0 : 1; }
-  const size_t smem = (size_t)256 * p.M * 12;
-  static int minb3 = -1;   // experiment: trade a few spills for 3 resident CTAs per SM
-  if (minb3 < 0) { const char* e = getenv("SFB_GEOM_MINB3"); minb3 = (e && e[0] == '1') ? 1 : 0; }
 #define SFB_GB(DD)                                                                                         \
   if (p.sh_factored) {                                                                                     \
     if (vec && p.wide256 && p.M == (DD + 1) * (DD + 1) && (3 * (DD + 1) * (DD + 1)) % 8 == 0)             \
-      geom_backward_kernel<DD, true, false, 2, true, true><<<blocks, 256, 0, s>>>(p, g);                   \
-    else if (vec) geom_backward_kernel<DD, true, false, 1, false, true><<<blocks, 256, 0, s>>>(p, g);      \
-    else geom_backward_kernel<DD, false, false, 1, false, true><<<blocks, 256, 0, s>>>(p, g);              \
-  } else if (vec && !no_tma && p.M == (DD + 1) * (DD + 1) && smem <= 96 * 1024) {                                \
-    static bool attr_set = false;                                                                          \
-    if (!attr_set) {                                                                                       \
-      cudaFuncSetAttribute(geom_backward_kernel<DD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                           96 * 1024);                                                                     \
-      attr_set = true;                                                                                     \
-    }                                                                                                      \
-    geom_backward_kernel<DD, true, true><<<blocks, 256, smem, s>>>(p, g);                                  \
+      geom_backward_kernel<DD, true, 2, true, true><<<blocks, 256, 0, s>>>(p, g);                          \
+    else if (vec) geom_backward_kernel<DD, true, 1, false, true><<<blocks, 256, 0, s>>>(p, g);             \
+    else geom_backward_kernel<DD, false, 1, false, true><<<blocks, 256, 0, s>>>(p, g);                     \
   } else if (vec && p.wide256 && p.M == (DD + 1) * (DD + 1) && (3 * (DD + 1) * (DD + 1)) % 8 == 0) {       \
-    geom_backward_kernel<DD, true, false, 2, true><<<blocks, 256, 0, s>>>(p, g);                           \
-  } else if (vec && minb3 && DD == 3) geom_backward_kernel<3, true, false, 3><<<blocks, 256, 0, s>>>(p, g); \
-  else if (vec) geom_backward_kernel<DD, true, false><<<blocks, 256, 0, s>>>(p, g);                        \
-  else            geom_backward_kernel<DD, false, false><<<blocks, 256, 0, s>>>(p, g);
+    geom_backward_kernel<DD, true, 2, true><<<blocks, 256, 0, s>>>(p, g);                                  \
+  } else if (vec) geom_backward_kernel<DD, true><<<blocks, 256, 0, s>>>(p, g);                             \
+  else            geom_backward_kernel<DD, false><<<blocks, 256, 0, s>>>(p, g);
   switch (p.shs ? p.D : 0) {
     case 0: SFB_GB(0) break;
     case 1: SFB_GB(1) break;

@@ -103,36 +103,21 @@ __device__ __forceinline__ void sh_to_rgb(const float* sh, float3 mean, const fl
   }
 }
 
-// TMA_SH: the block's SH rows (256 x M*3 floats, one contiguous slab of the [P][M][3] tensor) are brought
-// into shared memory by ONE bulk async copy (cp.async.bulk -> UBLKCP) issued at kernel start and awaited on an
-// mbarrier only where the colours are needed, so the 192 B/Gaussian stream overlaps the projection math and
-// reaches DRAM as full sequential bursts instead of 32 strided 16-byte requests per load instruction.
+// (A bulk-copy (cp.async.bulk) staging of the block's SH slab was measured equal to the L2-prefetch + 256-bit-load path
+// used here — 85 vs 86 us at 1M splats, round 1 — while costing 48 KB of shared memory per CTA; it was removed.)
 // TIGHT (opt-in, SFB_TIGHT_RECT=1; NOT reference-identical lists): the tile rectangle is intersected with the
 // footprint box below, so tiles in which the splat provably fails the alpha >= 1/255 test on every pixel are never
 // emitted.  The image and the gradients do not change (those tiles' instances are no-ops), but tiles_touched / R / the
 // key and index buffers shrink, which is why it is a separate instantiation and off by default.
-template <int D, bool VEC_SH, bool TMA_SH, bool TIGHT>
+template <int D, bool VEC_SH, bool TIGHT>
 __device__ __forceinline__ void preprocess_body(const FwdParams& p, const GeomState& g, int* __restrict__ radii) {
   __shared__ Cam cam;
   __shared__ uint32_t s_tiles[8];
   __shared__ uint32_t s_nkey[8];
-  __shared__ uint64_t s_bar;
-  extern __shared__ __align__(128) float s_shrows[];
   if (p.zero_ptr) {   // clear the depth sort's scratch on the way (it runs right behind this kernel): one memset node less
     const uint32_t per = (p.zero_words + gridDim.x - 1) / gridDim.x;
     const uint32_t z0 = blockIdx.x * per, z1 = min(z0 + per, p.zero_words);
     for (uint32_t i = z0 + threadIdx.x; i < z1; i += 256) p.zero_ptr[i] = 0u;
-  }
-  if (TMA_SH) {
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int row0 = blockIdx.x * 256;
-      const int rows = min(256, p.P - row0);
-      const uint32_t bytes = (uint32_t)rows * (uint32_t)p.M * 12u;
-      mbar_expect_tx(&s_bar, bytes);
-      bulk_g2s(s_shrows, p.shs + (size_t)row0 * p.M * 3, bytes, &s_bar);
-    }
   }
   if (threadIdx.x < 16) {
     cam.view[threadIdx.x] = p.viewmatrix[threadIdx.x];
@@ -152,7 +137,7 @@ __device__ __forceinline__ void preprocess_body(const FwdParams& p, const GeomSt
                               __ldg(p.means3D + 3 * idx + 2));
     float3 p_view = xform4x3(cam.view, mean);
     if (p_view.z > 0.2f) {
-      if (!TMA_SH && p.shs) {   // start pulling this splat's SH row towards L2 while the projection math runs
+      if (p.shs) {   // start pulling this splat's SH row towards L2 while the projection math runs
         const char* row = reinterpret_cast<const char*>(p.shs + (size_t)idx * p.M * 3);
         prefetch_l2(row);
         prefetch_l2(row + 128);
@@ -248,18 +233,7 @@ __device__ __forceinline__ void preprocess_body(const FwdParams& p, const GeomSt
             rgb[2] = __ldg(p.colors_precomp + 3 * (size_t)idx + 2);
           } else {
             float sh[((3 * (D + 1) * (D + 1) + 3) / 4) * 4];
-            if (TMA_SH) {
-              mbar_wait(&s_bar, 0);
-              constexpr int NV = (3 * (D + 1) * (D + 1) + 3) / 4;
-              const float4* row = reinterpret_cast<const float4*>(s_shrows + (size_t)threadIdx.x * p.M * 3);
-#pragma unroll
-              for (int i = 0; i < NV; i++) {
-                const float4 v = row[i];
-                sh[4 * i + 0] = v.x; sh[4 * i + 1] = v.y; sh[4 * i + 2] = v.z; sh[4 * i + 3] = v.w;
-              }
-            } else {
-              load_sh<D, VEC_SH>(p.shs, idx, p.M, sh, p.wide256 != 0);
-            }
+            load_sh<D, VEC_SH>(p.shs, idx, p.M, sh, p.wide256 != 0);
             sh_to_rgb<D>(sh, mean, cam.campos, rgb, clamp_mask);
           }
           // Conservative half-extents (pixels) of the region where this splat can reach alpha >= 1/255:
@@ -309,7 +283,6 @@ __device__ __forceinline__ void preprocess_body(const FwdParams& p, const GeomSt
     g.depth_idx[0][idx] = (uint32_t)idx;
     my_key = key;
   }
-  if (TMA_SH) mbar_wait(&s_bar, 0);   // never retire the CTA with the bulk copy still landing in its smem
   // num_rendered = sum of tiles_touched: order-independent, so one atomic per block is exact.
   // ... and counters[2] = max(~key) = ~(smallest depth key of a visible splat): lets the depth sort rebase
   // its keys so that the top digit pass degenerates to a copy for bounded scenes.
@@ -340,10 +313,10 @@ __device__ __forceinline__ void preprocess_body(const FwdParams& p, const GeomSt
   }
 }
 
-template <int D, bool VEC_SH, bool TMA_SH, bool TIGHT = false>
+template <int D, bool VEC_SH, bool TIGHT = false>
 __global__ void __launch_bounds__(256)
 preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
-  preprocess_body<D, VEC_SH, TMA_SH, TIGHT>(p, g, radii);
+  preprocess_body<D, VEC_SH, TIGHT>(p, g, radii);
 }
 
 // Opt-in occupancy variant (SFB_PRE_OCC4=1): the same body under __launch_bounds__(256, 4) — 64 registers and ~50 bytes
@@ -353,15 +326,7 @@ preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
 template <int D>
 __global__ void __launch_bounds__(256, 4)
 preprocess_kernel_occ4(FwdParams p, GeomState g, int* __restrict__ radii) {
-  preprocess_body<D, true, false, false>(p, g, radii);
-}
-
-// The bulk-copy (TMA) staging of the SH slab is opt-in (SFB_TMA=1): on B200 it measured equal to the
-// prefetch + 128-bit-load path for this kernel (85 vs 86 us at 1M splats) while costing 48 KB of smem per CTA.
-static bool tma_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SFB_TMA"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
+  preprocess_body<D, true, false>(p, g, radii);
 }
 
 static bool pre_occ4_enabled() {
@@ -374,25 +339,15 @@ template <int D>
 static void launch_pre_d(const FwdParams& p, const GeomState& g, int* radii, cudaStream_t s) {
   int blocks = (p.P + 255) / 256;
   bool vec = p.shs && ((p.M * 3) % 4 == 0) && ((reinterpret_cast<size_t>(p.shs) & 15) == 0);
-  // the bulk-copy path moves whole rows: use it when every coefficient of the row is active
-  bool tma = vec && !p.tight_rect && tma_enabled() && p.M == (D + 1) * (D + 1) && (size_t)256 * p.M * 12 <= 96 * 1024;
-  if (tma) {
-    const size_t smem = (size_t)256 * p.M * 12;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(preprocess_kernel<D, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      attr_set = true;
-    }
-    preprocess_kernel<D, true, true><<<blocks, 256, smem, s>>>(p, g, radii);
-  } else if (vec && !p.tight_rect && pre_occ4_enabled()) {
+  if (vec && !p.tight_rect && pre_occ4_enabled()) {
     preprocess_kernel_occ4<D><<<blocks, 256, 0, s>>>(p, g, radii);
   } else if (p.tight_rect) {
-    if (vec) preprocess_kernel<D, true, false, true><<<blocks, 256, 0, s>>>(p, g, radii);
-    else     preprocess_kernel<D, false, false, true><<<blocks, 256, 0, s>>>(p, g, radii);
+    if (vec) preprocess_kernel<D, true, true><<<blocks, 256, 0, s>>>(p, g, radii);
+    else     preprocess_kernel<D, false, true><<<blocks, 256, 0, s>>>(p, g, radii);
   } else if (vec) {
-    preprocess_kernel<D, true, false><<<blocks, 256, 0, s>>>(p, g, radii);
+    preprocess_kernel<D, true><<<blocks, 256, 0, s>>>(p, g, radii);
   } else {
-    preprocess_kernel<D, false, false><<<blocks, 256, 0, s>>>(p, g, radii);
+    preprocess_kernel<D, false><<<blocks, 256, 0, s>>>(p, g, radii);
   }
 }
 

@@ -24,7 +24,7 @@ constexpr int RB = 256;  // batch = block size
 // skip / stop decision with the colour pass, so one extra FADD per contribution replaces that whole pass.
 // REC: record, per list entry, which warps (8x4 patches) accumulated it.  The backward sweeps exactly those
 // (warp, entry) pairs instead of every pair whose footprint box touches the patch (3.1 M -> 1.9 M per view).
-template <bool CULL, bool ALPHA, bool REC>
+template <bool ALPHA>
 __global__ void __launch_bounds__(RB, 6)   // <= 42 registers: the sweep loop needs ~40; the fetch-phase culling math may spill
 render_forward_kernel(int W, int H, int grid_x, uint2* __restrict__ ranges,
                       const uint32_t* __restrict__ point_list, uint32_t idx_mask,
@@ -32,22 +32,22 @@ render_forward_kernel(int W, int H, int grid_x, uint2* __restrict__ ranges,
                       const float* __restrict__ bg, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ out_alpha,
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, uint8_t* __restrict__ hit,
-                      bool refine_enabled, float4* __restrict__ zero16, uint32_t zero_per_cta, uint32_t zero_total) {
+                      float4* __restrict__ zero16, uint32_t zero_per_cta, uint32_t zero_total) {
   // one struct = one base register: every access below is base + immediate (+ j * stride)
   struct Smem {
     float4 q0[RB];   // x, y, conA, conB
     float4 q1[RB];   // conC, opacity, depth, r
     float4 q2[RB];   // g, b, -, -   (16-byte stride like q0 / q1: one address register + immediates)
-    uint8_t mask[CULL ? RB : 1];
-    uint8_t list[CULL ? RB / 32 : 1][CULL ? RB : 1];
-    uint8_t hitw[REC ? RB / 32 : 1][REC ? RB : 1];   // [warp][entry]: 1 = some pixel of the warp accumulated it
+    uint8_t mask[RB];
+    uint8_t list[RB / 32][RB];
+    uint8_t hitw[RB / 32][RB];   // [warp][entry]: 1 = some pixel of the warp accumulated it
   };
   __shared__ Smem sm;
   float4* const s_q0 = sm.q0;
   float4* const s_q1 = sm.q1;
   float4* const s_q2 = sm.q2;
   uint8_t* const s_mask = sm.mask;
-  uint8_t (*const s_list)[CULL ? RB : 1] = sm.list;
+  uint8_t (*const s_list)[RB] = sm.list;
 
   const int tile = blockIdx.x;
   // Prologue: clear this CTA's slice of the backward's per-splat gradient accumulators (GradRec[P]).  The kernel is
@@ -88,16 +88,13 @@ render_forward_kernel(int W, int H, int grid_x, uint2* __restrict__ ranges,
       s_q0[threadIdx.x] = a;
       s_q1[threadIdx.x] = b;
       s_q2[threadIdx.x] = c;
-      if (CULL) {
-        mask = patch_mask(a.x, a.y, c.z, c.w, tx0, ty0);
-        if (refine_enabled) mask = refine_patch_mask(mask, a.x, a.y, a.z, a.w, b.x, b.y, c.z, tx0, ty0);
-      }
+      mask = refine_patch_mask(patch_mask(a.x, a.y, c.z, c.w, tx0, ty0), a.x, a.y, a.z, a.w, b.x, b.y, c.z, tx0, ty0);
     }
-    if (CULL) s_mask[threadIdx.x] = (uint8_t)mask;
-    if (REC) reinterpret_cast<uint2*>(&sm.hitw[0][0])[threadIdx.x] = make_uint2(0u, 0u);   // 8 warps x 256 B
+    s_mask[threadIdx.x] = (uint8_t)mask;
+    reinterpret_cast<uint2*>(&sm.hitw[0][0])[threadIdx.x] = make_uint2(0u, 0u);   // 8 warps x 256 B
     __syncthreads();
-    int n = todo < RB ? todo : RB;
-    if (CULL) {
+    int n;
+    {
       int cnt = 0;
       const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
@@ -116,7 +113,7 @@ render_forward_kernel(int W, int H, int grid_x, uint2* __restrict__ ranges,
     if (!done) {
       int lastj = -1;
       for (int k = 0; k < n; k++) {
-        const int j = CULL ? (int)s_list[warp][k] : k;
+        const int j = (int)s_list[warp][k];
         const float4 q0 = s_q0[j];
         const float dx = q0.x - pixfx, dy = q0.y - pixfy;
         const float4 q1 = s_q1[j];
@@ -137,11 +134,11 @@ render_forward_kernel(int W, int H, int grid_x, uint2* __restrict__ ranges,
         if (ALPHA) Ac = __fmaf_rn(1.0f, w, Ac);
         T = test_T;
         lastj = j;                                     // list order is kept by the compaction: the last one wins
-        if (REC) sm.hitw[warp][j] = 1;                 // same value from every contributing lane: benign
+        sm.hitw[warp][j] = 1;                          // same value from every contributing lane: benign
       }
       if (lastj >= 0) last_contributor = (uint32_t)(base + lastj + 1);   // 1-based position in the tile list
     }
-    if (REC) {
+    {
       __syncthreads();
       const int nfetch = todo < RB ? todo : RB;
       if ((int)threadIdx.x < nfetch) {
@@ -165,12 +162,6 @@ render_forward_kernel(int W, int H, int grid_x, uint2* __restrict__ ranges,
   }
 }
 
-static bool cull_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SFB_NO_CULL"); v = (e && e[0] == '1') ? 0 : 1; }
-  return v == 1;
-}
-
 void launch_render_forward(int W, int H, uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
                            const SplatRec* rec,
                            const float* bg, float* out_color, float* out_depth, float* out_alpha, float* final_T,
@@ -180,22 +171,12 @@ void launch_render_forward(int W, int H, uint2* ranges, const uint32_t* point_li
   float4* const zero16 = (zero_grad && P > 0 && P < ((size_t)1 << 30)) ? reinterpret_cast<float4*>(zero_grad) : nullptr;
   const uint32_t zero_total = zero16 ? (uint32_t)(P * 3) : 0u;
   const uint32_t zero_per_cta = zero16 ? (zero_total + (uint32_t)(gx * gy) - 1u) / (uint32_t)(gx * gy) : 0u;
-#define SFB_RF(C, A, R)                                                                                       \
-  render_forward_kernel<C, A, R><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, idx_mask, rec, bg, out_color, \
-                                                        out_depth, out_alpha, final_T, n_contrib, hit, refine,  \
-                                                        zero16, zero_per_cta, zero_total)
-  const bool cull = cull_enabled();
-  static int refine_i = -1;   // SFB_NO_REFINE=1: footprint boxes only (A/B knob)
-  if (refine_i < 0) { const char* e = getenv("SFB_NO_REFINE"); refine_i = (e && e[0] == '1') ? 0 : 1; }
-  const bool refine = refine_i == 1;
-  if (hit) {
-    if (cull) { if (out_alpha) SFB_RF(true, true, true); else SFB_RF(true, false, true); }
-    else      { if (out_alpha) SFB_RF(false, true, true); else SFB_RF(false, false, true); }
-  } else {
-    if (cull) { if (out_alpha) SFB_RF(true, true, false); else SFB_RF(true, false, false); }
-    else      { if (out_alpha) SFB_RF(false, true, false); else SFB_RF(false, false, false); }
-  }
-#undef SFB_RF
+  if (out_alpha)
+    render_forward_kernel<true><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, idx_mask, rec, bg, out_color, out_depth,
+                                                       out_alpha, final_T, n_contrib, hit, zero16, zero_per_cta, zero_total);
+  else
+    render_forward_kernel<false><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, idx_mask, rec, bg, out_color, out_depth,
+                                                        out_alpha, final_T, n_contrib, hit, zero16, zero_per_cta, zero_total);
 }
 
 }  // namespace sfb

@@ -54,6 +54,10 @@ def densify_masks(xyz_gradient_accum, denom, scaling, opacity, max_radii2D, grad
     lib = _lib.load()
     P = scaling.shape[0]
     dev = scaling.device
+    if scaling.dim() != 2 or scaling.shape[1] not in (1, 3):
+        raise Exception("scaling must have dimensions (num_points, 3), or (num_points, 1) for an isotropic model")
+    if scaling.shape[1] == 1:        # the reference's use_isotropic model keeps one raw scale per Gaussian
+        scaling = scaling.expand(P, 3)   # (scene/gaussian_model.py:64-68 repeats it the same way)
     sc = scaling.detach().float().contiguous()
     op = opacity.detach().float().contiguous().reshape(-1)
     acc, den = xyz_gradient_accum.detach().float().contiguous(), denom.detach().float().contiguous()

@@ -226,7 +226,7 @@ class ViewParallelRasterizer:
                                         shs=p.get("shs"), colors_precomp=p.get("colors_precomp"),
                                         scales=p["scales"], rotations=p["rotations"])
         fn = color.grad_fn
-        radii_s, geom, binning, img = fn.saved_tensors
+        radii_s, geom, binning, img = fn.saved_tensors[:4]
         R = fn.num_rendered
         H, W = self.H, self.W
         gx, gy = (W + 15) // 16, (H + 15) // 16

@@ -64,6 +64,8 @@ class _FusedLoss(torch.autograd.Function):
         ctx.save_for_backward(*(t for t in (g_img, g_op) if t is not None))
         ctx.has = (g_img is not None, g_op is not None)
         loss, l1, ss, ml1 = scal[3], scal[0], scal[1], scal[2]
+        if float(lambda_dssim) == 0.0:     # the SSIM map is not evaluated then: do not report a made-up 0
+            ss = torch.full_like(ss, float("nan"))
         ctx.mark_non_differentiable(l1, ss, ml1)
         return loss, l1, ss, ml1
 
@@ -81,7 +83,8 @@ def photometric_loss(image, gt_image, lambda_dssim, opacity=None, gt_mask=None, 
     """train.py:183-184 (+ :189-193 when opacity / gt_mask are given):
         loss = (1 - lambda_dssim) * l1_loss(image, gt) + lambda_dssim * (1 - ssim(image, gt))
                [+ lambda_mask * F.l1_loss(clamp(opacity, 0, 1), gt_mask)]
-    Returns (loss, Ll1, ssim, mask_l1): 0-dim tensors; `loss` carries the gradient."""
+    Returns (loss, Ll1, ssim, mask_l1): 0-dim tensors; `loss` carries the gradient.  ssim is NaN when
+    lambda_dssim == 0 (it is not evaluated then)."""
     if (opacity is None) != (gt_mask is None):
         raise Exception("opacity and gt_mask go together")
     return _FusedLoss.apply(image, gt_image, opacity, gt_mask, float(lambda_dssim), float(lambda_mask))

@@ -45,6 +45,7 @@ _ARENA = None
 # (SFB_BWD_SH_FACTORED); `shs` then gets no .grad from autograd — the caller rebuilds the multi-view sum with
 # sh_grad_combine().
 _SH_COLOR_OUT = None
+_WARNED_DEPTH = False
 
 
 def set_grad_arena(slab, fields, sh_color_out=None):
@@ -201,10 +202,12 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.M = M
         ctx.shapes = tuple(None if t is None else t.shape for t in
                            (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
-        ctx.saved_inputs = saved
         ctx.acc_fresh = [True]      # the forward left the gradient accumulators cleared; true for ONE backward
-        ctx.save_for_backward(radii, geom, binning, img)
+        # the prepared inputs go through save_for_backward (None entries are allowed): autograd's version counters then
+        # catch an in-place update between forward and backward instead of silently using the new values
+        ctx.save_for_backward(radii, geom, binning, img, *saved)
         ctx.mark_non_differentiable(radii)
+        ctx.set_materialize_grads(False)     # unused outputs arrive as None in backward (no zero tensors to allocate)
         if with_alpha:
             return color, radii, depth, alpha
         # always four outputs so that backward has a fixed arity; the wrapper drops the placeholder
@@ -213,11 +216,17 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out_color, _grad_radii, _grad_depth, grad_out_alpha=None):
         # Like the pinned reference build, depth is a forward-only output: its cotangent is not
-        # propagated (every shipped recipe keeps lambda_depth = 0).
+        # propagated (every shipped recipe keeps lambda_depth = 0).  Say so once if a loss uses it.
+        global _WARNED_DEPTH
+        if _grad_depth is not None and not _WARNED_DEPTH:
+            _WARNED_DEPTH = True
+            import warnings
+            warnings.warn("splatfields_b200: the rasterizer's depth output is forward-only (as in the pinned "
+                          "depth-diff-gaussian-rasterization build): the gradient of a depth loss is NOT propagated "
+                          "to the Gaussians", RuntimeWarning, stacklevel=2)
         lib = _lib.load()
         rs = ctx.raster_settings
-        radii, geom, binning, img = ctx.saved_tensors
-        means3D, sh, col, sc, rot, cov, bg, vm, pm, cp = ctx.saved_inputs
+        radii, geom, binning, img, means3D, sh, col, sc, rot, cov, bg, vm, pm, cp = ctx.saved_tensors
         sh_means3D, sh_means2D, sh_sh, sh_col, sh_op, sh_sc, sh_rot, sh_cov = ctx.shapes
         dev = means3D.device
         P = means3D.shape[0]

@@ -67,7 +67,8 @@ def run_cuda(sc, cam, H, W, bg, sh_degree, dL=None, device="cuda", debug=False):
     # internals through the export entry points (needs the autograd ctx buffers)
     fn = color.grad_fn
     if fn is not None:
-        radii_s, geom, binning, img = fn.saved_tensors
+        radii_s, geom, binning, img = fn.saved_tensors[:4]
+        saved_inputs = fn.saved_tensors[4:]
         lib = _lib.load()
         P = t["means3D"].shape[0]
         R = fn.num_rendered
@@ -76,7 +77,7 @@ def run_cuda(sc, cam, H, W, bg, sh_degree, dL=None, device="cuda", debug=False):
                  cov3D=torch.zeros(P, 6, device=dev), conic_opacity=torch.zeros(P, 4, device=dev),
                  rgb=torch.zeros(P, 3, device=dev), clamped=torch.zeros(P, 3, dtype=torch.uint8, device=dev),
                  tiles_touched=torch.zeros(P, dtype=torch.int32, device=dev))
-        dp = lambda k: fn.saved_inputs[k].data_ptr() if fn.saved_inputs[k] is not None else None
+        dp = lambda k: saved_inputs[k].data_ptr() if saved_inputs[k] is not None else None
         # saved_inputs = (means3D, sh, col, scales, rotations, cov3D_precomp, bg, view, proj, campos)
         _lib.check(lib.sfb_export_geom(P, geom.data_ptr(), dp(3), 1.0, dp(4), dp(5),
                                        e["means2D"].data_ptr(), e["depths"].data_ptr(),

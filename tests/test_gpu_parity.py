@@ -26,7 +26,7 @@ CASES = [
 ]
 
 
-def _compare(O, sc, cam, H, W, deg, bg=(1.0, 1.0, 1.0), check_grads=True, ill_conditioned=False):
+def _compare(O, sc, cam, H, W, deg, bg=(1.0, 1.0, 1.0), check_grads=True, ill_conditioned=False, min_ok=0.99):
     gen = torch.Generator().manual_seed(77)
     dL = torch.randn(3, H, W, generator=gen).numpy()
     f, _ = run_oracle(O, sc, cam, H, W, bg, deg)
@@ -52,7 +52,7 @@ def _compare(O, sc, cam, H, W, deg, bg=(1.0, 1.0, 1.0), check_grads=True, ill_co
     assert np.array_equal(c["ranges"], f["ranges"])
 
     # ---- image: 1e-5 abs away from decision thresholds ----
-    assert ok.mean() > 0.97, f"too many threshold-sensitive pixels: {1 - ok.mean():.4f}"
+    assert ok.mean() >= min_ok, f"too many threshold-sensitive pixels: {1 - ok.mean():.4f}"
     assert np.abs(c["color"] - f["color"])[:, ok].max() <= IMG_ATOL
     assert np.abs(c["depth"] - f["depth"])[:, ok].max() <= IMG_ATOL * max(1.0, float(f["depth"].max()))
     assert np.abs(c["final_T"] - f["final_T"])[ok].max() <= IMG_ATOL
