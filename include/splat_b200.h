@@ -65,6 +65,25 @@ int sfb_rasterize_forward(
     sfb_alloc_fn img_alloc, void* img_user,
     int* num_rendered, int debug, void* stream);
 
+/* View-parallel training: one process per GPU, splats replicated, rank r renders camera r — the serial
+ * per-view loop of train.py:169 — and the per-splat gradients of all views are summed (train.py:242-252).  sfb_xchg
+ * describes the symmetric (peer-mapped) buffers that sum travels through; the caller allocates one buffer of
+ * sfb_xchg_bytes() bytes per rank (same size everywhere), zero-filled once, and maps every rank's buffer into every
+ * process (e.g. torch.distributed._symmetric_memory: buffer_ptrs / multicast_ptr).  Pass it to sfb_rasterize_backward
+ * (the geometry kernel then writes its packed gradient records into `local` and its colour gradients into EVERY
+ * rank's buffer as it computes them) and then call sfb_xchg_finish once per step on every rank. */
+#define SFB_XCHG_MAX_RANKS 16
+typedef struct sfb_xchg {
+  int rank, world;                  /* this rank, number of ranks (<= SFB_XCHG_MAX_RANKS) */
+  int P, ngeo;                      /* Gaussians; floats per packed record: 12 with shs (11 used), 16 with colors_precomp (14 used) */
+  void* local;                      /* this rank's buffer */
+  void* peers[SFB_XCHG_MAX_RANKS];  /* rank r's buffer as mapped into this process (peers[rank] may equal local) */
+  void* mc;                         /* NVSwitch multicast mapping of the buffers (multimem.* instructions), or NULL */
+  int max_ctas;                     /* 0: default grid of sfb_xchg_finish (2 CTAs per SM).  The kernel's CTAs wait for the
+                                       other ranks on the device, so ALL ranks' CTAs must be able to run at the same time:
+                                       a test that emulates several ranks on ONE device passes (2 * SMs) / world here */
+} sfb_xchg;
+
 /* Backward.  Replaces _C.rasterize_gaussians_backward.  dL_dout_color [3][H][W] is the
  * cotangent of out_color; dL_dout_alpha [1][H][W] (or NULL) the cotangent of the fused out_alpha.  Outputs (all caller-allocated, fully written by the call — no pre-zeroing
  * needed): dL_dmeans2D [P][3] (xy = gradient w.r.t. the NDC-scaled screen mean, z = 0; this is what
@@ -75,7 +94,10 @@ int sfb_rasterize_forward(
  * gradients only for the corresponding precomputed inputs); a NULL output is simply not written.
  * flags: SFB_BWD_ACC_FRESH = this is the FIRST backward on these scratch buffers since the forward that filled them
  * (the forward leaves the per-splat gradient accumulators inside geom_buffer cleared, so the backward can skip its
- * 48 B/Gaussian memset); pass 0 when in doubt or when running backward again on the same buffers (retain_graph). */
+ * 48 B/Gaussian memset); pass 0 when in doubt or when running backward again on the same buffers (retain_graph).
+ * xchg (or NULL) + xchg_epoch: view-parallel exchange mode (sfb_xchg above; needs scales / rotations): the parameter
+ * gradients leave through the symmetric buffers instead of dL_dmeans3D / dL_dopacity / dL_dscales / dL_drotations /
+ * dL_dcolors / dL_dsh, which may all be NULL; dL_dmeans2D (a per-view quantity) is still written. */
 #define SFB_BWD_ACC_FRESH 1
 /* SFB_BWD_SH_FACTORED (with shs): dL_dcolors (required) receives the gradient w.r.t. the SH-evaluated colour BEFORE its
  * max(0, .) clamp — i.e. the render backward's colour gradient with the clamped channels zeroed — and dL_dsh may be
@@ -92,7 +114,20 @@ int sfb_rasterize_backward(
     const float* dL_dout_color, const float* dL_dout_alpha,
     float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D, float* dL_dcov3D,
     float* dL_dsh, float* dL_dscales, float* dL_drotations,
-    int debug, int flags, void* stream);
+    int debug, int flags,
+    const sfb_xchg* xchg /* or NULL */, unsigned xchg_epoch,   /* exchange mode: parameter-gradient outputs may be NULL */
+    void* stream);
+
+size_t sfb_xchg_bytes(int P, int world, int ngeo, int with_colour_tables /* 1 with shs */);
+/* Second half of the exchange, same `epoch` as the backward of this step (1, 2, 3, ... identical on every rank, +1 per
+ * step): waits (on the device) until every rank's backward has finished, sums the packed records over the ranks
+ * (multimem.ld_reduce / multimem.st through the switch when x->mc, peer loads / stores otherwise), rebuilds
+ * dL_dsh [P][M][3] = sum_v basis(dir_v) (x) colour gradient of view v (campos_views [world][3]; with shs), and writes
+ * the summed dL_dmeans3D [P][3], dL_dopacity [P], dL_dscales [P][3], dL_drotations [P][4] (+ dL_dcolors [P][3] without
+ * shs).  Asynchronous on `stream`; no NCCL involved. */
+int sfb_xchg_finish(const sfb_xchg* x, unsigned epoch, int sh_degree, int M, const float* means3D,
+                    const float* campos_views, float* dL_dmeans3D, float* dL_dopacity, float* dL_dscales,
+                    float* dL_drotations, float* dL_dcolors, float* dL_dsh, void* stream);
 
 /* Multi-view sum of SH gradients from their factored form (view-parallel training; the serial loop
  * it replaces is train.py:169-242, whose loss.backward() accumulates the V per-view dL_dsh into features.grad):
@@ -102,13 +137,6 @@ int sfb_rasterize_backward(
  * V backward calls run with SFB_BWD_SH_FACTORED.  1 <= V <= 64.  Views are summed in index order (reproducible). */
 int sfb_sh_grad_combine(int P, int V, int sh_degree, int M, const float* means3D, const float* campos,
                         const float* dL_dcolor_views, float* dL_dsh, void* stream);
-
-/* Early hand-off of the factored colour gradient.  The NEXT sfb_rasterize_backward call made with SFB_BWD_SH_FACTORED
- * (from any thread: PyTorch runs backward on an autograd worker) writes dL_dcolors with a small kernel of its own right
- * after the render backward, records `cuda_event` (a cudaEvent_t) on its stream, and only then launches the geometry
- * kernel — so a stream that waits on the event can start the all-gather of dL_dcolors while the geometry kernel
- * runs.  One-shot: the call consumes the event; pass NULL to cancel. */
-int sfb_backward_midpoint_event(void* cuda_event);
 
 /* Replaces _C.mark_visible: present[i] = 1 iff the view-space z of means3D[i] is > 0.2. */
 int sfb_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

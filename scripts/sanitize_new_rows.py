@@ -1,5 +1,5 @@
 """Small invocations of every kernel added after the last sanitizer pass (activate, knn, sh_grad_combine, factored
-geometry backward, extract_dcolor) for `compute-sanitizer --tool memcheck|racecheck python scripts/sanitize_new_rows.py`."""
+geometry backward) for `compute-sanitizer --tool memcheck|racecheck python scripts/sanitize_new_rows.py`."""
 import math
 import os
 import sys
@@ -29,16 +29,12 @@ def main():
                                          1.0, cam.world_view_transform, cam.full_proj_transform, 3, cam.camera_center,
                                          False, False)
     lib = _lib.load()
-    for early in (False, True):
+    for _ in range(1):
         color, radii, depth = GaussianRasterizer(rset)(means3D=t["means3D"], means2D=torch.zeros(P, 3, device=dev,
                                                        requires_grad=True), opacities=t["opacities"], shs=t["shs"],
                                                        scales=t["scales"], rotations=t["rotations"])
         dcol = torch.empty(P, 3, device=dev)
         rasterizer.set_grad_arena(None, None, dcol)
-        if early:
-            ev = torch.cuda.Event()
-            ev.record()
-            _lib.check(lib.sfb_backward_midpoint_event(ev.cuda_event))
         color.sum().backward()
         rasterizer.set_grad_arena(None, None)
         out = torch.empty(P, 16, 3, device=dev)

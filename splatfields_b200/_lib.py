@@ -23,13 +23,22 @@ SYMBOLS = (
     "sfb_export_geom", "sfb_export_binning", "sfb_export_img", "sfb_last_launch_count",
     "sfb_profile_enable", "sfb_profile_count", "sfb_profile_read", "sfb_profile_name",
     "sfb_loss_scratch_bytes", "sfb_loss_window", "sfb_l1_ssim_loss", "sfb_densify_stats", "sfb_densify_masks",
-    "sfb_sh_grad_combine", "sfb_backward_midpoint_event", "sfb_activate_forward", "sfb_activate_backward", "sfb_knn_scratch_bytes",
+    "sfb_sh_grad_combine", "sfb_xchg_bytes", "sfb_xchg_finish", "sfb_activate_forward", "sfb_activate_backward", "sfb_knn_scratch_bytes",
     "sfb_knn3_mean_dist2",
 )
 
 
 BWD_ACC_FRESH = 1     # include/splat_b200.h: SFB_BWD_ACC_FRESH
 BWD_SH_FACTORED = 2   # include/splat_b200.h: SFB_BWD_SH_FACTORED
+
+
+XCHG_MAX_RANKS = 16   # include/splat_b200.h: SFB_XCHG_MAX_RANKS
+
+
+class XchgDesc(C.Structure):
+    """include/splat_b200.h: sfb_xchg — the symmetric buffers of the view-parallel gradient exchange."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("P", C.c_int), ("ngeo", C.c_int), ("local", C.c_void_p),
+                ("peers", C.c_void_p * XCHG_MAX_RANKS), ("mc", C.c_void_p), ("max_ctas", C.c_int)]
 
 
 class SplatB200Error(RuntimeError):
@@ -65,7 +74,8 @@ def load():
         vp, vp, vp, cf, cf, vp,                   # view, proj, campos, tanfovx, tanfovy, radii
         vp, vp, vp, vp, vp,                       # geom, binning, img, dL_dout_color, dL_dout_alpha (nullable)
         vp, vp, vp, vp, vp, vp, vp, vp,           # 8 gradient outputs
-        ci, ci, vp]                               # debug, flags (SFB_BWD_ACC_FRESH), stream
+        ci, ci,                                   # debug, flags (SFB_BWD_ACC_FRESH | SFB_BWD_SH_FACTORED)
+        C.POINTER(XchgDesc), C.c_uint, vp]        # xchg (nullable), xchg_epoch, stream
     lib.sfb_mark_visible.restype = ci
     lib.sfb_mark_visible.argtypes = [ci, vp, vp, vp, vp, vp]
     lib.sfb_export_geom.restype = ci
@@ -94,8 +104,10 @@ def load():
     lib.sfb_densify_masks.argtypes = [ci, vp, vp, vp, vp, vp, ci, cf, cf, cf, cf, cf, vp, vp, vp, vp, vp]
     lib.sfb_sh_grad_combine.restype = ci
     lib.sfb_sh_grad_combine.argtypes = [ci, ci, ci, ci, vp, vp, vp, vp, vp]
-    lib.sfb_backward_midpoint_event.restype = ci
-    lib.sfb_backward_midpoint_event.argtypes = [vp]
+    lib.sfb_xchg_bytes.restype = C.c_size_t
+    lib.sfb_xchg_bytes.argtypes = [ci, ci, ci, ci]
+    lib.sfb_xchg_finish.restype = ci
+    lib.sfb_xchg_finish.argtypes = [C.POINTER(XchgDesc), C.c_uint, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_activate_forward.restype = ci
     lib.sfb_activate_forward.argtypes = [ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_activate_backward.restype = ci
@@ -104,7 +116,7 @@ def load():
     lib.sfb_knn_scratch_bytes.argtypes = [ci]
     lib.sfb_knn3_mean_dist2.restype = ci
     lib.sfb_knn3_mean_dist2.argtypes = [ci, vp, vp, vp, vp]
-    if lib.sfb_abi_version() != 4:
+    if lib.sfb_abi_version() != 5:
         raise SplatB200Error("libsplat_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -20,7 +20,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 # per-file extra flags: the preprocess kernel's float math feeds integer tile keys and must be
 # bit-reproducible against the CPU oracle -> no implicit FMA contraction there.
 EXTRA = {"preprocess.cu": ["-fmad=false"]}
-SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "render_fwd.cu", "render_bwd.cu", "geom_bwd.cu",
+SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "render_fwd.cu", "render_bwd.cu", "geom_bwd.cu", "exchange.cu",
            "loss.cu", "densify.cu", "activate.cu", "knn.cu"]
 
 

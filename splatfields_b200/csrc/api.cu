@@ -7,14 +7,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <atomic>
 #include <string>
 
 namespace {
 
 thread_local std::string g_err;
 int g_launches = 0;   // process-wide: autograd runs backward on its own thread
-std::atomic<void*> g_mid_event{nullptr};   // sfb_backward_midpoint_event: consumed by the next factored backward (any thread)
 thread_local uint32_t* g_pinned = nullptr;  // pinned (portable, mapped) word the preprocess kernel stores num_rendered into
 constexpr int MAX_DEVICES = 64;
 thread_local cudaEvent_t g_evt[MAX_DEVICES] = {};   // one per device: an event can only be recorded on its own device's streams
@@ -113,7 +111,7 @@ void prof_end(cudaStream_t s) {
 
 extern "C" {
 
-int sfb_abi_version(void) { return 4; }
+int sfb_abi_version(void) { return 5; }
 const char* sfb_last_error(void) { return g_err.c_str(); }
 int sfb_last_launch_count(void) { return g_launches; }
 
@@ -269,7 +267,8 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
                            const float* dL_dout_color, const float* dL_dout_alpha, float* dL_dmeans2D,
                            float* dL_dcolors, float* dL_dopacity,
                            float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscales,
-                           float* dL_drotations, int debug, int flags, void* stream) {
+                           float* dL_drotations, int debug, int flags, const sfb_xchg* xchg, unsigned xchg_epoch,
+                           void* stream) {
   using namespace sfb;
   g_err.clear();
   g_launches = 0;
@@ -277,15 +276,25 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   if (P == 0) return SFB_OK;
   if (P < 0 || W <= 0 || H <= 0 || num_rendered < 0) return fail(SFB_ERR_ARG, "bad sizes");
   if (!geom_buffer || !binning_buffer || !img_buffer) return fail(SFB_ERR_ARG, "null scratch buffer");
-  if (!dL_dout_color || !dL_dmeans2D || !dL_dopacity || !dL_dmeans3D)
-    return fail(SFB_ERR_ARG, "null gradient buffer");
-  if (colors_precomp && !dL_dcolors) return fail(SFB_ERR_ARG, "dL_dcolors required with colors_precomp");
-  if (cov3D_precomp && !dL_dcov3D) return fail(SFB_ERR_ARG, "dL_dcov3D required with cov3D_precomp");
-  const bool sh_factored = (flags & SFB_BWD_SH_FACTORED) != 0;
-  if (sh_factored && (!shs || !dL_dcolors)) return fail(SFB_ERR_ARG, "SFB_BWD_SH_FACTORED needs shs and dL_dcolors");
-  if (shs && !dL_dsh && !sh_factored) return fail(SFB_ERR_ARG, "dL_dsh required with shs");
-  if (!cov3D_precomp && (!dL_dscales || !dL_drotations || !scales || !rotations))
-    return fail(SFB_ERR_ARG, "dL_dscales / dL_drotations required with scales / rotations");
+  if (!dL_dout_color || !dL_dmeans2D) return fail(SFB_ERR_ARG, "null gradient buffer");
+  const bool sh_factored = (flags & SFB_BWD_SH_FACTORED) != 0 || (xchg && shs);
+  if (xchg) {
+    // exchange mode: the parameter gradients leave through the symmetric buffer, the per-parameter outputs are unused
+    if (cov3D_precomp || !scales || !rotations) return fail(SFB_ERR_ARG, "sfb_xchg needs scales / rotations (no cov3D_precomp)");
+    if (xchg->P != P || xchg->world < 1 || xchg->world > XCHG_MAX_RANKS || xchg->rank < 0 || xchg->rank >= xchg->world ||
+        !xchg->local || xchg->ngeo != (shs ? 12 : 16))
+      return fail(SFB_ERR_ARG, "sfb_xchg does not match this call (P, world <= 16, rank, ngeo = 12 with shs / 16 without)");
+    for (int r = 0; r < xchg->world; r++)
+      if (!xchg->peers[r]) return fail(SFB_ERR_ARG, "sfb_xchg: null peer mapping");
+  } else {
+    if (!dL_dopacity || !dL_dmeans3D) return fail(SFB_ERR_ARG, "null gradient buffer");
+    if (colors_precomp && !dL_dcolors) return fail(SFB_ERR_ARG, "dL_dcolors required with colors_precomp");
+    if (cov3D_precomp && !dL_dcov3D) return fail(SFB_ERR_ARG, "dL_dcov3D required with cov3D_precomp");
+    if (sh_factored && (!shs || !dL_dcolors)) return fail(SFB_ERR_ARG, "SFB_BWD_SH_FACTORED needs shs and dL_dcolors");
+    if (shs && !dL_dsh && !sh_factored) return fail(SFB_ERR_ARG, "dL_dsh required with shs");
+    if (!cov3D_precomp && (!dL_dscales || !dL_drotations || !scales || !rotations))
+      return fail(SFB_ERR_ARG, "dL_dscales / dL_drotations required with scales / rotations");
+  }
   const size_t HW = (size_t)H * W;
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y, T = gx * gy;
   RedzoneList rz;
@@ -317,19 +326,6 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   g_launches++;
   CK_LAUNCH("render backward", debug, s);
 
-  // Optional early hand-off of the colour gradient (view-parallel exchange): produce it now, record the caller's
-  // event, and let the geometry kernel run while the caller's all-gather is already on the wire.
-  void* mid_evt = sh_factored ? g_mid_event.exchange(nullptr) : nullptr;
-  if (mid_evt) {
-    prof_begin("extract_dcolor", s);
-    launch_extract_dcolor(P, g, radii, dL_dcolors, s);
-    prof_end(s);
-    g_launches++;
-    CK_LAUNCH("colour gradient extraction", debug, s);
-    CK(cudaEventRecord((cudaEvent_t)mid_evt, s));
-    dL_dcolors = nullptr;                       // already written; the geometry kernel must not write it again
-  }
-
   BwdParams bp;
   bp.P = P; bp.D = sh_degree; bp.M = M; bp.W = W; bp.H = H;
   bp.means3D = means3D; bp.shs = shs; bp.colors_precomp = colors_precomp; bp.scales = scales;
@@ -342,6 +338,18 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   bp.dL_dmeans2D = dL_dmeans2D; bp.dL_dcolors = dL_dcolors; bp.dL_dopacity = dL_dopacity;
   bp.dL_dmeans3D = dL_dmeans3D; bp.dL_dcov3D = dL_dcov3D; bp.dL_dsh = dL_dsh; bp.dL_dscales = dL_dscales;
   bp.dL_drot = dL_drotations;
+  bp.x_geo = nullptr; bp.x_ngeo = 0; bp.x_mc = 0; bp.x_ndst = 0; bp.x_nranks = 0;
+  if (xchg) {
+    const XchgLayout xl = XchgLayout::make((size_t)P, xchg->world, xchg->ngeo, shs != nullptr);
+    bp.x_geo = reinterpret_cast<float*>((char*)xchg->local + xl.geo_off);
+    bp.x_ngeo = xchg->ngeo;
+    bp.x_nranks = xchg->world;
+    // slot `rank` of this step's colour-gradient table, on every rank
+    const size_t slot = xl.gc_off[xchg_epoch & 1u] + (size_t)xchg->rank * (size_t)P * 12;
+    for (int r = 0; r < xchg->world; r++) bp.x_gc_peer[r] = reinterpret_cast<float*>((char*)xchg->peers[r] + slot);
+    if (xchg->mc) { bp.x_mc = 1; bp.x_ndst = 1; bp.x_gc_dst[0] = reinterpret_cast<float*>((char*)xchg->mc + slot); }
+    else { bp.x_ndst = xchg->world; for (int r = 0; r < xchg->world; r++) bp.x_gc_dst[r] = bp.x_gc_peer[r]; }
+  }
   prof_begin("geom_backward", s);
   launch_geom_backward(bp, g, s);
   prof_end(s);
@@ -358,8 +366,44 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   return SFB_OK;
 }
 
-int sfb_backward_midpoint_event(void* cuda_event) {
-  g_mid_event.store(cuda_event);
+size_t sfb_xchg_bytes(int P, int world, int ngeo, int with_colour_tables) {
+  if (P < 0 || world < 1 || (ngeo != 12 && ngeo != 16)) return 0;
+  return sfb::XchgLayout::make((size_t)P, world, ngeo, with_colour_tables != 0).bytes;
+}
+
+int sfb_xchg_finish(const sfb_xchg* x, unsigned epoch, int sh_degree, int M, const float* means3D,
+                    const float* campos_views, float* dL_dmeans3D, float* dL_dopacity, float* dL_dscales,
+                    float* dL_drotations, float* dL_dcolors, float* dL_dsh, void* stream) {
+  using namespace sfb;
+  g_err.clear();
+  if (!x || x->world < 1 || x->world > XCHG_MAX_RANKS || x->rank < 0 || x->rank >= x->world || !x->local ||
+      (x->ngeo != 12 && x->ngeo != 16) || x->P < 0)
+    return fail(SFB_ERR_ARG, "sfb_xchg_finish: bad descriptor");
+  if (x->P == 0) return SFB_OK;
+  const bool has_sh = x->ngeo == 12;
+  if (!dL_dmeans3D || !dL_dopacity || !dL_dscales || !dL_drotations || (has_sh ? (!dL_dsh || !means3D || !campos_views) : !dL_dcolors))
+    return fail(SFB_ERR_ARG, "sfb_xchg_finish: null pointer");
+  if (has_sh && (sh_degree < 0 || sh_degree > 3 || M < (sh_degree + 1) * (sh_degree + 1)))
+    return fail(SFB_ERR_ARG, "sfb_xchg_finish: sh_degree / M mismatch");
+  cudaStream_t s = (cudaStream_t)stream;
+  const XchgLayout xl = XchgLayout::make((size_t)x->P, x->world, x->ngeo, has_sh);
+  XchgDev d;
+  d.rank = x->rank; d.world = x->world; d.P = x->P; d.ngeo = x->ngeo;
+  d.flags = reinterpret_cast<uint32_t*>(x->local);
+  d.geo = reinterpret_cast<float*>((char*)x->local + xl.geo_off);
+  d.geo_mc = x->mc ? reinterpret_cast<float*>((char*)x->mc + xl.geo_off) : nullptr;
+  for (int r = 0; r < x->world; r++) {
+    if (!x->peers[r]) return fail(SFB_ERR_ARG, "sfb_xchg_finish: null peer mapping");
+    d.peer_flags[r] = reinterpret_cast<uint32_t*>(x->peers[r]);
+    d.peer_geo[r] = reinterpret_cast<float*>((char*)x->peers[r] + xl.geo_off);
+  }
+  d.gc = reinterpret_cast<const float*>((char*)x->local + xl.gc_off[epoch & 1u]);
+  prof_begin("xchg_finish", s);
+  launch_xchg_finish(d, x->max_ctas, epoch, sh_degree, M, means3D, campos_views, dL_dmeans3D, dL_dopacity, dL_dscales, dL_drotations,
+                     dL_dcolors, has_sh ? dL_dsh : nullptr, s);
+  prof_end(s);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SFB_ERR_CUDA, "xchg finish", e);
   return SFB_OK;
 }
 

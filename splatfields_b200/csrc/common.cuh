@@ -369,6 +369,7 @@ void launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* p
                             GradRec* grad, cudaStream_t s);
 
 // geom_bwd.cu
+constexpr int XCHG_MAX_RANKS = 16;
 struct BwdParams {
   int P, D, M, W, H;
   const float *means3D, *shs, *colors_precomp, *scales, *rotations, *cov3D_precomp;
@@ -378,9 +379,40 @@ struct BwdParams {
   int sh_factored;  // SFB_BWD_SH_FACTORED: dL_dcolors receives the clamp-masked colour gradient, dL_dsh may be nullptr
   const int* radii;
   float *dL_dmeans2D, *dL_dcolors, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drot;
+  // view-parallel exchange over NVLink (exchange.cu); x_geo == nullptr: off
+  float* x_geo;                 // this rank's packed gradient records [P][x_ngeo] (x_ngeo = 12: SH colours, 16: precomputed)
+  int x_ngeo, x_mc, x_ndst, x_nranks;
+  float* x_gc_dst[XCHG_MAX_RANKS];    // slot `rank` of the colour-gradient table: x_mc ? {multicast address} : one per rank
+  float* x_gc_peer[XCHG_MAX_RANKS];   // the same slot through every rank's unicast mapping (ragged tail)
 };
 void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s);
-void launch_extract_dcolor(int P, const GeomState& g, const int* radii, float* out /* [P][3] */, cudaStream_t s);
+
+// exchange.cu
+// Layout of one rank's symmetric exchange buffer (identical on every rank; include/splat_b200.h: sfb_xchg):
+//   [flags: 256 B][packed gradient records: P * ngeo floats][colour-gradient tables: 2 parities x world x P x 3 floats]
+struct XchgLayout {
+  size_t geo_off, gc_off[2], bytes;
+  static XchgLayout make(size_t P, int world, int ngeo, bool with_gc) {
+    XchgLayout l;
+    size_t o = 256;
+    l.geo_off = o; o = align_up(o + P * (size_t)ngeo * 4, 256);
+    for (int k = 0; k < 2; k++) { l.gc_off[k] = o; if (with_gc) o = align_up(o + (size_t)world * P * 12, 256); }
+    l.bytes = o;
+    return l;
+  }
+};
+struct XchgDev {                 // device-side view of the exchange for one step
+  int rank, world, P, ngeo;
+  uint32_t* flags;               // this rank's flag words
+  uint32_t* peer_flags[XCHG_MAX_RANKS];
+  float* geo;                    // this rank's packed records (sums after the exchange)
+  float* geo_mc;                 // the same array through the multicast mapping, or nullptr
+  float* peer_geo[XCHG_MAX_RANKS];
+  const float* gc;               // this step's colour-gradient table [world][P][3] (local)
+};
+void launch_xchg_finish(const XchgDev& x, int max_ctas, uint32_t epoch, int D, int M, const float* means3D, const float* campos,
+                        float* dL_dmeans3D, float* dL_dopacity, float* dL_dscales, float* dL_drot, float* dL_dcolors,
+                        float* dL_dsh, cudaStream_t s);
 // dL_dsh[i] = sum over V views of basis(normalize(means3D[i] - campos[v])) (x) dcolor[v][i]   (view-parallel exchange)
 void launch_sh_grad_combine(int P, int V, int D, int M, const float* means3D, const float* campos /* [V][3] */,
                             const float* dcolor /* [V][P][3] */, float* dL_dsh /* [P][M][3] */, bool wide256,

@@ -1,0 +1,294 @@
+// exchange.cu — view-parallel gradient exchange.
+//
+// The reference renders the views of one iteration serially and lets autograd add their per-splat gradients up
+// (train.py:169-252).  With one view per GPU those sums have to cross NVLink once per step.  Two implementations of
+// the same sum live here:
+//
+//  * sh_grad_combine_kernel — the rebuild step of the NCCL formulation (all-gather of the [P,3] colour gradients +
+//    all-reduce of the [P,11] geometry gradients by torch.distributed; host_api exchange="factored").
+//  * xchg_finish_kernel — the whole exchange in ONE kernel over symmetric (peer-mapped / NVSwitch-multicast) memory,
+//    fed directly by the backward kernel (geom_backward_kernel<PUSH>, which has already written this rank's colour
+//    gradients into every rank's table with multimem.st while it was computing):
+//        0. cross-rank barrier on flags in the symmetric buffers (every rank's backward has finished),
+//        1. this rank's 1/N slice of the packed geometry records is summed over the ranks INSIDE THE SWITCH
+//           (multimem.ld_reduce.add.v4.f32) and broadcast back to every rank (multimem.st) — the NVLS all-reduce,
+//           two 16-byte instructions per 16 bytes, no staging buffers, no ring;
+//           without multicast support the same slice is summed from the peers' unicast mappings in rank order,
+//        2. meanwhile the other CTAs rebuild the SH gradient rows  sum_v basis(dir_v) (x) gc_v  from the local table,
+//        3. second barrier (every slice has been broadcast), then the records are unpacked into the caller's
+//           per-parameter gradient arrays.
+//    HBM-bound streaming work + 2 x 48 B/splat over NVLink per rank; nothing here goes through NCCL.
+#include "common.cuh"
+
+namespace sfb {
+
+namespace {
+
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+__constant__ float SHX_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float SHX_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                -0.5900435899266435f};
+
+// real SH basis of utils/sh_utils.py:57-112 at direction (x, y, z), the same expressions as geom_backward_kernel
+template <int D>
+__device__ __forceinline__ void sh_basis(float x, float y, float z, float* basis) {
+  basis[0] = SH_C0;
+  if (D > 0) { basis[1] = -SH_C1 * y; basis[2] = SH_C1 * z; basis[3] = -SH_C1 * x; }
+  if (D > 1) {
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    basis[4] = SHX_C2[0] * xy; basis[5] = SHX_C2[1] * yz; basis[6] = SHX_C2[2] * (2.f * zz - xx - yy);
+    basis[7] = SHX_C2[3] * xz; basis[8] = SHX_C2[4] * (xx - yy);
+    if (D > 2) {
+      basis[9] = SHX_C3[0] * y * (3.f * xx - yy); basis[10] = SHX_C3[1] * xy * z;
+      basis[11] = SHX_C3[2] * y * (4.f * zz - xx - yy); basis[12] = SHX_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+      basis[13] = SHX_C3[4] * x * (4.f * zz - xx - yy); basis[14] = SHX_C3[5] * z * (xx - yy);
+      basis[15] = SHX_C3[6] * x * (xx - 3.f * yy);
+    }
+  }
+}
+
+// dL_dsh row of Gaussian i: sum over the V views (index order: bit-reproducible) of basis(dir_v) (x) gc_v, each product
+// rounded on its own (as geom_backward_kernel stores it for a single view) before it enters the sum.
+template <int D, bool W256>
+__device__ __forceinline__ void sh_row_rebuild(size_t i, int P, int V, int M, const float* __restrict__ means3D,
+                                               const float* s_cam, const float* __restrict__ dcolor,
+                                               float* __restrict__ dL_dsh) {
+  constexpr int NB = (D + 1) * (D + 1);
+  constexpr int NF8 = (3 * NB + 7) / 8;
+  const float mx = means3D[3 * i], my = means3D[3 * i + 1], mz = means3D[3 * i + 2];
+  float acc[NF8 * 8];
+#pragma unroll
+  for (int k = 0; k < NF8 * 8; k++) acc[k] = 0.f;
+  for (int v = 0; v < V; v++) {
+    const float* gp = dcolor + ((size_t)v * P + i) * 3;
+    // (ld.global.cg: in the NVLink exchange this table is written by the PEERS while the kernel is already resident)
+    const float g0 = __ldcg(gp), g1 = __ldcg(gp + 1), g2 = __ldcg(gp + 2);
+    if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;     // culled in this view (or no gradient reached it)
+    const float vx = mx - s_cam[3 * v], vy = my - s_cam[3 * v + 1], vz = mz - s_cam[3 * v + 2];
+    const float ilen = rsqrtf(vx * vx + vy * vy + vz * vz);
+    float basis[NB];
+    sh_basis<D>(vx * ilen, vy * ilen, vz * ilen, basis);
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+      acc[3 * k] = __fadd_rn(acc[3 * k], __fmul_rn(basis[k], g0));
+      acc[3 * k + 1] = __fadd_rn(acc[3 * k + 1], __fmul_rn(basis[k], g1));
+      acc[3 * k + 2] = __fadd_rn(acc[3 * k + 2], __fmul_rn(basis[k], g2));
+    }
+  }
+  float* dsh = dL_dsh + i * M * 3;
+  if (W256) {      // launcher: M == NB, rows are 32-byte aligned multiples of 32 bytes
+#pragma unroll
+    for (int k = 0; k < (3 * NB) / 8; k++) stg256(dsh + 8 * k, acc + 8 * k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3 * NB; k++) dsh[k] = acc[k];
+    for (int k = 3 * NB; k < 3 * M; k++) dsh[k] = 0.f;      // coefficients above the active degree
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// Rebuild step of the NCCL formulation.  One thread per Gaussian, 12 + 12*V bytes in, 12*M out: HBM-bound.
+template <int D, bool W256>
+__global__ void __launch_bounds__(256)
+sh_grad_combine_kernel(int P, int V, int M, const float* __restrict__ means3D, const float* __restrict__ campos,
+                       const float* __restrict__ dcolor, float* __restrict__ dL_dsh) {
+  __shared__ float s_cam[3 * 64];
+  for (int k = threadIdx.x; k < 3 * V; k += blockDim.x) s_cam[k] = campos[k];
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  sh_row_rebuild<D, W256>((size_t)idx, P, V, M, means3D, s_cam, dcolor, dL_dsh);
+}
+
+void launch_sh_grad_combine(int P, int V, int D, int M, const float* means3D, const float* campos,
+                            const float* dcolor, float* dL_dsh, bool wide256, cudaStream_t s) {
+  if (P <= 0) return;
+  const int blocks = (P + 255) / 256;
+  const bool w256 = wide256 && (M * 12) % 32 == 0 && (reinterpret_cast<size_t>(dL_dsh) & 31) == 0;
+#define SFB_SC(DD)                                                                                              \
+  if (w256 && M == (DD + 1) * (DD + 1) && (3 * (DD + 1) * (DD + 1)) % 8 == 0)                                   \
+    sh_grad_combine_kernel<DD, true><<<blocks, 256, 0, s>>>(P, V, M, means3D, campos, dcolor, dL_dsh);          \
+  else                                                                                                          \
+    sh_grad_combine_kernel<DD, false><<<blocks, 256, 0, s>>>(P, V, M, means3D, campos, dcolor, dL_dsh);
+  switch (D) {
+    case 0: SFB_SC(0) break;
+    case 1: SFB_SC(1) break;
+    case 2: SFB_SC(2) break;
+    default: SFB_SC(3) break;
+  }
+#undef SFB_SC
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The exchange over symmetric memory.
+namespace {
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Wait until *p >= epoch (flags only grow).  Bounded: a peer that never arrives must not hang the GPU — after ~4 s the
+// kernel traps and the caller gets a CUDA error.
+__device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t epoch) {
+  const long long t0 = clock64();
+  while ((int32_t)(ld_acquire_sys(p) - epoch) < 0) {
+    __nanosleep(64);
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 mm_ld_reduce_add(const float* mc_addr) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st(float* mc_addr, const float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w) : "memory");
+}
+
+}  // namespace
+
+// flags inside every rank's symmetric buffer (uint32 words; only ever grow, one epoch pair per step)
+//   [FLAG_A + r]  rank r's backward of step `epoch` is complete (its records are in its buffer, its colour gradients in mine)
+//   [FLAG_B + r]  rank r has broadcast its slice of the sums of step `epoch`
+//   [FLAG_DONE]   local: CTAs of this launch that finished their part of the slice reduction
+constexpr int FLAG_A = 0, FLAG_B = 16, FLAG_DONE = 32, FLAG_TICKET = 33;
+
+template <int D, bool MC, bool HAS_SH, bool W256>
+__global__ void __launch_bounds__(256, 2)
+xchg_finish_kernel(XchgDev x, uint32_t epoch, int V, int M, const float* __restrict__ means3D,
+                   const float* __restrict__ campos, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dopacity,
+                   float* __restrict__ dL_dscales, float* __restrict__ dL_drot, float* __restrict__ dL_dcolors,
+                   float* __restrict__ dL_dsh) {
+  __shared__ float s_cam[3 * XCHG_MAX_RANKS];
+  __shared__ uint32_t s_ticket;
+  const int N = x.world;
+  // ---- 0. announce (stream order: this rank's backward has completed) and wait for everybody
+  if (blockIdx.x == 0 && threadIdx.x < N) {
+    __threadfence_system();
+    st_release_sys(x.peer_flags[threadIdx.x] + FLAG_A + x.rank, epoch);
+  }
+  if (HAS_SH) for (int k = threadIdx.x; k < 3 * V; k += blockDim.x) s_cam[k] = campos[k];
+  if (threadIdx.x < N) spin_until(x.flags + FLAG_A + threadIdx.x, epoch);
+  __syncthreads();
+
+  // ---- 1. sum this rank's slice of the packed records over the ranks, broadcast the sums (in place)
+  // The slice is split over the first `nred` CTAs; the rest start on the SH rows right away (they only need barrier A).
+  const size_t C = (size_t)x.P * (size_t)(x.ngeo / 4);                  // 16-byte chunks of the record array
+  const size_t c0 = C * (size_t)x.rank / (size_t)N, c1 = C * (size_t)(x.rank + 1) / (size_t)N;
+  const int nred = HAS_SH ? max(1, (int)gridDim.x / 2) : (int)gridDim.x;
+  if ((int)blockIdx.x < nred) {
+    const size_t stride = (size_t)nred * 256;
+    for (size_t c = c0 + (size_t)blockIdx.x * 256 + threadIdx.x; c < c1; c += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {        // four independent round trips through the switch in flight per thread
+        const size_t cu = c + (size_t)u * stride;
+        if (cu < c1) {
+          if (MC) v[u] = mm_ld_reduce_add(x.geo_mc + 4 * cu);
+          else {
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < N; r++) {  // rank order: every rank would get the same bits, and only one computes them
+              const float4 t = ld_relaxed_sys_v4(x.peer_geo[r] + 4 * cu);
+              v[u].x += t.x; v[u].y += t.y; v[u].z += t.z; v[u].w += t.w;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const size_t cu = c + (size_t)u * stride;
+        if (cu < c1) {
+          if (MC) mm_st(x.geo_mc + 4 * cu, v[u]);
+          else for (int r = 0; r < N; r++) *reinterpret_cast<float4*>(x.peer_geo[r] + 4 * cu) = v[u];
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      if (atomicAdd(x.flags + FLAG_DONE, 1u) == (uint32_t)nred - 1u) {    // last CTA of the reduction: tell every rank
+        x.flags[FLAG_DONE] = 0u;                                           // (reset for the next launch)
+        __threadfence_system();
+        for (int r = 0; r < N; r++) st_release_sys(x.peer_flags[r] + FLAG_B + x.rank, epoch);
+      }
+    }
+  }
+
+  // ---- 2. SH rows from the local colour-gradient table (work queue of 256-splat chunks over all CTAs)
+  if (HAS_SH) {
+    const uint32_t nchunks = (uint32_t)((x.P + 255) / 256);
+    while (true) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_ticket = atomicAdd(x.flags + FLAG_TICKET, 1u);
+      __syncthreads();
+      const uint32_t t = s_ticket;
+      if (t >= nchunks) break;
+      const size_t i = (size_t)t * 256 + threadIdx.x;
+      if (i < (size_t)x.P) sh_row_rebuild<D, W256>(i, x.P, V, M, means3D, s_cam, x.gc, dL_dsh);
+    }
+  }
+
+  // ---- 3. every slice has been broadcast: unpack the summed records into the per-parameter arrays
+  if (threadIdx.x < N) spin_until(x.flags + FLAG_B + threadIdx.x, epoch);
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < (size_t)x.P; i += (size_t)gridDim.x * 256) {
+    const float4* rec = reinterpret_cast<const float4*>(x.geo + i * (size_t)x.ngeo);
+    const float4 a = __ldcg(rec), b = __ldcg(rec + 1), c = __ldcg(rec + 2);
+    dL_dmeans3D[3 * i] = a.x; dL_dmeans3D[3 * i + 1] = a.y; dL_dmeans3D[3 * i + 2] = a.z;
+    dL_dopacity[i] = a.w;
+    dL_dscales[3 * i] = b.x; dL_dscales[3 * i + 1] = b.y; dL_dscales[3 * i + 2] = b.z;
+    dL_drot[4 * i] = b.w; dL_drot[4 * i + 1] = c.x; dL_drot[4 * i + 2] = c.y; dL_drot[4 * i + 3] = c.z;
+    if (!HAS_SH) {
+      const float4 d = __ldcg(rec + 3);
+      dL_dcolors[3 * i] = d.x; dL_dcolors[3 * i + 1] = d.y; dL_dcolors[3 * i + 2] = d.z;
+    }
+  }
+}
+
+void launch_xchg_finish(const XchgDev& x, int max_ctas, uint32_t epoch, int D, int M, const float* means3D, const float* campos,
+                        float* dL_dmeans3D, float* dL_dopacity, float* dL_dscales, float* dL_drot, float* dL_dcolors,
+                        float* dL_dsh, cudaStream_t s) {
+  const bool has_sh = dL_dsh != nullptr;
+  const bool mc = x.geo_mc != nullptr;
+  const bool w256 = has_sh && (M * 12) % 32 == 0 && (reinterpret_cast<size_t>(dL_dsh) & 31) == 0 && M == (D + 1) * (D + 1) &&
+                    (3 * (D + 1) * (D + 1)) % 8 == 0;
+  cudaMemsetAsync(x.flags + FLAG_TICKET, 0, sizeof(uint32_t), s);      // the SH work queue's ticket
+  // 2 CTAs per SM (launch bound): the whole grid is resident, so CTAs spinning on a flag can never keep the CTAs
+  // that produce this rank's own signals off the SMs
+  const int grid = max_ctas > 0 ? min(max_ctas, 2 * NUM_SMS_B200) : 2 * NUM_SMS_B200;
+#define SFB_XF(DD, MCV, SHV, WV)                                                                                    \
+  xchg_finish_kernel<DD, MCV, SHV, WV><<<grid, 256, 0, s>>>(x, epoch, x.world, M, means3D, campos, dL_dmeans3D,     \
+                                                            dL_dopacity, dL_dscales, dL_drot, dL_dcolors, dL_dsh)
+#define SFB_XD(DD)                                                                                                  \
+  do {                                                                                                              \
+    if (mc) { if (w256) SFB_XF(DD, true, true, true); else SFB_XF(DD, true, true, false); }                         \
+    else    { if (w256) SFB_XF(DD, false, true, true); else SFB_XF(DD, false, true, false); }                       \
+  } while (0)
+  if (!has_sh) { if (mc) SFB_XF(0, true, false, false); else SFB_XF(0, false, false, false); }
+  else switch (D) {
+    case 0: SFB_XD(0); break;
+    case 1: SFB_XD(1); break;
+    case 2: SFB_XD(2); break;
+    default: SFB_XD(3); break;
+  }
+#undef SFB_XD
+#undef SFB_XF
+}
+
+}  // namespace sfb

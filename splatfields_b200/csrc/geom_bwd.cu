@@ -27,9 +27,14 @@ struct CamB {
 // 1M splats, round 1: the whole 48 KB slab has to land before any thread can start and only 2 CTAs fit per SM — and
 // was removed; the rows move as L2-prefetched 256-bit loads and 256-bit stores.)
 // FACT: factored SH gradient (SFB_BWD_SH_FACTORED) — dL_dcolors receives the clamp-masked colour gradient and the
-// dL_dsh rows are not written (sh_grad_combine_kernel below rebuilds their multi-view sum).  A template flag, so
+// dL_dsh rows are not written (exchange.cu rebuilds their multi-view sum).  A template flag, so
 // that the default instantiations carry no trace of it (a run-time branch cost 4 registers and 10 us at 1M splats).
-template <int D, bool VEC, int MINB = 1, bool W256 = false, bool FACT = false>
+// PUSH: view-parallel exchange over NVLink (exchange.cu): the 11 (SH colours) / 14 (precomputed colours)
+// parameter gradients leave as ONE packed record per Gaussian in this rank's symmetric buffer (where the reduction
+// kernel's multimem.ld_reduce finds them), and with FACT the clamp-masked colour gradient is written straight into
+// slot `rank` of EVERY rank's buffer while this kernel is still computing — one multimem.st per 16 bytes through
+// the NVSwitch multicast mapping (or one st.global per peer without multicast): the all-gather rides on the kernel.
+template <int D, bool VEC, int MINB = 1, bool W256 = false, bool FACT = false, bool PUSH = false>
 __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, GeomState g) {
   __shared__ CamB cam;
   if (threadIdx.x < 16) {
@@ -40,9 +45,9 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
   __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = idx < p.P;
-  if (!in_range) return;
-  const size_t i = (size_t)idx;
-  const bool visible = p.radii[idx] > 0;
+  if (!PUSH && !in_range) return;          // (PUSH: the whole block meets again at the colour-gradient hand-off)
+  const size_t i = (size_t)(in_range ? idx : 0);
+  const bool visible = in_range && p.radii[idx] > 0;
   if (visible && p.shs) {   // pull the SH row towards L2 while the covariance math runs
     const char* row = reinterpret_cast<const char*>(p.shs + i * p.M * 3);
     prefetch_l2(row);
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
       drot[2] = 2.f * (qx * (Dr[1] + Dr[3]) + qr * (Dr[2] - Dr[6]) + qz * (Dr[5] + Dr[7])) - 4.f * qy * (Dr[0] + Dr[8]);
       drot[3] = 2.f * (qr * (Dr[3] - Dr[1]) + qx * (Dr[2] + Dr[6]) + qy * (Dr[5] + Dr[7])) - 4.f * qz * (Dr[0] + Dr[4]);
     }
-  } else if (p.shs && !FACT) {
+  } else if (in_range && p.shs && !FACT) {
     float* dsh = p.dL_dsh + i * p.M * 3;
     if (VEC && W256) {
       const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -313,6 +318,40 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
     }
   }
 
+  if (PUSH) {
+    // the block's colour gradients as 192 contiguous 16-byte chunks: one multicast (or per-peer) store each
+    __shared__ __align__(16) float s_gc[256 * 3];
+    if (FACT) {
+      s_gc[3 * threadIdx.x] = gcol[0]; s_gc[3 * threadIdx.x + 1] = gcol[1]; s_gc[3 * threadIdx.x + 2] = gcol[2];
+      __syncthreads();
+      const size_t row0 = (size_t)blockIdx.x * 256;
+      const int nfl = 3 * (int)min((size_t)256, (size_t)p.P - row0);       // floats of this block's slab
+      if ((int)threadIdx.x * 4 < nfl) {
+        const float4 v = reinterpret_cast<const float4*>(s_gc)[threadIdx.x];
+        const size_t off = row0 * 3 + (size_t)threadIdx.x * 4;                // float offset inside the [P][3] slot
+        if ((int)threadIdx.x * 4 + 4 <= nfl) {
+          if (p.x_mc) {
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.x_gc_dst[0] + off), "f"(v.x),
+                         "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+          } else {
+            for (int r = 0; r < p.x_ndst; r++) *reinterpret_cast<float4*>(p.x_gc_dst[r] + off) = v;
+          }
+        } else {     // ragged tail of the last block (P * 3 not a multiple of 4): scalar stores to every rank
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+          for (int e = 0; (int)threadIdx.x * 4 + e < nfl; e++)
+            for (int r = 0; r < p.x_nranks; r++) p.x_gc_peer[r][off + e] = vv[e];
+        }
+      }
+    }
+    if (!in_range) return;
+    float4* rec = reinterpret_cast<float4*>(p.x_geo + i * (size_t)p.x_ngeo);
+    rec[0] = make_float4(dmean[0], dmean[1], dmean[2], gop);
+    rec[1] = make_float4(dscale[0], dscale[1], dscale[2], drot[0]);
+    rec[2] = make_float4(drot[1], drot[2], drot[3], 0.f);
+    if (!FACT) rec[3] = make_float4(gcol[0], gcol[1], gcol[2], 0.f);          // precomputed colours: 14 floats (+2 pad)
+    p.dL_dmeans2D[3 * i] = gm2[0]; p.dL_dmeans2D[3 * i + 1] = gm2[1]; p.dL_dmeans2D[3 * i + 2] = 0.f;
+    return;
+  }
   p.dL_dmeans3D[3 * i] = dmean[0]; p.dL_dmeans3D[3 * i + 1] = dmean[1]; p.dL_dmeans3D[3 * i + 2] = dmean[2];
   p.dL_dmeans2D[3 * i] = gm2[0]; p.dL_dmeans2D[3 * i + 1] = gm2[1]; p.dL_dmeans2D[3 * i + 2] = 0.f;
   if (p.dL_dcolors) { p.dL_dcolors[3 * i] = gcol[0]; p.dL_dcolors[3 * i + 1] = gcol[1]; p.dL_dcolors[3 * i + 2] = gcol[2]; }
@@ -325,119 +364,19 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
   if (p.dL_drot) { p.dL_drot[4 * i] = drot[0]; p.dL_drot[4 * i + 1] = drot[1]; p.dL_drot[4 * i + 2] = drot[2]; p.dL_drot[4 * i + 3] = drot[3]; }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// View-parallel exchange of the SH gradient in factored form.
-//
-// Per view v and Gaussian i the SH gradient is a rank-1 block: dL_dsh[i][k][c] = basis_k(dir(v, i)) * gc[v][i][c], with
-// dir = normalize(mean_i - campos_v) known to every rank (splats are replicated, cameras are 3 floats each) and
-// gc = the clamp-masked colour gradient (3 floats).  So the ranks exchange gc (12 B per Gaussian and view) instead of
-// all-reducing the 3*M-float rows (192 B at degree 3), and every rank rebuilds the summed rows here — with the same
-// basis arithmetic as geom_backward_kernel above and a fixed v = 0..V-1 summation order (bit-reproducible, unlike
-// a ring all-reduce).  One thread per Gaussian, 12 + 12*V bytes in, 12*M out: HBM-bound streaming work.
-template <int D, bool W256>
-__global__ void __launch_bounds__(256)
-sh_grad_combine_kernel(int P, int V, int M, const float* __restrict__ means3D, const float* __restrict__ campos,
-                       const float* __restrict__ dcolor, float* __restrict__ dL_dsh) {
-  constexpr int NB = (D + 1) * (D + 1);
-  constexpr int NF8 = (3 * NB + 7) / 8;
-  __shared__ float s_cam[3 * 64];
-  for (int k = threadIdx.x; k < 3 * V; k += blockDim.x) s_cam[k] = campos[k];
-  __syncthreads();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P) return;
-  const size_t i = (size_t)idx;
-  const float mx = means3D[3 * i], my = means3D[3 * i + 1], mz = means3D[3 * i + 2];
-  float acc[NF8 * 8];
-#pragma unroll
-  for (int k = 0; k < NF8 * 8; k++) acc[k] = 0.f;
-  for (int v = 0; v < V; v++) {
-    const float* gp = dcolor + ((size_t)v * P + i) * 3;
-    const float g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
-    if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;     // culled in this view (or no gradient reached it)
-    const float vx = mx - s_cam[3 * v], vy = my - s_cam[3 * v + 1], vz = mz - s_cam[3 * v + 2];
-    const float ilen = rsqrtf(vx * vx + vy * vy + vz * vz);
-    const float x = vx * ilen, y = vy * ilen, z = vz * ilen;
-    float basis[NB];
-    basis[0] = SH_C0;
-    if (D > 0) { basis[1] = -SH_C1 * y; basis[2] = SH_C1 * z; basis[3] = -SH_C1 * x; }
-    if (D > 1) {
-      const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-      basis[4] = SHB_C2[0] * xy; basis[5] = SHB_C2[1] * yz; basis[6] = SHB_C2[2] * (2.f * zz - xx - yy);
-      basis[7] = SHB_C2[3] * xz; basis[8] = SHB_C2[4] * (xx - yy);
-      if (D > 2) {
-        basis[9] = SHB_C3[0] * y * (3.f * xx - yy); basis[10] = SHB_C3[1] * xy * z;
-        basis[11] = SHB_C3[2] * y * (4.f * zz - xx - yy); basis[12] = SHB_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-        basis[13] = SHB_C3[4] * x * (4.f * zz - xx - yy); basis[14] = SHB_C3[5] * z * (xx - yy);
-        basis[15] = SHB_C3[6] * x * (xx - 3.f * yy);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < NB; k++) {
-      // the product is rounded on its own (as geom_backward_kernel stores it) before it enters the sum over views
-      acc[3 * k] = __fadd_rn(acc[3 * k], __fmul_rn(basis[k], g0));
-      acc[3 * k + 1] = __fadd_rn(acc[3 * k + 1], __fmul_rn(basis[k], g1));
-      acc[3 * k + 2] = __fadd_rn(acc[3 * k + 2], __fmul_rn(basis[k], g2));
-    }
-  }
-  float* dsh = dL_dsh + i * M * 3;
-  if (W256) {      // launcher: M == NB, rows are 32-byte aligned multiples of 32 bytes
-#pragma unroll
-    for (int k = 0; k < (3 * NB) / 8; k++) stg256(dsh + 8 * k, acc + 8 * k);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 3 * NB; k++) dsh[k] = acc[k];
-    for (int k = 3 * NB; k < 3 * M; k++) dsh[k] = 0.f;      // coefficients above the active degree
-  }
-}
-
-// The clamp-masked colour gradient on its own, straight from the render backward's accumulators: 12 of the 48 bytes
-// of a GradRec + 1 byte of clamp flags in, 12 bytes out.  Lets the view-parallel exchange start its all-gather
-// BEFORE the geometry kernel runs (sfb_backward_midpoint_event).
-__global__ void __launch_bounds__(256)
-extract_dcolor_kernel(int P, const GradRec* __restrict__ grad, const uint8_t* __restrict__ clamped,
-                      const int* __restrict__ radii, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  float g[3] = {0.f, 0.f, 0.f};
-  if (radii[i] > 0) {
-    const float4* gp = reinterpret_cast<const float4*>(grad + i);
-    const float4 g1 = gp[1], g2 = gp[2];
-    const uint8_t cm = clamped[i];
-    g[0] = (cm & 1) ? 0.f : g1.z; g[1] = (cm & 2) ? 0.f : g1.w; g[2] = (cm & 4) ? 0.f : g2.x;
-  }
-  out[3 * (size_t)i] = g[0]; out[3 * (size_t)i + 1] = g[1]; out[3 * (size_t)i + 2] = g[2];
-}
-
-void launch_extract_dcolor(int P, const GeomState& g, const int* radii, float* out, cudaStream_t s) {
-  if (P > 0) extract_dcolor_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.grad, g.clamped, radii, out);
-}
-
-void launch_sh_grad_combine(int P, int V, int D, int M, const float* means3D, const float* campos,
-                            const float* dcolor, float* dL_dsh, bool wide256, cudaStream_t s) {
-  if (P <= 0) return;
-  const int blocks = (P + 255) / 256;
-  const bool w256 = wide256 && (M * 12) % 32 == 0 && (reinterpret_cast<size_t>(dL_dsh) & 31) == 0;
-#define SFB_SC(DD)                                                                                              \
-  if (w256 && M == (DD + 1) * (DD + 1) && (3 * (DD + 1) * (DD + 1)) % 8 == 0)                                   \
-    sh_grad_combine_kernel<DD, true><<<blocks, 256, 0, s>>>(P, V, M, means3D, campos, dcolor, dL_dsh);          \
-  else                                                                                                          \
-    sh_grad_combine_kernel<DD, false><<<blocks, 256, 0, s>>>(P, V, M, means3D, campos, dcolor, dL_dsh);
-  switch (D) {
-    case 0: SFB_SC(0) break;
-    case 1: SFB_SC(1) break;
-    case 2: SFB_SC(2) break;
-    default: SFB_SC(3) break;
-  }
-#undef SFB_SC
-}
-
 void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s) {
   if (p.P <= 0) return;
   const int blocks = (p.P + 255) / 256;
   const bool vec = p.shs && ((p.M * 3) % 4 == 0) && ((reinterpret_cast<size_t>(p.shs) & 15) == 0) &&
                    ((reinterpret_cast<size_t>(p.dL_dsh) & 15) == 0);
 #define SFB_GB(DD)                                                                                         \
-  if (p.sh_factored) {                                                                                     \
+  if (p.x_geo) {     /* exchange over NVLink: packed records + pushed colour gradients */                 \
+    if (p.shs && vec && p.wide256 && p.M == (DD + 1) * (DD + 1) && (3 * (DD + 1) * (DD + 1)) % 8 == 0)    \
+      geom_backward_kernel<DD, true, 2, true, true, true><<<blocks, 256, 0, s>>>(p, g);                    \
+    else if (p.shs && vec) geom_backward_kernel<DD, true, 1, false, true, true><<<blocks, 256, 0, s>>>(p, g); \
+    else if (p.shs) geom_backward_kernel<DD, false, 1, false, true, true><<<blocks, 256, 0, s>>>(p, g);    \
+    else geom_backward_kernel<DD, false, 1, false, false, true><<<blocks, 256, 0, s>>>(p, g);              \
+  } else if (p.sh_factored) {                                                                                     \
     if (vec && p.wide256 && p.M == (DD + 1) * (DD + 1) && (3 * (DD + 1) * (DD + 1)) % 8 == 0)             \
       geom_backward_kernel<DD, true, 2, true, true><<<blocks, 256, 0, s>>>(p, g);                          \
     else if (vec) geom_backward_kernel<DD, true, 1, false, true><<<blocks, 256, 0, s>>>(p, g);             \

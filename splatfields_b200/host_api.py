@@ -3,14 +3,18 @@
 * ViewParallelRasterizer — the multi-GPU unit of BASELINE.json's metric: one process per GPU, splats
   replicated, each rank renders ITS camera (the reference renders the views of one iteration serially in
   the loop at train.py:169 and averages the losses at train.py:242); the per-splat gradients of all
-  ranks are summed over a flat fp32 slab [59, P] that the backward kernel writes directly (no gather /
-  flatten copy).  Exchange "factored" (default with SH colours): the SH gradient of one view is the rank-1
-  block basis(dir) (x) dL_dcolour, and dir is known to every rank, so the ranks all-gather the 3 floats of
-  dL_dcolour per splat instead of all-reducing the 48 SH floats; only the 11 geometry floats go through
-  the all-reduce, and every rank rebuilds the summed SH rows with one kernel (sfb_sh_grad_combine) while
-  that all-reduce is in flight: 161 instead of 413 bytes per splat on the wire at 8 ranks.  Exchange
-  "allreduce": ONE NCCL all-reduce of the whole slab (the plain formulation, kept for A/B and for
-  precomputed colours).
+  ranks are summed into a flat fp32 slab [59, P].  Three exchanges produce that sum:
+  - "nvlink" (default on CUDA with more than one rank): the library's own kernels over symmetric (peer-mapped /
+    NVSwitch-multicast) memory — the geometry backward pushes its colour gradients into every rank's table while
+    it computes and leaves the 11 (14) parameter gradients as packed records, and ONE kernel (sfb_xchg_finish)
+    sums those records through the switch (multimem.ld_reduce / multimem.st), rebuilds the SH rows and unpacks
+    the sums into the slab.  No NCCL collective on the data path.
+  - "factored": the same factorisation over torch.distributed collectives (all-gather of the [P, 3] colour
+    gradients + all-reduce of the [P, 11] geometry gradients, SH rows rebuilt by sfb_sh_grad_combine); runs on
+    any backend (the gloo tests use it).
+  - "allreduce": ONE all-reduce of the whole slab (the plain formulation; per-rank means).
+  The SH gradient of one view is the rank-1 block basis(dir) (x) dL_dcolour and dir is known to every rank,
+  which is why 3 floats per splat and view travel instead of the 48 SH floats.
 * forward_backward_host — the same step for callers that hold HOST buffers: pinned host -> device copies
   of every input, forward + backward, device -> pinned host copies of image, depth, radii and gradients.
 
@@ -41,11 +45,13 @@ class ViewParallelRasterizer:
         self.device = torch.device(device)
         self.world = int(world_size)
         self.sh_degree = int(sh_degree)
-        exchange = exchange or os.environ.get("SFB_EXCHANGE", "factored")
-        if exchange not in ("factored", "allreduce"):
-            raise Exception("exchange must be 'factored' or 'allreduce'")
-        # the factored form exists for SH colours only; a single rank has nothing to exchange
-        self.exchange = exchange if (self.world > 1 and "shs" in scene) else "allreduce"
+        exchange = exchange or os.environ.get("SFB_EXCHANGE") or ("nvlink" if self.device.type == "cuda" else "factored")
+        if exchange not in ("nvlink", "factored", "allreduce"):
+            raise Exception("exchange must be 'nvlink', 'factored' or 'allreduce'")
+        # a single rank has nothing to exchange; the factored form exists for SH colours only
+        if self.world <= 1 or (exchange == "factored" and "shs" not in scene):
+            exchange = "allreduce"
+        self.exchange = exchange
         self.H, self.W = H, W
         self.P = scene["means3D"].shape[0]
         self.params = {k: v.detach().to(self.device, copy=True).contiguous().requires_grad_(True)
@@ -70,20 +76,41 @@ class ViewParallelRasterizer:
         self._combine = rasterizer.sh_grad_combine
         self.time_exchange = False       # bench: record CUDA events around the gradient exchange of every step
         self.exchange_events = []
-        # opt-in (SFB_EARLY_GATHER=1): start the all-gather of the colour gradients before the geometry kernel
-        # (sfb_backward_midpoint_event); CUDA only
-        self.early_gather = (self.exchange == "factored" and self.device.type == "cuda"
-                             and os.environ.get("SFB_EARLY_GATHER", "0") == "1")
-        if self.early_gather:
-            self._mid_event = torch.cuda.Event()
-            self._mid_event.record(torch.cuda.current_stream(self.device))     # materialises the cudaEvent_t handle
-            self._side = torch.cuda.Stream(self.device)
+        self.xchg = None
+        if self.exchange == "nvlink":
+            self._setup_nvlink("shs" in scene)
+        if self.exchange in ("factored", "nvlink") and "shs" in scene:
+            self._gather_campos(cam)
         if self.exchange == "factored":
             assert self.fields[-1][0] == "shs"          # the SH rows are the tail of the slab
             self.geo_floats = self.floats_per_splat - self.fields[-1][1]
             self.dcolor_mine = torch.empty(self.P * 3, dtype=torch.float32, device=self.device)
             self.dcolor_views = torch.empty(self.world * self.P * 3, dtype=torch.float32, device=self.device)
-            self._gather_campos(cam)
+
+    def _setup_nvlink(self, has_sh: bool) -> None:
+        """Symmetric buffers of the NVLink exchange (include/splat_b200.h: sfb_xchg): torch allocates and maps them
+        (torch.distributed._symmetric_memory — plumbing), the library's kernels do the rest."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        lib = _lib.load()
+        ngeo = 12 if has_sh else 16
+        nbytes = int(lib.sfb_xchg_bytes(self.P, self.world, ngeo, int(has_sh)))
+        buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, dist.group.WORLD)
+        d = _lib.XchgDesc()
+        d.rank, d.world, d.P, d.ngeo = int(hdl.rank), int(hdl.world_size), self.P, ngeo
+        d.local = buf.data_ptr()
+        for r, ptr in enumerate(hdl.buffer_ptrs):
+            d.peers[r] = int(ptr)
+        mc = int(hdl.multicast_ptr) if os.environ.get("SFB_XCHG_NO_MULTICAST", "0") != "1" else 0
+        d.mc = mc if mc else None
+        d.max_ctas = 0
+        self.xchg, self._xchg_buf, self._xchg_hdl = d, buf, hdl
+        self.xchg_epoch = 0
+        self.xchg_multicast = bool(mc)
+        torch.cuda.synchronize(self.device)
+        dist.barrier()                       # every rank's buffer is zeroed and mapped before the first step
 
     def _gather_campos(self, cam) -> None:
         """Every rank needs every camera centre (3 floats per view) to rebuild the SH rows: one tiny all-gather per
@@ -103,14 +130,14 @@ class ViewParallelRasterizer:
             tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5), viewmatrix=cam.world_view_transform,
             projmatrix=cam.full_proj_transform, campos=cam.camera_center)
         self.rast = self.rast_factory(self.settings, cam)
-        if self.exchange == "factored":
+        if self.exchange in ("factored", "nvlink") and "shs" in self.params:
             self._gather_campos(cam)
 
     def set_means(self, means3D: torch.Tensor, same_on_all_ranks: bool = False) -> None:
         """Replace the means, e.g. canonical means + this job's per-frame offset.  The factored exchange rebuilds the
         SH rows from the means THIS rank holds, so it needs identical means on every rank; ranks that render
         different time steps must use exchange="allreduce" (precomputed colours, the 4D recipe's input, always do)."""
-        if self.exchange == "factored" and not same_on_all_ranks:
+        if self.exchange in ("factored", "nvlink") and "shs" in self.params and not same_on_all_ranks:
             raise Exception("per-rank means with the factored SH exchange: construct with exchange='allreduce', "
                             "or pass same_on_all_ranks=True if every rank sets the same means")
         with torch.no_grad():
@@ -121,7 +148,10 @@ class ViewParallelRasterizer:
         self.slab.zero_()
         if self.exchange == "factored":
             self.dcolor_mine.zero_()
-        return self._exchange(0, early=False)
+        if self.exchange == "nvlink":
+            # zero records and a zero slot in every rank's colour table: a backward over zero cotangents does that
+            raise Exception("idle_step is not available with exchange='nvlink': give every rank a job per round")
+        return self._exchange(0)
 
     # -- one fwd + bwd (+ gradient exchange); returns the number of library kernel launches issued
     def step(self, cotangent: torch.Tensor, keep: bool = False) -> int:
@@ -135,9 +165,11 @@ class ViewParallelRasterizer:
                                         scales=p["scales"], rotations=p["rotations"])
         n = lib.sfb_last_launch_count()
         factored = self.exchange == "factored"
-        rasterizer.set_grad_arena(self.slab, self.fields, self.dcolor_mine.view(self.P, 3) if factored else None)
-        if self.early_gather:
-            _lib.check(lib.sfb_backward_midpoint_event(self._mid_event.cuda_event))
+        nvlink = self.exchange == "nvlink"
+        if nvlink:
+            self.xchg_epoch += 1
+        rasterizer.set_grad_arena(self.slab, self.fields, self.dcolor_mine.view(self.P, 3) if factored else None,
+                                  (self.xchg, self.xchg_epoch) if nvlink else None)
         try:
             # mean over views (train.py:242) folded into the cotangent: backward is linear in it
             color.backward(cotangent if self.world == 1 else cotangent * (1.0 / self.world))
@@ -147,39 +179,46 @@ class ViewParallelRasterizer:
         # normally a no-op: the backward kernel already wrote into the slab slices (the .grad tensors ARE
         # those slices); copy only if autograd handed back separate storage.
         for name, dst in self.grads().items():
-            if factored and name == "shs":
-                continue                     # rebuilt below from the gathered colour gradients
+            if nvlink or (factored and name == "shs"):
+                continue                     # filled by the exchange below
             g = p[name].grad
             if g is None:
                 dst.zero_()
             elif g.data_ptr() != dst.data_ptr():
                 dst.copy_(g.reshape(-1))
-        n = self._exchange(n, early=self.early_gather)
+        n = self._exchange(n)
         if keep:
             self.last = (color.detach(), radii, depth.detach())
         return n
 
-    def _exchange(self, n: int, early: bool = False) -> int:
-        """Sum the gradient slab over the ranks (module docstring); n = launch counter to continue; early = this
-        step's backward recorded _mid_event behind the colour-gradient kernel."""
+    def _exchange(self, n: int) -> int:
+        """Sum the gradient slab over the ranks (module docstring); n = launch counter to continue."""
         p = self.params
         factored = self.exchange == "factored"
         ev = None
         if self.time_exchange and self.world > 1 and self.device.type == "cuda":
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        if factored:
+        if self.exchange == "nvlink":
+            lib = _lib.load()
+            g = self.grads()
+            has_sh = "shs" in p
+            M = p["shs"].shape[1] if has_sh else 0
+            gp = lambda name: g[name].data_ptr() if name in g else None
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream(self.device).cuda_stream
+                import ctypes as C
+                _lib.check(lib.sfb_xchg_finish(
+                    C.byref(self.xchg), int(self.xchg_epoch), self.sh_degree, int(M),
+                    p["means3D"].data_ptr(), self.campos_views.data_ptr() if has_sh else None,
+                    gp("means3D"), gp("opacities"), gp("scales"), gp("rotations"), gp("colors_precomp"), gp("shs"),
+                    stream))
+            n += 1
+        elif factored:
             import torch.distributed as dist
             # all-gather 3 floats / splat / view, all-reduce the 11 geometry floats; the SH rows are rebuilt
             # locally while the all-reduce is still in flight (it only depends on the all-gather)
-            if early:
-                # the library recorded _mid_event between the colour-gradient kernel and the geometry kernel: the
-                # collective is enqueued behind that event only, so it overlaps the geometry kernel
-                self._side.wait_event(self._mid_event)
-                with torch.cuda.stream(self._side):
-                    h_ag = dist.all_gather_into_tensor(self.dcolor_views, self.dcolor_mine, async_op=True)
-            else:
-                h_ag = dist.all_gather_into_tensor(self.dcolor_views, self.dcolor_mine, async_op=True)
+            h_ag = dist.all_gather_into_tensor(self.dcolor_views, self.dcolor_mine, async_op=True)
             h_ar = dist.all_reduce(self.slab[:self.geo_floats * self.P], op=dist.ReduceOp.SUM, async_op=True)
             h_ag.wait()
             sh_out = self.slab[self.geo_floats * self.P:]
@@ -207,6 +246,10 @@ class ViewParallelRasterizer:
         N = self.world
         if N <= 1:
             return 0.0
+        if self.exchange == "nvlink":     # received: the other views' colour gradients + this rank's share of the
+            ngeo = self.xchg.ngeo         # switch-reduced records and everybody else's broadcast sums
+            gc = (N - 1) * 12.0 if "shs" in self.params else 0.0
+            return gc + 4.0 * ngeo * (1.0 / N + (N - 1.0) / N)
         if self.exchange == "factored":
             return 2.0 * (N - 1) / N * 4 * self.geo_floats + (N - 1) * 12.0
         return 2.0 * (N - 1) / N * 4 * self.floats_per_splat

@@ -45,13 +45,18 @@ _ARENA = None
 # (SFB_BWD_SH_FACTORED); `shs` then gets no .grad from autograd — the caller rebuilds the multi-view sum with
 # sh_grad_combine().
 _SH_COLOR_OUT = None
+# Exchange over NVLink (host_api.ViewParallelRasterizer exchange="nvlink"): (_lib.XchgDesc, epoch) for the NEXT backward.
+# The parameter gradients then leave through the symmetric buffers (sfb_xchg_finish sums them over the ranks) and
+# autograd gets no .grad for the parameters — only means2D's (a per-view quantity).
+_XCHG = None
 _WARNED_DEPTH = False
 
 
-def set_grad_arena(slab, fields, sh_color_out=None):
-    global _ARENA, _SH_COLOR_OUT
+def set_grad_arena(slab, fields, sh_color_out=None, xchg=None):
+    global _ARENA, _SH_COLOR_OUT, _XCHG
     _ARENA = None if slab is None else (slab, tuple(fields))
     _SH_COLOR_OUT = sh_color_out
+    _XCHG = xchg
 
 
 def sh_grad_combine(means3D, campos_views, dcolor_views, sh_degree, out):
@@ -233,6 +238,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         H, W = int(rs.image_height), int(rs.image_width)
         M = ctx.M
         f32 = dict(dtype=torch.float32, device=dev)
+        if _XCHG is not None:
+            return _RasterizeGaussians._backward_exchange(ctx, grad_out_color, grad_out_alpha, lib)
         dL_dmeans3D = _arena_out("means3D", P, (P, 3), **f32)
         dL_dmeans2D = torch.empty((P, 3), **f32)
         dL_dcolors = _arena_out("colors_precomp", P, (P, 3), **f32) if col is not None else None
@@ -262,7 +269,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cp), float(rs.tanfovx), float(rs.tanfovy), _ptr(radii),
                     _ptr(geom), _ptr(binning), _ptr(img), _ptr(g), _ptr(ga),
                     _ptr(dL_dmeans2D), _ptr(dL_dcolors), _ptr(dL_dopacity), _ptr(dL_dmeans3D), _ptr(dL_dcov3D),
-                    _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drot), int(bool(rs.debug)), flags, stream)
+                    _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drot), int(bool(rs.debug)), flags, None, 0, stream)
             _lib.check(rc)
 
         def shaped(t, shape):
@@ -280,6 +287,41 @@ class _RasterizeGaussians(torch.autograd.Function):
             None,
         )
         return grads
+
+
+    @staticmethod
+    def _backward_exchange(ctx, grad_out_color, grad_out_alpha, lib):
+        """Backward in exchange mode (_XCHG): packed gradient records + pushed colour gradients, no per-parameter
+        outputs (include/splat_b200.h: sfb_xchg)."""
+        import ctypes as C
+        desc, epoch = _XCHG
+        rs = ctx.raster_settings
+        radii, geom, binning, img, means3D, sh, col, sc, rot, cov, bg, vm, pm, cp = ctx.saved_tensors
+        dev = means3D.device
+        P = means3D.shape[0]
+        H, W = int(rs.image_height), int(rs.image_width)
+        if cov is not None:
+            raise Exception("the gradient exchange needs scales / rotations (no cov3D_precomp)")
+        dL_dmeans2D = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        g = _prep(grad_out_color)
+        if g is None:
+            g = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
+        ga = _prep(grad_out_alpha) if (ctx.with_alpha and grad_out_alpha is not None) else None
+        flags = _lib.BWD_ACC_FRESH if ctx.acc_fresh[0] else 0
+        ctx.acc_fresh[0] = False
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.sfb_rasterize_backward(
+                P, int(rs.sh_degree), int(ctx.M), int(ctx.num_rendered), W, H,
+                _ptr(bg), _ptr(means3D), _ptr(sh), _ptr(col), _ptr(sc), float(rs.scale_modifier), _ptr(rot),
+                None, _ptr(vm), _ptr(pm), _ptr(cp), float(rs.tanfovx), float(rs.tanfovy), _ptr(radii),
+                _ptr(geom), _ptr(binning), _ptr(img), _ptr(g), _ptr(ga),
+                _ptr(dL_dmeans2D), None, None, None, None, None, None, None, int(bool(rs.debug)), flags,
+                C.byref(desc), int(epoch), stream)
+        _lib.check(rc)
+        sh_means2D = ctx.shapes[1]
+        return (None, dL_dmeans2D.reshape(sh_means2D) if sh_means2D is not None else None,
+                None, None, None, None, None, None, None, None)
 
 
 class GaussianRasterizer(nn.Module):

@@ -1,0 +1,122 @@
+"""Two (or more) ranks of the NVLink gradient exchange emulated on ONE GPU, in ONE process: every "rank" owns a buffer
+of sfb_xchg_bytes() bytes on the same device, the peer table points at the other buffers, and the ranks'
+sfb_xchg_finish kernels run concurrently on separate streams (each limited to its share of the SMs, so that all of
+them are resident while they wait for each other's flags).  Exercises the unicast (non-multicast) protocol of
+csrc/exchange.cu and geom_backward_kernel<PUSH> end to end; the multicast path needs NVSwitch peers
+(scripts/check_exchange.py on >= 2 GPUs).
+
+Run as a script by tests/test_gpu_exchange.py (a process of its own: a protocol bug traps the kernel, which poisons the
+CUDA context).  Prints one JSON line; exit code 1 on mismatch."""
+import ctypes as C
+import json
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from splatfields_b200 import _lib, rasterizer, synth
+from splatfields_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+
+
+def settings(cam, H, W, deg, dev):
+    camd = cam.to(dev)
+    return GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5),
+        bg=torch.ones(3, device=dev), scale_modifier=1.0, viewmatrix=camd.world_view_transform,
+        projmatrix=camd.full_proj_transform, sh_degree=deg, campos=camd.camera_center, prefiltered=False, debug=False)
+
+
+def run(world, P, H, W, deg, precomp_rgb, steps=3):
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    sc = synth.make_scene(P, 5, scale_mult=2.5, precomp_rgb=precomp_rgb)
+    if not precomp_rgb:
+        sc["shs"][::7, 0, 1] = -3.0          # exercise the colour clamp
+    t = {k: v.to(dev) for k, v in sc.items()}
+    cams = [synth.orbit_camera(r, H, W) for r in range(world)]
+    ngeo = 16 if precomp_rgb else 12
+    nbytes = int(lib.sfb_xchg_bytes(P, world, ngeo, int(not precomp_rgb)))
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+    descs = []
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    for r in range(world):
+        d = _lib.XchgDesc()
+        d.rank, d.world, d.P, d.ngeo = r, world, P, ngeo
+        d.local = bufs[r].data_ptr()
+        for q in range(world):
+            d.peers[q] = bufs[q].data_ptr()
+        d.mc = None
+        d.max_ctas = (2 * sms) // world
+        descs.append(d)
+    campos = torch.stack([c.camera_center for c in cams]).to(dev).contiguous()
+    M = 0 if precomp_rgb else t["shs"].shape[1]
+    names = ["means3D", "opacities", "scales", "rotations"] + (["colors_precomp"] if precomp_rgb else ["shs"])
+    worst = {}
+    ok = True
+    streams = [torch.cuda.Stream(dev) for _ in range(world)]
+    for step in range(1, steps + 1):
+        Gs = [torch.randn(3, H, W, generator=torch.Generator().manual_seed(100 * step + r)).to(dev) for r in range(world)]
+        # reference: plain backward per view, summed in view order
+        ref = {n: torch.zeros_like(t[n]) for n in names}
+        for r in range(world):
+            leaf = {k: v.clone().requires_grad_(True) for k, v in t.items()}
+            m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
+            color, _, _ = GaussianRasterizer(settings(cams[r], H, W, deg, dev))(
+                means3D=leaf["means3D"], means2D=m2d, opacities=leaf["opacities"], shs=leaf.get("shs"),
+                colors_precomp=leaf.get("colors_precomp"), scales=leaf["scales"], rotations=leaf["rotations"])
+            color.backward(Gs[r])
+            for n in names:
+                ref[n] += leaf[n].grad
+        # exchange mode: every rank's backward (packed records + pushed colour gradients) ...
+        for r in range(world):
+            leaf = {k: v.clone().requires_grad_(True) for k, v in t.items()}
+            m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
+            color, _, _ = GaussianRasterizer(settings(cams[r], H, W, deg, dev))(
+                means3D=leaf["means3D"], means2D=m2d, opacities=leaf["opacities"], shs=leaf.get("shs"),
+                colors_precomp=leaf.get("colors_precomp"), scales=leaf["scales"], rotations=leaf["rotations"])
+            rasterizer.set_grad_arena(None, (), None, (descs[r], step))
+            try:
+                color.backward(Gs[r])
+            finally:
+                rasterizer.set_grad_arena(None, None)
+            assert leaf["means3D"].grad is None and m2d.grad is not None
+        torch.cuda.synchronize()
+        # ... then the ranks' finish kernels side by side
+        outs = []
+        for r in range(world):
+            o = {n: torch.full_like(t[n], float("nan")) for n in names}
+            outs.append(o)
+            gp = lambda n: o[n].data_ptr() if n in o else None
+            streams[r].wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(streams[r]):
+                _lib.check(lib.sfb_xchg_finish(
+                    C.byref(descs[r]), step, deg, int(M), t["means3D"].data_ptr(),
+                    None if precomp_rgb else campos.data_ptr(), gp("means3D"), gp("opacities"), gp("scales"),
+                    gp("rotations"), gp("colors_precomp"), gp("shs"), streams[r].cuda_stream))
+        torch.cuda.synchronize()
+        for n in names:
+            scale = float(ref[n].abs().max())
+            for r in range(world):
+                err = float((outs[r][n] - ref[n]).abs().max()) / max(scale, 1e-30)
+                worst[n] = max(worst.get(n, 0.0), err)
+                ok = ok and scale > 0 and err < 2e-5 and bool(torch.equal(outs[r][n], outs[0][n]))
+    return ok, worst
+
+
+def main():
+    res = []
+    allok = True
+    for world, P, H, W, deg, rgb in ((2, 20_000, 160, 208, 3, False), (4, 9_001, 96, 128, 2, False),
+                                     (2, 12_000, 128, 128, 0, True), (3, 7_777, 96, 96, 1, False)):
+        ok, worst = run(world, P, H, W, deg, rgb)
+        res.append({"world": world, "P": P, "deg": deg, "precomp_rgb": rgb, "ok": ok, "max_err_over_max_abs": worst})
+        allok = allok and ok
+    print(json.dumps({"check": "emulated ranks on one GPU: NVLink exchange == sum of the views' plain backward passes",
+                      "cases": res, "ok": allok}), flush=True)
+    sys.exit(0 if allok else 1)
+
+
+if __name__ == "__main__":
+    main()

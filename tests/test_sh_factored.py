@@ -145,29 +145,3 @@ def test_sh_grad_combine_argument_errors(cuda_lib):
     with pytest.raises(Exception):
         rasterizer.sh_grad_combine(means, torch.zeros(1, 3, device=dev), torch.zeros(1, 8, 3, device=dev), 3,
                                    torch.empty(8, 9, 3, device=dev))           # M < (deg+1)^2
-
-
-@pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("SFB_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="experimental opt-in path (SFB_EARLY_GATHER): written after the round's GPU budget was "
-                           "spent, not yet run on hardware; enable with SFB_TEST_EXPERIMENTAL=1")
-def test_midpoint_event_hands_colour_gradient_off_early(cuda_lib):
-    """sfb_backward_midpoint_event: the colour gradient written by the extraction kernel equals the one the geometry
-    kernel writes, every other gradient is unchanged, and the caller's event has been recorded."""
-    from splatfields_b200 import _lib
-    dev = torch.device("cuda")
-    P, H, W, deg = 20000, 160, 208, 3
-    sc, cams, Gs = _views(P, H, W, 23, 1)
-    base, dcol0, _, _ = _cuda_backward(sc, cams[0], H, W, deg, Gs[0], True, dev)
-    ev = torch.cuda.Event()
-    ev.record()
-    torch.cuda.synchronize()
-    _lib.check(cuda_lib.sfb_backward_midpoint_event(ev.cuda_event))
-    early, dcol1, _, _ = _cuda_backward(sc, cams[0], H, W, deg, Gs[0], True, dev)
-    assert ev.query()
-    assert torch.allclose(dcol1, dcol0, rtol=1e-4, atol=1e-6 * float(dcol0.abs().max()))
-    for k in ("means3D", "opacities", "scales", "rotations", "means2D"):
-        assert torch.allclose(early[k], base[k], rtol=1e-4, atol=1e-6 * float(base[k].abs().max())), k
-    # one-shot: the next backward takes the normal path again
-    again, dcol2, _, _ = _cuda_backward(sc, cams[0], H, W, deg, Gs[0], True, dev)
-    assert torch.allclose(dcol2, dcol0, rtol=1e-4, atol=1e-6 * float(dcol0.abs().max()))
