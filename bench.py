@@ -242,6 +242,15 @@ def roofline_report(acc, nprof, stats, P, HW, ms_step):
     return roofline, stages
 
 
+EXCHANGE_TEXT = {
+    "nvlink": "own kernels over NVLink symmetric memory - colour gradients pushed to every rank by the geometry backward "
+              "(multimem.st), packed [P,11] records summed in the switch (multimem.ld_reduce) and broadcast, SH rows "
+              "rebuilt per rank; no NCCL collective on the data path",
+    "factored": "NCCL all-gather of [P,3] colour gradients + all-reduce of [P,11] geometry gradients, SH rows rebuilt per rank",
+    "allreduce": "1 NCCL all-reduce of [P,59] fp32 grads",
+}
+
+
 def run_ours(args):
     rank, world, local = _dist_env()
     if not torch.cuda.is_available():
@@ -292,48 +301,72 @@ def run_ours(args):
     value = world * P / (ms_step * 1e-3) / 1e6
 
     # ---- end-to-end through the host-buffer API: `e2e` ----
-    # HostPipeline.submit/wait: every step uploads ALL inputs (+ cotangent) from pinned host memory and
-    # downloads image, depth, radii and the gradient slab into pinned host memory; upload of step k+1,
-    # kernels of step k and download of step k-1 overlap on three streams.  Wall clock, max over ranks.
+    # HostPipeline.submit/wait: every step uploads the job's inputs (all splat parameters + this rank's cotangent) from
+    # pinned host memory and downloads image, depth, radii and the per-splat gradients into pinned host memory; upload
+    # of step k+1, kernels of step k and download of step k-1 overlap on three streams.  With N ranks the job's ONE host
+    # copy of the splats is split by rows over the ranks (each uploads 1/N, NCCL all-gathers the rest over NVLink) and
+    # each rank downloads 1/N of the summed gradient slab.  Wall clock, max over ranks.
     from splatfields_b200.host_api import HostPipeline
-    host_in, host_out = vp.pinned_host_buffers(sc, G)
+
+    def time_pipeline(pipe, host_in, outs):
+        for k in range(3):
+            pipe.submit(host_in, outs[k % 2])
+        pipe.drain()
+        sync_all()
+        t0 = time.perf_counter()
+        first = pipe.n
+        for k in range(args.steps):
+            t = pipe.submit(host_in, outs[k % 2])
+            if t > first:
+                pipe.wait(t - 1)
+        pipe.wait(pipe.n - 1)
+        pipe.drain()
+        wall = time.perf_counter() - t0
+        sync_all()
+        ms = torch.tensor([wall * 1e3], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / args.steps
+
+    slab0, params0 = vp.slab, {k: p.data for k, p in vp.params.items()}
+    factored_host = world == 1       # single rank: SH gradient downloaded in factored form (56 instead of 236 B/splat)
+    host_in, host_out = vp.pinned_host_buffers(sc, G, shard=world > 1, factored=factored_host)
     host_out2 = {k: torch.empty_like(v).pin_memory() for k, v in host_out.items()}
-    outs = (host_out, host_out2)
-    pipe = HostPipeline(vp)
-    for k in range(3):
-        pipe.submit(host_in, outs[k % 2])
-    pipe.drain()
-    sync_all()
-    t0 = time.perf_counter()
-    first = pipe.n
-    for k in range(args.steps):
-        t = pipe.submit(host_in, outs[k % 2])
-        if t > first:
-            pipe.wait(t - 1)
-    pipe.wait(pipe.n - 1)
-    pipe.drain()
-    wall = time.perf_counter() - t0
-    sync_all()
-    ms_e2e = torch.tensor([wall * 1e3], device=dev)
-    if dist is not None:
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    ms_e2e_step = float(ms_e2e.item()) / args.steps
-    # the same step, fully synchronous (one call = H2D + fwd + bwd + D2H, nothing overlapped)
-    forward_backward_host(vp, host_in, host_out)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    nsync = max(3, min(args.steps, 10))
-    for _ in range(nsync):
-        forward_backward_host(vp, host_in, host_out)
-    ms_sync_step = (time.perf_counter() - t0) * 1e3 / nsync
-    sync_all()
-    clocks = sampler.stop() if rank == 0 else None     # samples span both timed regions (value + e2e)
-    h2d = sum(t.numel() * t.element_size() for t in host_in.values())
-    d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+    pipe = HostPipeline(vp, factored=factored_host)
+    ms_e2e_step = time_pipeline(pipe, host_in, (host_out, host_out2))
+    h2d, d2h = pipe.h2d_bytes(host_in), pipe.d2h_bytes(host_out)
+    vp.factored_output = None
     e2e = {"value": world * P / (ms_e2e_step * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e_step,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "api": "splatfields_b200.host_api.HostPipeline.submit/wait (pinned host buffers, 3 streams, depth 2)",
-           "synchronous_ms_per_step": ms_sync_step}
+           "api": "splatfields_b200.host_api.HostPipeline.submit/wait (pinned host buffers on the GPU's NUMA node, "
+                  "3 streams, depth 2)",
+           "gradient_format": ("factored SH gradient: [P,11] geometry + [P,3] colour gradients "
+                               "(host_api.sh_rows_from_factored rebuilds [P,16,3] rows on demand)") if factored_host
+           else f"full [P,59] slab, rows sharded over the {world} ranks (each rank moves 1/{world} of the splats "
+                f"through its PCIe link; the parameters are all-gathered over NVLink)",
+           "bytes_note": "per rank"}
+    if world == 1:
+        # context: the same pipeline with the full [P,16,3] SH gradient rows downloaded, and the fully synchronous call
+        del pipe, host_out, host_out2
+        host_in_f, host_out_f = vp.pinned_host_buffers(sc, G, shard=False, factored=False)
+        host_out_f2 = {k: torch.empty_like(v).pin_memory() for k, v in host_out_f.items()}
+        pipe_f = HostPipeline(vp, factored=False)
+        ms_full = time_pipeline(pipe_f, host_in_f, (host_out_f, host_out_f2))
+        e2e["full_rows"] = {"value": P / (ms_full * 1e-3) / 1e6, "ms_per_step": ms_full,
+                            "d2h_bytes_per_step": int(pipe_f.d2h_bytes(host_out_f))}
+        forward_backward_host(vp, host_in_f, host_out_f)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nsync = max(3, min(args.steps, 10))
+        for _ in range(nsync):
+            forward_backward_host(vp, host_in_f, host_out_f)
+        e2e["synchronous_ms_per_step"] = (time.perf_counter() - t0) * 1e3 / nsync
+        del pipe_f, host_out_f, host_out_f2
+    vp.slab = slab0
+    for k, p_ in vp.params.items():
+        p_.data = params0[k]
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None     # samples span both timed regions (value + e2e)
 
     # ---- roofline of the dominant kernel (profiled steps, outside the timed regions) ----
     roofline, stages = None, None
@@ -360,6 +393,21 @@ def run_ours(args):
         stats = vp.list_stats()
         roofline, stages = roofline_report(acc, nprof, stats, P, H * W, ms_step)
 
+    # ---- exchange check: this exchange against the plain NCCL all-reduce of the whole slab, same views ----
+    exchange_check = None
+    if world > 1 and vp.exchange != "allreduce":
+        vp.step(Gd)
+        mine = {k: v.clone() for k, v in vp.grads().items()}
+        vref = ViewParallelRasterizer(sc, cam, H, W, SH_DEGREE, device=dev, world_size=world, exchange="allreduce")
+        vref.step(Gd)
+        worst = 0.0
+        for k, v in vref.grads().items():
+            worst = max(worst, float((mine[k] - v).abs().max()) / max(float(v.abs().max()), 1e-30))
+        wt = torch.tensor([worst], device=dev)
+        dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        exchange_check = {"max_abs_err_over_max_abs_vs_nccl_allreduce": float(wt.item()), "ok": bool(wt.item() < 2e-5)}
+        del vref, mine
+
     # ---- CPU baseline: the oracle port on the host cores, bounded sample (N = 1 only) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -377,18 +425,19 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "P": P, "H": H, "W": W, "sh_degree": SH_DEGREE,
                        "parallelism": (f"view-parallel x{world} (one camera per GPU, splats replicated; gradient "
-                                       f"exchange: " + ("all-gather of [P,3] colour gradients + all-reduce of [P,11] "
-                                                        "geometry gradients, SH rows rebuilt per rank"
-                                                        if vp.exchange == "factored" else
-                                                        "1 all-reduce of [P,59] fp32 grads") + ")")
+                                       f"exchange: " + EXCHANGE_TEXT[vp.exchange] + ")")
                        if world > 1 else "single view",
                        "l2": "inputs larger than L2 (236 MB of splat parameters + 0.5 GB of scratch per step "
                              "vs 126 MB L2)"},
             "views_per_s": world / (ms_step * 1e-3), "host_enqueue_ms_per_step": host_enqueue_ms,
             "exchange": None if world == 1 else {
-                "mode": vp.exchange, "ms_per_step": float(np.mean(exch_ms)) if exch_ms else None,
-                "wire_bytes_per_splat_per_rank": vp.bytes_on_wire_per_splat(),
-                "note": "device time from the first collective to the end of the exchange on rank 0 (profiled steps)"},
+                "mode": vp.exchange, "multicast": getattr(vp, "xchg_multicast", None),
+                "ms_per_step": float(np.mean(exch_ms)) if exch_ms else None,
+                "nvlink_bytes_received_per_splat_per_rank": vp.bytes_on_wire_per_splat(),
+                "nvlink_MB_received_per_rank_per_step": vp.bytes_on_wire_per_splat() * P / 1e6,
+                "exchange_check": exchange_check,
+                "note": "ms_per_step: device time from the end of the backward to the end of the exchange on rank 0 "
+                        "(profiled steps); with 'nvlink' the colour gradients have already left inside the backward"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "stages": stages,
         }

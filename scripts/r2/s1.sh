@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round-2 session 1 (1 GPU): network probe for the pinned reference rasterizer, device capability probe,
-# the GPU suite as it stands, and the A/Bs left open by round 1 (preprocess occupancy, tight rectangles).
+# Round-2 session 1 (1 GPU): network probe for the pinned reference rasterizer, device capability probe, smoke of the
+# new staging paths, the GPU suite, the A/B matrix of the render-kernel changes, bench, ncu of the two render kernels.
 TAG=${1:-r2s1}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
@@ -18,35 +18,60 @@ mkdir -p $OUT
   (ip route 2>/dev/null || route -n 2>/dev/null) | head -5
   echo "== local copies"
   python -c "import diff_gaussian_rasterization" 2>&1 | tail -1
-  find / -xdev \( -iname '*diff_gaussian*' -o -iname '*diff-gaussian*' -o -iname 'simple_knn*' \) -not -path '*/repo*' 2>/dev/null | head
+  find / -xdev \( -iname '*diff_gaussian*' -o -iname '*diff-gaussian*' -o -iname 'simple_knn*' \) -not -path '*/repo*' -not -path '/proc/*' 2>/dev/null | grep -v "$PWD" | head
 } > $OUT/network_probe.log 2>&1
-tail -30 $OUT/network_probe.log
+tail -22 $OUT/network_probe.log
 nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > $OUT/device.log 2>&1
 nvidia-smi topo -m >> $OUT/device.log 2>&1
 python - >> $OUT/device.log 2>&1 <<'PY'
-import torch
+import torch, os
 from cuda import cuda
 cuda.cuInit(0)
 err, dev = cuda.cuDeviceGet(0)
 for name in ("CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED", "CU_DEVICE_ATTRIBUTE_HANDLE_TYPE_FABRIC_SUPPORTED",
-             "CU_DEVICE_ATTRIBUTE_VIRTUAL_MEMORY_MANAGEMENT_SUPPORTED", "CU_DEVICE_ATTRIBUTE_GPU_DIRECT_RDMA_SUPPORTED",
-             "CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_BLOCK_OPTIN", "CU_DEVICE_ATTRIBUTE_NUMA_ID", "CU_DEVICE_ATTRIBUTE_HOST_NUMA_ID"):
+             "CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_BLOCK_OPTIN", "CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_MULTIPROCESSOR",
+             "CU_DEVICE_ATTRIBUTE_NUMA_ID", "CU_DEVICE_ATTRIBUTE_HOST_NUMA_ID"):
     a = getattr(cuda.CUdevice_attribute, name, None)
-    if a is None:
-        print(name, "n/a"); continue
-    print(name, cuda.cuDeviceGetAttribute(a, dev))
-import os
+    print(name, cuda.cuDeviceGetAttribute(a, dev) if a is not None else "n/a")
 print("cpus", os.cpu_count(), "affinity", len(os.sched_getaffinity(0)))
 os.system("lscpu | grep -i -E 'numa|model name|socket' | head -8")
-try:
-    import torch.distributed._symmetric_memory as sm
-    print("symmetric_memory:", [n for n in dir(sm) if not n.startswith('__')][:60])
-except Exception as e:
-    print("symm import failed", e)
+from splatfields_b200.host_api import numa_local
+with numa_local(torch.device("cuda:0")) as n:
+    print("numa_local cpus:", getattr(n, "cpus", None) and (len(n.cpus), n.cpus[:4], n.cpus[-4:]))
 PY
-cat $OUT/device.log | tail -40
-timeout 900 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log; tail -3 $OUT/pytest_gpu.log | cut -c1-300
-for v in 0 1; do echo "== SFB_PRE_OCC4=$v"; SFB_PRE_OCC4=$v timeout 120 python scripts/quick_perf.py --config lego_1m | tee -a $OUT/quick_perf_pre_occ4_$v.jsonl | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['fwd_ms'], d['bwd_ms'], d['fwd_stages'], d['bwd_stages'])"; done
-for c in lego_1m dtu_500k; do timeout 300 python scripts/ab_tight_rect.py --config $c >> $OUT/ab_tight_rect.jsonl 2>> $OUT/ab_tight_rect.err; done; cat $OUT/ab_tight_rect.jsonl | cut -c1-600
-for c in dtu_500k owlii_2m; do timeout 120 python scripts/quick_perf.py --config $c >> $OUT/quick_perf.jsonl; done; cut -c1-900 $OUT/quick_perf.jsonl
-timeout 300 python bench.py --steps 100 --warmup 10 > $OUT/bench_n1.json 2> $OUT/bench_n1.err; cut -c1-400 $OUT/bench_n1.json
+tail -16 $OUT/device.log
+# smoke of both staging paths first: a broken TMA path must not take the whole session down
+for st in tma ldg; do echo "== smoke SFB_FWD_STAGE=$st SFB_BWD_STAGE=$st"; SFB_FWD_STAGE=$st SFB_BWD_STAGE=$st timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -2; done | tee $OUT/smoke.log
+timeout 1200 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log; tail -4 $OUT/pytest_gpu.log | cut -c1-400
+qp() { # name, env...
+  local name=$1; shift
+  env "$@" timeout 150 python scripts/quick_perf.py --config lego_1m --iters 30 > $OUT/qp_$name.json 2>$OUT/qp_$name.err
+  python - "$name" $OUT/qp_$name.json <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+    f,b=d['fwd_stages'],d['bwd_stages']
+    print("%-14s total %.3f fwd %.3f bwd %.3f | pre %.3f rfwd %.3f rbwd %.3f geom %.3f tsort %.3f dsort %.3f dup %.3f" % (sys.argv[1], d['total_ms'], d['fwd_ms'], d['bwd_ms'], f.get('preprocess',0), f.get('render_forward',0), b.get('render_backward',0), b.get('geom_backward',0), f.get('tile_sort.scatter',0)+f.get('tile_sort.hist',0), f.get('depth_sort.scatter',0)+f.get('depth_sort.hist',0), f.get('duplicate',0)))
+except Exception as e:
+    print(sys.argv[1], "FAILED", e)
+PY
+}
+{
+qp default SFB_X=0
+qp fwd_ldg SFB_FWD_STAGE=ldg
+qp bwd_ldg SFB_BWD_STAGE=ldg
+qp bwd_b256 SFB_BWD_BATCH=256
+qp bwd_noorder SFB_BWD_ORDER=0
+qp bwd_r1like SFB_BWD_BATCH=256 SFB_BWD_ORDER=0 SFB_BWD_STAGE=ldg SFB_FWD_STAGE=ldg
+qp pre_occ4 SFB_PRE_OCC4=1
+qp default2 SFB_X=0
+} | tee $OUT/ab_matrix.txt
+for c in dtu_500k owlii_2m lego_100k; do timeout 150 python scripts/quick_perf.py --config $c >> $OUT/quick_perf.jsonl; done; cut -c1-700 $OUT/quick_perf.jsonl
+timeout 400 python bench.py --steps 100 --warmup 10 > $OUT/bench_n1.json 2> $OUT/bench_n1.err; cut -c1-600 $OUT/bench_n1.json; tail -3 $OUT/bench_n1.err
+KERNELS='render_forward_kernel|render_backward_mma_kernel|preprocess_kernel|geom_backward_kernel'
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"$KERNELS" -s 16 -c 4 -f -o $OUT/prof \
+    python scripts/quick_perf.py --config lego_1m --iters 1 --warmup 3 > $OUT/ncu_full.log 2>&1
+tail -2 $OUT/ncu_full.log | cut -c1-200
+ncu -i $OUT/prof.ncu-rep --page raw --csv > $OUT/ncu_raw.csv 2>/dev/null
+python scripts/ncu_summary.py $OUT/ncu_raw.csv > $OUT/ncu_full_summary.txt 2>&1; grep -c "^==" $OUT/ncu_full_summary.txt
+ls $OUT | head -40

@@ -163,10 +163,10 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   if (debug) redzone_collector() = &rz;
   GeomState g = GeomState::from_chunk(gchunk, (size_t)P);
   redzone_collector() = nullptr;
-  char* ichunk = (char*)img_alloc(img_user, ImgState::required(HW));
+  char* ichunk = (char*)img_alloc(img_user, ImgState::required(HW, (size_t)T));
   if (!ichunk) return fail(SFB_ERR_ALLOC, "image buffer allocation failed");
   if (debug) redzone_collector() = &rz;
-  ImgState img = ImgState::from_chunk(ichunk, HW);
+  ImgState img = ImgState::from_chunk(ichunk, HW, (size_t)T);
   redzone_collector() = nullptr;
   if (debug && redzones_fill(rz, s)) return fail(SFB_ERR_CUDA, "red-zone fill");
 
@@ -226,7 +226,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
     const size_t tzero = radix_sort_zero_words((int)R, tile_bits(T));
     prof_begin("duplicate", s);
     launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, b.tile_key[0], b.inst_idx[0],
-                     pk.idx_bits, tzero ? b.sort_hist : nullptr, tzero, b.ranges, T, s);
+                     pk.idx_bits, tzero ? b.sort_hist : nullptr, tzero, b.ranges, T, img.tile_bcount, s);
     prof_end(s);
     g_launches++;
     CK_LAUNCH("duplicate", debug, s);
@@ -237,12 +237,14 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
     CK_LAUNCH("tile sort", debug, s);
   } else {
     CK(cudaMemsetAsync(b.ranges, 0, sizeof(uint2) * (size_t)T, s));     // nothing to render: every tile is (0, 0)
+    CK(cudaMemsetAsync(img.tile_bcount, 0, sizeof(uint32_t) * TILE_BUCKETS, s));
   }
 
   prof_begin("render_forward", s);
-  launch_render_forward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, bg, out_color, out_depth,
-                        out_alpha,
-                        img.final_T, img.n_contrib, b.hit, g.grad, (size_t)P, s);
+  if (launch_render_forward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, bg, out_color, out_depth,
+                            out_alpha, img.final_T, img.n_contrib, b.hit, img.tile_bcount, img.tile_btile, g.grad,
+                            (size_t)P, s) != 0)
+    return fail(SFB_ERR_CUDA, g_err.c_str());
   prof_end(s);
   g_launches++;
   CK_LAUNCH("render forward", debug, s);
@@ -306,7 +308,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   const bool packed = pk.idx_bits > 0;
   BinState b = BinState::from_chunk(bchunk, (size_t)num_rendered, (size_t)T, packed);
   char* ichunk = (char*)img_buffer;
-  ImgState img = ImgState::from_chunk(ichunk, HW);
+  ImgState img = ImgState::from_chunk(ichunk, HW, (size_t)T);
   redzone_collector() = nullptr;
   const int tfinal = num_rendered > 0 ? tile_sort_final(T) : 0;
 
@@ -319,9 +321,10 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
     prof_end(s);
   }
   prof_begin("render_backward", s);
-  launch_render_backward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, bg, img.final_T,
-                         img.n_contrib,
-                         dL_dout_color, dL_dout_alpha, b.hit, g.grad, s);
+  if (launch_render_backward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, (size_t)P, bg, img.final_T,
+                             img.n_contrib, dL_dout_color, dL_dout_alpha, b.hit, img.tile_bcount, img.tile_btile, g.grad,
+                             s) != 0)
+    return fail(SFB_ERR_CUDA, g_err.c_str());
   prof_end(s);
   g_launches++;
   CK_LAUNCH("render backward", debug, s);
@@ -502,7 +505,7 @@ int sfb_export_img(int W, int H, const void* img_buffer, float* final_T, uint32_
   if (W <= 0 || H <= 0 || !img_buffer) return fail(SFB_ERR_ARG, "bad arguments");
   const size_t HW = (size_t)H * W;
   char* ichunk = (char*)img_buffer;
-  ImgState img = ImgState::from_chunk(ichunk, HW);
+  ImgState img = ImgState::from_chunk(ichunk, HW, (size_t)(((W + 15) / 16) * ((H + 15) / 16)));
   if (final_T) CK(cudaMemcpyAsync(final_T, img.final_T, sizeof(float) * HW, cudaMemcpyDeviceToDevice, s));
   if (n_contrib) CK(cudaMemcpyAsync(n_contrib, img.n_contrib, sizeof(uint32_t) * HW, cudaMemcpyDeviceToDevice, s));
   return SFB_OK;

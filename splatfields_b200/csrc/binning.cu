@@ -478,7 +478,7 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
                  const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ tile_keys,
                  uint32_t* __restrict__ inst_idx /* nullptr: packed mode, tile_keys[k] = tile << idx_bits | index */,
                  int idx_bits, uint32_t* __restrict__ zero_ptr, uint32_t zero_words, uint2* __restrict__ ranges_init,
-                 int T) {
+                 int T, uint32_t* __restrict__ bcount_zero) {
   // Prologue: this kernel runs right in front of the tile sort anyway, so its blocks also clear the sort's scratch
   // (digit histograms, tickets, look-back state) and set the tile ranges to "empty" — two memset nodes less per forward.
   if (zero_ptr) {
@@ -486,6 +486,7 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
     const uint32_t z0 = blockIdx.x * per, z1 = min(z0 + per, zero_words);
     for (uint32_t i = z0 + threadIdx.x; i < z1; i += DUP_THREADS) zero_ptr[i] = 0u;
   }
+  if (bcount_zero && blockIdx.x == 0 && threadIdx.x < TILE_BUCKETS) bcount_zero[threadIdx.x] = 0u;
   if (ranges_init) {
     const int per = (T + (int)gridDim.x - 1) / (int)gridDim.x;
     const int t0 = blockIdx.x * per, t1 = min(t0 + per, T);
@@ -621,10 +622,11 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
 void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
                       const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
                       uint32_t* inst_idx, int idx_bits, uint32_t* zero_ptr, size_t zero_words, uint2* ranges_init, int T,
-                      cudaStream_t s) {
+                      uint32_t* bcount_zero, cudaStream_t s) {
   int nb = (P + DUP_GPB - 1) / DUP_GPB;
   duplicate_kernel<<<nb, DUP_THREADS, 0, s>>>(P, grid_x, sorted_idx, tiles_touched, rect, block_offsets,
-                                              tile_keys, inst_idx, idx_bits, zero_ptr, (uint32_t)zero_words, ranges_init, T);
+                                              tile_keys, inst_idx, idx_bits, zero_ptr, (uint32_t)zero_words, ranges_init, T,
+                                              bcount_zero);
 }
 
 // point_list == nullptr: packed mode (tile_keys[i] = tile << idx_bits | index)

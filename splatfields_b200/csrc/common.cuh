@@ -13,6 +13,7 @@ constexpr int TILE_X = 16;
 constexpr int TILE_Y = 16;
 constexpr int TILE_PIX = TILE_X * TILE_Y;
 constexpr int NUM_SMS_B200 = 148;
+constexpr int TILE_BUCKETS = 32;     // cost buckets of the backward's tile order (deepest contributor of a tile / 32)
 
 // One record per Gaussian, written by preprocess, gathered (L2-resident) by both render kernels.
 // 48 bytes = three 16-byte loads, always exactly two 32-byte sectors.
@@ -68,6 +69,50 @@ __device__ __forceinline__ float splat_exp(float power) {
 #endif
 }
 
+// ---- staged splat rows of the two render kernels ----
+// A list entry is staged in shared memory as one 64-byte row of four float4:
+//   [0] x, y, a', b'    [1] c', opacity, depth, r    [2] g, b, hx, hy    [3] A, B, C, -  (true conic, backward flush)
+// The first 48 bytes arrive as the SplatRec (TMA row gather or three 16-byte loads); the thread that owns the row then
+// rewrites the conic in place, pre-multiplied for the sweep:  a' = -k/2 A,  b' = -k B,  c' = -k/2 C  with k = log2(e)
+// (k = 1 in the expf build), so that  k * power = a' dx^2 + b' dx dy + c' dy^2  costs 5 instead of 9 flops per pixel
+// and feeds ex2 directly.  Forward and backward use the SAME expression (render_power below): a pixel the forward
+// accumulated is never skipped by the backward and vice versa.
+#ifdef SFB_EXACT_EXP
+constexpr float RENDER_K = 1.0f;
+#else
+constexpr float RENDER_K = 1.4426950408889634f;
+#endif
+__device__ __forceinline__ void prescale_conic(float A, float B, float C, float& a, float& b, float& c) {
+  a = (-0.5f * RENDER_K) * A; b = (-RENDER_K) * B; c = (-0.5f * RENDER_K) * C;
+}
+// k * power at offset (dx, dy) from the splat centre
+__device__ __forceinline__ float render_power(float a, float b, float c, float dx, float dy) {
+  const float m = __fmaf_rn(b, dy, __fmul_rn(a, dx));
+  return __fmaf_rn(m, dx, __fmul_rn(__fmul_rn(c, dy), dy));
+}
+// exp(power) from k * power
+__device__ __forceinline__ float render_exp(float kp) {
+#ifdef SFB_EXACT_EXP
+  return expf(kp);
+#else
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(kp));
+  return r;
+#endif
+}
+
+// ---- TMA row gather (cp.async.bulk.tensor ... tile::gather4 -> UTMALDG): four rows of a 2-D tensor per instruction ----
+// dst: 4 consecutive box rows in shared memory (128-byte aligned); tmap: CUtensorMap over the row table with
+// box = {row floats, 1}; col: first column; r0..r3: row indices; completion on the mbarrier (box bytes x 4).
+__device__ __forceinline__ void tma_gather4(void* dst_smem, const void* tmap, int col, int r0, int r1, int r2, int r3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)),
+      "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"((uint32_t)__cvta_generic_to_shared(bar))
+      : "memory");
+}
+
 // Non-blocking L2 prefetch of the 128-byte line holding p (no register, no scoreboard).
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -80,14 +125,21 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "SFB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra SFB_DONE;\n\t"
-      "bra SFB_WAIT;\n\t"
-      "SFB_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0u;
+}
+// Bounded: a transaction count that never completes (a bad tensor map, a miscounted expect_tx) must not hang the GPU —
+// after ~2 s the kernel traps and the caller gets a CUDA error.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > 4000000000LL) __trap();
 }
 // global -> shared, completion signalled on the mbarrier (bytes: multiple of 16, both sides 16-byte aligned)
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
@@ -283,15 +335,19 @@ struct BinState {
 struct ImgState {
   float* final_T;           // [H*W]
   uint32_t* n_contrib;      // [H*W]
-  static ImgState from_chunk(char*& chunk, size_t N) {
+  uint32_t* tile_bcount;    // [TILE_BUCKETS]      tiles per cost bucket (written by the forward render)
+  uint32_t* tile_btile;     // [TILE_BUCKETS][T]   tile ids of every bucket, in arrival order
+  static ImgState from_chunk(char*& chunk, size_t N, size_t T) {
     ImgState s;
     s.final_T = carve<float>(chunk, N);
     s.n_contrib = carve<uint32_t>(chunk, N);
+    s.tile_bcount = carve<uint32_t>(chunk, TILE_BUCKETS);
+    s.tile_btile = carve<uint32_t>(chunk, (size_t)TILE_BUCKETS * T);
     return s;
   }
-  static size_t required(size_t N) {
+  static size_t required(size_t N, size_t T) {
     char* p = nullptr;
-    from_chunk(p, N);
+    from_chunk(p, N, T);
     return reinterpret_cast<size_t>(p) + 256;
   }
 };
@@ -348,25 +404,28 @@ void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint3
                       const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
                       uint32_t* inst_idx /* nullptr: packed */, int idx_bits,
                       uint32_t* zero_ptr /* or nullptr */, size_t zero_words, uint2* ranges_init /* or nullptr */, int T,
-                      cudaStream_t s);
+                      uint32_t* bcount_zero /* [TILE_BUCKETS] or nullptr: cleared on the way */, cudaStream_t s);
 void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_list /* nullptr: packed */,
                         int idx_bits, const SplatRec* rec, uint64_t* out_keys, uint32_t* out_list, cudaStream_t s);
 
 // render_fwd.cu
-void launch_render_forward(int W, int H, uint2* ranges /* empty tiles are normalised to (0, 0) in place */,
+// returns 0, or -1 with set_error() (tensor-map encoding failed)
+int launch_render_forward(int W, int H, uint2* ranges /* empty tiles are normalised to (0, 0) in place */,
                            const uint32_t* point_list, uint32_t idx_mask,
                            const SplatRec* rec,
                            const float* bg, float* out_color, float* out_depth, float* out_alpha, float* final_T,
-                           uint32_t* n_contrib, uint8_t* hit /* [R] or nullptr: do not record */,
+                           uint32_t* n_contrib, uint8_t* hit /* [R] */,
+                           uint32_t* bcount, uint32_t* btile /* backward tile order (ImgState), bcount zeroed */,
                            GradRec* zero_grad /* [P] or nullptr: cleared by the CTAs as a prologue */, size_t P,
                            cudaStream_t s);
 
 // render_bwd.cu
-void launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
-                            const SplatRec* rec,
-                            const float* bg, const float* final_T, const uint32_t* n_contrib,
-                            const float* dL_dpixels, const float* dL_dalpha_img, const uint8_t* hit /* or nullptr */,
-                            GradRec* grad, cudaStream_t s);
+int launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
+                           const SplatRec* rec, size_t P,
+                           const float* bg, const float* final_T, const uint32_t* n_contrib,
+                           const float* dL_dpixels, const float* dL_dalpha_img, const uint8_t* hit,
+                           const uint32_t* bcount /* [TILE_BUCKETS] tiles per cost bucket (forward) */,
+                           const uint32_t* btile /* [TILE_BUCKETS][T] tile ids per bucket */, GradRec* grad, cudaStream_t s);
 
 // geom_bwd.cu
 constexpr int XCHG_MAX_RANKS = 16;

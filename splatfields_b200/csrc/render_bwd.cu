@@ -16,11 +16,12 @@
 // Accumulation order differs from the reference's (as it does between two runs of the reference), so
 // parity here is tolerance-based: 1e-3 relative on every per-splat gradient.
 #include "common.cuh"
+#include <cuda.h>
 #include <cstdlib>
+#include <cstring>
 
 namespace sfb {
 
-constexpr int BB = 256;
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -59,32 +60,60 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
+constexpr int NT = 256;          // threads per CTA = pixels of a tile
+constexpr int NW = NT / 32;      // warps = 8x4 pixel patches
+
+// BBT = list entries per batch.  128 (default): 54 KB of shared memory and 64 registers -> 4 CTAs per SM;
+// 256: 67.5 KB / 80 registers -> 3 CTAs per SM (the round-1 configuration, kept for the A/B in profiles/).
+template <int BBT>
 struct SmemBwdMma {
-  float4 q0[BB];
-  float4 q1[BB];
-  float4 q2[BB];            // g, b, -, - (16-byte stride like q0 / q1: one address register + immediates)
-  uint32_t id[BB];
-  float acc[BB * 9];
-  uint32_t maxc[BB / 32];
-  uint8_t mask[BB];
-  uint8_t list[BB / 32][BB];
-  float2 stage[BB / 32][MG * 32];   // per warp: [entry row][pixel ^ swizzle] = (sG, w)
-  float2 dlp[BB / 32][4][32];       // per warp: (hi, lo) of dL/dC_c per pixel; channel 3 = zeros
+  float4 row[BBT][4];               // staged 64-byte rows (common.cuh); [3] = true conic A, B, C + Gaussian index bits
+  float acc[BBT * 9];
+  uint64_t bar;
+  uint32_t maxc[NW];
+  uint32_t tile;
+  uint8_t mask[BBT];
+  uint8_t list[NW][BBT];
+  float2 stage[NW][MG * 32];        // per warp: [entry row][pixel ^ swizzle] = (sG, w)
+  float2 dlp[NW][4][32];            // per warp: (hi, lo) of dL/dC_c per pixel; channel 3 = zeros
 };
 
-template <bool ALPHA>
-__global__ void __launch_bounds__(BB, 3)
+// Tile order: the forward left every tile in one of TILE_BUCKETS cost buckets (deepest contributor of the tile / 32)
+// with a unique rank inside its bucket; CTA i takes the i-th tile counting from the most expensive bucket down, so the
+// long tiles start first and the kernel's tail consists of cheap ones.
+__device__ __forceinline__ int ordered_tile(int i, int T, const uint32_t* __restrict__ bcount,
+                                            const uint32_t* __restrict__ btile, uint32_t* s_tile) {
+  if (threadIdx.x < 32) {
+    const int b = TILE_BUCKETS - 1 - (int)threadIdx.x;          // lane 0 = most expensive bucket
+    const uint32_t c = bcount[b];
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((int)threadIdx.x >= o) inc += t;
+    }
+    const uint32_t ex = inc - c;
+    if ((uint32_t)i >= ex && (uint32_t)i < inc) *s_tile = btile[(size_t)b * T + ((uint32_t)i - ex)];
+  }
+  __syncthreads();
+  return (int)*s_tile;
+}
+
+template <bool ALPHA, int BBT, int MINB, bool TMA>
+__global__ void __launch_bounds__(NT, MINB)
 render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
                            const uint32_t* __restrict__ point_list, uint32_t idx_mask,
-                           const SplatRec* __restrict__ rec,
+                           const SplatRec* __restrict__ rec, const __grid_constant__ CUtensorMap rec_map,
                            const float* __restrict__ bg, const float* __restrict__ final_T,
                            const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
                            const float* __restrict__ dL_dalpha_img, const uint8_t* __restrict__ hit,
+                           const uint32_t* __restrict__ bcount, const uint32_t* __restrict__ btile,
                            GradRec* __restrict__ grad) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemBwdMma& sm = *reinterpret_cast<SmemBwdMma*>(smem_raw);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemBwdMma<BBT>& sm = *reinterpret_cast<SmemBwdMma<BBT>*>(smem_raw);
 
-  const int tile = blockIdx.x;
+  if (TMA && threadIdx.x == 0) mbar_init(&sm.bar, 1);
+  const int tile = bcount ? ordered_tile((int)blockIdx.x, (int)gridDim.x, bcount, btile, &sm.tile) : (int)blockIdx.x;
   const int tile_x = tile % grid_x, tile_y = tile / grid_x;
   const float tx0 = (float)(tile_x * TILE_X), ty0 = (float)(tile_y * TILE_Y);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -144,34 +173,57 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
   __syncthreads();
   uint32_t hi = 0;
 #pragma unroll
-  for (int w = 0; w < BB / 32; w++) hi = max(hi, sm.maxc[w]);
+  for (int w = 0; w < NW; w++) hi = max(hi, sm.maxc[w]);
 
   // mma.sync needs the whole warp converged; fail loudly rather than reduce garbage if it ever is not
   if (__activemask() != 0xffffffffu) __trap();
 
-  for (int top = (int)hi; top > 0; top -= BB) {
-    const int n = top < BB ? top : BB;
+  uint32_t phase = 0;
+  for (int top = (int)hi; top > 0; top -= BBT) {
+    // smem slot j holds list position top-1-j (back to front)
+    const int n = top < BBT ? top : BBT;
     __syncthreads();
     uint32_t mask = 0u;
-    if ((int)threadIdx.x < n) {
-      uint32_t id = point_list[range.x + (uint32_t)(top - 1 - (int)threadIdx.x)] & idx_mask;
-      const float4* rp = reinterpret_cast<const float4*>(rec + id);
-      float4 a = __ldg(rp), b = __ldg(rp + 1), c = __ldg(rp + 2);
-      sm.q0[threadIdx.x] = a;
-      sm.q1[threadIdx.x] = b;
-      sm.q2[threadIdx.x] = c;
-      sm.id[threadIdx.x] = id;
-      mask = (uint32_t)hit[range.x + (uint32_t)(top - 1 - (int)threadIdx.x)];
+    {
+      uint32_t id = 0u;
+      const bool mine = (int)threadIdx.x < n;
+      const uint32_t pos = range.x + (uint32_t)(top - 1 - (int)threadIdx.x);
+      if (mine) { id = point_list[pos] & idx_mask; mask = (uint32_t)hit[pos]; }
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
+      if (TMA) {
+        // every fourth thread gathers its own and its three neighbours' rows (entries past n re-read row 0)
+        if (threadIdx.x < (unsigned)BBT) {        // (whole warps: BBT is a multiple of 32)
+          const uint32_t i1 = __shfl_down_sync(0xffffffffu, id, 1), i2 = __shfl_down_sync(0xffffffffu, id, 2),
+                         i3 = __shfl_down_sync(0xffffffffu, id, 3);
+          if (threadIdx.x == 0) mbar_expect_tx(&sm.bar, (uint32_t)((n + 3) / 4) * 256u);
+          if ((threadIdx.x & 3) == 0 && mine)
+            tma_gather4(&sm.row[threadIdx.x][0], &rec_map, 0, (int)id, (int)i1, (int)i2, (int)i3, &sm.bar);
+        }
+        mbar_wait(&sm.bar, phase);
+        phase ^= 1u;
+        if (mine) { a = sm.row[threadIdx.x][0]; b = sm.row[threadIdx.x][1]; }
+      } else if (mine) {
+        const float4* rp = reinterpret_cast<const float4*>(rec + id);
+        a = __ldg(rp); b = __ldg(rp + 1); c = __ldg(rp + 2);
+        sm.row[threadIdx.x][2] = c;
+      }
+      if (mine) {
+        float ka, kb, kc;
+        prescale_conic(a.z, a.w, b.x, ka, kb, kc);
+        sm.row[threadIdx.x][0] = make_float4(a.x, a.y, ka, kb);
+        sm.row[threadIdx.x][1] = make_float4(kc, b.y, b.z, b.w);
+        sm.row[threadIdx.x][3] = make_float4(a.z, a.w, b.x, __uint_as_float(id));
+        if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // rows are overwritten by the TMA unit next batch
+      }
     }
-    sm.mask[threadIdx.x] = (uint8_t)mask;
-#pragma unroll
-    for (int k = 0; k < 9; k++) sm.acc[k * BB + threadIdx.x] = 0.f;
+    if (threadIdx.x < (unsigned)BBT) sm.mask[threadIdx.x] = (uint8_t)mask;
+    for (int k = threadIdx.x; k < 9 * BBT; k += NT) sm.acc[k] = 0.f;
     __syncthreads();
     int nsweep = 0;
     {
       const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-      for (int c8 = 0; c8 < BB / 32; c8++) {
+      for (int c8 = 0; c8 < BBT / 32; c8++) {
         const int idx = c8 * 32 + lane;
         const bool h = (sm.mask[idx] >> warp) & 1;
         const uint32_t bal = __ballot_sync(0xffffffffu, h);
@@ -189,37 +241,34 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
       auto entry = [&](const int i, const int j) {
         float sG = 0.f, wgt = 0.f;
         if (j >= jmin) {
-          const float4 q0 = sm.q0[j];
-          const float4 q1 = sm.q1[j];
+          const float4 q0 = sm.row[j][0];
+          const float4 q1 = sm.row[j][1];
           const float dx = q0.x - pixfx, dy = q0.y - pixfy;
-          const float s = __fmaf_rn(__fmul_rn(q0.z, dx), dx, __fmul_rn(__fmul_rn(q1.x, dy), dy));
-          const float power = __fmaf_rn(s, -0.5f, -__fmul_rn(__fmul_rn(q0.w, dx), dy));
-          if (power <= 0.0f) {
-            const float G = splat_exp(power);
-            const float alpha = fminf(0.99f, __fmul_rn(q1.y, G));
-            if (alpha >= 1.0f / 255.0f) {
-              const float2 q2 = make_float2(sm.q2[j].x, sm.q2[j].y);
-              float inv;
-              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - alpha));
-              T *= inv;
-              wgt = alpha * T;
-              // colour accumulated BEHIND this splat: acc <- alpha c + (1 - alpha) acc, applied after its use below
-              // (the reference carries last_alpha / last_color to the next iteration; same values, fewer registers)
-              const float d0 = q1.w - acc0, d1 = q2.x - acc1, d2 = q2.y - acc2;
-              float dL_dalpha = d0 * dLp0;
-              dL_dalpha = fmaf(d1, dLp1, dL_dalpha);
-              dL_dalpha = fmaf(d2, dLp2, dL_dalpha);
-              acc0 = fmaf(alpha, d0, acc0);
-              acc1 = fmaf(alpha, d1, acc1);
-              acc2 = fmaf(alpha, d2, acc2);
-              if (ALPHA) {
-                const float da = 1.f - acca;
-                dL_dalpha = fmaf(da, dLpa, dL_dalpha);
-                acca = fmaf(alpha, da, acca);
-              }
-              dL_dalpha = fmaf(dL_dalpha, T, -Tf_bg * inv);
-              sG = q1.y * dL_dalpha * G;
+          const float kp = render_power(q0.z, q0.w, q1.x, dx, dy);
+          const float G = render_exp(kp);
+          const float alpha = fminf(0.99f, __fmul_rn(q1.y, G));
+          if (!((kp > 0.0f) | (alpha < 1.0f / 255.0f))) {        // the forward's own test: same pixels, same entries
+            const float2 q2 = make_float2(sm.row[j][2].x, sm.row[j][2].y);
+            float inv;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - alpha));
+            T *= inv;
+            wgt = alpha * T;
+            // colour accumulated BEHIND this splat: acc <- alpha c + (1 - alpha) acc, applied after its use below
+            // (the reference carries last_alpha / last_color to the next iteration; same values, fewer registers)
+            const float d0 = q1.w - acc0, d1 = q2.x - acc1, d2 = q2.y - acc2;
+            float dL_dalpha = d0 * dLp0;
+            dL_dalpha = fmaf(d1, dLp1, dL_dalpha);
+            dL_dalpha = fmaf(d2, dLp2, dL_dalpha);
+            acc0 = fmaf(alpha, d0, acc0);
+            acc1 = fmaf(alpha, d1, acc1);
+            acc2 = fmaf(alpha, d2, acc2);
+            if (ALPHA) {
+              const float da = 1.f - acca;
+              dL_dalpha = fmaf(da, dLpa, dL_dalpha);
+              acca = fmaf(alpha, da, acca);
             }
+            dL_dalpha = fmaf(dL_dalpha, T, -Tf_bg * inv);
+            sG = q1.y * dL_dalpha * G;
           }
         }
         st[i * 32 + (lane ^ ((i & 3) << 2))] = make_float2(sG, wgt);
@@ -279,9 +328,9 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
 #pragma unroll
       for (int k = 0; k < 9; k++) { a[k] = sm.acc[threadIdx.x * 9 + k]; nz |= (a[k] != 0.f); }
       if (nz) {
-        const float4 q0 = sm.q0[threadIdx.x];
-        const float4 q1 = sm.q1[threadIdx.x];
-        const float conA = q0.z, conB = q0.w, conC = q1.x, op = q1.y;
+        const float4 q0 = sm.row[threadIdx.x][0];
+        const float4 q3 = sm.row[threadIdx.x][3];
+        const float conA = q3.x, conB = q3.y, conC = q3.z, op = sm.row[threadIdx.x][1].y;
         // tile-centre moments -> splat-centre moments: dx = cx - X, dy = cy - Y
         const float cx = q0.x - (tx0 + 7.5f), cy = q0.y - (ty0 + 7.5f);
         const float S0 = a[0];
@@ -294,7 +343,7 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
         const float gy = -(conC * Sy + conB * Sx) * ddely_dy;
         const float gA = -0.5f * Sxx, gB = -Sxy, gC = -0.5f * Syy;
         const float gop = S0 / op;
-        float* gp = reinterpret_cast<float*>(grad + sm.id[threadIdx.x]);
+        float* gp = reinterpret_cast<float*>(grad + __float_as_uint(q3.w));
         red_add_v4(gp, gx, gy, gA, gB);
         red_add_v4(gp + 4, gC, S0 != 0.f ? gop : 0.f, a[6], a[7]);
         atomicAdd(gp + 8, a[8]);
@@ -304,29 +353,51 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
 }
 
 
-void launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
-                            const SplatRec* rec,
-                            const float* bg, const float* final_T, const uint32_t* n_contrib,
-                            const float* dL_dpixels, const float* dL_dalpha_img, const uint8_t* hit, GradRec* grad,
-                            cudaStream_t s) {
+bool make_rec_tensor_map(const SplatRec* rec, size_t P, void* out_map);   // render_fwd.cu
+
+// A/B knobs of the round-2 sessions (profiles/): SFB_BWD_STAGE=ldg (three 16-byte loads per thread instead of the TMA
+// row gather), SFB_BWD_BATCH=256 (round-1 batch size: 3 CTAs per SM), SFB_BWD_ORDER=0 (tiles in launch order).
+static int env_choice(const char* name, const char* alt) {
+  const char* e = getenv(name);
+  return (e && strcmp(e, alt) == 0) ? 1 : 0;
+}
+
+int launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
+                           const SplatRec* rec, size_t P,
+                           const float* bg, const float* final_T, const uint32_t* n_contrib,
+                           const float* dL_dpixels, const float* dL_dalpha_img, const uint8_t* hit,
+                           const uint32_t* bcount, const uint32_t* btile, GradRec* grad,
+                           cudaStream_t s) {
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
-  // > 48 KB of dynamic shared memory needs the attribute on EVERY device the process uses (it is per device)
-  static bool attr_set[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaFuncSetAttribute(render_backward_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(SmemBwdMma));
-    cudaFuncSetAttribute(render_backward_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(SmemBwdMma));
-    attr_set[dev] = true;
+  static int cfg = -1;
+  if (cfg < 0) cfg = env_choice("SFB_BWD_STAGE", "ldg") | (env_choice("SFB_BWD_BATCH", "256") << 1) |
+                     (env_choice("SFB_BWD_ORDER", "0") << 2);
+  const bool tma = !(cfg & 1), big = (cfg & 2) != 0, ordered = !(cfg & 4);
+  if (!ordered) { bcount = nullptr; btile = nullptr; }
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (tma && !make_rec_tensor_map(rec, P, &map)) {
+    set_error("cuTensorMapEncodeTiled failed for the splat record table (TMA staging of the tile lists)");
+    return -1;
   }
-  if (dL_dalpha_img)
-    render_backward_mma_kernel<true><<<gx * gy, BB, sizeof(SmemBwdMma), s>>>(
-        W, H, gx, ranges, point_list, idx_mask, rec, bg, final_T, n_contrib, dL_dpixels, dL_dalpha_img, hit, grad);
-  else
-    render_backward_mma_kernel<false><<<gx * gy, BB, sizeof(SmemBwdMma), s>>>(
-        W, H, gx, ranges, point_list, idx_mask, rec, bg, final_T, n_contrib, dL_dpixels, dL_dalpha_img, hit, grad);
+  // > 48 KB of dynamic shared memory needs the attribute on EVERY device the process uses (it is per device and the
+  // call is cheap: it is made with every launch)
+#define SFB_RBK(A, B, MB, TM)                                                                                       \
+  do {                                                                                                              \
+    auto kern = render_backward_mma_kernel<A, B, MB, TM>;                                                           \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemBwdMma<B>));            \
+    kern<<<gx * gy, NT, sizeof(SmemBwdMma<B>), s>>>(W, H, gx, ranges, point_list, idx_mask, rec, map, bg, final_T,  \
+                                                   n_contrib, dL_dpixels, dL_dalpha_img, hit, bcount, btile, grad); \
+  } while (0)
+#define SFB_RBA(A)                                                                                                  \
+  do {                                                                                                              \
+    if (big) { if (tma) SFB_RBK(A, 256, 3, true); else SFB_RBK(A, 256, 3, false); }                                 \
+    else     { if (tma) SFB_RBK(A, 128, 4, true); else SFB_RBK(A, 128, 4, false); }                                 \
+  } while (0)
+  if (dL_dalpha_img) SFB_RBA(true); else SFB_RBA(false);
+#undef SFB_RBA
+#undef SFB_RBK
+  return 0;
 }
 
 }  // namespace sfb

@@ -5,49 +5,55 @@
 //
 // One CTA per tile, 256 threads = one pixel each; a warp covers an 8x4 pixel patch (not a 16x2 strip)
 // so that the pixels of a warp see nearly the same set of contributing splats.  The tile's list is
-// consumed in batches of 256: every thread gathers one 48-byte SplatRec (three 16-byte loads out of L2,
-// where the whole record array of a 1M-splat scene stays resident) into shared memory, then all threads
-// sweep the batch reading the records as warp-wide broadcasts.
+// consumed in batches of 256 entries staged in shared memory as 64-byte rows (common.cuh):
+//   * TMA staging (default): the 48-byte SplatRec rows of a batch are gathered by the TMA unit —
+//     cp.async.bulk.tensor.2d ... tile::gather4 (SASS: UTMALDG), four list entries per instruction, 64 instructions
+//     per batch issued by every fourth thread — into one of two buffers; completion is an mbarrier transaction
+//     count.  The gather of batch k+1 is issued before batch k is swept, so its L2 round trip runs under the sweep.
+//   * LDG staging (SFB_FWD_STAGE=ldg, kept for the A/B in profiles/): every thread loads one record with three
+//     16-byte loads and stores it to shared memory; single buffer.
+// The thread that owns a row then computes its culling mask and rewrites the conic pre-multiplied for the sweep;
+// all threads sweep the batch reading the rows as warp-wide broadcasts.
 #include "common.cuh"
+#include <cuda.h>
 #include <cstdlib>
+#include <cstring>
 
 namespace sfb {
 
 constexpr int RB = 256;  // batch = block size
 
-// CULL: each fetched splat gets an 8-bit mask of the 8x4 patches (= warps) its alpha >= 1/255 footprint box
-// can touch (SplatRec::hx/hy, computed conservatively in preprocess); every warp then sweeps only its own
-// compacted sub-list.  Skipped (splat, patch) pairs are pairs the reference's own `alpha < 1/255` test would
-// reject for all 32 pixels, so the output is bit-identical; the sweep shrinks ~3x on dense scenes.
+// Each fetched splat gets an 8-bit mask of the 8x4 patches (= warps) its alpha >= 1/255 footprint can touch
+// (SplatRec::hx/hy box computed conservatively in preprocess, then the exact ellipse-vs-patch test of common.cuh);
+// every warp sweeps only its own compacted sub-list.  Skipped (splat, patch) pairs are pairs the reference's own
+// `alpha < 1/255` test would reject for all 32 pixels, so the output is unchanged; the sweep shrinks ~3x on dense scenes.
 // ALPHA: also accumulate the coverage image A = sum(alpha * T) — the image the reference obtains from a SECOND
 // full rasterizer pass with colours = 1 and bg = 0 (gaussian_renderer/__init__.py:104-115); it shares every
 // skip / stop decision with the colour pass, so one extra FADD per contribution replaces that whole pass.
-// REC: record, per list entry, which warps (8x4 patches) accumulated it.  The backward sweeps exactly those
-// (warp, entry) pairs instead of every pair whose footprint box touches the patch (3.1 M -> 1.9 M per view).
-template <bool ALPHA>
+// The kernel records, per list entry, which warps (8x4 patches) accumulated it (hit[R], one byte): the backward
+// sweeps exactly those (warp, entry) pairs (3.1 M -> 1.9 M per view on lego_1m).
+template <int NBUF>
+struct SmemFwd {
+  float4 row[NBUF][RB][4];   // 64-byte rows (common.cuh); 128-byte aligned for the TMA unit
+  uint64_t bar[2];
+  uint8_t mask[RB];
+  uint8_t list[RB / 32][RB];
+  uint8_t hitw[RB / 32][RB];   // [warp][entry]: 1 = some pixel of the warp accumulated it
+};
+
+template <bool ALPHA, bool TMA>
 __global__ void __launch_bounds__(RB, 6)   // <= 42 registers: the sweep loop needs ~40; the fetch-phase culling math may spill
 render_forward_kernel(int W, int H, int grid_x, uint2* __restrict__ ranges,
                       const uint32_t* __restrict__ point_list, uint32_t idx_mask,
-                      const SplatRec* __restrict__ rec,
+                      const SplatRec* __restrict__ rec, const __grid_constant__ CUtensorMap rec_map,
                       const float* __restrict__ bg, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ out_alpha,
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, uint8_t* __restrict__ hit,
+                      uint32_t* __restrict__ bcount, uint32_t* __restrict__ btile,
                       float4* __restrict__ zero16, uint32_t zero_per_cta, uint32_t zero_total) {
-  // one struct = one base register: every access below is base + immediate (+ j * stride)
-  struct Smem {
-    float4 q0[RB];   // x, y, conA, conB
-    float4 q1[RB];   // conC, opacity, depth, r
-    float4 q2[RB];   // g, b, -, -   (16-byte stride like q0 / q1: one address register + immediates)
-    uint8_t mask[RB];
-    uint8_t list[RB / 32][RB];
-    uint8_t hitw[RB / 32][RB];   // [warp][entry]: 1 = some pixel of the warp accumulated it
-  };
-  __shared__ Smem sm;
-  float4* const s_q0 = sm.q0;
-  float4* const s_q1 = sm.q1;
-  float4* const s_q2 = sm.q2;
-  uint8_t* const s_mask = sm.mask;
-  uint8_t (*const s_list)[RB] = sm.list;
+  __shared__ __align__(128) SmemFwd<TMA ? 2 : 1> sm;
+  __shared__ uint32_t s_deepest;
+  if (threadIdx.x == 0) s_deepest = 0u;
 
   const int tile = blockIdx.x;
   // Prologue: clear this CTA's slice of the backward's per-splat gradient accumulators (GradRec[P]).  The kernel is
@@ -72,61 +78,98 @@ render_forward_kernel(int W, int H, int grid_x, uint2* __restrict__ ranges,
     range.x = 0u;
     if (threadIdx.x == 0) ranges[tile] = make_uint2(0u, 0u);
   }
-  int todo = (int)(range.y - range.x);
+  const int total = (int)(range.y - range.x);
+  const int nbatch = (total + RB - 1) / RB;
   bool done = !inside;
 
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, Ac = 0.f;
   uint32_t last_contributor = 0;
 
-  for (int base = 0; todo > 0; base += RB, todo -= RB) {
-    if (__syncthreads_count(done) == RB) break;
-    uint32_t mask = 0u;
-    if ((int)threadIdx.x < todo) {
-      uint32_t id = point_list[range.x + base + threadIdx.x] & idx_mask;
-      const float4* rp = reinterpret_cast<const float4*>(rec + id);
-      float4 a = __ldg(rp), b = __ldg(rp + 1), c = __ldg(rp + 2);
-      s_q0[threadIdx.x] = a;
-      s_q1[threadIdx.x] = b;
-      s_q2[threadIdx.x] = c;
-      mask = refine_patch_mask(patch_mask(a.x, a.y, c.z, c.w, tx0, ty0), a.x, a.y, a.z, a.w, b.x, b.y, c.z, tx0, ty0);
+  // TMA: gather the rows of batch `it` into buffer `buf`; every fourth thread issues one gather4 for its own and its
+  // three neighbours' list entries (entries past the end of the list re-read row 0: harmless, never swept)
+  auto issue = [&](const int it, const int buf) {
+    const int cnt = min(RB, total - it * RB);
+    uint32_t id = 0u;
+    if ((int)threadIdx.x < cnt) id = point_list[range.x + (uint32_t)(it * RB) + threadIdx.x] & idx_mask;
+    const uint32_t i1 = __shfl_down_sync(0xffffffffu, id, 1), i2 = __shfl_down_sync(0xffffffffu, id, 2),
+                   i3 = __shfl_down_sync(0xffffffffu, id, 3);
+    if (threadIdx.x == 0) mbar_expect_tx(&sm.bar[buf], (uint32_t)((cnt + 3) / 4) * 256u);
+    if ((threadIdx.x & 3) == 0 && (int)threadIdx.x < cnt)
+      tma_gather4(&sm.row[buf][threadIdx.x][0], &rec_map, 0, (int)id, (int)i1, (int)i2, (int)i3, &sm.bar[buf]);
+  };
+
+  if (TMA) {
+    if (threadIdx.x == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); }
+    __syncthreads();
+    if (nbatch > 0) issue(0, 0);
+  }
+
+  for (int it = 0; it < nbatch; it++) {
+    const int buf = TMA ? (it & 1) : 0;
+    const int base = it * RB;
+    const int cnt = min(RB, total - base);
+    // every thread has left batch it-1 here: its buffer may be refilled
+    const bool all_done = __syncthreads_count(done) == RB;
+    if (all_done) {
+      if (TMA) mbar_wait(&sm.bar[buf], (uint32_t)(it >> 1) & 1u);   // batch `it` is in flight: it must land before the CTA retires
+      break;
     }
-    s_mask[threadIdx.x] = (uint8_t)mask;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
+    float4* const myrow = &sm.row[buf][threadIdx.x][0];
+    if (TMA) {
+      if (it + 1 < nbatch) issue(it + 1, buf ^ 1);
+      mbar_wait(&sm.bar[buf], (uint32_t)(it >> 1) & 1u);
+      if ((int)threadIdx.x < cnt) { a = myrow[0]; b = myrow[1]; c = myrow[2]; }
+    } else if ((int)threadIdx.x < cnt) {
+      const uint32_t id = point_list[range.x + (uint32_t)base + threadIdx.x] & idx_mask;
+      const float4* rp = reinterpret_cast<const float4*>(rec + id);
+      a = __ldg(rp); b = __ldg(rp + 1); c = __ldg(rp + 2);
+      myrow[2] = c;
+    }
+    uint32_t mask = 0u;
+    if ((int)threadIdx.x < cnt) {
+      mask = refine_patch_mask(patch_mask(a.x, a.y, c.z, c.w, tx0, ty0), a.x, a.y, a.z, a.w, b.x, b.y, c.z, tx0, ty0);
+      float ka, kb, kc;
+      prescale_conic(a.z, a.w, b.x, ka, kb, kc);
+      myrow[0] = make_float4(a.x, a.y, ka, kb);
+      myrow[1] = make_float4(kc, b.y, b.z, b.w);
+      if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these rows are overwritten by the TMA unit later
+    }
+    sm.mask[threadIdx.x] = (uint8_t)mask;
     reinterpret_cast<uint2*>(&sm.hitw[0][0])[threadIdx.x] = make_uint2(0u, 0u);   // 8 warps x 256 B
     __syncthreads();
     int n;
     {
-      int cnt = 0;
+      int k = 0;
       const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
       for (int c8 = 0; c8 < RB / 32; c8++) {
         const int idx = c8 * 32 + lane;
-        const bool hit = (s_mask[idx] >> warp) & 1;
-        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-        if (hit) s_list[warp][cnt + __popc(bal & lt)] = (uint8_t)idx;
-        cnt += __popc(bal);
+        const bool h = (sm.mask[idx] >> warp) & 1;
+        const uint32_t bal = __ballot_sync(0xffffffffu, h);
+        if (h) sm.list[warp][k + __popc(bal & lt)] = (uint8_t)idx;
+        k += __popc(bal);
       }
       __syncwarp();
-      n = cnt;
+      n = k;
     }
     // Sweep.  `done` pixels skip the whole batch; a pixel that saturates leaves the loop (no per-iteration flag
     // bookkeeping: the loop body is the kernel, every instruction in it is paid ~150 M times per view).
     if (!done) {
       int lastj = -1;
+      const float4* const rows = &sm.row[buf][0][0];
       for (int k = 0; k < n; k++) {
-        const int j = (int)s_list[warp][k];
-        const float4 q0 = s_q0[j];
+        const int j = (int)sm.list[warp][k];
+        const float4 q0 = rows[4 * j];
+        const float4 q1 = rows[4 * j + 1];
         const float dx = q0.x - pixfx, dy = q0.y - pixfy;
-        const float4 q1 = s_q1[j];
-        // -0.5f*(A*dx*dx + C*dy*dy) - B*dx*dy, in the op order nvcc gives that expression
-        const float s = __fmaf_rn(__fmul_rn(q0.z, dx), dx, __fmul_rn(__fmul_rn(q1.x, dy), dy));
-        const float power = __fmaf_rn(s, -0.5f, -__fmul_rn(__fmul_rn(q0.w, dx), dy));
-        if (power > 0.0f) continue;
-        const float alpha = fminf(0.99f, __fmul_rn(q1.y, splat_exp(power)));
-        if (alpha < 1.0f / 255.0f) continue;
+        const float kp = render_power(q0.z, q0.w, q1.x, dx, dy);
+        const float alpha = fminf(0.99f, __fmul_rn(q1.y, render_exp(kp)));
+        if ((kp > 0.0f) | (alpha < 1.0f / 255.0f)) continue;     // the reference's two skips (power > 0, alpha < 1/255)
         const float test_T = __fmul_rn(T, 1.0f - alpha);
         if (test_T < 0.0001f) { done = true; break; }
         const float w = __fmul_rn(alpha, T);
-        const float2 q2 = make_float2(s_q2[j].x, s_q2[j].y);
+        const float4 q2 = rows[4 * j + 2];
         C0 = __fmaf_rn(q1.w, w, C0);
         C1 = __fmaf_rn(q2.x, w, C1);
         C2 = __fmaf_rn(q2.y, w, C2);
@@ -138,15 +181,12 @@ render_forward_kernel(int W, int H, int grid_x, uint2* __restrict__ ranges,
       }
       if (lastj >= 0) last_contributor = (uint32_t)(base + lastj + 1);   // 1-based position in the tile list
     }
-    {
-      __syncthreads();
-      const int nfetch = todo < RB ? todo : RB;
-      if ((int)threadIdx.x < nfetch) {
-        uint32_t bits = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < cnt) {
+      uint32_t bits = 0;
 #pragma unroll
-        for (int w = 0; w < RB / 32; w++) bits |= (uint32_t)sm.hitw[w][threadIdx.x] << w;
-        hit[range.x + base + threadIdx.x] = (uint8_t)bits;
-      }
+      for (int w = 0; w < RB / 32; w++) bits |= (uint32_t)sm.hitw[w][threadIdx.x] << w;
+      hit[range.x + (uint32_t)base + threadIdx.x] = (uint8_t)bits;
     }
   }
   if (inside) {
@@ -160,23 +200,83 @@ render_forward_kernel(int W, int H, int grid_x, uint2* __restrict__ ranges,
     out_depth[pix] = Dp;
     if (ALPHA) out_alpha[pix] = Ac;     // bg = 0 in the reference's alpha pass
   }
+  // Tile order of the backward: cost bucket = deepest contributor of the tile / 32; a unique rank inside the bucket
+  // comes from one atomic per tile (render_bwd.cu: ordered_tile).
+  {
+    const uint32_t m = __reduce_max_sync(0xffffffffu, last_contributor);
+    if (lane == 0 && m) atomicMax(&s_deepest, m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t b = min(s_deepest >> 5, (uint32_t)(TILE_BUCKETS - 1));
+      const uint32_t r = atomicAdd(&bcount[b], 1u);
+      btile[(size_t)b * gridDim.x + r] = (uint32_t)tile;
+    }
+  }
 }
 
-void launch_render_forward(int W, int H, uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
-                           const SplatRec* rec,
-                           const float* bg, float* out_color, float* out_depth, float* out_alpha, float* final_T,
-                           uint32_t* n_contrib, uint8_t* hit, GradRec* zero_grad, size_t P, cudaStream_t s) {
+// ---- tensor map over the SplatRec table: [P] rows of 12 floats, box = 16 floats x 1 row (the 4 floats past the row
+// are out of bounds of the 12-wide tensor and arrive as zeros), so that a gathered row fills one 64-byte smem row.
+// cuTensorMapEncodeTiled comes from the driver through the runtime (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool make_rec_tensor_map(const SplatRec* rec, size_t P, void* out_map) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || P == 0) return false;
+  const cuuint64_t dims[2] = {12, (cuuint64_t)P};
+  const cuuint64_t strides[1] = {sizeof(SplatRec)};          // bytes between rows (dimension 1)
+  const cuuint32_t box[2] = {16, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<SplatRec*>(rec), dims,
+            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool fwd_stage_tma() {      // SFB_FWD_STAGE=ldg: three 16-byte loads per thread instead of the TMA row gather (A/B)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SFB_FWD_STAGE"); v = (e && e[0] == 'l') ? 0 : 1; }
+  return v == 1;
+}
+
+int launch_render_forward(int W, int H, uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
+                          const SplatRec* rec,
+                          const float* bg, float* out_color, float* out_depth, float* out_alpha, float* final_T,
+                          uint32_t* n_contrib, uint8_t* hit, uint32_t* bcount, uint32_t* btile, GradRec* zero_grad,
+                          size_t P, cudaStream_t s) {
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
   // GradRec = 3 x 16 bytes; 32-bit word counts cover P < 2^30 (checked by the caller for num_rendered anyway)
   float4* const zero16 = (zero_grad && P > 0 && P < ((size_t)1 << 30)) ? reinterpret_cast<float4*>(zero_grad) : nullptr;
   const uint32_t zero_total = zero16 ? (uint32_t)(P * 3) : 0u;
   const uint32_t zero_per_cta = zero16 ? (zero_total + (uint32_t)(gx * gy) - 1u) / (uint32_t)(gx * gy) : 0u;
-  if (out_alpha)
-    render_forward_kernel<true><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, idx_mask, rec, bg, out_color, out_depth,
-                                                       out_alpha, final_T, n_contrib, hit, zero16, zero_per_cta, zero_total);
-  else
-    render_forward_kernel<false><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, idx_mask, rec, bg, out_color, out_depth,
-                                                        out_alpha, final_T, n_contrib, hit, zero16, zero_per_cta, zero_total);
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  const bool tma = fwd_stage_tma();
+  if (tma && !make_rec_tensor_map(rec, P, &map)) {
+    set_error("cuTensorMapEncodeTiled failed for the splat record table (TMA staging of the tile lists)");
+    return -1;
+  }
+#define SFB_RF(A, TM)                                                                                               \
+  render_forward_kernel<A, TM><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, idx_mask, rec, map, bg, out_color, \
+                                                      out_depth, out_alpha, final_T, n_contrib, hit, bcount, btile, \
+                                                      zero16, zero_per_cta, zero_total)
+  if (tma) { if (out_alpha) SFB_RF(true, true); else SFB_RF(false, true); }
+  else     { if (out_alpha) SFB_RF(true, false); else SFB_RF(false, false); }
+#undef SFB_RF
+  return 0;
 }
 
 }  // namespace sfb

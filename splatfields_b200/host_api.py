@@ -44,6 +44,11 @@ class ViewParallelRasterizer:
                  bg=(1.0, 1.0, 1.0), exchange: str | None = None):
         self.device = torch.device(device)
         self.world = int(world_size)
+        self.rank = 0
+        if self.world > 1:
+            import torch.distributed as dist
+            self.rank = dist.get_rank()
+        self.factored_output = None      # single rank: a [P*3] tensor here keeps the SH gradient factored (HostPipeline)
         self.sh_degree = int(sh_degree)
         exchange = exchange or os.environ.get("SFB_EXCHANGE") or ("nvlink" if self.device.type == "cuda" else "factored")
         if exchange not in ("nvlink", "factored", "allreduce"):
@@ -168,7 +173,8 @@ class ViewParallelRasterizer:
         nvlink = self.exchange == "nvlink"
         if nvlink:
             self.xchg_epoch += 1
-        rasterizer.set_grad_arena(self.slab, self.fields, self.dcolor_mine.view(self.P, 3) if factored else None,
+        sh_out = self.dcolor_mine if factored else (self.factored_output if self.world == 1 else None)
+        rasterizer.set_grad_arena(self.slab, self.fields, None if sh_out is None else sh_out.view(self.P, 3),
                                   (self.xchg, self.xchg_epoch) if nvlink else None)
         try:
             # mean over views (train.py:242) folded into the cotangent: backward is linear in it
@@ -179,8 +185,8 @@ class ViewParallelRasterizer:
         # normally a no-op: the backward kernel already wrote into the slab slices (the .grad tensors ARE
         # those slices); copy only if autograd handed back separate storage.
         for name, dst in self.grads().items():
-            if nvlink or (factored and name == "shs"):
-                continue                     # filled by the exchange below
+            if nvlink or (sh_out is not None and name == "shs"):
+                continue                     # filled by the exchange below / kept factored
             g = p[name].grad
             if g is None:
                 dst.zero_()
@@ -292,21 +298,98 @@ class ViewParallelRasterizer:
                     max_list=int(lens.max()), R_fwd=r_fwd, R_bwd=r_bwd)
 
     # -- pinned host mirrors of every input and output of one step
-    def pinned_host_buffers(self, scene: dict, cotangent: torch.Tensor):
-        pin = lambda t: t.detach().cpu().contiguous().pin_memory()
-        host_in = {k: pin(v) for k, v in scene.items()}
-        host_in["dL_dcolor"] = pin(cotangent)
-        host_out = dict(color=torch.empty(3, self.H, self.W).pin_memory(),
-                        depth=torch.empty(1, self.H, self.W).pin_memory(),
-                        radii=torch.empty(self.P, dtype=torch.int32).pin_memory(),
-                        grads=torch.empty(self.floats_per_splat * self.P).pin_memory())
+    def shard_rows(self):
+        """Rows [r0, r1) of the P splats this rank moves between host and device in sharded host-buffer steps."""
+        per = (self.P + self.world - 1) // self.world
+        r = self.rank if self.world > 1 else 0
+        return min(r * per, self.P), min((r + 1) * per, self.P), per
+
+    def pinned_host_buffers(self, scene: dict, cotangent: torch.Tensor, shard: bool = False, factored: bool = False):
+        """Pinned host mirrors of one step.  shard=True (world > 1): the job's ONE host copy of the splats is split by
+        rows over the ranks — this rank's buffers hold rows shard_rows() of every parameter and of every gradient
+        field.  factored=True (world == 1): the SH gradient stays in its factored form (grads = 11 geometry floats +
+        3 colour-gradient floats per splat, rebuilt on demand by sh_rows_from_factored)."""
+        r0, r1, _ = self.shard_rows() if shard else (0, self.P, self.P)
+        with numa_local(self.device):       # first touch on the GPU's own NUMA node
+            pin = lambda t: t.detach().cpu().contiguous().pin_memory()
+            host_in = {k: pin(v[r0:r1]) for k, v in scene.items()}
+            host_in["dL_dcolor"] = pin(cotangent)
+            nfl = (self.floats_per_splat - (self.fields[-1][1] - 3 if factored else 0)) * (r1 - r0)
+            host_out = dict(color=torch.empty(3, self.H, self.W).pin_memory(),
+                            depth=torch.empty(1, self.H, self.W).pin_memory(),
+                            radii=torch.empty(self.P, dtype=torch.int32).pin_memory(),
+                            grads=torch.empty(nfl).pin_memory())
         self._cot_dev = torch.empty_like(cotangent, device=self.device)
         return host_in, host_out
 
 
+class numa_local:
+    """Context manager: run the calling thread on the CPUs next to `device` (NVML's ideal affinity), so that pinned
+    host buffers allocated inside land on the GPU's own NUMA node (first touch); restores the affinity afterwards.
+    A no-op when NVML or the affinity calls are unavailable."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.saved = None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                tok = vis.split(",")[idx].strip()
+                h = pynvml.nvmlDeviceGetHandleByIndex(int(tok)) if tok.isdigit() else pynvml.nvmlDeviceGetHandleByUUID(tok)
+            else:
+                h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.saved = os.sched_getaffinity(0)
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+            self.cpus = sorted(os.sched_getaffinity(0))
+        except Exception:
+            self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:
+                pass
+        return False
+
+
+def sh_rows_from_factored(means3D, campos, dcolor, sh_degree, M=16):
+    """dL_dsh [P, M, 3] from the factored gradient of ONE view (host or device tensors, plain torch): the rows the
+    rasterizer would have written — basis(normalize(means3D - campos)) (x) dcolor.  For host-side consumers of
+    HostPipeline(factored=True) that need the rows of some splats."""
+    d = means3D - campos.reshape(1, 3)
+    d = d / d.norm(dim=1, keepdim=True)
+    x, y, z = d[:, 0], d[:, 1], d[:, 2]
+    C0, C1 = 0.28209479177387814, 0.4886025119029199
+    C2 = (1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396)
+    C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+          1.445305721320277, -0.5900435899266435)
+    b = [torch.full_like(x, C0)]
+    if sh_degree > 0:
+        b += [-C1 * y, C1 * z, -C1 * x]
+    if sh_degree > 1:
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        b += [C2[0] * xy, C2[1] * yz, C2[2] * (2 * zz - xx - yy), C2[3] * xz, C2[4] * (xx - yy)]
+    if sh_degree > 2:
+        b += [C3[0] * y * (3 * xx - yy), C3[1] * xy * z, C3[2] * y * (4 * zz - xx - yy),
+              C3[3] * z * (2 * zz - 3 * xx - 3 * yy), C3[4] * x * (4 * zz - xx - yy), C3[5] * z * (xx - yy),
+              C3[6] * x * (xx - 3 * yy)]
+    B = torch.stack(b, dim=1)                                     # [P, (deg+1)^2]
+    out = torch.zeros(means3D.shape[0], M, 3, dtype=means3D.dtype, device=means3D.device)
+    out[:, :B.shape[1], :] = B.unsqueeze(2) * dcolor.unsqueeze(1)
+    return out
+
+
 def forward_backward_host(vp: ViewParallelRasterizer, host_in: dict, host_out: dict) -> None:
-    """HOST buffers in, HOST buffers out: H2D of all splat parameters + cotangent, fwd + bwd
-    (+ all-reduce), D2H of image, depth, radii and the gradient slab; returns when the host buffers are valid."""
+    """HOST buffers in, HOST buffers out, nothing overlapped: H2D of all splat parameters + cotangent, fwd + bwd
+    (+ exchange), D2H of image, depth, radii and the gradient slab; returns when the host buffers are valid.
+    (Whole-scene buffers: pinned_host_buffers(shard=False).)"""
     with torch.no_grad():
         for k, v in vp.params.items():
             v.copy_(host_in[k], non_blocking=True)
@@ -323,21 +406,36 @@ def forward_backward_host(vp: ViewParallelRasterizer, host_in: dict, host_out: d
 class HostPipeline:
     """Asynchronous HOST-buffer front end: `submit(host_in, host_out)` / `wait(ticket)`.
 
-    Every step still moves all of its inputs host->device and all of its results device->host, but on
-    three streams with double-buffered device staging, so that the upload of step k+1, the kernels of step
-    k and the download of step k-1 overlap (PCIe is full duplex; the kernels take ~1/4 of either copy).
-    """
+    Every step moves all of its inputs host->device and all of its results device->host, on three streams with
+    double-buffered device staging, so that the upload of step k+1, the kernels of step k and the download of step
+    k-1 overlap (PCIe is full duplex; the kernels take ~1/4 of either copy).
 
-    def __init__(self, vp: ViewParallelRasterizer, depth: int = 2):
+    shard=True (the default with more than one rank): the job has ONE host copy of the splats, so every rank uploads
+    rows shard_rows() of each parameter and the ranks all-gather the rest over NVLink (5 in-place NCCL all-gathers on
+    the compute stream) instead of pushing the same 236 B/splat through the host N times; likewise every rank
+    downloads its rows of the SUMMED gradient slab (identical on all ranks) plus its own image, depth and radii.
+    factored=True (single rank): the SH gradient is downloaded in its factored form (3 floats per splat,
+    SFB_BWD_SH_FACTORED; sh_rows_from_factored rebuilds rows on demand): 56 instead of 236 bytes per splat."""
+
+    def __init__(self, vp: ViewParallelRasterizer, depth: int = 2, shard: bool | None = None, factored: bool = False):
         self.vp = vp
         dev = vp.device
         self.depth = depth
+        self.shard = (vp.world > 1) if shard is None else bool(shard and vp.world > 1)
+        self.factored = bool(factored)
+        if self.factored and (vp.world > 1 or "shs" not in vp.params):
+            raise Exception("factored host output is the single-rank SH path")
+        self.r0, self.r1, self.per = vp.shard_rows() if self.shard else (0, vp.P, vp.P)
         self.s_h2d = torch.cuda.Stream(dev)
         self.s_comp = torch.cuda.Stream(dev)
         self.s_d2h = torch.cuda.Stream(dev)
-        self.in_dev = [{k: torch.empty_like(v.detach()) for k, v in vp.params.items()} for _ in range(depth)]
+        # staging: per parameter [world * per, ...] rows so that every rank's shard has the same size (in-place all-gather)
+        rows = self.per * vp.world if self.shard else vp.P
+        self.in_dev = [{k: torch.empty((rows,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
+                        for k, v in vp.params.items()} for _ in range(depth)]
         self.cot_dev = [torch.empty(3, vp.H, vp.W, device=dev) for _ in range(depth)]
         self.slabs = [torch.empty_like(vp.slab) for _ in range(depth)]
+        self.dcol = [torch.empty(vp.P * 3, dtype=torch.float32, device=dev) for _ in range(depth)] if self.factored else None
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]
         self.ev_comp = [torch.cuda.Event() for _ in range(depth)]
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]
@@ -346,15 +444,22 @@ class HostPipeline:
         for s in (self.s_h2d, self.s_comp, self.s_d2h):
             s.wait_stream(torch.cuda.current_stream(dev))
 
+    def h2d_bytes(self, host_in: dict) -> int:
+        return sum(t.numel() * t.element_size() for t in host_in.values())
+
+    def d2h_bytes(self, host_out: dict) -> int:
+        return sum(t.numel() * t.element_size() for t in host_out.values())
+
     def submit(self, host_in: dict, host_out: dict) -> int:
         vp, k = self.vp, self.n
         b = k % self.depth
+        r0, r1 = self.r0, self.r1
         # upload into staging set b (free once the compute that last read it has finished)
         with torch.cuda.stream(self.s_h2d):
             if k >= self.depth:
                 self.s_h2d.wait_event(self.ev_comp[b])
             for name, t in self.in_dev[b].items():
-                t.copy_(host_in[name], non_blocking=True)
+                t[r0:r1].copy_(host_in[name], non_blocking=True)
             self.cot_dev[b].copy_(host_in["dL_dcolor"], non_blocking=True)
             self.ev_in[b].record(self.s_h2d)
         # compute on the staged inputs, gradients into slab b (free once its previous download is done)
@@ -362,9 +467,17 @@ class HostPipeline:
             self.s_comp.wait_event(self.ev_in[b])
             if k >= self.depth:
                 self.s_comp.wait_event(self.ev_out[b])
+            if self.shard:
+                import torch.distributed as dist
+                for name, t in self.in_dev[b].items():      # in place: this rank's rows sit where the gather puts them
+                    flat = t.view(-1)
+                    n = flat.numel() // vp.world
+                    dist.all_gather_into_tensor(flat, flat[vp.rank * n:(vp.rank + 1) * n])
             for name, p in vp.params.items():
-                p.data = self.in_dev[b][name]
+                p.data = self.in_dev[b][name][:vp.P]
             vp.slab = self.slabs[b]
+            if self.factored:
+                vp.factored_output = self.dcol[b]
             vp.step(self.cot_dev[b], keep=True)
             color, radii, depth = vp.last
             self.ev_comp[b].record(self.s_comp)
@@ -375,7 +488,19 @@ class HostPipeline:
             host_out["color"].copy_(color, non_blocking=True)
             host_out["depth"].copy_(depth, non_blocking=True)
             host_out["radii"].copy_(radii, non_blocking=True)
-            host_out["grads"].copy_(self.slabs[b], non_blocking=True)
+            # gradient fields, rows [r0, r1) of each (the slab is field-major: every field is one [P, n] run)
+            off_dev, off_host = 0, 0
+            for name, nf in vp.fields:
+                if self.factored and name == "shs":
+                    src = self.dcol[b]
+                    nf_out = 3
+                else:
+                    src = self.slabs[b][off_dev * vp.P:(off_dev + nf) * vp.P]
+                    nf_out = nf
+                cnt = (r1 - r0) * nf_out
+                host_out["grads"][off_host:off_host + cnt].copy_(src[r0 * nf_out:r1 * nf_out], non_blocking=True)
+                off_dev += nf
+                off_host += cnt
             self.ev_out[b].record(self.s_d2h)
         self.live[b] = (color, radii, depth)
         self.n += 1
