@@ -78,6 +78,55 @@ def build(force: bool = False, verbose: bool = False, variant: str = "", force_s
     return LIB
 
 
+MANIFEST = os.path.join(HERE, "sass_manifest.json")
+
+
+def sass_digest(lib: str = LIB) -> dict:
+    """sha256 over the SASS of every kernel in the library (mangled name + instruction text and operands, addresses and
+    encodings stripped): identifies the machine code independently of link order and file timestamps."""
+    import hashlib
+    import re
+    cuobjdump = os.path.join(os.path.dirname(nvcc()), "cuobjdump")
+    txt = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True, check=True).stdout
+    kernels, cur = {}, None
+    for ln in txt.splitlines():
+        m = re.search(r"Function : (\S+)", ln)
+        if m:
+            cur = m.group(1)
+            kernels[cur] = hashlib.sha256()
+        elif cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+            ins = re.sub(r"\s+", " ", re.sub(r"/\*[0-9a-f]+\*/", "", ln)).strip()
+            kernels[cur].update(ins.encode() + b"\n")
+    h = hashlib.sha256()
+    for name in sorted(kernels):
+        h.update(name.encode() + b"=" + kernels[name].hexdigest().encode() + b"\n")
+    ver = subprocess.run([nvcc(), "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    return {"digest": h.hexdigest(), "kernels": len(kernels), "nvcc": ver}
+
+
+def write_manifest() -> dict:
+    import json
+    d = sass_digest(build())
+    with open(MANIFEST, "w") as f:
+        json.dump(d, f, indent=1)
+        f.write("\n")
+    return d
+
+
+def check_manifest() -> dict:
+    """The committed manifest must describe the library that was just built from the committed sources."""
+    import json
+    got = sass_digest(LIB)
+    want = json.load(open(MANIFEST))
+    if got["digest"] != want["digest"] or got["kernels"] != want["kernels"]:
+        raise RuntimeError(f"libsplat_b200.so does not match splatfields_b200/sass_manifest.json: built {got}, "
+                           f"manifest {want} (after changing a kernel: python -m splatfields_b200.build --write-manifest)")
+    return got
+
+
 if __name__ == "__main__":
+    if "--write-manifest" in sys.argv:
+        print(write_manifest())
+        sys.exit(0)
     var = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), "")
     print(build(force="--force" in sys.argv, verbose="--quiet" not in sys.argv, variant=var))

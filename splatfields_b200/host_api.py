@@ -239,6 +239,40 @@ class ViewParallelRasterizer:
             self.exchange_events.append(ev)
         return n
 
+    def side_outputs(self, mode: str = "last") -> dict:
+        """The per-view side outputs the densification bookkeeping consumes (radii -> max_radii2D, train.py:280-286;
+        viewspace_points.grad -> add_densification_stats, train.py:306-311, scene/gaussian_model.py:427-430), made
+        IDENTICAL on every rank so that the replicated splat sets take the same clone / split / prune decisions.
+        Call after step(..., keep=True).
+          mode="last": the last view's values (rank world-1), i.e. exactly what the reference's serial loop keeps
+                       (train.py:178 overwrites render_pkg per view): dict(radii [P] int32, visibility_filter [P] bool,
+                       viewspace_grad [P,3]) — feed them to densify.add_densification_stats as they are.
+          mode="all":  statistics over ALL views of the step: radii = max over views, grad_norm = sum over the views of
+                       ||viewspace_grad[:, :2]|| where the splat was visible, count = number of such views
+                       (xyz_gradient_accum += grad_norm; denom += count).
+        Two small collectives (16 B/splat), off the critical path of the gradient exchange."""
+        import torch.distributed as dist
+        if self.last is None:
+            raise Exception("side_outputs() needs step(..., keep=True)")
+        radii = self.last[1].to(torch.int32).contiguous()
+        g2 = self.means2D.grad
+        g2 = torch.zeros(self.P, 3, device=self.device) if g2 is None else g2.detach().contiguous()
+        if mode == "last":
+            if self.world > 1:
+                radii, g2 = radii.clone(), g2.clone()
+                dist.broadcast(radii, src=self.world - 1)
+                dist.broadcast(g2, src=self.world - 1)
+            return dict(radii=radii, visibility_filter=radii > 0, viewspace_grad=g2)
+        if mode != "all":
+            raise Exception("mode must be 'last' or 'all'")
+        vis = (radii > 0).to(torch.float32)
+        stats = torch.stack([g2[:, :2].norm(dim=1) * vis, vis])           # [2, P]
+        rmax = radii.clone()
+        if self.world > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+            dist.all_reduce(rmax, op=dist.ReduceOp.MAX)
+        return dict(radii=rmax, visibility_filter=rmax > 0, grad_norm=stats[0], count=stats[1])
+
     def exchange_ms(self) -> list:
         """Device time of the gradient exchange (collectives + SH rebuild) of the steps run with time_exchange."""
         torch.cuda.synchronize(self.device)

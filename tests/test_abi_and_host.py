@@ -28,6 +28,14 @@ def test_library_exports_every_declared_symbol():
     assert lib.sfb_last_error() == b""
 
 
+def test_committed_sass_manifest_describes_the_built_library():
+    """splatfields_b200/sass_manifest.json (checked by __graft_entry__.build() after a forced rebuild) is up to date:
+    regenerate it with `python -m splatfields_b200.build --write-manifest` after touching a kernel."""
+    _built()
+    from splatfields_b200 import build
+    assert build.check_manifest()["kernels"] > 50
+
+
 def test_loss_window_is_the_reference_window_bit_for_bit():
     """Host-side piece of the fused loss: the 11 weights equal loss_utils.gaussian(11, 1.5) as the reference computed
     them (golden file), and the scratch size follows the documented layout (3 maps + block partials)."""

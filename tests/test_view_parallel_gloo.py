@@ -254,3 +254,87 @@ def test_slab_layout_follows_sh_coefficient_count():
     vp = ViewParallelRasterizer(rgb, synth.orbit_camera(0, 16, 16), 16, 16, 0, device="cpu")
     assert [k for k in vp.grads()] == ["means3D", "opacities", "scales", "rotations", "colors_precomp"]
     assert vp.floats_per_splat == 14 and vp.exchange == "allreduce"
+
+
+# ------------------------------------------------------------------------------------------------ side outputs
+class _StubRastSide(_StubRast):
+    """Stand-in whose radii and means2D gradient depend on the camera, like the rasterizer's per-view side outputs."""
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        color, _, depth = super().forward(means3D, means2D, opacities, shs=shs, scales=scales, rotations=rotations)
+        hom = torch.cat([means3D, torch.ones_like(means3D[:, :1])], 1) @ self.cam.full_proj_transform
+        radii = (hom[:, 0].detach() * 7).round().clamp(min=0).to(torch.int32)          # some splats invisible (0)
+        color = color + (means2D[:, :2] * hom[:, :2].detach()).sum() * 1e-3
+        return color, radii, depth
+
+
+def _serial_side(sc, world, P, H, W):
+    """The reference's serial loop (train.py:169-178): only the LAST view's radii / viewspace gradient survive."""
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+    per_view = []
+    for r in range(world):
+        c = synth.orbit_camera(r, H, W)
+        Gr = torch.randn(3, H, W, generator=torch.Generator().manual_seed(100 + r))
+        m2d = torch.zeros(P, 3, requires_grad=True)
+        col, radii, _ = _StubRastSide(c, H, W)(leaves["means3D"], m2d, leaves["opacities"], shs=leaves["shs"],
+                                               scales=leaves["scales"], rotations=leaves["rotations"])
+        ((col * Gr).sum() / world).backward()
+        per_view.append((radii, m2d.grad.clone()))
+    return per_view
+
+
+def _worker_side(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P, H, W = 40, 8, 12
+        sc = synth.make_scene(P, 5)
+        cam = synth.orbit_camera(rank, H, W)
+        vp = ViewParallelRasterizer(sc, cam, H, W, 3, device="cpu", world_size=world, exchange="allreduce")
+        vp.rast = _StubRastSide(cam, H, W)
+        G = torch.randn(3, H, W, generator=torch.Generator().manual_seed(100 + rank))
+        vp.step(G, keep=True)
+        last = vp.side_outputs("last")
+        allv = vp.side_outputs("all")
+        per_view = _serial_side(sc, world, P, H, W)
+        r_last, g_last = per_view[-1]
+        ok = torch.equal(last["radii"], r_last) and torch.allclose(last["viewspace_grad"], g_last, rtol=1e-5, atol=1e-7)
+        ok = ok and torch.equal(last["visibility_filter"], r_last > 0)
+        rmax = torch.stack([r for r, _ in per_view]).max(0).values
+        gsum = sum(g[:, :2].norm(dim=1) * (r > 0) for r, g in per_view)
+        cnt = sum((r > 0).float() for r, _ in per_view)
+        ok = ok and torch.equal(allv["radii"], rmax) and torch.allclose(allv["grad_norm"], gsum, rtol=1e-5, atol=1e-7)
+        ok = ok and torch.equal(allv["count"], cnt) and bool((cnt == 0).any()) and bool((cnt > 0).any())
+        # the bookkeeping that follows (scene/gaussian_model.py:427-430, train.py:280-282) gives every rank the same state
+        acc, den, mr = torch.zeros(P), torch.zeros(P), torch.zeros(P)
+        f = last["visibility_filter"]
+        acc[f] += last["viewspace_grad"][f, :2].norm(dim=1)
+        den[f] += 1
+        mr[f] = torch.max(mr[f], last["radii"][f].float())
+        state = torch.stack([acc, den, mr])
+        ref = state.clone()
+        dist.broadcast(ref, src=0)
+        ok = ok and torch.equal(state, ref)
+        ret.put(bool(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_side_outputs_match_the_serial_loop_on_every_rank():
+    """radii / viewspace gradient of the LAST view (train.py:178) reach every rank; the 'all' statistics are the
+    max / sum over the views; the densification state built from them is identical across ranks."""
+    world = 3
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_worker_side, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert [ret.get(timeout=5) for _ in range(world)] == [True] * world
