@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--rounds", type=int, default=24)
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--views", type=int, default=6)
+    ap.add_argument("--exchange", default=None, help="nvlink (default when every rank has a job in every round) | allreduce")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -31,9 +32,12 @@ def main():
     P, H, W = cfg["P"], cfg["H"], cfg["W"]
     sc = synth.make_scene(P, cfg["seed"], scale_mult=cfg["scale_mult"], precomp_rgb=cfg["precomp_rgb"])
     base = sc["means3D"].to(dev)
-    vp = ViewParallelRasterizer(sc, synth.config_camera("owlii_2m", 0), H, W, 0, device=dev, world_size=world,
-                                exchange="allreduce")
     jobs = synth.view_time_jobs(a.frames, a.views, rank, world)[: a.rounds + 3]
+    # ranks render different time steps: the [P, 14] parameter gradients are summed as they are (no SH factorisation);
+    # the NVLink exchange needs a job on every rank in every round (no idle contributions)
+    exchange = a.exchange or ("nvlink" if (a.frames * a.views) % world == 0 else "allreduce")
+    vp = ViewParallelRasterizer(sc, synth.config_camera("owlii_2m", 0), H, W, 0, device=dev, world_size=world,
+                                exchange=exchange)
     G = torch.randn(3, H, W, generator=torch.Generator().manual_seed(rank)).to(dev)
     offsets = {f: synth.frame_offset(P, f / a.frames, cfg["seed"]).to(dev) for f in {j[0] for j in jobs if j}}
 
@@ -67,7 +71,8 @@ def main():
         dist.all_reduce(njobs)
     if rank == 0:
         t = float(ms.item()) * 1e-3
-        print(json.dumps({"config": "owlii_2m view x time", "world": world, "jobs": int(njobs.item()),
+        print(json.dumps({"config": "owlii_2m view x time", "world": world, "exchange": vp.exchange,
+                          "multicast": getattr(vp, "xchg_multicast", None), "jobs": int(njobs.item()),
                           "rounds": len(jobs) - 3, "ms_per_round": t * 1e3 / max(len(jobs) - 3, 1),
                           "jobs_per_s": float(njobs.item()) / t, "msplats_s": float(njobs.item()) * P / t / 1e6}),
               flush=True)

@@ -210,12 +210,13 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   if (num_rendered) *num_rendered = (int)R;
 
   const InstPacking pk = inst_packing((size_t)P, (size_t)T);
-  const bool packed = pk.idx_bits > 0;
-  char* bchunk = (char*)binning_alloc(binning_user, BinState::required((size_t)R, (size_t)T, packed));
+  if (!pk.ok) return fail(SFB_ERR_ARG, "ceil(log2 P) + ceil(log2 tiles) > 40 bits is not supported");
+  const bool split = pk.high_bits > 0;
+  char* bchunk = (char*)binning_alloc(binning_user, BinState::required((size_t)R, (size_t)T, split));
   if (!bchunk) return fail(SFB_ERR_ALLOC, "binning buffer allocation failed");
   RedzoneList rzb;
   if (debug) redzone_collector() = &rzb;
-  BinState b = BinState::from_chunk(bchunk, (size_t)R, (size_t)T, packed);
+  BinState b = BinState::from_chunk(bchunk, (size_t)R, (size_t)T, split);
   redzone_collector() = nullptr;
   if (debug && redzones_fill(rzb, s)) return fail(SFB_ERR_CUDA, "red-zone fill");
 
@@ -225,15 +226,16 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
     // every tile range to "empty"); stage 3: stable sort by tile id
     const size_t tzero = radix_sort_zero_words((int)R, tile_bits(T));
     prof_begin("duplicate", s);
-    launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, b.tile_key[0], b.inst_idx[0],
-                     pk.idx_bits, tzero ? b.sort_hist : nullptr, tzero, b.ranges, T, img.tile_bcount, s);
+    launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, b.tile_key[0], b.inst_hi[0],
+                     pk.low_bits, tzero ? b.sort_hist : nullptr, tzero, b.ranges, T, img.tile_bcount, s);
     prof_end(s);
     g_launches++;
     CK_LAUNCH("duplicate", debug, s);
-    // packed: bare 32-bit words, digits start above the index bits; unpacked: (tile, index) pairs from bit 0.
+    // bare 32-bit words (+ one side byte per instance when the index does not fit), digits start above the index bits.
     // The last pass also writes the per-tile [start, end) ranges (K5): it sees every sorted key on its way out.
-    tfinal = radix_sort_pairs(b.tile_key, b.inst_idx, b.sort_hist, (int)R, tile_bits(T), s, &g_launches, kTileSortNames,
-                              nullptr, pk.idx_bits, tzero != 0, b.ranges, pk.idx_bits);
+    tfinal = radix_sort_pairs(b.tile_key, nullptr, b.sort_hist, (int)R, tile_bits(T), s, &g_launches, kTileSortNames,
+                              nullptr, pk.low_bits, tzero != 0, b.ranges, pk.low_bits, split ? b.inst_hi : nullptr,
+                              split ? pk.low_bits : 0);
     CK_LAUNCH("tile sort", debug, s);
   } else {
     CK(cudaMemsetAsync(b.ranges, 0, sizeof(uint2) * (size_t)T, s));     // nothing to render: every tile is (0, 0)
@@ -241,7 +243,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   }
 
   prof_begin("render_forward", s);
-  if (launch_render_forward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, bg, out_color, out_depth,
+  if (launch_render_forward(W, H, b.ranges, b.point_list(tfinal), pk.idx_mask, g.rec, bg, out_color, out_depth,
                             out_alpha, img.final_T, img.n_contrib, b.hit, img.tile_bcount, img.tile_btile, g.grad,
                             (size_t)P, s) != 0)
     return fail(SFB_ERR_CUDA, g_err.c_str());
@@ -305,8 +307,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   GeomState g = GeomState::from_chunk(gchunk, (size_t)P);
   char* bchunk = (char*)binning_buffer;
   const InstPacking pk = inst_packing((size_t)P, (size_t)T);
-  const bool packed = pk.idx_bits > 0;
-  BinState b = BinState::from_chunk(bchunk, (size_t)num_rendered, (size_t)T, packed);
+  BinState b = BinState::from_chunk(bchunk, (size_t)num_rendered, (size_t)T, pk.high_bits > 0);
   char* ichunk = (char*)img_buffer;
   ImgState img = ImgState::from_chunk(ichunk, HW, (size_t)T);
   redzone_collector() = nullptr;
@@ -321,7 +322,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
     prof_end(s);
   }
   prof_begin("render_backward", s);
-  if (launch_render_backward(W, H, b.ranges, b.point_list(tfinal, packed), pk.idx_mask, g.rec, (size_t)P, bg, img.final_T,
+  if (launch_render_backward(W, H, b.ranges, b.point_list(tfinal), pk.idx_mask, g.rec, (size_t)P, bg, img.final_T,
                              img.n_contrib, dL_dout_color, dL_dout_alpha, b.hit, img.tile_bcount, img.tile_btile, g.grad,
                              s) != 0)
     return fail(SFB_ERR_CUDA, g_err.c_str());
@@ -487,11 +488,10 @@ int sfb_export_binning(int P, int num_rendered, int W, int H, const void* geom_b
   GeomState g = GeomState::from_chunk(gchunk, (size_t)P);
   char* bchunk = (char*)binning_buffer;
   const InstPacking pk = inst_packing((size_t)P, (size_t)T);
-  const bool packed = pk.idx_bits > 0;
-  BinState b = BinState::from_chunk(bchunk, (size_t)num_rendered, (size_t)T, packed);
+  BinState b = BinState::from_chunk(bchunk, (size_t)num_rendered, (size_t)T, pk.high_bits > 0);
   const int tfinal = num_rendered > 0 ? tile_sort_final(T) : 0;
   if (point_list_keys || point_list)
-    launch_export_keys(num_rendered, b.tile_key[tfinal], packed ? nullptr : b.inst_idx[tfinal], pk.idx_bits, g.rec,
+    launch_export_keys(num_rendered, T, b.tile_key[tfinal], pk.high_bits > 0, pk.low_bits, b.ranges, g.rec,
                        point_list_keys, point_list, s);
   if (ranges) CK(cudaMemcpyAsync(ranges, b.ranges, sizeof(uint2) * (size_t)T, cudaMemcpyDeviceToDevice, s));
   CK_LAUNCH("export_binning", 0, s);

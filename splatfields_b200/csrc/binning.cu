@@ -114,16 +114,20 @@ radix_hist_all_kernel(uint32_t* __restrict__ keys, int n, int npass, int4 shifts
 
 // IPT items per thread: 16 (4096-item tiles) for large inputs, 4 (1024-item tiles) when 4096-item tiles
 // would leave most SMs idle and every block a long latency chain.
-// HAS_VALS = false sorts bare 32-bit words (the packed tile|index instances): nothing but keys is staged or moved.
+// VM (value mode): 0 sorts bare 32-bit words (the packed tile|index instances: nothing but keys is staged or moved),
+// 2 moves a 32-bit value with every key (the depth sort: depth bits -> Gaussian index), 1 moves ONE BYTE with every key
+// (instances whose tile | index does not fit 32 bits: the index bits that do not fit ride along, 5 instead of 8 bytes
+// per instance and pass) and, on the last pass (merge_bits > 0), re-assembles the full index
+// (key & low mask) | byte << merge_bits  as the only output word: the render kernels read a plain index list.
 // NB = digit bits the ranking resolves with ballots (6, 7 or 8 >= log2(bins)).
 // For 4096-item tiles the IPT ranking rounds of a warp are split into CH independent chains (CH * bins <= SORT_MAX_BINS;
 // chain c = items [c*IPT/CH, (c+1)*IPT/CH) of every lane) with their own digit counters, so the load -> add -> store ->
 // shuffle dependency that serialises the rounds is IPT/CH long; the counters of the chains are stitched together by
 // the per-digit exclusive prefix that already runs over the warps.
-template <int IPT, bool HAS_VALS, int NB>
+template <int IPT, int VM, int NB>
 __global__ void __launch_bounds__(SORT_THREADS, 3)
-onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift, int bins,
+onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const void* __restrict__ vals_in_v,
+                     uint32_t* __restrict__ keys_out, void* __restrict__ vals_out_v, int merge_bits, int n, int shift, int bins,
                      const uint32_t* __restrict__ digit_totals /* [SORT_MAX_BINS] for this pass */,
                      uint32_t* __restrict__ tile_state /* [nblocks][bins], zeroed */,
                      uint32_t* __restrict__ ticket /* zeroed */,
@@ -136,7 +140,14 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   __shared__ uint32_t s_lstart[SORT_MAX_BINS];    // block-local start of each digit run
   __shared__ int32_t s_gofs[SORT_MAX_BINS];       // global position - local position, per digit
   __shared__ uint32_t s_key[OS_TILE];
-  __shared__ uint32_t s_val[HAS_VALS ? OS_TILE : 1];
+  __shared__ uint32_t s_val[VM == 2 ? OS_TILE : (VM == 1 ? OS_TILE / 4 : 1)];
+  constexpr bool HAS_VALS = VM != 0;
+  const uint32_t* const vals_in = reinterpret_cast<const uint32_t*>(vals_in_v);
+  const uint8_t* const vals_in8 = reinterpret_cast<const uint8_t*>(vals_in_v);
+  uint32_t* const vals_out = reinterpret_cast<uint32_t*>(vals_out_v);
+  uint8_t* const vals_out8 = reinterpret_cast<uint8_t*>(vals_out_v);
+  uint8_t* const s_val8 = reinterpret_cast<uint8_t*>(s_val);
+  const uint32_t merge_mask = (VM == 1 && merge_bits > 0) ? ((1u << merge_bits) - 1u) : 0u;
   __shared__ uint32_t s_wsum[NW];
   __shared__ uint32_t s_ticket;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -149,8 +160,12 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
       const int k = base + i * SORT_THREADS + threadIdx.x;
       if (k < n) {
         const uint32_t kk = keys_in[k];
-        keys_out[k] = kk;
-        if (HAS_VALS) vals_out[k] = vals_in[k];
+        if (VM == 1 && merge_mask) keys_out[k] = (kk & merge_mask) | ((uint32_t)vals_in8[k] << merge_bits);
+        else {
+          keys_out[k] = kk;
+          if (VM == 2) vals_out[k] = vals_in[k];
+          if (VM == 1) vals_out8[k] = vals_in8[k];
+        }
         if (ranges) {   // tile boundaries of an already sorted sequence: compare with the predecessor
           const uint32_t t = kk >> tile_shift;
           const uint32_t tp = k > 0 ? (keys_in[k - 1] >> tile_shift) : 0xFFFFFFFFu;
@@ -178,7 +193,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   for (int i = 0; i < IPT; i++) {   // all loads of the tile in flight before the first use
     const int k = seg + i * 32 + lane;
     key[i] = k < n ? keys_in[k] : 0xFFFFFFFFu;
-    if (PRELOAD_VALS) val[i] = k < n ? vals_in[k] : 0u;
+    if (PRELOAD_VALS) val[i] = k < n ? (VM == 1 ? (uint32_t)vals_in8[k] : vals_in[k]) : 0u;
   }
   // Round i ranks item i of every lane: lanes with equal digits find each other through a peer mask; the lowest
   // of them bumps the warp's private digit counter and broadcasts the old value.  All peer masks of the tile are
@@ -317,7 +332,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
       const uint32_t dd = (key[i] >> shift) & mask;
       const uint32_t lp = s_lstart[dd] + s_cnt[warp][(i / RPC) * bins + dd] + rank[i];
       s_key[lp] = key[i];
-      if (HAS_VALS) s_val[lp] = val[i];
+      if (VM == 2) s_val[lp] = val[i];
+      if (VM == 1) s_val8[lp] = (uint8_t)val[i];
     }
   }
   __syncthreads();
@@ -326,8 +342,12 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     const uint32_t kk = s_key[q];
     const uint32_t dd = (kk >> shift) & mask;
     const int32_t dst = (int32_t)q + s_gofs[dd];
-    keys_out[dst] = kk;
-    if (HAS_VALS) vals_out[dst] = s_val[q];
+    if (VM == 1 && merge_mask) keys_out[dst] = (kk & merge_mask) | ((uint32_t)s_val8[q] << merge_bits);
+    else {
+      keys_out[dst] = kk;
+      if (VM == 2) vals_out[dst] = s_val[q];
+      if (VM == 1) vals_out8[dst] = s_val8[q];
+    }
     if (ranges) {
       // Fused K5 (identifyTileRanges) on the LAST pass of the tile sort: the block's staged items are in final order
       // inside each digit run, and a run is contiguous in the output.  Inside a run a tile boundary is seen by comparing
@@ -367,8 +387,8 @@ size_t radix_sort_zero_words(int n, int nbits) {
 static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint32_t* scratch, int n, int nbits,
                                      cudaStream_t s, int* launches, const char* const* names,
                                      const uint32_t* bias_c, int first_bit, bool scratch_zeroed, uint2* ranges,
-                                     int tile_shift) {
-  const bool has_vals = vals != nullptr && vals[0] != nullptr;
+                                     int tile_shift, uint8_t* const* vals8, int merge_bits) {
+  const int vm = (vals8 && vals8[0]) ? 1 : ((vals != nullptr && vals[0] != nullptr) ? 2 : 0);
   const int npass = (nbits + 7) / 8;
   // 1024-item tiles only for really small inputs: with the ballot ranking 4096-item tiles win from ~0.3 M items
   // (measured: 1 M pairs 87 -> 65 us, 0.5 M 63 -> 54 us, 0.1 M 43 -> 51 us), although they fill < 2 CTAs per SM
@@ -401,18 +421,19 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
   uint32_t* state = state0;
   for (int pass = 0; pass < npass; pass++) {
     prof_begin(names[2], s);
-    uint32_t* vin = has_vals ? vals[cur] : nullptr;
-    uint32_t* vout = has_vals ? vals[cur ^ 1] : nullptr;
+    void* vin = vm == 2 ? (void*)vals[cur] : (vm == 1 ? (void*)vals8[cur] : nullptr);
+    void* vout = vm == 2 ? (void*)vals[cur ^ 1] : (vm == 1 ? (void*)vals8[cur ^ 1] : nullptr);
+    const int mb = (vm == 1 && pass == npass - 1) ? merge_bits : 0;
 #define SFB_OS2(IPTV, HV, NBV)                                                                                 \
-  onesweep_pass_kernel<IPTV, HV, NBV><<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vin, keys[cur ^ 1], vout, n,   \
+  onesweep_pass_kernel<IPTV, HV, NBV><<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vin, keys[cur ^ 1], vout, mb, n, \
                                                                         shifts[pass], nbins[pass],                \
                                                                         hist_all + pass * SORT_MAX_BINS, state, tickets + pass, \
                                                                         pass == npass - 1 ? ranges : nullptr, tile_shift)
 #define SFB_OS(IPTV, HV)                                                                                       \
   do { if (nb == 6) SFB_OS2(IPTV, HV, 6); else if (nb == 7) SFB_OS2(IPTV, HV, 7); else SFB_OS2(IPTV, HV, 8); } while (0)
     const int nb = nbins[pass] <= 64 ? 6 : (nbins[pass] <= 128 ? 7 : 8);
-    if (small) { if (has_vals) SFB_OS(4, true);  else SFB_OS(4, false); }
-    else       { if (has_vals) SFB_OS(16, true); else SFB_OS(16, false); }
+    if (small) { if (vm == 2) SFB_OS(4, 2); else if (vm == 1) SFB_OS(4, 1); else SFB_OS(4, 0); }
+    else       { if (vm == 2) SFB_OS(16, 2); else if (vm == 1) SFB_OS(16, 1); else SFB_OS(16, 0); }
 #undef SFB_OS2
 #undef SFB_OS
     prof_end(s);
@@ -425,10 +446,10 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
 
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
                      int* launches, const char* const* names, const uint32_t* bias_c, int first_bit,
-                     bool scratch_zeroed, uint2* ranges, int tile_shift) {
+                     bool scratch_zeroed, uint2* ranges, int tile_shift, uint8_t* const* vals8, int merge_bits) {
   if (n <= 0 || nbits <= 0) return 0;
   return radix_sort_pairs_onesweep(keys, vals, hist, n, nbits, s, launches, names, bias_c, first_bit, scratch_zeroed,
-                                   ranges, tile_shift);
+                                   ranges, tile_shift, vals8, merge_bits);
 }
 
 // ------------------------------------------------------------------ instance emission in depth order
@@ -476,8 +497,8 @@ __global__ void __launch_bounds__(DUP_THREADS)
 duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
                  const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ rect,
                  const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ tile_keys,
-                 uint32_t* __restrict__ inst_idx /* nullptr: packed mode, tile_keys[k] = tile << idx_bits | index */,
-                 int idx_bits, uint32_t* __restrict__ zero_ptr, uint32_t zero_words, uint2* __restrict__ ranges_init,
+                 uint8_t* __restrict__ inst_hi /* nullptr: the whole index fits the word; else index >> idx_bits */,
+                 int idx_bits /* tile_keys[k] = tile << idx_bits | (index & ((1 << idx_bits) - 1)) */, uint32_t* __restrict__ zero_ptr, uint32_t zero_words, uint2* __restrict__ ranges_init,
                  int T, uint32_t* __restrict__ bcount_zero) {
   // Prologue: this kernel runs right in front of the tile sort anyway, so its blocks also clear the sort's scratch
   // (digit histograms, tickets, look-back state) and set the tile ranges to "empty" — two memset nodes less per forward.
@@ -608,11 +629,12 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
       const uint32_t w = x1 - x0;
       const uint32_t yy = t / w, xx = t - yy * w;
       const uint32_t tile = (y0 + yy) * (uint32_t)grid_x + (x0 + xx);
-      if (inst_idx) {
-        tile_keys[out0 + cb + q] = tile;
-        inst_idx[out0 + cb + q] = s_gidx[sidx];
+      const uint32_t gi = s_gidx[sidx];
+      if (inst_hi) {
+        tile_keys[out0 + cb + q] = (tile << idx_bits) | (gi & ((1u << idx_bits) - 1u));
+        inst_hi[out0 + cb + q] = (uint8_t)(gi >> idx_bits);
       } else {
-        tile_keys[out0 + cb + q] = (tile << idx_bits) | s_gidx[sidx];
+        tile_keys[out0 + cb + q] = (tile << idx_bits) | gi;
       }
     }
     __syncthreads();
@@ -621,32 +643,45 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
 
 void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
                       const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
-                      uint32_t* inst_idx, int idx_bits, uint32_t* zero_ptr, size_t zero_words, uint2* ranges_init, int T,
+                      uint8_t* inst_hi, int idx_bits, uint32_t* zero_ptr, size_t zero_words, uint2* ranges_init, int T,
                       uint32_t* bcount_zero, cudaStream_t s) {
   int nb = (P + DUP_GPB - 1) / DUP_GPB;
   duplicate_kernel<<<nb, DUP_THREADS, 0, s>>>(P, grid_x, sorted_idx, tiles_touched, rect, block_offsets,
-                                              tile_keys, inst_idx, idx_bits, zero_ptr, (uint32_t)zero_words, ranges_init, T,
+                                              tile_keys, inst_hi, idx_bits, zero_ptr, (uint32_t)zero_words, ranges_init, T,
                                               bcount_zero);
 }
 
-// point_list == nullptr: packed mode (tile_keys[i] = tile << idx_bits | index)
-__global__ void export_keys_kernel(int R, const uint32_t* __restrict__ tile_keys,
-                                   const uint32_t* __restrict__ point_list, int idx_bits,
+// Inspection (parity tests): the reference's (tile << 32 | depth bits) keys and the index list from the sorted words.
+// merged == false: words are tile << idx_bits | index.  merged == true (split instances): the words are bare indices
+// and the tile of position i is the one whose [start, end) range holds i — one thread per tile fills its run.
+__global__ void export_keys_kernel(int R, const uint32_t* __restrict__ words, int idx_bits,
                                    const SplatRec* __restrict__ rec, uint64_t* __restrict__ out_keys,
                                    uint32_t* __restrict__ out_list) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R) return;
-  uint32_t tile, idx;
-  if (point_list) { tile = tile_keys[i]; idx = point_list[i]; }
-  else { const uint32_t w = tile_keys[i]; tile = w >> idx_bits; idx = w & ((1u << idx_bits) - 1u); }
+  const uint32_t w = words[i];
+  const uint32_t tile = w >> idx_bits, idx = w & ((1u << idx_bits) - 1u);
   if (out_keys) out_keys[i] = ((uint64_t)tile << 32) | __float_as_uint(rec[idx].depth);
   if (out_list) out_list[i] = idx;
 }
+__global__ void export_keys_merged_kernel(int T, const uint2* __restrict__ ranges, const uint32_t* __restrict__ words,
+                                          const SplatRec* __restrict__ rec, uint64_t* __restrict__ out_keys,
+                                          uint32_t* __restrict__ out_list) {
+  const int t = blockIdx.x;
+  const uint2 r = ranges[t];
+  if (r.y <= r.x || r.x == 0xFFFFFFFFu) return;
+  for (uint32_t i = r.x + threadIdx.x; i < r.y; i += blockDim.x) {
+    const uint32_t idx = words[i];
+    if (out_keys) out_keys[i] = ((uint64_t)t << 32) | __float_as_uint(rec[idx].depth);
+    if (out_list) out_list[i] = idx;
+  }
+}
 
-void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_list, int idx_bits,
+void launch_export_keys(int R, int T, const uint32_t* words, bool merged, int idx_bits, const uint2* ranges,
                         const SplatRec* rec, uint64_t* out_keys, uint32_t* out_list, cudaStream_t s) {
-  if (R > 0)
-    export_keys_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, tile_keys, point_list, idx_bits, rec, out_keys, out_list);
+  if (R <= 0) return;
+  if (merged) export_keys_merged_kernel<<<T, 256, 0, s>>>(T, ranges, words, rec, out_keys, out_list);
+  else export_keys_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, words, idx_bits, rec, out_keys, out_list);
 }
 
 }  // namespace sfb

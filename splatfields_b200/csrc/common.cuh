@@ -282,53 +282,66 @@ struct GeomState {
   }
 };
 
-// Instance packing: when ceil(log2 P) + ceil(log2 T) <= 32 an instance is ONE 32-bit word,
-// tile << idx_bits | gaussian index, and the tile sort moves bare keys (half the bytes of (key, value) pairs).
+// Instance packing.  An instance is ONE 32-bit word, tile << low_bits | (gaussian index & low mask), and the tile sort
+// moves bare keys.  When ceil(log2 P) + ceil(log2 T) <= 32 the whole index fits (high_bits = 0).  Otherwise (e.g. 2 M
+// splats at 1080p: 21 + 13 bits) the word keeps the low 32 - tile_bits index bits and the remaining high_bits <= 8 ride
+// along as one byte per instance — 5 instead of 8 bytes per instance and pass — until the last sort pass re-assembles
+// the full index as its only output word.  Either way the render kernels read a plain index list: word & idx_mask.
 struct InstPacking {
-  int idx_bits;     // bits of the Gaussian index inside the word (0 = unpacked: separate key / value arrays)
-  uint32_t idx_mask;
+  int low_bits;       // index bits inside the word
+  int high_bits;      // index bits in the side byte (0: none)
+  uint32_t idx_mask;  // mask of the sorted list the render kernels read (high_bits > 0: the list holds merged indices)
+  bool ok;            // false: ceil(log2 P) + ceil(log2 T) > 40 (not supported)
 };
 inline int ceil_log2(size_t n) { int b = 0; while (((size_t)1 << b) < n) b++; return b; }
 inline int tile_bits_for(size_t T) { int b = 1; while (((size_t)1 << b) < T) b++; return b; }
-// SFB_NO_PACK=1 forces the unpacked layout (what scenes with ceil(log2 P) + ceil(log2 T) > 32 get, e.g. 2 M splats at
-// 1080p) so that the parity tests can drive that path with small scenes.
-inline bool inst_packing_allowed() {
+// SFB_NO_PACK=1 forces the split layout (two index bits in the side byte) so that the parity tests can drive that
+// path with small scenes.
+inline bool inst_split_forced() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("SFB_NO_PACK"); v = (e && e[0] == '1') ? 0 : 1; }
+  if (v < 0) { const char* e = getenv("SFB_NO_PACK"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
 inline InstPacking inst_packing(size_t P, size_t T) {
   InstPacking k;
-  const int ib = ceil_log2(P < 2 ? 2 : P);
-  if (inst_packing_allowed() && ib + tile_bits_for(T) <= 32) { k.idx_bits = ib; k.idx_mask = ib >= 32 ? 0xFFFFFFFFu : ((1u << ib) - 1u); }
-  else { k.idx_bits = 0; k.idx_mask = 0xFFFFFFFFu; }
+  const int ib = ceil_log2(P < 2 ? 2 : P), tb = tile_bits_for(T);
+  k.ok = true;
+  if (ib + tb <= 32 && !(inst_split_forced() && ib > 2)) {
+    k.low_bits = ib; k.high_bits = 0;
+    k.idx_mask = ib >= 32 ? 0xFFFFFFFFu : ((1u << ib) - 1u);
+  } else {
+    k.low_bits = ib + tb <= 32 ? ib - 2 : 32 - tb;
+    k.high_bits = ib - k.low_bits;
+    k.idx_mask = 0xFFFFFFFFu;
+    k.ok = k.high_bits <= 8;
+  }
   return k;
 }
 
 // ---- R-sized scratch ("binningBuffer") ----
 struct BinState {
-  uint32_t* tile_key[2];    // [R]  ping-pong tile ids (unpacked) or packed tile|index words
-  uint32_t* inst_idx[2];    // [R]  ping-pong Gaussian indices (unpacked mode only; nullptr when packed)
+  uint32_t* tile_key[2];    // [R]  ping-pong instance words (tile | index); the final half is the list the render kernels read
+  uint8_t* inst_hi[2];      // [R]  ping-pong high index bits (split instances only; nullptr otherwise)
   uint32_t* sort_hist;      // sort scratch
   uint2* ranges;            // [T]
   uint8_t* hit;             // [R]  per sorted instance: bit w = warp (8x4 patch) w accumulated it in the forward
 
-  static BinState from_chunk(char*& chunk, size_t R, size_t T, bool packed) {
+  static BinState from_chunk(char*& chunk, size_t R, size_t T, bool split) {
     BinState b;
     for (int i = 0; i < 2; i++) b.tile_key[i] = carve<uint32_t>(chunk, R);
-    for (int i = 0; i < 2; i++) b.inst_idx[i] = packed ? nullptr : carve<uint32_t>(chunk, R);
+    for (int i = 0; i < 2; i++) b.inst_hi[i] = split ? carve<uint8_t>(chunk, R + 16) : nullptr;
     b.sort_hist = carve<uint32_t>(chunk, sort_scratch_words(R));
     b.ranges = carve<uint2>(chunk, T);
     b.hit = carve<uint8_t>(chunk, R + 256);
     return b;
   }
-  static size_t required(size_t R, size_t T, bool packed) {
+  static size_t required(size_t R, size_t T, bool split) {
     char* p = nullptr;
-    from_chunk(p, R, T, packed);
+    from_chunk(p, R, T, split);
     return reinterpret_cast<size_t>(p) + 256;
   }
   // the sorted instance list the render kernels walk: entries are `word & idx_mask`
-  const uint32_t* point_list(int final_buf, bool packed) const { return packed ? tile_key[final_buf] : inst_idx[final_buf]; }
+  const uint32_t* point_list(int final_buf) const { return tile_key[final_buf]; }
 };
 
 // ---- pixel-sized scratch ("imgBuffer") ----
@@ -396,17 +409,19 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n
                      int first_bit = 0 /* digits start at this bit; vals[0] == nullptr sorts bare keys */,
                      bool scratch_zeroed = false /* the first radix_sort_zero_words(n, nbits) words of hist are already 0 */,
                      uint2* ranges = nullptr /* fused K5: [T] pre-set to (0xFFFFFFFF, 0); filled by the last pass */,
-                     int tile_shift = 0 /* tile id = key >> tile_shift */);
+                     int tile_shift = 0 /* tile id = key >> tile_shift */,
+                     uint8_t* const* vals8 = nullptr /* one side byte per key (ping-pong), vals == nullptr */,
+                     int merge_bits = 0 /* last pass writes (key & ((1 << merge_bits) - 1)) | byte << merge_bits */);
 size_t radix_sort_zero_words(int n, int nbits);
 void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
                                 uint32_t* block_sums, cudaStream_t s);
 void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
                       const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
-                      uint32_t* inst_idx /* nullptr: packed */, int idx_bits,
+                      uint8_t* inst_hi /* nullptr: the whole index fits the word */, int idx_bits,
                       uint32_t* zero_ptr /* or nullptr */, size_t zero_words, uint2* ranges_init /* or nullptr */, int T,
                       uint32_t* bcount_zero /* [TILE_BUCKETS] or nullptr: cleared on the way */, cudaStream_t s);
-void launch_export_keys(int R, const uint32_t* tile_keys, const uint32_t* point_list /* nullptr: packed */,
-                        int idx_bits, const SplatRec* rec, uint64_t* out_keys, uint32_t* out_list, cudaStream_t s);
+void launch_export_keys(int R, int T, const uint32_t* words, bool merged /* words are bare indices */, int idx_bits,
+                        const uint2* ranges, const SplatRec* rec, uint64_t* out_keys, uint32_t* out_list, cudaStream_t s);
 
 // render_fwd.cu
 // returns 0, or -1 with set_error() (tensor-map encoding failed)
