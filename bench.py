@@ -432,6 +432,7 @@ def run_ours(args):
             "views_per_s": world / (ms_step * 1e-3), "host_enqueue_ms_per_step": host_enqueue_ms,
             "exchange": None if world == 1 else {
                 "mode": vp.exchange, "multicast": getattr(vp, "xchg_multicast", None),
+                "fallback_reason": vp.exchange_fallback_reason,
                 "ms_per_step": float(np.mean(exch_ms)) if exch_ms else None,
                 "nvlink_bytes_received_per_splat_per_rank": vp.bytes_on_wire_per_splat(),
                 "nvlink_MB_received_per_rank_per_step": vp.bytes_on_wire_per_splat() * P / 1e6,

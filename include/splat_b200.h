@@ -154,6 +154,10 @@ int sfb_export_geom(int P, const void* geom_buffer, const float* scales, float s
 int sfb_export_binning(int P, int num_rendered, int W, int H, const void* geom_buffer,
                        const void* binning_buffer, uint64_t* point_list_keys, uint32_t* point_list,
                        uint32_t* ranges, void* stream);
+/* The staging primitive of the render kernels on its own (tests): out [n][16] = for every list entry i the 64-byte
+ * shared-memory row the TMA unit delivers (cp.async.bulk.tensor ... tile::gather4 on a tensor map over the 48-byte
+ * record table): table[idx[i]][0..11] followed by four zeros.  table [P][12] fp32, idx [n] (each < P). */
+int sfb_debug_gather_rows(int P, const float* table, int n, const uint32_t* idx, float* out, void* stream);
 /* final_T [H][W], n_contrib [H][W] (uint32; position+1 of the last contributor in the tile list). */
 int sfb_export_img(int W, int H, const void* img_buffer, float* final_T, uint32_t* n_contrib, void* stream);
 

@@ -40,6 +40,7 @@ with numa_local(torch.device("cuda:0")) as n:
     print("numa_local cpus:", getattr(n, "cpus", None) and (len(n.cpus), n.cpus[:4], n.cpus[-4:]))
 PY
 tail -16 $OUT/device.log
+echo "== TMA row gather primitive"; timeout 200 python -m pytest tests/test_gpu_properties.py -m gpu -q -k tma_row 2>&1 | tail -4 | tee $OUT/tma_probe.log
 # smoke of both staging paths first: a broken TMA path must not take the whole session down
 for st in tma ldg; do echo "== smoke SFB_FWD_STAGE=$st SFB_BWD_STAGE=$st"; SFB_FWD_STAGE=$st SFB_BWD_STAGE=$st timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -2; done | tee $OUT/smoke.log
 timeout 1200 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log; tail -4 $OUT/pytest_gpu.log | cut -c1-400

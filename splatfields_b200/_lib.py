@@ -20,7 +20,7 @@ _lib = None
 # every symbol include/splat_b200.h declares
 SYMBOLS = (
     "sfb_abi_version", "sfb_last_error", "sfb_rasterize_forward", "sfb_rasterize_backward", "sfb_mark_visible",
-    "sfb_export_geom", "sfb_export_binning", "sfb_export_img", "sfb_last_launch_count",
+    "sfb_export_geom", "sfb_export_binning", "sfb_export_img", "sfb_debug_gather_rows", "sfb_last_launch_count",
     "sfb_profile_enable", "sfb_profile_count", "sfb_profile_read", "sfb_profile_name",
     "sfb_loss_scratch_bytes", "sfb_loss_window", "sfb_l1_ssim_loss", "sfb_densify_stats", "sfb_densify_masks",
     "sfb_sh_grad_combine", "sfb_xchg_bytes", "sfb_xchg_finish", "sfb_activate_forward", "sfb_activate_backward", "sfb_knn_scratch_bytes",
@@ -84,6 +84,8 @@ def load():
     lib.sfb_export_binning.argtypes = [ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
     lib.sfb_export_img.restype = ci
     lib.sfb_export_img.argtypes = [ci, ci, vp, vp, vp, vp]
+    lib.sfb_debug_gather_rows.restype = ci
+    lib.sfb_debug_gather_rows.argtypes = [ci, vp, ci, vp, vp, vp]
     lib.sfb_profile_enable.restype = None
     lib.sfb_profile_enable.argtypes = [ci]
     lib.sfb_profile_read.restype = ci

@@ -498,6 +498,18 @@ int sfb_export_binning(int P, int num_rendered, int W, int H, const void* geom_b
   return SFB_OK;
 }
 
+int sfb_debug_gather_rows(int P, const float* table, int n, const uint32_t* idx, float* out, void* stream) {
+  g_err.clear();
+  if (P <= 0 || n < 0 || !table || !idx || !out) return fail(SFB_ERR_ARG, "bad arguments");
+  if ((reinterpret_cast<size_t>(table) & 15) != 0 || (reinterpret_cast<size_t>(out) & 15) != 0)
+    return fail(SFB_ERR_ARG, "table / out must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (sfb::launch_gather_rows_probe(reinterpret_cast<const sfb::SplatRec*>(table), (size_t)P, idx, n, out, s) != 0)
+    return fail(SFB_ERR_CUDA, g_err.c_str());
+  CK_LAUNCH("gather_rows_probe", 0, s);
+  return SFB_OK;
+}
+
 int sfb_export_img(int W, int H, const void* img_buffer, float* final_T, uint32_t* n_contrib, void* stream) {
   using namespace sfb;
   g_err.clear();

@@ -434,6 +434,8 @@ int launch_render_forward(int W, int H, uint2* ranges /* empty tiles are normali
                            GradRec* zero_grad /* [P] or nullptr: cleared by the CTAs as a prologue */, size_t P,
                            cudaStream_t s);
 
+int launch_gather_rows_probe(const SplatRec* table, size_t P, const uint32_t* idx, int n, float* out, cudaStream_t s);
+
 // render_bwd.cu
 int launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
                            const SplatRec* rec, size_t P,

@@ -246,6 +246,40 @@ bool make_rec_tensor_map(const SplatRec* rec, size_t P, void* out_map) {
             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Stand-alone exercise of the staging primitive (sfb_debug_gather_rows): out[i][0..15] = the 64-byte shared-memory row
+// the TMA unit delivers for list entry i — table[idx[i]][0..11] followed by four zeros.  One CTA per 256 entries.
+__global__ void __launch_bounds__(RB)
+gather_rows_probe_kernel(const __grid_constant__ CUtensorMap map, const uint32_t* __restrict__ idx, int n,
+                         float* __restrict__ out) {
+  __shared__ __align__(128) float4 row[RB][4];
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  const int base = blockIdx.x * RB;
+  const int cnt = min(RB, n - base);
+  uint32_t id = 0u;
+  if ((int)threadIdx.x < cnt) id = idx[base + threadIdx.x];
+  const uint32_t i1 = __shfl_down_sync(0xffffffffu, id, 1), i2 = __shfl_down_sync(0xffffffffu, id, 2),
+                 i3 = __shfl_down_sync(0xffffffffu, id, 3);
+  if (threadIdx.x == 0) mbar_expect_tx(&bar, (uint32_t)((cnt + 3) / 4) * 256u);
+  if ((threadIdx.x & 3) == 0 && (int)threadIdx.x < cnt)
+    tma_gather4(&row[threadIdx.x][0], &map, 0, (int)id, (int)i1, (int)i2, (int)i3, &bar);
+  mbar_wait(&bar, 0);
+  if ((int)threadIdx.x < cnt) {
+    float4* o = reinterpret_cast<float4*>(out + (size_t)(base + threadIdx.x) * 16);
+#pragma unroll
+    for (int k = 0; k < 4; k++) o[k] = row[threadIdx.x][k];
+  }
+}
+
+int launch_gather_rows_probe(const SplatRec* table, size_t P, const uint32_t* idx, int n, float* out, cudaStream_t s) {
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (!make_rec_tensor_map(table, P, &map)) { set_error("cuTensorMapEncodeTiled failed"); return -1; }
+  if (n > 0) gather_rows_probe_kernel<<<(n + RB - 1) / RB, RB, 0, s>>>(map, idx, n, out);
+  return 0;
+}
+
 static bool fwd_stage_tma() {      // SFB_FWD_STAGE=ldg: three 16-byte loads per thread instead of the TMA row gather (A/B)
   static int v = -1;
   if (v < 0) { const char* e = getenv("SFB_FWD_STAGE"); v = (e && e[0] == 'l') ? 0 : 1; }

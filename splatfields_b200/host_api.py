@@ -82,8 +82,16 @@ class ViewParallelRasterizer:
         self.time_exchange = False       # bench: record CUDA events around the gradient exchange of every step
         self.exchange_events = []
         self.xchg = None
+        self.exchange_fallback_reason = None
         if self.exchange == "nvlink":
-            self._setup_nvlink("shs" in scene)
+            try:
+                self._setup_nvlink("shs" in scene)
+            except Exception as ex:      # no symmetric-memory support on this system: the NCCL formulation of the same sum
+                import sys
+                self.exchange_fallback_reason = f"{type(ex).__name__}: {ex}"
+                self.exchange = "factored" if "shs" in scene else "allreduce"
+                sys.stderr.write(f"splatfields_b200: NVLink exchange unavailable ({self.exchange_fallback_reason}); "
+                                 f"using exchange='{self.exchange}' over torch.distributed\n")
         if self.exchange in ("factored", "nvlink") and "shs" in scene:
             self._gather_campos(cam)
         if self.exchange == "factored":

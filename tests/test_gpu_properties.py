@@ -231,3 +231,22 @@ def test_second_backward_on_the_same_buffers(cuda_lib):
         assert scale > 0, name
         # float atomics reorder between runs: equal up to summation noise, nowhere near a factor of two
         assert (a - b).abs().max().item() <= 1e-4 * scale, name
+
+
+def test_tma_row_gather_delivers_the_indexed_rows(cuda_lib):
+    """The staging primitive of both render kernels (cp.async.bulk.tensor ... tile::gather4 on a tensor map over the
+    48-byte record table, completion on an mbarrier): every gathered 64-byte row is the indexed record + 4 zeros, for
+    ragged counts (not a multiple of 4 / 256), repeated and extreme indices."""
+    from splatfields_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(3)
+    for P, n in ((1, 1), (7, 5), (1000, 256), (100_000, 1023), (1_000_000, 4099)):
+        table = torch.randn(P, 12, generator=g).to(dev)
+        idx = torch.randint(0, P, (n,), generator=g, dtype=torch.int64)
+        idx[0], idx[-1] = P - 1, 0
+        idx = idx.to(torch.int32).to(dev)
+        out = torch.full((n, 16), float("nan"), device=dev)
+        _lib.check(cuda_lib.sfb_debug_gather_rows(P, table.data_ptr(), n, idx.data_ptr(), out.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert torch.equal(out[:, :12], table[idx.long()]), (P, n)
+        assert torch.all(out[:, 12:] == 0), (P, n)
