@@ -196,10 +196,11 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   CK(cudaEventRecord(evt, s));
 
   // stage 1: stable sort of the Gaussians by depth bits (culled ones carry 0xFFFFFFFF and sink)
+  const uint32_t* top_total0 = nullptr;
   int dfinal = radix_sort_pairs(g.depth_key, g.depth_idx, g.sort_hist, P, 32, s, &g_launches, kDepthSortNames,
-                                g.counters + 2, 0, dzero != 0);
+                                g.counters + 2, 0, dzero != 0, nullptr, 0, nullptr, 0, &top_total0);
   CK_LAUNCH("depth sort", debug, s);
-  const uint32_t* sorted_idx = g.depth_idx[dfinal];
+  const SortedIdx sorted_idx{g.depth_idx[dfinal], g.depth_idx[dfinal ^ 1], top_total0, (uint32_t)P};
   launch_instance_block_sums(P, sorted_idx, g.tiles_touched, g.block_sums, s);
   g_launches += 2;
   CK_LAUNCH("instance scan", debug, s);

@@ -132,7 +132,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const void* __restric
                      uint32_t* __restrict__ tile_state /* [nblocks][bins], zeroed */,
                      uint32_t* __restrict__ ticket /* zeroed */,
                      uint2* __restrict__ ranges /* nullptr, or [T] = (0xFFFFFFFF, 0): fused K5, last tile-sort pass */,
-                     int tile_shift /* tile id = key >> tile_shift */) {
+                     int tile_shift /* tile id = key >> tile_shift */,
+                     int skip_identity /* the consumers pick this pass's INPUT themselves when it is the identity */) {
   constexpr int NW = SORT_THREADS / 32;
   constexpr int OS_TILE = SORT_THREADS * IPT;
   constexpr int CH = IPT == 16 ? (NB == 6 ? 4 : (NB == 7 ? 2 : 1)) : 1;
@@ -154,6 +155,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const void* __restric
   const uint32_t mask = (uint32_t)bins - 1;
   if (digit_totals[0] == (uint32_t)n) {
     // every key has digit 0 in this pass: the stable sort is the identity permutation -> plain coalesced copy
+    // (or nothing at all when the consumers select the input buffer themselves: SortedIdx in common.cuh)
+    if (skip_identity) return;
     const int base = blockIdx.x * OS_TILE;
 #pragma unroll
     for (int i = 0; i < IPT; i++) {
@@ -387,7 +390,8 @@ size_t radix_sort_zero_words(int n, int nbits) {
 static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint32_t* scratch, int n, int nbits,
                                      cudaStream_t s, int* launches, const char* const* names,
                                      const uint32_t* bias_c, int first_bit, bool scratch_zeroed, uint2* ranges,
-                                     int tile_shift, uint8_t* const* vals8, int merge_bits) {
+                                     int tile_shift, uint8_t* const* vals8, int merge_bits,
+                                     const uint32_t** last_total0) {
   const int vm = (vals8 && vals8[0]) ? 1 : ((vals != nullptr && vals[0] != nullptr) ? 2 : 0);
   const int npass = (nbits + 7) / 8;
   // 1024-item tiles only for really small inputs: with the ballot ranking 4096-item tiles win from ~0.3 M items
@@ -428,7 +432,8 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
   onesweep_pass_kernel<IPTV, HV, NBV><<<nblocks, SORT_THREADS, 0, s>>>(keys[cur], vin, keys[cur ^ 1], vout, mb, n, \
                                                                         shifts[pass], nbins[pass],                \
                                                                         hist_all + pass * SORT_MAX_BINS, state, tickets + pass, \
-                                                                        pass == npass - 1 ? ranges : nullptr, tile_shift)
+                                                                        pass == npass - 1 ? ranges : nullptr, tile_shift, \
+                                                                        (pass == npass - 1 && last_total0 && !ranges && vm != 1) ? 1 : 0)
 #define SFB_OS(IPTV, HV)                                                                                       \
   do { if (nb == 6) SFB_OS2(IPTV, HV, 6); else if (nb == 7) SFB_OS2(IPTV, HV, 7); else SFB_OS2(IPTV, HV, 8); } while (0)
     const int nb = nbins[pass] <= 64 ? 6 : (nbins[pass] <= 128 ? 7 : 8);
@@ -441,23 +446,27 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
     state += (size_t)nblocks * nbins[pass];
     cur ^= 1;
   }
+  if (last_total0) *last_total0 = (!ranges && vm != 1) ? hist_all + (npass - 1) * SORT_MAX_BINS : nullptr;
   return cur;
 }
 
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n, int nbits, cudaStream_t s,
                      int* launches, const char* const* names, const uint32_t* bias_c, int first_bit,
-                     bool scratch_zeroed, uint2* ranges, int tile_shift, uint8_t* const* vals8, int merge_bits) {
+                     bool scratch_zeroed, uint2* ranges, int tile_shift, uint8_t* const* vals8, int merge_bits,
+                     const uint32_t** last_total0) {
+  if (last_total0) *last_total0 = nullptr;
   if (n <= 0 || nbits <= 0) return 0;
   return radix_sort_pairs_onesweep(keys, vals, hist, n, nbits, s, launches, names, bias_c, first_bit, scratch_zeroed,
-                                   ranges, tile_shift, vals8, merge_bits);
+                                   ranges, tile_shift, vals8, merge_bits, last_total0);
 }
 
 // ------------------------------------------------------------------ instance emission in depth order
 constexpr int DUP_THREADS = 256;   // DUP_GPB (Gaussians / depth ranks per block) lives in common.cuh: it sizes block_sums
 
 __global__ void __launch_bounds__(DUP_THREADS)
-instance_block_sums_kernel(int P, const uint32_t* __restrict__ sorted_idx,
+instance_block_sums_kernel(int P, SortedIdx sorted,
                            const uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ block_sums) {
+  const uint32_t* __restrict__ sorted_idx = sorted.get();
   __shared__ uint32_t s_w[DUP_THREADS / 32];
   uint32_t v = 0;
   for (int j = blockIdx.x * DUP_GPB + threadIdx.x; j < min(P, (blockIdx.x + 1) * DUP_GPB); j += DUP_THREADS)
@@ -473,7 +482,7 @@ instance_block_sums_kernel(int P, const uint32_t* __restrict__ sorted_idx,
   }
 }
 
-void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
+void launch_instance_block_sums(int P, const SortedIdx& sorted_idx, const uint32_t* tiles_touched,
                                 uint32_t* block_sums, cudaStream_t s) {
   int nb = (P + DUP_GPB - 1) / DUP_GPB;
   prof_begin("instance_block_sums", s);
@@ -494,7 +503,7 @@ constexpr int DUP_CHUNK = 4096;
 constexpr int DUP_SPT = DUP_CHUNK / DUP_THREADS;   // slots per thread in the scan (16)
 
 __global__ void __launch_bounds__(DUP_THREADS)
-duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
+duplicate_kernel(int P, int grid_x, SortedIdx sorted,
                  const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ rect,
                  const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ tile_keys,
                  uint8_t* __restrict__ inst_hi /* nullptr: the whole index fits the word; else index >> idx_bits */,
@@ -513,6 +522,7 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
     const int t0 = blockIdx.x * per, t1 = min(t0 + per, T);
     for (int i = t0 + threadIdx.x; i < t1; i += DUP_THREADS) ranges_init[i] = make_uint2(0xFFFFFFFFu, 0u);
   }
+  const uint32_t* __restrict__ sorted_idx = sorted.get();
   __shared__ uint32_t s_pref[DUP_GPB + 1];
   __shared__ uint32_t s_gidx[DUP_GPB];
   __shared__ uint2 s_rect[DUP_GPB];
@@ -641,7 +651,7 @@ duplicate_kernel(int P, int grid_x, const uint32_t* __restrict__ sorted_idx,
   }
 }
 
-void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
+void launch_duplicate(int P, int grid_x, const SortedIdx& sorted_idx, const uint32_t* tiles_touched,
                       const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
                       uint8_t* inst_hi, int idx_bits, uint32_t* zero_ptr, size_t zero_words, uint2* ranges_init, int T,
                       uint32_t* bcount_zero, cudaStream_t s) {

@@ -411,11 +411,23 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n
                      uint2* ranges = nullptr /* fused K5: [T] pre-set to (0xFFFFFFFF, 0); filled by the last pass */,
                      int tile_shift = 0 /* tile id = key >> tile_shift */,
                      uint8_t* const* vals8 = nullptr /* one side byte per key (ping-pong), vals == nullptr */,
-                     int merge_bits = 0 /* last pass writes (key & ((1 << merge_bits) - 1)) | byte << merge_bits */);
+                     int merge_bits = 0 /* last pass writes (key & ((1 << merge_bits) - 1)) | byte << merge_bits */,
+                     const uint32_t** last_total0 = nullptr /* non-null: the last pass may return at once when it is the
+                        identity; receives the device word to compare with n (SortedIdx), or nullptr */);
 size_t radix_sort_zero_words(int n, int nbits);
-void launch_instance_block_sums(int P, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
+// Result of the depth sort as its consumers see it.  The most significant radix pass of a bounded scene is the identity
+// (depth keys are rebased to key - min: < 2^24), known on the device only: instead of copying 8 B/Gaussian through
+// that pass, the pass returns at once and the consumers read its input.
+struct SortedIdx {
+  const uint32_t* primary;   // the last pass's output
+  const uint32_t* alt;       // the last pass's input
+  const uint32_t* total0;    // number of keys with digit 0 in the last pass (nullptr: the pass always runs)
+  uint32_t n;
+  __device__ __forceinline__ const uint32_t* get() const { return (total0 && *total0 == n) ? alt : primary; }
+};
+void launch_instance_block_sums(int P, const SortedIdx& sorted_idx, const uint32_t* tiles_touched,
                                 uint32_t* block_sums, cudaStream_t s);
-void launch_duplicate(int P, int grid_x, const uint32_t* sorted_idx, const uint32_t* tiles_touched,
+void launch_duplicate(int P, int grid_x, const SortedIdx& sorted_idx, const uint32_t* tiles_touched,
                       const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
                       uint8_t* inst_hi /* nullptr: the whole index fits the word */, int idx_bits,
                       uint32_t* zero_ptr /* or nullptr */, size_t zero_words, uint2* ranges_init /* or nullptr */, int T,
