@@ -350,7 +350,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
     bp.x_ngeo = xchg->ngeo;
     bp.x_nranks = xchg->world;
     // slot `rank` of this step's colour-gradient table, on every rank
-    const size_t slot = xl.gc_off[xchg_epoch & 1u] + (size_t)xchg->rank * (size_t)P * 12;
+    const size_t slot = xl.gc_off[xchg_epoch & 1u] + (size_t)xchg->rank * xl.gc_slot_floats * 4;
     for (int r = 0; r < xchg->world; r++) bp.x_gc_peer[r] = reinterpret_cast<float*>((char*)xchg->peers[r] + slot);
     if (xchg->mc) { bp.x_mc = 1; bp.x_ndst = 1; bp.x_gc_dst[0] = reinterpret_cast<float*>((char*)xchg->mc + slot); }
     else { bp.x_ndst = xchg->world; for (int r = 0; r < xchg->world; r++) bp.x_gc_dst[r] = bp.x_gc_peer[r]; }
@@ -403,6 +403,7 @@ int sfb_xchg_finish(const sfb_xchg* x, unsigned epoch, int sh_degree, int M, con
     d.peer_geo[r] = reinterpret_cast<float*>((char*)x->peers[r] + xl.geo_off);
   }
   d.gc = reinterpret_cast<const float*>((char*)x->local + xl.gc_off[epoch & 1u]);
+  d.gc_slot_floats = xl.gc_slot_floats;
   prof_begin("xchg_finish", s);
   launch_xchg_finish(d, x->max_ctas, epoch, sh_degree, M, means3D, campos_views, dL_dmeans3D, dL_dopacity, dL_dscales, dL_drotations,
                      dL_dcolors, has_sh ? dL_dsh : nullptr, s);

@@ -479,12 +479,13 @@ void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s
 // Layout of one rank's symmetric exchange buffer (identical on every rank; include/splat_b200.h: sfb_xchg):
 //   [flags: 256 B][packed gradient records: P * ngeo floats][colour-gradient tables: 2 parities x world x P x 3 floats]
 struct XchgLayout {
-  size_t geo_off, gc_off[2], bytes;
+  size_t geo_off, gc_off[2], gc_slot_floats, bytes;
   static XchgLayout make(size_t P, int world, int ngeo, bool with_gc) {
     XchgLayout l;
     size_t o = 256;
     l.geo_off = o; o = align_up(o + P * (size_t)ngeo * 4, 256);
-    for (int k = 0; k < 2; k++) { l.gc_off[k] = o; if (with_gc) o = align_up(o + (size_t)world * P * 12, 256); }
+    l.gc_slot_floats = align_up(P * 3, 64);            // one view's [P][3] slot, padded to 256 bytes (16-byte stores)
+    for (int k = 0; k < 2; k++) { l.gc_off[k] = o; if (with_gc) o = align_up(o + (size_t)world * l.gc_slot_floats * 4, 256); }
     l.bytes = o;
     return l;
   }
@@ -496,7 +497,8 @@ struct XchgDev {                 // device-side view of the exchange for one ste
   float* geo;                    // this rank's packed records (sums after the exchange)
   float* geo_mc;                 // the same array through the multicast mapping, or nullptr
   float* peer_geo[XCHG_MAX_RANKS];
-  const float* gc;               // this step's colour-gradient table [world][P][3] (local)
+  const float* gc;               // this step's colour-gradient table: world slots of gc_slot_floats floats ([P][3] each)
+  size_t gc_slot_floats;
 };
 void launch_xchg_finish(const XchgDev& x, int max_ctas, uint32_t epoch, int D, int M, const float* means3D, const float* campos,
                         float* dL_dmeans3D, float* dL_dopacity, float* dL_dscales, float* dL_drot, float* dL_dcolors,

@@ -53,7 +53,8 @@ __device__ __forceinline__ void sh_basis(float x, float y, float z, float* basis
 // dL_dsh row of Gaussian i: sum over the V views (index order: bit-reproducible) of basis(dir_v) (x) gc_v, each product
 // rounded on its own (as geom_backward_kernel stores it for a single view) before it enters the sum.
 template <int D, bool W256>
-__device__ __forceinline__ void sh_row_rebuild(size_t i, int P, int V, int M, const float* __restrict__ means3D,
+__device__ __forceinline__ void sh_row_rebuild(size_t i, size_t view_stride /* floats between the views' [P][3] slots */,
+                                               int V, int M, const float* __restrict__ means3D,
                                                const float* s_cam, const float* __restrict__ dcolor,
                                                float* __restrict__ dL_dsh) {
   constexpr int NB = (D + 1) * (D + 1);
@@ -63,7 +64,7 @@ __device__ __forceinline__ void sh_row_rebuild(size_t i, int P, int V, int M, co
 #pragma unroll
   for (int k = 0; k < NF8 * 8; k++) acc[k] = 0.f;
   for (int v = 0; v < V; v++) {
-    const float* gp = dcolor + ((size_t)v * P + i) * 3;
+    const float* gp = dcolor + (size_t)v * view_stride + i * 3;
     // (ld.global.cg: in the NVLink exchange this table is written by the PEERS while the kernel is already resident)
     const float g0 = __ldcg(gp), g1 = __ldcg(gp + 1), g2 = __ldcg(gp + 2);
     if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;     // culled in this view (or no gradient reached it)
@@ -102,7 +103,7 @@ sh_grad_combine_kernel(int P, int V, int M, const float* __restrict__ means3D, c
   __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P) return;
-  sh_row_rebuild<D, W256>((size_t)idx, P, V, M, means3D, s_cam, dcolor, dL_dsh);
+  sh_row_rebuild<D, W256>((size_t)idx, (size_t)P * 3, V, M, means3D, s_cam, dcolor, dL_dsh);
 }
 
 void launch_sh_grad_combine(int P, int V, int D, int M, const float* means3D, const float* campos,
@@ -240,7 +241,7 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int V, int M, const float* __restr
       const uint32_t t = s_ticket;
       if (t >= nchunks) break;
       const size_t i = (size_t)t * 256 + threadIdx.x;
-      if (i < (size_t)x.P) sh_row_rebuild<D, W256>(i, x.P, V, M, means3D, s_cam, x.gc, dL_dsh);
+      if (i < (size_t)x.P) sh_row_rebuild<D, W256>(i, x.gc_slot_floats, V, M, means3D, s_cam, x.gc, dL_dsh);
     }
   }
 
