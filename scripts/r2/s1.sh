@@ -62,6 +62,7 @@ qp default SFB_X=0
 qp fwd_ldg SFB_FWD_STAGE=ldg
 qp bwd_ldg SFB_BWD_STAGE=ldg
 qp bwd_b256 SFB_BWD_BATCH=256
+qp bwd_b128x3 SFB_BWD_BATCH=128x3
 qp bwd_noorder SFB_BWD_ORDER=0
 qp bwd_r1like SFB_BWD_BATCH=256 SFB_BWD_ORDER=0 SFB_BWD_STAGE=ldg SFB_FWD_STAGE=ldg
 qp pre_occ4 SFB_PRE_OCC4=1

@@ -356,7 +356,8 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
 bool make_rec_tensor_map(const SplatRec* rec, size_t P, void* out_map);   // render_fwd.cu
 
 // A/B knobs of the round-2 sessions (profiles/): SFB_BWD_STAGE=ldg (three 16-byte loads per thread instead of the TMA
-// row gather), SFB_BWD_BATCH=256 (round-1 batch size: 3 CTAs per SM), SFB_BWD_ORDER=0 (tiles in launch order).
+// row gather), SFB_BWD_BATCH=256 (round-1 batch size: 3 CTAs per SM) or 128x3 (128-entry batches without the 64-register
+// cap), SFB_BWD_ORDER=0 (tiles in launch order).
 static int env_choice(const char* name, const char* alt) {
   const char* e = getenv(name);
   return (e && strcmp(e, alt) == 0) ? 1 : 0;
@@ -371,8 +372,8 @@ int launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* po
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
   static int cfg = -1;
   if (cfg < 0) cfg = env_choice("SFB_BWD_STAGE", "ldg") | (env_choice("SFB_BWD_BATCH", "256") << 1) |
-                     (env_choice("SFB_BWD_ORDER", "0") << 2);
-  const bool tma = !(cfg & 1), big = (cfg & 2) != 0, ordered = !(cfg & 4);
+                     (env_choice("SFB_BWD_ORDER", "0") << 2) | (env_choice("SFB_BWD_BATCH", "128x3") << 3);
+  const bool tma = !(cfg & 1), big = (cfg & 2) != 0, ordered = !(cfg & 4), b128x3 = (cfg & 8) != 0;
   if (!ordered) { bcount = nullptr; btile = nullptr; }
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
@@ -392,6 +393,7 @@ int launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* po
 #define SFB_RBA(A)                                                                                                  \
   do {                                                                                                              \
     if (big) { if (tma) SFB_RBK(A, 256, 3, true); else SFB_RBK(A, 256, 3, false); }                                 \
+    else if (b128x3) { SFB_RBK(A, 128, 3, true); }   /* 128-entry batches at 80 registers (3 CTAs / SM) */            \
     else     { if (tma) SFB_RBK(A, 128, 4, true); else SFB_RBK(A, 128, 4, false); }                                 \
   } while (0)
   if (dL_dalpha_img) SFB_RBA(true); else SFB_RBA(false);
