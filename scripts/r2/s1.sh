@@ -76,4 +76,10 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:"$KE
 tail -2 $OUT/ncu_full.log | cut -c1-200
 ncu -i $OUT/prof.ncu-rep --page raw --csv > $OUT/ncu_raw.csv 2>/dev/null
 python scripts/ncu_summary.py $OUT/ncu_raw.csv > $OUT/ncu_full_summary.txt 2>&1; grep -c "^==" $OUT/ncu_full_summary.txt
+K='activate_forward_kernel|activate_backward_kernel|knn_query_kernel|knn_boxes_kernel|knn_morton_kernel|sh_grad_combine_kernel|ssim_stats_kernel|ssim_grad_kernel|densify_stats_kernel|densify_masks_kernel'
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"$K" -c 20 -f -o $OUT/prof_next_rows \
+    python scripts/quick_perf_next_rows.py --iters 1 --warmup 0 > $OUT/ncu_next_rows.log 2>&1
+ncu -i $OUT/prof_next_rows.ncu-rep --page raw --csv > $OUT/ncu_next_rows_raw.csv 2>/dev/null
+python scripts/ncu_summary.py $OUT/ncu_next_rows_raw.csv > $OUT/ncu_next_rows_summary.txt 2>&1; grep -c "^==" $OUT/ncu_next_rows_summary.txt
+rm -f $OUT/prof_next_rows.ncu-rep
 ls $OUT | head -40
