@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
+#include <cstddef>
 
 namespace sfb {
 
@@ -68,15 +69,17 @@ constexpr int NW = NT / 32;      // warps = 8x4 pixel patches
 template <int BBT>
 struct SmemBwdMma {
   float4 row[BBT][4];               // staged 64-byte rows (common.cuh); [3] = true conic A, B, C + Gaussian index bits
-  float acc[BBT * 9];
+  float2 stage[NW][MG * 32];        // per warp: [entry row][pixel ^ swizzle] = (sG, w)
+  float2 dlp[NW][4][32];            // per warp: (hi, lo) of dL/dC_c per pixel; channel 3 = zeros
+  alignas(16) uint8_t list[NW][BBT];   // per warp: compacted entry slots (read 16 at a time)
+  alignas(16) float acc[BBT * 9];
   uint64_t bar;
   uint32_t maxc[NW];
   uint32_t tile;
   uint8_t mask[BBT];
-  uint8_t list[NW][BBT];
-  float2 stage[NW][MG * 32];        // per warp: [entry row][pixel ^ swizzle] = (sG, w)
-  float2 dlp[NW][4][32];            // per warp: (hi, lo) of dL/dC_c per pixel; channel 3 = zeros
 };
+static_assert(offsetof(SmemBwdMma<128>, list) % 16 == 0 && offsetof(SmemBwdMma<256>, list) % 16 == 0, "16-byte list loads");
+static_assert(offsetof(SmemBwdMma<128>, stage) % 16 == 0 && offsetof(SmemBwdMma<128>, bar) % 8 == 0, "smem alignment");
 
 // Tile order: the forward left every tile in one of TILE_BUCKETS cost buckets (deepest contributor of the tile / 32)
 // with a unique rank inside its bucket; CTA i takes the i-th tile counting from the most expensive bucket down, so the
