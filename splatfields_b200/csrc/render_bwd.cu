@@ -102,7 +102,7 @@ __device__ __forceinline__ int ordered_tile(int i, int T, const uint32_t* __rest
   return (int)*s_tile;
 }
 
-template <bool ALPHA, int BBT, int MINB, bool TMA>
+template <bool ALPHA, int BBT, int MINB, bool TMA, bool PRED>
 __global__ void __launch_bounds__(NT, MINB)
 render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
                            const uint32_t* __restrict__ point_list, uint32_t idx_mask,
@@ -243,7 +243,39 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
       // ---- phase A: per-pixel chain over up to 16 entries; (sG, w) of every pixel go to the staging rows
       auto entry = [&](const int i, const int j) {
         float sG = 0.f, wgt = 0.f;
-        if (j >= jmin) {
+        if (PRED) {
+          // Predicated body (no branch per entry): a pixel that does not take the entry runs the same instructions with
+          // alpha_eff = 0 — T, the running colour and the staged (sG, w) come out unchanged / zero — which costs nothing
+          // extra in SIMT, drops the divergence bookkeeping and lets the 16 unrolled entries overlap their loads / exp.
+          const float4 q0 = sm.row[j][0];
+          const float4 q1 = sm.row[j][1];
+          const float dx = q0.x - pixfx, dy = q0.y - pixfy;
+          const float kp = render_power(q0.z, q0.w, q1.x, dx, dy);
+          const float G = render_exp(kp);
+          const float alpha = fminf(0.99f, __fmul_rn(q1.y, G));
+          const bool c = (j >= jmin) & !((kp > 0.0f) | (alpha < 1.0f / 255.0f));   // the forward's own test
+          const float ae = c ? alpha : 0.f;
+          const float2 q2 = make_float2(sm.row[j][2].x, sm.row[j][2].y);
+          float inv;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - alpha));
+          inv = c ? inv : 1.f;
+          T *= inv;
+          wgt = ae * T;
+          const float d0 = q1.w - acc0, d1 = q2.x - acc1, d2 = q2.y - acc2;
+          float dL_dalpha = d0 * dLp0;
+          dL_dalpha = fmaf(d1, dLp1, dL_dalpha);
+          dL_dalpha = fmaf(d2, dLp2, dL_dalpha);
+          acc0 = fmaf(ae, d0, acc0);
+          acc1 = fmaf(ae, d1, acc1);
+          acc2 = fmaf(ae, d2, acc2);
+          if (ALPHA) {
+            const float da = 1.f - acca;
+            dL_dalpha = fmaf(da, dLpa, dL_dalpha);
+            acca = fmaf(ae, da, acca);
+          }
+          dL_dalpha = fmaf(dL_dalpha, T, -Tf_bg * inv);
+          sG = c ? q1.y * dL_dalpha * G : 0.f;
+        } else if (j >= jmin) {
           const float4 q0 = sm.row[j][0];
           const float4 q1 = sm.row[j][1];
           const float dx = q0.x - pixfx, dy = q0.y - pixfy;
@@ -360,7 +392,7 @@ bool make_rec_tensor_map(const SplatRec* rec, size_t P, void* out_map);   // ren
 
 // A/B knobs of the round-2 sessions (profiles/): SFB_BWD_STAGE=ldg (three 16-byte loads per thread instead of the TMA
 // row gather), SFB_BWD_BATCH=256 (round-1 batch size: 3 CTAs per SM) or 128x3 (128-entry batches without the 64-register
-// cap), SFB_BWD_ORDER=0 (tiles in launch order).
+// cap), SFB_BWD_ORDER=0 (tiles in launch order), SFB_BWD_SWEEP=branch (branching per-entry body).
 static int env_choice(const char* name, const char* alt) {
   const char* e = getenv(name);
   return (e && strcmp(e, alt) == 0) ? 1 : 0;
@@ -375,8 +407,9 @@ int launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* po
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
   static int cfg = -1;
   if (cfg < 0) cfg = env_choice("SFB_BWD_STAGE", "ldg") | (env_choice("SFB_BWD_BATCH", "256") << 1) |
-                     (env_choice("SFB_BWD_ORDER", "0") << 2) | (env_choice("SFB_BWD_BATCH", "128x3") << 3);
-  const bool tma = !(cfg & 1), big = (cfg & 2) != 0, ordered = !(cfg & 4), b128x3 = (cfg & 8) != 0;
+                     (env_choice("SFB_BWD_ORDER", "0") << 2) | (env_choice("SFB_BWD_BATCH", "128x3") << 3) |
+                     (env_choice("SFB_BWD_SWEEP", "branch") << 4);
+  const bool tma = !(cfg & 1), big = (cfg & 2) != 0, ordered = !(cfg & 4), b128x3 = (cfg & 8) != 0, pred = !(cfg & 16);
   if (!ordered) { bcount = nullptr; btile = nullptr; }
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
@@ -386,9 +419,10 @@ int launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* po
   }
   // > 48 KB of dynamic shared memory needs the attribute on EVERY device the process uses (it is per device and the
   // call is cheap: it is made with every launch)
-#define SFB_RBK(A, B, MB, TM)                                                                                       \
+#define SFB_RBK(A, B, MB, TM) do { if (pred) SFB_RBP(A, B, MB, TM, true); else SFB_RBP(A, B, MB, TM, false); } while (0)
+#define SFB_RBP(A, B, MB, TM, PR)                                                                                   \
   do {                                                                                                              \
-    auto kern = render_backward_mma_kernel<A, B, MB, TM>;                                                           \
+    auto kern = render_backward_mma_kernel<A, B, MB, TM, PR>;                                                       \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemBwdMma<B>));            \
     kern<<<gx * gy, NT, sizeof(SmemBwdMma<B>), s>>>(W, H, gx, ranges, point_list, idx_mask, rec, map, bg, final_T,  \
                                                    n_contrib, dL_dpixels, dL_dalpha_img, hit, bcount, btile, grad); \
@@ -402,6 +436,7 @@ int launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* po
   if (dL_dalpha_img) SFB_RBA(true); else SFB_RBA(false);
 #undef SFB_RBA
 #undef SFB_RBK
+#undef SFB_RBP
   return 0;
 }
 
