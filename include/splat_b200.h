@@ -129,6 +129,11 @@ int sfb_xchg_finish(const sfb_xchg* x, unsigned epoch, int sh_degree, int M, con
                     const float* campos_views, float* dL_dmeans3D, float* dL_dopacity, float* dL_dscales,
                     float* dL_drotations, float* dL_dcolors, float* dL_dsh, void* stream);
 
+/* Synchronises `stream` and reads this rank's exchange error word: 0 = every sfb_xchg_finish so far completed;
+ * otherwise (1: a rank never announced its backward | 2: a rank never broadcast its sums) | epoch << 8 — the device-side
+ * waits are bounded (about 2 s), a kernel that gives up leaves its outputs untouched and records the failure here. */
+int sfb_xchg_status(const sfb_xchg* x, unsigned* status, void* stream);
+
 /* Multi-view sum of SH gradients from their factored form (view-parallel training; the serial loop
  * it replaces is train.py:169-242, whose loss.backward() accumulates the V per-view dL_dsh into features.grad):
  *     dL_dsh[i][k][c] = sum_{v < V} basis_k(normalize(means3D[i] - campos[v])) * dL_dcolor_views[v][i][c]

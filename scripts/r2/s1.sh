@@ -42,8 +42,8 @@ PY
 tail -16 $OUT/device.log
 echo "== TMA row gather primitive"; timeout 200 python -m pytest tests/test_gpu_properties.py -m gpu -q -k tma_row 2>&1 | tail -4 | tee $OUT/tma_probe.log
 # smoke of both staging paths first: a broken TMA path must not take the whole session down
-for st in tma ldg; do echo "== smoke SFB_FWD_STAGE=$st SFB_BWD_STAGE=$st"; SFB_FWD_STAGE=$st SFB_BWD_STAGE=$st timeout 300 python __graft_entry__.py --smoke-only 2>&1 | tail -2; done | tee $OUT/smoke.log
-echo "== smoke SFB_SWEEP=branch SFB_BWD_SWEEP=branch SFB_BWD_BATCH=256 (round-1-like arms)"; SFB_SWEEP=branch SFB_BWD_SWEEP=branch SFB_BWD_BATCH=256 SFB_BWD_ORDER=0 timeout 300 python __graft_entry__.py --smoke-only 2>&1 | tail -2 | tee -a $OUT/smoke.log
+for st in ldg tma; do echo "== smoke SFB_FWD_STAGE=$st SFB_BWD_STAGE=$st"; SFB_FWD_STAGE=$st SFB_BWD_STAGE=$st timeout 300 python __graft_entry__.py --smoke-only 2>&1 | tail -2; done | tee $OUT/smoke.log
+echo "== smoke SFB_BWD_SWEEP=pred SFB_BWD_BATCH=128"; SFB_BWD_SWEEP=pred SFB_BWD_BATCH=128 timeout 300 python __graft_entry__.py --smoke-only 2>&1 | tail -2 | tee -a $OUT/smoke.log
 timeout 1200 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log; tail -4 $OUT/pytest_gpu.log | cut -c1-400
 qp() { # name, env...
   local name=$1; shift
@@ -60,14 +60,14 @@ PY
 }
 {
 qp default SFB_X=0
-qp fwd_ldg SFB_FWD_STAGE=ldg
-qp fwd_branch SFB_SWEEP=branch
-qp bwd_ldg SFB_BWD_STAGE=ldg
-qp bwd_branch SFB_BWD_SWEEP=branch
-qp bwd_b256 SFB_BWD_BATCH=256
+qp fwd_tma SFB_FWD_STAGE=tma
+qp bwd_tma SFB_BWD_STAGE=tma
+qp bwd_pred SFB_BWD_SWEEP=pred
+qp bwd_b128 SFB_BWD_BATCH=128
+qp bwd_b128_pred SFB_BWD_BATCH=128 SFB_BWD_SWEEP=pred
 qp bwd_b128x3 SFB_BWD_BATCH=128x3
+qp bwd_b128x3_pred SFB_BWD_BATCH=128x3 SFB_BWD_SWEEP=pred
 qp bwd_noorder SFB_BWD_ORDER=0
-qp bwd_r1like SFB_BWD_BATCH=256 SFB_BWD_ORDER=0 SFB_BWD_STAGE=ldg SFB_FWD_STAGE=ldg SFB_SWEEP=branch SFB_BWD_SWEEP=branch
 qp pre_occ4 SFB_PRE_OCC4=1
 qp default2 SFB_X=0
 } | tee $OUT/ab_matrix.txt

@@ -23,7 +23,7 @@ SYMBOLS = (
     "sfb_export_geom", "sfb_export_binning", "sfb_export_img", "sfb_debug_gather_rows", "sfb_last_launch_count",
     "sfb_profile_enable", "sfb_profile_count", "sfb_profile_read", "sfb_profile_name",
     "sfb_loss_scratch_bytes", "sfb_loss_window", "sfb_l1_ssim_loss", "sfb_densify_stats", "sfb_densify_masks",
-    "sfb_sh_grad_combine", "sfb_xchg_bytes", "sfb_xchg_finish", "sfb_activate_forward", "sfb_activate_backward", "sfb_knn_scratch_bytes",
+    "sfb_sh_grad_combine", "sfb_xchg_bytes", "sfb_xchg_finish", "sfb_xchg_status", "sfb_activate_forward", "sfb_activate_backward", "sfb_knn_scratch_bytes",
     "sfb_knn3_mean_dist2",
 )
 
@@ -110,6 +110,8 @@ def load():
     lib.sfb_xchg_bytes.argtypes = [ci, ci, ci, ci]
     lib.sfb_xchg_finish.restype = ci
     lib.sfb_xchg_finish.argtypes = [C.POINTER(XchgDesc), C.c_uint, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.sfb_xchg_status.restype = ci
+    lib.sfb_xchg_status.argtypes = [C.POINTER(XchgDesc), C.POINTER(C.c_uint), vp]
     lib.sfb_activate_forward.restype = ci
     lib.sfb_activate_forward.argtypes = [ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_activate_backward.restype = ci

@@ -413,6 +413,15 @@ int sfb_xchg_finish(const sfb_xchg* x, unsigned epoch, int sh_degree, int M, con
   return SFB_OK;
 }
 
+int sfb_xchg_status(const sfb_xchg* x, unsigned* status, void* stream) {
+  g_err.clear();
+  if (!x || !x->local || !status) return fail(SFB_ERR_ARG, "sfb_xchg_status: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(status, reinterpret_cast<const uint32_t*>(x->local) + 34, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return SFB_OK;
+}
+
 int sfb_sh_grad_combine(int P, int V, int sh_degree, int M, const float* means3D, const float* campos,
                         const float* dL_dcolor_views, float* dL_dsh, void* stream) {
   using namespace sfb;

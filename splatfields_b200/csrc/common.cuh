@@ -71,35 +71,17 @@ __device__ __forceinline__ float splat_exp(float power) {
 
 // ---- staged splat rows of the two render kernels ----
 // A list entry is staged in shared memory as one 64-byte row of four float4:
-//   [0] x, y, a', b'    [1] c', opacity, depth, r    [2] g, b, hx, hy    [3] A, B, C, -  (true conic, backward flush)
-// The first 48 bytes arrive as the SplatRec (TMA row gather or three 16-byte loads); the thread that owns the row then
-// rewrites the conic in place, pre-multiplied for the sweep:  a' = -k/2 A,  b' = -k B,  c' = -k/2 C  with k = log2(e)
-// (k = 1 in the expf build), so that  k * power = a' dx^2 + b' dx dy + c' dy^2  costs 5 instead of 9 flops per pixel
-// and feeds ex2 directly.  Forward and backward use the SAME expression (render_power below): a pixel the forward
-// accumulated is never skipped by the backward and vice versa.
-#ifdef SFB_EXACT_EXP
-constexpr float RENDER_K = 1.0f;
-#else
-constexpr float RENDER_K = 1.4426950408889634f;
-#endif
-__device__ __forceinline__ void prescale_conic(float A, float B, float C, float& a, float& b, float& c) {
-  a = (-0.5f * RENDER_K) * A; b = (-RENDER_K) * B; c = (-0.5f * RENDER_K) * C;
+//   [0] x, y, conA, conB    [1] conC, opacity, depth, r    [2] g, b, hx, hy    [3] -, -, -, Gaussian index (backward)
+// The first 48 bytes are the SplatRec as it sits in HBM (TMA row gather, or three 16-byte loads).
+// power = -0.5 (A dx^2 + C dy^2) - B dx dy  is evaluated in the op order nvcc gives the reference's expression
+// (round 2 tried a conic pre-multiplied by -log2(e)/2 — 5 instead of 9 flops — and lost the needle-splat parity case:
+// with a nearly singular conic the three terms cancel to 1e-4 of their size, so the ROUNDING ORDER is part of the result;
+// measured 1.4e-4 image error against 1e-5 allowed).  Forward and backward share the expression.
+__device__ __forceinline__ float render_power(float A, float B, float C, float dx, float dy) {
+  const float s = __fmaf_rn(__fmul_rn(A, dx), dx, __fmul_rn(__fmul_rn(C, dy), dy));
+  return __fmaf_rn(s, -0.5f, -__fmul_rn(__fmul_rn(B, dx), dy));
 }
-// k * power at offset (dx, dy) from the splat centre
-__device__ __forceinline__ float render_power(float a, float b, float c, float dx, float dy) {
-  const float m = __fmaf_rn(b, dy, __fmul_rn(a, dx));
-  return __fmaf_rn(m, dx, __fmul_rn(__fmul_rn(c, dy), dy));
-}
-// exp(power) from k * power
-__device__ __forceinline__ float render_exp(float kp) {
-#ifdef SFB_EXACT_EXP
-  return expf(kp);
-#else
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(kp));
-  return r;
-#endif
-}
+__device__ __forceinline__ float render_exp(float power) { return splat_exp(power); }
 
 // ---- TMA row gather (cp.async.bulk.tensor ... tile::gather4 -> UTMALDG): four rows of a 2-D tensor per instruction ----
 // dst: 4 consecutive box rows in shared memory (128-byte aligned); tmap: CUtensorMap over the row table with

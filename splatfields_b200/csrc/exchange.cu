@@ -137,14 +137,16 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Wait until *p >= epoch (flags only grow).  Bounded: a peer that never arrives must not hang the GPU — after ~4 s the
-// kernel traps and the caller gets a CUDA error.
-__device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t epoch) {
+// Wait until *p >= epoch (flags only grow).  Bounded: a peer that never arrives must not hang the GPU — after ~2 s the
+// wait gives up and returns false; the kernel then records the failure in its rank's error word (sfb_xchg_status) and
+// retires without touching the outputs.
+__device__ __forceinline__ bool spin_until(const uint32_t* p, uint32_t epoch) {
   const long long t0 = clock64();
   while ((int32_t)(ld_acquire_sys(p) - epoch) < 0) {
     __nanosleep(64);
-    if (clock64() - t0 > 8000000000LL) __trap();
+    if (clock64() - t0 > 4000000000LL) return false;
   }
+  return true;
 }
 __device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) {
   float4 v;
@@ -168,7 +170,8 @@ __device__ __forceinline__ void mm_st(float* mc_addr, const float4 v) {
 //   [FLAG_A + r]  rank r's backward of step `epoch` is complete (its records are in its buffer, its colour gradients in mine)
 //   [FLAG_B + r]  rank r has broadcast its slice of the sums of step `epoch`
 //   [FLAG_DONE]   local: CTAs of this launch that finished their part of the slice reduction
-constexpr int FLAG_A = 0, FLAG_B = 16, FLAG_DONE = 32, FLAG_TICKET = 33;
+//   [FLAG_ERR]    local: 0, or (1 | 2: which barrier timed out) | epoch << 8   (sfb_xchg_status)
+constexpr int FLAG_A = 0, FLAG_B = 16, FLAG_DONE = 32, FLAG_TICKET = 33, FLAG_ERR = 34;
 
 template <int D, bool MC, bool HAS_SH, bool W256>
 __global__ void __launch_bounds__(256, 2)
@@ -185,8 +188,13 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int V, int M, const float* __restr
     st_release_sys(x.peer_flags[threadIdx.x] + FLAG_A + x.rank, epoch);
   }
   if (HAS_SH) for (int k = threadIdx.x; k < 3 * V; k += blockDim.x) s_cam[k] = campos[k];
-  if (threadIdx.x < N) spin_until(x.flags + FLAG_A + threadIdx.x, epoch);
-  __syncthreads();
+  {
+    const bool ok = threadIdx.x < N ? spin_until(x.flags + FLAG_A + threadIdx.x, epoch) : true;
+    if (!__syncthreads_and(ok)) {           // a peer never announced: give up (all threads of the CTA together)
+      if (threadIdx.x == 0) atomicMax(x.flags + FLAG_ERR, 1u | (epoch << 8));
+      return;
+    }
+  }
 
   // ---- 1. sum this rank's slice of the packed records over the ranks, broadcast the sums (in place)
   // The slice is split over the first `nred` CTAs; the rest start on the SH rows right away (they only need barrier A).
@@ -246,8 +254,13 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int V, int M, const float* __restr
   }
 
   // ---- 3. every slice has been broadcast: unpack the summed records into the per-parameter arrays
-  if (threadIdx.x < N) spin_until(x.flags + FLAG_B + threadIdx.x, epoch);
-  __syncthreads();
+  {
+    const bool ok = threadIdx.x < N ? spin_until(x.flags + FLAG_B + threadIdx.x, epoch) : true;
+    if (!__syncthreads_and(ok)) {
+      if (threadIdx.x == 0) atomicMax(x.flags + FLAG_ERR, 2u | (epoch << 8));
+      return;
+    }
+  }
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < (size_t)x.P; i += (size_t)gridDim.x * 256) {
     const float4* rec = reinterpret_cast<const float4*>(x.geo + i * (size_t)x.ngeo);
     const float4 a = __ldcg(rec), b = __ldcg(rec + 1), c = __ldcg(rec + 2);

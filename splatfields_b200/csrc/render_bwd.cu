@@ -64,8 +64,8 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 constexpr int NT = 256;          // threads per CTA = pixels of a tile
 constexpr int NW = NT / 32;      // warps = 8x4 pixel patches
 
-// BBT = list entries per batch.  128 (default): 54 KB of shared memory and 64 registers -> 4 CTAs per SM;
-// 256: 67.5 KB / 80 registers -> 3 CTAs per SM (the round-1 configuration, kept for the A/B in profiles/).
+// BBT = list entries per batch.  256 (default): 67.5 KB of shared memory / 80 registers -> 3 CTAs per SM;
+// 128: 54 KB / 64 registers -> 4 CTAs per SM (measured slower in round 2: twice the per-batch overhead and spills).
 template <int BBT>
 struct SmemBwdMma {
   float4 row[BBT][4];               // staged 64-byte rows (common.cuh); [3] = true conic A, B, C + Gaussian index bits
@@ -211,11 +211,8 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
         sm.row[threadIdx.x][2] = c;
       }
       if (mine) {
-        float ka, kb, kc;
-        prescale_conic(a.z, a.w, b.x, ka, kb, kc);
-        sm.row[threadIdx.x][0] = make_float4(a.x, a.y, ka, kb);
-        sm.row[threadIdx.x][1] = make_float4(kc, b.y, b.z, b.w);
-        sm.row[threadIdx.x][3] = make_float4(a.z, a.w, b.x, __uint_as_float(id));
+        if (!TMA) { sm.row[threadIdx.x][0] = a; sm.row[threadIdx.x][1] = b; }
+        sm.row[threadIdx.x][3] = make_float4(0.f, 0.f, 0.f, __uint_as_float(id));
         if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // rows are overwritten by the TMA unit next batch
       }
     }
@@ -364,8 +361,9 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
       for (int k = 0; k < 9; k++) { a[k] = sm.acc[threadIdx.x * 9 + k]; nz |= (a[k] != 0.f); }
       if (nz) {
         const float4 q0 = sm.row[threadIdx.x][0];
+        const float4 q1 = sm.row[threadIdx.x][1];
         const float4 q3 = sm.row[threadIdx.x][3];
-        const float conA = q3.x, conB = q3.y, conC = q3.z, op = sm.row[threadIdx.x][1].y;
+        const float conA = q0.z, conB = q0.w, conC = q1.x, op = q1.y;
         // tile-centre moments -> splat-centre moments: dx = cx - X, dy = cy - Y
         const float cx = q0.x - (tx0 + 7.5f), cy = q0.y - (ty0 + 7.5f);
         const float S0 = a[0];
@@ -390,9 +388,9 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
 
 bool make_rec_tensor_map(const SplatRec* rec, size_t P, void* out_map);   // render_fwd.cu
 
-// A/B knobs of the round-2 sessions (profiles/): SFB_BWD_STAGE=ldg (three 16-byte loads per thread instead of the TMA
-// row gather), SFB_BWD_BATCH=256 (round-1 batch size: 3 CTAs per SM) or 128x3 (128-entry batches without the 64-register
-// cap), SFB_BWD_ORDER=0 (tiles in launch order), SFB_BWD_SWEEP=branch (branching per-entry body).
+// A/B knobs of the round-2 sessions (profiles/): SFB_BWD_STAGE=tma (TMA row gather instead of three 16-byte loads per
+// thread), SFB_BWD_BATCH=128 (128-entry batches, 64 registers, 4 CTAs per SM) or 128x3 (128-entry batches at 80
+// registers), SFB_BWD_ORDER=0 (tiles in launch order), SFB_BWD_SWEEP=pred (predicated per-entry body).
 static int env_choice(const char* name, const char* alt) {
   const char* e = getenv(name);
   return (e && strcmp(e, alt) == 0) ? 1 : 0;
@@ -406,10 +404,10 @@ int launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* po
                            cudaStream_t s) {
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
   static int cfg = -1;
-  if (cfg < 0) cfg = env_choice("SFB_BWD_STAGE", "ldg") | (env_choice("SFB_BWD_BATCH", "256") << 1) |
+  if (cfg < 0) cfg = env_choice("SFB_BWD_STAGE", "tma") | (env_choice("SFB_BWD_BATCH", "128") << 1) |
                      (env_choice("SFB_BWD_ORDER", "0") << 2) | (env_choice("SFB_BWD_BATCH", "128x3") << 3) |
-                     (env_choice("SFB_BWD_SWEEP", "branch") << 4);
-  const bool tma = !(cfg & 1), big = (cfg & 2) != 0, ordered = !(cfg & 4), b128x3 = (cfg & 8) != 0, pred = !(cfg & 16);
+                     (env_choice("SFB_BWD_SWEEP", "pred") << 4);
+  const bool tma = (cfg & 1) != 0, b128 = (cfg & 2) != 0, ordered = !(cfg & 4), b128x3 = (cfg & 8) != 0, pred = (cfg & 16) != 0;
   if (!ordered) { bcount = nullptr; btile = nullptr; }
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
@@ -429,9 +427,9 @@ int launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* po
   } while (0)
 #define SFB_RBA(A)                                                                                                  \
   do {                                                                                                              \
-    if (big) { if (tma) SFB_RBK(A, 256, 3, true); else SFB_RBK(A, 256, 3, false); }                                 \
-    else if (b128x3) { SFB_RBK(A, 128, 3, true); }   /* 128-entry batches at 80 registers (3 CTAs / SM) */            \
-    else     { if (tma) SFB_RBK(A, 128, 4, true); else SFB_RBK(A, 128, 4, false); }                                 \
+    if (b128) { if (tma) SFB_RBK(A, 128, 4, true); else SFB_RBK(A, 128, 4, false); }                                \
+    else if (b128x3) { SFB_RBK(A, 128, 3, false); }   /* 128-entry batches at 80 registers (3 CTAs / SM) */           \
+    else     { if (tma) SFB_RBK(A, 256, 3, true); else SFB_RBK(A, 256, 3, false); }                                 \
   } while (0)
   if (dL_dalpha_img) SFB_RBA(true); else SFB_RBA(false);
 #undef SFB_RBA

@@ -6,12 +6,16 @@
 // One CTA per tile, 256 threads = one pixel each; a warp covers an 8x4 pixel patch (not a 16x2 strip)
 // so that the pixels of a warp see nearly the same set of contributing splats.  The tile's list is
 // consumed in batches of 256 entries staged in shared memory as 64-byte rows (common.cuh):
-//   * TMA staging (default): the 48-byte SplatRec rows of a batch are gathered by the TMA unit —
+//   * LDG staging (default): every thread loads one record with three 16-byte loads (the record table stays
+//     L2-resident) and stores it to shared memory; single buffer.
+//   * TMA staging (SFB_FWD_STAGE=tma): the 48-byte SplatRec rows of a batch are gathered by the TMA unit —
 //     cp.async.bulk.tensor.2d ... tile::gather4 (SASS: UTMALDG), four list entries per instruction, 64 instructions
 //     per batch issued by every fourth thread — into one of two buffers; completion is an mbarrier transaction
-//     count.  The gather of batch k+1 is issued before batch k is swept, so its L2 round trip runs under the sweep.
-//   * LDG staging (SFB_FWD_STAGE=ldg, kept for the A/B in profiles/): every thread loads one record with three
-//     16-byte loads and stores it to shared memory; single buffer.
+//     count; the gather of batch k+1 is issued before batch k is swept.  Measured SLOWER on B200 for this access
+//     pattern (0.156 vs 0.148 ms per lego_1m forward, profiles/r02a_ab_matrix.txt): a tile is saturated after ~1.2
+//     batches, so there is little to overlap, and 64 four-row gathers of 48-byte rows through the SM's one TMA unit take
+//     longer than 768 independent 16-byte loads through the LSU.  Kept as a tested variant (it goes through the parity
+//     suite) and as the evidence the A/B rests on.
 // The thread that owns a row then computes its culling mask and rewrites the conic pre-multiplied for the sweep;
 // all threads sweep the batch reading the rows as warp-wide broadcasts.
 #include "common.cuh"
@@ -41,7 +45,7 @@ struct SmemFwd {
   uint8_t hitw[RB / 32][RB];   // [warp][entry]: 1 = some pixel of the warp accumulated it
 };
 
-template <bool ALPHA, bool TMA, bool PRED>
+template <bool ALPHA, bool TMA>
 __global__ void __launch_bounds__(RB, 6)   // <= 42 registers: the sweep loop needs ~40; the fetch-phase culling math may spill
 render_forward_kernel(int W, int H, int grid_x, uint2* __restrict__ ranges,
                       const uint32_t* __restrict__ point_list, uint32_t idx_mask,
@@ -129,11 +133,7 @@ render_forward_kernel(int W, int H, int grid_x, uint2* __restrict__ ranges,
     uint32_t mask = 0u;
     if ((int)threadIdx.x < cnt) {
       mask = refine_patch_mask(patch_mask(a.x, a.y, c.z, c.w, tx0, ty0), a.x, a.y, a.z, a.w, b.x, b.y, c.z, tx0, ty0);
-      float ka, kb, kc;
-      prescale_conic(a.z, a.w, b.x, ka, kb, kc);
-      myrow[0] = make_float4(a.x, a.y, ka, kb);
-      myrow[1] = make_float4(kc, b.y, b.z, b.w);
-      if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these rows are overwritten by the TMA unit later
+      if (!TMA) { myrow[0] = a; myrow[1] = b; }
     }
     sm.mask[threadIdx.x] = (uint8_t)mask;
     reinterpret_cast<uint2*>(&sm.hitw[0][0])[threadIdx.x] = make_uint2(0u, 0u);   // 8 warps x 256 B
@@ -153,54 +153,11 @@ render_forward_kernel(int W, int H, int grid_x, uint2* __restrict__ ranges,
       __syncwarp();
       n = k;
     }
-    // Sweep.  The loop body is the kernel: every instruction in it is paid ~100 M times per view.
-    if (PRED) {
-      // Predicated body: no branch per entry.  A lane that skips the entry (or has saturated: `done` is sticky) runs
-      // the same instructions with its accumulations predicated off, which costs nothing extra in SIMT (the warp issues
-      // an instruction as long as one lane needs it) and removes the per-entry divergence bookkeeping (BSSY / BSYNC /
-      // BREAK, ~10 of ~40 instructions); four entries are unrolled per trip (one 32-bit load of list bytes, independent
-      // loads / exp of consecutive entries overlap), with one warp vote per trip to leave once every lane is done.
-      if (!__all_sync(0xffffffffu, done)) {
-        int lastj = -1;
-        const float4* const rows = &sm.row[buf][0][0];
-        auto body = [&](const int j) {
-          const float4 q0 = rows[4 * j];
-          const float4 q1 = rows[4 * j + 1];
-          const float dx = q0.x - pixfx, dy = q0.y - pixfy;
-          const float kp = render_power(q0.z, q0.w, q1.x, dx, dy);
-          const float alpha = fminf(0.99f, __fmul_rn(q1.y, render_exp(kp)));
-          bool c = !done & !((kp > 0.0f) | (alpha < 1.0f / 255.0f));   // the reference's two skips
-          const float test_T = __fmul_rn(T, 1.0f - alpha);
-          const bool sat = c & (test_T < 0.0001f);                       // ... and its stop, BEFORE this contributor
-          done |= sat;
-          c &= !sat;
-          // weight 0 instead of a branch: C += rgb * 0 leaves finite accumulators untouched (a NON-FINITE colour or
-          // depth would poison every pixel of a warp that sweeps the entry, not only the pixels it contributes to)
-          const float w = c ? __fmul_rn(alpha, T) : 0.0f;
-          const float4 q2 = rows[4 * j + 2];
-          C0 = __fmaf_rn(q1.w, w, C0);
-          C1 = __fmaf_rn(q2.x, w, C1);
-          C2 = __fmaf_rn(q2.y, w, C2);
-          Dp = __fmaf_rn(q1.z, w, Dp);
-          if (ALPHA) Ac = __fmaf_rn(1.0f, w, Ac);
-          T = c ? test_T : T;
-          lastj = c ? j : lastj;                         // list order is kept by the compaction: the last one wins
-          if (c) sm.hitw[warp][j] = 1;                   // same value from every contributing lane: benign
-        };
-        int k = 0;
-        bool live = true;
-        for (; k + 4 <= n; k += 4) {
-          const uint32_t lw = *reinterpret_cast<const uint32_t*>(&sm.list[warp][k]);
-#pragma unroll
-          for (int u = 0; u < 4; u++) body((int)((lw >> (8 * u)) & 0xffu));
-          if (__all_sync(0xffffffffu, done)) { live = false; break; }
-        }
-        if (live)
-          for (; k < n; k++) body((int)sm.list[warp][k]);
-        if (lastj >= 0) last_contributor = (uint32_t)(base + lastj + 1);   // 1-based position in the tile list
-      }
-    } else if (!done) {
-      // branching body (round 1; SFB_SWEEP=branch): `done` pixels skip the whole batch, a pixel that saturates leaves the loop
+    // Sweep.  `done` pixels skip the whole batch; a pixel that saturates leaves the loop (no per-iteration flag
+    // bookkeeping: the loop body is the kernel, every instruction in it is paid ~100 M times per view).  A predicated
+    // (branch-free) body was measured slower in round 2 (0.152 vs 0.148 ms, profiles/r02a_ab_matrix.txt): a quarter of the
+    // swept (warp, entry) pairs have no contributing lane and leave the branching body after half of it.
+    if (!done) {
       int lastj = -1;
       const float4* const rows = &sm.row[buf][0][0];
       for (int k = 0; k < n; k++) {
@@ -325,9 +282,9 @@ int launch_gather_rows_probe(const SplatRec* table, size_t P, const uint32_t* id
   return 0;
 }
 
-static bool fwd_stage_tma() {      // SFB_FWD_STAGE=ldg: three 16-byte loads per thread instead of the TMA row gather (A/B)
+static bool fwd_stage_tma() {      // SFB_FWD_STAGE=tma: the TMA row gather instead of three 16-byte loads per thread
   static int v = -1;
-  if (v < 0) { const char* e = getenv("SFB_FWD_STAGE"); v = (e && e[0] == 'l') ? 0 : 1; }
+  if (v < 0) { const char* e = getenv("SFB_FWD_STAGE"); v = (e && e[0] == 't') ? 1 : 0; }
   return v == 1;
 }
 
@@ -348,19 +305,12 @@ int launch_render_forward(int W, int H, uint2* ranges, const uint32_t* point_lis
     set_error("cuTensorMapEncodeTiled failed for the splat record table (TMA staging of the tile lists)");
     return -1;
   }
-  static int pred_i = -1;      // SFB_SWEEP=branch: the branching sweep body of round 1 (A/B)
-  if (pred_i < 0) { const char* e = getenv("SFB_SWEEP"); pred_i = (e && e[0] == 'b') ? 0 : 1; }
-#define SFB_RF(A, TM, PR)                                                                                           \
-  render_forward_kernel<A, TM, PR><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, idx_mask, rec, map, bg, out_color, \
-                                                          out_depth, out_alpha, final_T, n_contrib, hit, bcount, btile, \
-                                                          zero16, zero_per_cta, zero_total)
-#define SFB_RFA(A)                                                                                                  \
-  do {                                                                                                              \
-    if (tma) { if (pred_i) SFB_RF(A, true, true); else SFB_RF(A, true, false); }                                    \
-    else     { if (pred_i) SFB_RF(A, false, true); else SFB_RF(A, false, false); }                                  \
-  } while (0)
-  if (out_alpha) SFB_RFA(true); else SFB_RFA(false);
-#undef SFB_RFA
+#define SFB_RF(A, TM)                                                                                               \
+  render_forward_kernel<A, TM><<<gx * gy, RB, 0, s>>>(W, H, gx, ranges, point_list, idx_mask, rec, map, bg, out_color, \
+                                                      out_depth, out_alpha, final_T, n_contrib, hit, bcount, btile, \
+                                                      zero16, zero_per_cta, zero_total)
+  if (tma) { if (out_alpha) SFB_RF(true, true); else SFB_RF(false, true); }
+  else     { if (out_alpha) SFB_RF(true, false); else SFB_RF(false, false); }
 #undef SFB_RF
   return 0;
 }

@@ -281,6 +281,17 @@ class ViewParallelRasterizer:
             dist.all_reduce(rmax, op=dist.ReduceOp.MAX)
         return dict(radii=rmax, visibility_filter=rmax > 0, grad_norm=stats[0], count=stats[1])
 
+    def exchange_status(self) -> int:
+        """0, or the NVLink exchange's error word (include/splat_b200.h: sfb_xchg_status); synchronises the stream."""
+        if self.xchg is None:
+            return 0
+        import ctypes as C
+        st = C.c_uint(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().sfb_xchg_status(C.byref(self.xchg), C.byref(st),
+                                                   torch.cuda.current_stream(self.device).cuda_stream))
+        return int(st.value)
+
     def exchange_ms(self) -> list:
         """Device time of the gradient exchange (collectives + SH rebuild) of the steps run with time_exchange."""
         torch.cuda.synchronize(self.device)

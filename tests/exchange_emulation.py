@@ -13,6 +13,10 @@ import math
 import os
 import sys
 
+# every stream gets a hardware queue of its own: the ranks' kernels wait for each other on the device, so they must
+# never be serialised behind one another by queue aliasing (default: 8 connections shared by all streams)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
@@ -96,6 +100,12 @@ def run(world, P, H, W, deg, precomp_rgb, steps=3):
                     None if precomp_rgb else campos.data_ptr(), gp("means3D"), gp("opacities"), gp("scales"),
                     gp("rotations"), gp("colors_precomp"), gp("shs"), streams[r].cuda_stream))
         torch.cuda.synchronize()
+        for r in range(world):
+            st = C.c_uint(0)
+            _lib.check(lib.sfb_xchg_status(C.byref(descs[r]), C.byref(st), None))
+            if st.value:
+                print(f"rank {r}: exchange error word {st.value:#x} (world {world}, step {step})", flush=True)
+                return False, {"status": st.value}
         for n in names:
             scale = float(ref[n].abs().max())
             for r in range(world):
