@@ -88,12 +88,13 @@ def run(world, P, H, W, deg, precomp_rgb, steps=3):
             assert leaf["means3D"].grad is None and m2d.grad is not None
         torch.cuda.synchronize()
         # ... then the ranks' finish kernels side by side
-        outs = []
+        # (all output tensors exist before the first finish kernel starts: a cudaMalloc issued while rank 0's kernel is
+        #  already spinning on rank 1's flag can wait for the device to drain, i.e. for the very kernel that waits for us)
+        outs = [{n: torch.full_like(t[n], float("nan")) for n in names} for _ in range(world)]
+        torch.cuda.synchronize()
         for r in range(world):
-            o = {n: torch.full_like(t[n], float("nan")) for n in names}
-            outs.append(o)
+            o = outs[r]
             gp = lambda n: o[n].data_ptr() if n in o else None
-            streams[r].wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(streams[r]):
                 _lib.check(lib.sfb_xchg_finish(
                     C.byref(descs[r]), step, deg, int(M), t["means3D"].data_ptr(),
@@ -104,7 +105,10 @@ def run(world, P, H, W, deg, precomp_rgb, steps=3):
             st = C.c_uint(0)
             _lib.check(lib.sfb_xchg_status(C.byref(descs[r]), C.byref(st), None))
             if st.value:
-                print(f"rank {r}: exchange error word {st.value:#x} (world {world}, step {step})", flush=True)
+                flags = [bufs[q][:256].view(torch.int32).tolist() for q in range(world)]
+                print(f"rank {r}: exchange error word {st.value:#x} (world {world}, step {step}); flag words "
+                      f"A/B/done/ticket/err per rank: " + str([(f[0:world], f[16:16 + world], f[32:35]) for f in flags]),
+                      flush=True)
                 return False, {"status": st.value}
         for n in names:
             scale = float(ref[n].abs().max())
