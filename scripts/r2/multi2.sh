@@ -27,6 +27,7 @@ PY
   tail -2 $OUT/bench_n${N}_$name.err | cut -c1-300
 }
 run_bench nvlink SFB_X=0
+if [ "$MODE" = lean8 ]; then run_bench factored SFB_EXCHANGE=factored; fi
 if [ "$MODE" = full ]; then
   run_bench nvlink_p2p SFB_XCHG_NO_MULTICAST=1
   run_bench factored SFB_EXCHANGE=factored
