@@ -79,9 +79,10 @@ typedef struct sfb_xchg {
   void* local;                      /* this rank's buffer */
   void* peers[SFB_XCHG_MAX_RANKS];  /* rank r's buffer as mapped into this process (peers[rank] may equal local) */
   void* mc;                         /* NVSwitch multicast mapping of the buffers (multimem.* instructions), or NULL */
-  int max_ctas;                     /* 0: default grid of sfb_xchg_finish (2 CTAs per SM).  The kernel's CTAs wait for the
+  int max_ctas;                     /* 0: default grid of the exchange kernels (2 CTAs per SM).  The kernel's CTAs wait for the
                                        other ranks on the device, so ALL ranks' CTAs must be able to run at the same time:
                                        a test that emulates several ranks on ONE device passes (2 * SMs) / world here */
+  const void* campos_views;         /* [world][3] floats: every rank's camera centre (fused exchange with shs), or NULL */
 } sfb_xchg;
 
 /* Backward.  Replaces _C.rasterize_gaussians_backward.  dL_dout_color [3][H][W] is the
@@ -95,9 +96,15 @@ typedef struct sfb_xchg {
  * flags: SFB_BWD_ACC_FRESH = this is the FIRST backward on these scratch buffers since the forward that filled them
  * (the forward leaves the per-splat gradient accumulators inside geom_buffer cleared, so the backward can skip its
  * 48 B/Gaussian memset); pass 0 when in doubt or when running backward again on the same buffers (retain_graph).
- * xchg (or NULL) + xchg_epoch: view-parallel exchange mode (sfb_xchg above; needs scales / rotations): the parameter
- * gradients leave through the symmetric buffers instead of dL_dmeans3D / dL_dopacity / dL_dscales / dL_drotations /
- * dL_dcolors / dL_dsh, which may all be NULL; dL_dmeans2D (a per-view quantity) is still written. */
+ * xchg (or NULL) + xchg_epoch: view-parallel exchange mode (sfb_xchg above; needs scales / rotations).
+ *   - With dL_dmeans3D, dL_dopacity, dL_dscales, dL_drotations and dL_dsh (shs; needs xchg->campos_views) or dL_dcolors
+ *     (colors_precomp) given, they receive the SUM OVER THE RANKS: the geometry backward and the exchange run as ONE
+ *     persistent kernel (chunks of 1024 Gaussians flow through "differentiate -> push / reduce over NVLink -> rebuild SH
+ *     rows -> unpack" while later chunks are still being differentiated); every rank must make this call with the same
+ *     xchg_epoch (1, 2, 3, ... +1 per step).  No sfb_xchg_finish.
+ *   - With those outputs NULL the parameter gradients stay in the symmetric buffers as packed records (+ pushed colour
+ *     gradients) and sfb_xchg_finish sums them afterwards.
+ *   dL_dmeans2D (a per-view quantity) is written either way. */
 #define SFB_BWD_ACC_FRESH 1
 /* SFB_BWD_SH_FACTORED (with shs): dL_dcolors (required) receives the gradient w.r.t. the SH-evaluated colour BEFORE its
  * max(0, .) clamp — i.e. the render backward's colour gradient with the clamped channels zeroed — and dL_dsh may be
@@ -130,9 +137,17 @@ int sfb_xchg_finish(const sfb_xchg* x, unsigned epoch, int sh_degree, int M, con
                     float* dL_drotations, float* dL_dcolors, float* dL_dsh, void* stream);
 
 /* Synchronises `stream` and reads this rank's exchange error word: 0 = every sfb_xchg_finish so far completed;
- * otherwise (1: a rank never announced its backward | 2: a rank never broadcast its sums) | epoch << 8 — the device-side
+ * otherwise (1: a rank never announced its backward | 2: a rank never broadcast its sums | 3: the fused kernel ran out
+ * of ready work for too long) | epoch << 8 — the device-side
  * waits are bounded (about 2 s), a kernel that gives up leaves its outputs untouched and records the failure here. */
 int sfb_xchg_status(const sfb_xchg* x, unsigned* status, void* stream);
+/* Measurement hooks.  sfb_xchg_timeline: synchronises `stream` and returns six device timestamps (globaltimer, ns) of
+ * the last sfb_xchg_finish launch on this rank: first CTA started, last CTA past the first cross-rank barrier, last CTA
+ * done with the slice reduction, with the SH rows, past the second barrier, done unpacking.  sfb_xchg_tune: share of the
+ * CTAs that start on the slice reduction (eighths of the grid, default 4) and reduction round trips in flight per
+ * thread (4, default, or 16); process-wide. */
+int sfb_xchg_timeline(const sfb_xchg* x, unsigned long long* ns6, void* stream);
+void sfb_xchg_tune(int nred_eighths, int depth);
 
 /* Multi-view sum of SH gradients from their factored form (view-parallel training; the serial loop
  * it replaces is train.py:169-242, whose loss.backward() accumulates the V per-view dL_dsh into features.grad):

@@ -27,12 +27,15 @@ def main():
     G = torch.randn(3, H, W, generator=torch.Generator().manual_seed(100 + rank)).to(dev)
     out = {}
     info = {}
-    for mode in ("allreduce", "factored", "nvlink", "nvlink_p2p"):
-        os.environ["SFB_XCHG_NO_MULTICAST"] = "1" if mode == "nvlink_p2p" else "0"
+    # nvlink: the fused backward + exchange kernel (multicast); _p2p: the same without the multicast mapping;
+    # _2k: backward, then sfb_xchg_finish (two kernels); _2k_p2p: that without multicast
+    for mode in ("allreduce", "factored", "nvlink", "nvlink_p2p", "nvlink_2k", "nvlink_2k_p2p"):
+        os.environ["SFB_XCHG_NO_MULTICAST"] = "1" if mode.endswith("_p2p") else "0"
+        os.environ["SFB_XCHG_FUSED"] = "0" if "_2k" in mode else "1"
         vp = ViewParallelRasterizer(sc, cam, H, W, deg, device=dev, world_size=world, exchange=mode.split("_")[0])
         assert vp.exchange == mode.split("_")[0]
         if vp.exchange == "nvlink":
-            info[mode] = {"multicast": vp.xchg_multicast}
+            info[mode] = {"multicast": vp.xchg_multicast, "fused": vp.xchg_fused}
         for _ in range(3):                 # several steps: buffers, flags and parities are reused across steps
             vp.step(G)
         torch.cuda.synchronize()
@@ -40,9 +43,10 @@ def main():
         del vp
     # precomputed colours: [14, P] records, plain sum
     sc2 = synth.make_scene(P, 10, scale_mult=1.5, precomp_rgb=True)
-    for mode in ("allreduce", "nvlink"):
+    for mode in ("allreduce", "nvlink", "nvlink_2k"):
         os.environ["SFB_XCHG_NO_MULTICAST"] = "0"
-        vp = ViewParallelRasterizer(sc2, cam, H, W, 0, device=dev, world_size=world, exchange=mode)
+        os.environ["SFB_XCHG_FUSED"] = "0" if "_2k" in mode else "1"
+        vp = ViewParallelRasterizer(sc2, cam, H, W, 0, device=dev, world_size=world, exchange=mode.split("_")[0])
         for _ in range(2):
             vp.step(G)
         torch.cuda.synchronize()
@@ -50,8 +54,10 @@ def main():
         del vp
     worst = {}
     ok = True
+    os.environ["SFB_XCHG_FUSED"] = "1"
     for mode, base in (("factored", "allreduce"), ("nvlink", "allreduce"), ("nvlink_p2p", "allreduce"),
-                       ("rgb_nvlink", "rgb_allreduce")):
+                       ("nvlink_2k", "allreduce"), ("nvlink_2k_p2p", "allreduce"),
+                       ("rgb_nvlink", "rgb_allreduce"), ("rgb_nvlink_2k", "rgb_allreduce")):
         for k in out[base]:
             a, b = out[mode][k], out[base][k]
             scale = float(b.abs().max())

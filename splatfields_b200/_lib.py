@@ -23,7 +23,7 @@ SYMBOLS = (
     "sfb_export_geom", "sfb_export_binning", "sfb_export_img", "sfb_debug_gather_rows", "sfb_last_launch_count",
     "sfb_profile_enable", "sfb_profile_count", "sfb_profile_read", "sfb_profile_name",
     "sfb_loss_scratch_bytes", "sfb_loss_window", "sfb_l1_ssim_loss", "sfb_densify_stats", "sfb_densify_masks",
-    "sfb_sh_grad_combine", "sfb_xchg_bytes", "sfb_xchg_finish", "sfb_xchg_status", "sfb_activate_forward", "sfb_activate_backward", "sfb_knn_scratch_bytes",
+    "sfb_sh_grad_combine", "sfb_xchg_bytes", "sfb_xchg_finish", "sfb_xchg_status", "sfb_xchg_timeline", "sfb_xchg_tune", "sfb_activate_forward", "sfb_activate_backward", "sfb_knn_scratch_bytes",
     "sfb_knn3_mean_dist2",
 )
 
@@ -38,7 +38,8 @@ XCHG_MAX_RANKS = 16   # include/splat_b200.h: SFB_XCHG_MAX_RANKS
 class XchgDesc(C.Structure):
     """include/splat_b200.h: sfb_xchg — the symmetric buffers of the view-parallel gradient exchange."""
     _fields_ = [("rank", C.c_int), ("world", C.c_int), ("P", C.c_int), ("ngeo", C.c_int), ("local", C.c_void_p),
-                ("peers", C.c_void_p * XCHG_MAX_RANKS), ("mc", C.c_void_p), ("max_ctas", C.c_int)]
+                ("peers", C.c_void_p * XCHG_MAX_RANKS), ("mc", C.c_void_p), ("max_ctas", C.c_int),
+                ("campos_views", C.c_void_p)]
 
 
 class SplatB200Error(RuntimeError):
@@ -112,6 +113,10 @@ def load():
     lib.sfb_xchg_finish.argtypes = [C.POINTER(XchgDesc), C.c_uint, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_xchg_status.restype = ci
     lib.sfb_xchg_status.argtypes = [C.POINTER(XchgDesc), C.POINTER(C.c_uint), vp]
+    lib.sfb_xchg_timeline.restype = ci
+    lib.sfb_xchg_timeline.argtypes = [C.POINTER(XchgDesc), C.POINTER(C.c_ulonglong), vp]
+    lib.sfb_xchg_tune.restype = None
+    lib.sfb_xchg_tune.argtypes = [ci, ci]
     lib.sfb_activate_forward.restype = ci
     lib.sfb_activate_forward.argtypes = [ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_activate_backward.restype = ci
@@ -120,7 +125,7 @@ def load():
     lib.sfb_knn_scratch_bytes.argtypes = [ci]
     lib.sfb_knn3_mean_dist2.restype = ci
     lib.sfb_knn3_mean_dist2.argtypes = [ci, vp, vp, vp, vp]
-    if lib.sfb_abi_version() != 5:
+    if lib.sfb_abi_version() != 6:
         raise SplatB200Error("libsplat_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

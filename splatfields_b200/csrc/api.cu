@@ -111,7 +111,7 @@ void prof_end(cudaStream_t s) {
 
 extern "C" {
 
-int sfb_abi_version(void) { return 5; }
+int sfb_abi_version(void) { return 6; }
 const char* sfb_last_error(void) { return g_err.c_str(); }
 int sfb_last_launch_count(void) { return g_launches; }
 
@@ -263,6 +263,26 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   return SFB_OK;
 }
 
+// device-side view of the symmetric buffers for one step (records of parity `par`, this step's colour table)
+static sfb::XchgDev make_xchg_dev(const sfb_xchg* x, const sfb::XchgLayout& xl, int par, unsigned epoch) {
+  using namespace sfb;
+  XchgDev d;
+  d.rank = x->rank; d.world = x->world; d.P = x->P; d.ngeo = x->ngeo; d.nch = xl.nch;
+  d.flags = reinterpret_cast<uint32_t*>(x->local);
+  d.cflags = reinterpret_cast<uint32_t*>((char*)x->local + xl.cflag_off);
+  d.geo = reinterpret_cast<float*>((char*)x->local + xl.geo_off[par]);
+  d.geo_mc = x->mc ? reinterpret_cast<float*>((char*)x->mc + xl.geo_off[par]) : nullptr;
+  for (int r = 0; r < XCHG_MAX_RANKS; r++) { d.peer_flags[r] = nullptr; d.peer_cflags[r] = nullptr; d.peer_geo[r] = nullptr; }
+  for (int r = 0; r < x->world; r++) {
+    d.peer_flags[r] = reinterpret_cast<uint32_t*>(x->peers[r]);
+    d.peer_cflags[r] = reinterpret_cast<uint32_t*>((char*)x->peers[r] + xl.cflag_off);
+    d.peer_geo[r] = reinterpret_cast<float*>((char*)x->peers[r] + xl.geo_off[par]);
+  }
+  d.gc = reinterpret_cast<const float*>((char*)x->local + xl.gc_off[epoch & 1u]);
+  d.gc_slot_floats = xl.gc_slot_floats;
+  return d;
+}
+
 int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W, int H, const float* bg,
                            const float* means3D, const float* shs, const float* colors_precomp,
                            const float* scales, float scale_modifier, const float* rotations,
@@ -344,9 +364,14 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   bp.dL_dmeans3D = dL_dmeans3D; bp.dL_dcov3D = dL_dcov3D; bp.dL_dsh = dL_dsh; bp.dL_dscales = dL_dscales;
   bp.dL_drot = dL_drotations;
   bp.x_geo = nullptr; bp.x_ngeo = 0; bp.x_mc = 0; bp.x_ndst = 0; bp.x_nranks = 0;
+  // Exchange mode with the summed outputs given: ONE fused kernel does the geometry backward AND the exchange
+  // (geom_bwd.cu); without them the records stay in the symmetric buffer for sfb_xchg_finish.
+  const bool want_fused = xchg && dL_dmeans3D && dL_dopacity && dL_dscales && dL_drotations &&
+                          (shs ? (dL_dsh != nullptr && xchg->campos_views != nullptr) : dL_dcolors != nullptr);
   if (xchg) {
     const XchgLayout xl = XchgLayout::make((size_t)P, xchg->world, xchg->ngeo, shs != nullptr);
-    bp.x_geo = reinterpret_cast<float*>((char*)xchg->local + xl.geo_off);
+    const int par = want_fused ? (int)(xchg_epoch & 1u) : 0;
+    bp.x_geo = reinterpret_cast<float*>((char*)xchg->local + xl.geo_off[par]);
     bp.x_ngeo = xchg->ngeo;
     bp.x_nranks = xchg->world;
     // slot `rank` of this step's colour-gradient table, on every rank
@@ -355,9 +380,27 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
     if (xchg->mc) { bp.x_mc = 1; bp.x_ndst = 1; bp.x_gc_dst[0] = reinterpret_cast<float*>((char*)xchg->mc + slot); }
     else { bp.x_ndst = xchg->world; for (int r = 0; r < xchg->world; r++) bp.x_gc_dst[r] = bp.x_gc_peer[r]; }
   }
-  prof_begin("geom_backward", s);
-  launch_geom_backward(bp, g, s);
-  prof_end(s);
+  bool fused_done = false;
+  if (want_fused) {
+    const XchgLayout xl = XchgLayout::make((size_t)P, xchg->world, xchg->ngeo, shs != nullptr);
+    FusedXchg f;
+    f.x = make_xchg_dev(xchg, xl, (int)(xchg_epoch & 1u), xchg_epoch);
+    f.epoch = xchg_epoch; f.V = xchg->world; f.M = M; f.direct = xchg->world == 2 ? 1 : 0;
+    f.campos_views = reinterpret_cast<const float*>(xchg->campos_views);
+    f.dL_dmeans3D = dL_dmeans3D; f.dL_dopacity = dL_dopacity; f.dL_dscales = dL_dscales; f.dL_drot = dL_drotations;
+    f.dL_dcolors = dL_dcolors; f.dL_dsh = dL_dsh;
+    BwdParams bf = bp;       // the geometry body writes records + pushed colour gradients, never the summed outputs
+    bf.dL_dcolors = nullptr; bf.dL_dopacity = nullptr; bf.dL_dmeans3D = nullptr; bf.dL_dcov3D = nullptr; bf.dL_dsh = nullptr;
+    bf.dL_dscales = nullptr; bf.dL_drot = nullptr;
+    prof_begin("geom_backward_exchange", s);
+    fused_done = launch_geom_exchange_fused(bf, g, f, xchg->max_ctas, s);
+    prof_end(s);
+    if (!fused_done) return fail(SFB_ERR_ARG, "fused exchange: unsupported SH layout (pass NULL gradient outputs and call sfb_xchg_finish)");
+  } else {
+    prof_begin("geom_backward", s);
+    launch_geom_backward(bp, g, s);
+    prof_end(s);
+  }
   g_launches++;
   CK_LAUNCH("geometry backward", debug, s);
   if (debug) {   // the forward (run with debug) left the pattern in place; nothing may have touched it since
@@ -392,18 +435,9 @@ int sfb_xchg_finish(const sfb_xchg* x, unsigned epoch, int sh_degree, int M, con
     return fail(SFB_ERR_ARG, "sfb_xchg_finish: sh_degree / M mismatch");
   cudaStream_t s = (cudaStream_t)stream;
   const XchgLayout xl = XchgLayout::make((size_t)x->P, x->world, x->ngeo, has_sh);
-  XchgDev d;
-  d.rank = x->rank; d.world = x->world; d.P = x->P; d.ngeo = x->ngeo;
-  d.flags = reinterpret_cast<uint32_t*>(x->local);
-  d.geo = reinterpret_cast<float*>((char*)x->local + xl.geo_off);
-  d.geo_mc = x->mc ? reinterpret_cast<float*>((char*)x->mc + xl.geo_off) : nullptr;
-  for (int r = 0; r < x->world; r++) {
+  for (int r = 0; r < x->world; r++)
     if (!x->peers[r]) return fail(SFB_ERR_ARG, "sfb_xchg_finish: null peer mapping");
-    d.peer_flags[r] = reinterpret_cast<uint32_t*>(x->peers[r]);
-    d.peer_geo[r] = reinterpret_cast<float*>((char*)x->peers[r] + xl.geo_off);
-  }
-  d.gc = reinterpret_cast<const float*>((char*)x->local + xl.gc_off[epoch & 1u]);
-  d.gc_slot_floats = xl.gc_slot_floats;
+  XchgDev d = make_xchg_dev(x, xl, 0, epoch);
   prof_begin("xchg_finish", s);
   launch_xchg_finish(d, x->max_ctas, epoch, sh_degree, M, means3D, campos_views, dL_dmeans3D, dL_dopacity, dL_dscales, dL_drotations,
                      dL_dcolors, has_sh ? dL_dsh : nullptr, s);
@@ -421,6 +455,19 @@ int sfb_xchg_status(const sfb_xchg* x, unsigned* status, void* stream) {
   CK(cudaStreamSynchronize(s));
   return SFB_OK;
 }
+
+int sfb_xchg_timeline(const sfb_xchg* x, unsigned long long* ns6, void* stream) {
+  g_err.clear();
+  if (!x || !x->local || !ns6) return fail(SFB_ERR_ARG, "sfb_xchg_timeline: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(ns6, reinterpret_cast<const uint32_t*>(x->local) + 36, 6 * sizeof(unsigned long long),
+                     cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  ns6[0] = ~ns6[0];
+  return SFB_OK;
+}
+
+void sfb_xchg_tune(int nred_eighths, int depth) { sfb::xchg_tune(nred_eighths, depth); }
 
 int sfb_sh_grad_combine(int P, int V, int sh_degree, int M, const float* means3D, const float* campos,
                         const float* dL_dcolor_views, float* dL_dsh, void* stream) {

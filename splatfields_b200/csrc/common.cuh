@@ -460,12 +460,20 @@ void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s
 // exchange.cu
 // Layout of one rank's symmetric exchange buffer (identical on every rank; include/splat_b200.h: sfb_xchg):
 //   [flags: 256 B][packed gradient records: P * ngeo floats][colour-gradient tables: 2 parities x world x P x 3 floats]
+//   [flags 256 B][chunk flags: (XCHG_MAX_RANKS + 1) x nch words][packed records, 2 parities][colour tables, 2 parities]
+// Chunk flags (fused backward + exchange, geom_bwd.cu): word r * nch + c = rank r has finished the geometry backward of
+// chunk c (XCHG_CHUNK splats) in step `epoch`; word XCHG_MAX_RANKS * nch + c = the sums of chunk c have been broadcast.
+// sfb_xchg_finish (exchange.cu) uses record parity 0 only.
+constexpr int XCHG_CHUNK = 1024;
 struct XchgLayout {
-  size_t geo_off, gc_off[2], gc_slot_floats, bytes;
+  size_t cflag_off, geo_off[2], gc_off[2], gc_slot_floats, bytes;
+  int nch;
   static XchgLayout make(size_t P, int world, int ngeo, bool with_gc) {
     XchgLayout l;
     size_t o = 256;
-    l.geo_off = o; o = align_up(o + P * (size_t)ngeo * 4, 256);
+    l.nch = (int)((P + XCHG_CHUNK - 1) / XCHG_CHUNK);
+    l.cflag_off = o; o = align_up(o + (size_t)(XCHG_MAX_RANKS + 1) * (size_t)l.nch * 4, 256);
+    for (int k = 0; k < 2; k++) { l.geo_off[k] = o; o = align_up(o + P * (size_t)ngeo * 4, 256); }
     l.gc_slot_floats = align_up(P * 3, 64);            // one view's [P][3] slot, padded to 256 bytes (16-byte stores)
     for (int k = 0; k < 2; k++) { l.gc_off[k] = o; if (with_gc) o = align_up(o + (size_t)world * l.gc_slot_floats * 4, 256); }
     l.bytes = o;
@@ -474,8 +482,11 @@ struct XchgLayout {
 };
 struct XchgDev {                 // device-side view of the exchange for one step
   int rank, world, P, ngeo;
+  int nch;                       // chunks of XCHG_CHUNK splats
   uint32_t* flags;               // this rank's flag words
   uint32_t* peer_flags[XCHG_MAX_RANKS];
+  uint32_t* cflags;              // this rank's chunk flags
+  uint32_t* peer_cflags[XCHG_MAX_RANKS];
   float* geo;                    // this rank's packed records (sums after the exchange)
   float* geo_mc;                 // the same array through the multicast mapping, or nullptr
   float* peer_geo[XCHG_MAX_RANKS];
@@ -485,6 +496,18 @@ struct XchgDev {                 // device-side view of the exchange for one ste
 void launch_xchg_finish(const XchgDev& x, int max_ctas, uint32_t epoch, int D, int M, const float* means3D, const float* campos,
                         float* dL_dmeans3D, float* dL_dopacity, float* dL_dscales, float* dL_drot, float* dL_dcolors,
                         float* dL_dsh, cudaStream_t s);
+void xchg_tune(int nred_eighths, int depth);
+// Fused geometry backward + exchange (geom_bwd.cu): ONE persistent kernel per step and rank.
+struct FusedXchg {
+  XchgDev x;                     // geo / geo_mc / peer_geo / gc point at THIS step's parity
+  uint32_t epoch;
+  int V, M;                      // views (= world), SH coefficients per colour channel
+  int direct;                    // 1: every rank sums the ranks' records itself (two ranks); 0: owner reduces + broadcasts
+  const float* campos_views;     // [V][3] (with shs)
+  float *dL_dmeans3D, *dL_dopacity, *dL_dscales, *dL_drot, *dL_dcolors, *dL_dsh;   // the SUMS over the ranks
+};
+// false: this configuration has no fused kernel (the caller runs launch_geom_backward + launch_xchg_finish instead)
+bool launch_geom_exchange_fused(const BwdParams& p, const GeomState& g, const FusedXchg& f, int max_ctas, cudaStream_t s);
 // dL_dsh[i] = sum over V views of basis(normalize(means3D[i] - campos[v])) (x) dcolor[v][i]   (view-parallel exchange)
 void launch_sh_grad_combine(int P, int V, int D, int M, const float* means3D, const float* campos /* [V][3] */,
                             const float* dcolor /* [V][P][3] */, float* dL_dsh /* [P][M][3] */, bool wide256,

@@ -19,78 +19,10 @@
 //           per-parameter gradient arrays.
 //    HBM-bound streaming work + 2 x 48 B/splat over NVLink per rank; nothing here goes through NCCL.
 #include "common.cuh"
+#include "xchg.cuh"
 
 namespace sfb {
 
-namespace {
-
-constexpr float SH_C0 = 0.28209479177387814f;
-constexpr float SH_C1 = 0.4886025119029199f;
-__constant__ float SHX_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
-                                -1.0925484305920792f, 0.5462742152960396f};
-__constant__ float SHX_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
-                                0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
-                                -0.5900435899266435f};
-
-// real SH basis of utils/sh_utils.py:57-112 at direction (x, y, z), the same expressions as geom_backward_kernel
-template <int D>
-__device__ __forceinline__ void sh_basis(float x, float y, float z, float* basis) {
-  basis[0] = SH_C0;
-  if (D > 0) { basis[1] = -SH_C1 * y; basis[2] = SH_C1 * z; basis[3] = -SH_C1 * x; }
-  if (D > 1) {
-    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-    basis[4] = SHX_C2[0] * xy; basis[5] = SHX_C2[1] * yz; basis[6] = SHX_C2[2] * (2.f * zz - xx - yy);
-    basis[7] = SHX_C2[3] * xz; basis[8] = SHX_C2[4] * (xx - yy);
-    if (D > 2) {
-      basis[9] = SHX_C3[0] * y * (3.f * xx - yy); basis[10] = SHX_C3[1] * xy * z;
-      basis[11] = SHX_C3[2] * y * (4.f * zz - xx - yy); basis[12] = SHX_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-      basis[13] = SHX_C3[4] * x * (4.f * zz - xx - yy); basis[14] = SHX_C3[5] * z * (xx - yy);
-      basis[15] = SHX_C3[6] * x * (xx - 3.f * yy);
-    }
-  }
-}
-
-// dL_dsh row of Gaussian i: sum over the V views (index order: bit-reproducible) of basis(dir_v) (x) gc_v, each product
-// rounded on its own (as geom_backward_kernel stores it for a single view) before it enters the sum.
-template <int D, bool W256>
-__device__ __forceinline__ void sh_row_rebuild(size_t i, size_t view_stride /* floats between the views' [P][3] slots */,
-                                               int V, int M, const float* __restrict__ means3D,
-                                               const float* s_cam, const float* __restrict__ dcolor,
-                                               float* __restrict__ dL_dsh) {
-  constexpr int NB = (D + 1) * (D + 1);
-  constexpr int NF8 = (3 * NB + 7) / 8;
-  const float mx = means3D[3 * i], my = means3D[3 * i + 1], mz = means3D[3 * i + 2];
-  float acc[NF8 * 8];
-#pragma unroll
-  for (int k = 0; k < NF8 * 8; k++) acc[k] = 0.f;
-  for (int v = 0; v < V; v++) {
-    const float* gp = dcolor + (size_t)v * view_stride + i * 3;
-    // (ld.global.cg: in the NVLink exchange this table is written by the PEERS while the kernel is already resident)
-    const float g0 = __ldcg(gp), g1 = __ldcg(gp + 1), g2 = __ldcg(gp + 2);
-    if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;     // culled in this view (or no gradient reached it)
-    const float vx = mx - s_cam[3 * v], vy = my - s_cam[3 * v + 1], vz = mz - s_cam[3 * v + 2];
-    const float ilen = rsqrtf(vx * vx + vy * vy + vz * vz);
-    float basis[NB];
-    sh_basis<D>(vx * ilen, vy * ilen, vz * ilen, basis);
-#pragma unroll
-    for (int k = 0; k < NB; k++) {
-      acc[3 * k] = __fadd_rn(acc[3 * k], __fmul_rn(basis[k], g0));
-      acc[3 * k + 1] = __fadd_rn(acc[3 * k + 1], __fmul_rn(basis[k], g1));
-      acc[3 * k + 2] = __fadd_rn(acc[3 * k + 2], __fmul_rn(basis[k], g2));
-    }
-  }
-  float* dsh = dL_dsh + i * M * 3;
-  if (W256) {      // launcher: M == NB, rows are 32-byte aligned multiples of 32 bytes
-#pragma unroll
-    for (int k = 0; k < (3 * NB) / 8; k++) stg256(dsh + 8 * k, acc + 8 * k);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 3 * NB; k++) dsh[k] = acc[k];
-    for (int k = 3 * NB; k < 3 * M; k++) dsh[k] = 0.f;      // coefficients above the active degree
-  }
-}
-
-}  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
 // Rebuild step of the NCCL formulation.  One thread per Gaussian, 12 + 12*V bytes in, 12*M out: HBM-bound.
@@ -127,61 +59,18 @@ void launch_sh_grad_combine(int P, int V, int D, int M, const float* means3D, co
 
 // ---------------------------------------------------------------------------------------------------------------
 // The exchange over symmetric memory.
-namespace {
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// Wait until *p >= epoch (flags only grow).  Bounded: a peer that never arrives must not hang the GPU — after ~2 s the
-// wait gives up and returns false; the kernel then records the failure in its rank's error word (sfb_xchg_status) and
-// retires without touching the outputs.
-__device__ __forceinline__ bool spin_until(const uint32_t* p, uint32_t epoch) {
-  const long long t0 = clock64();
-  while ((int32_t)(ld_acquire_sys(p) - epoch) < 0) {
-    __nanosleep(64);
-    if (clock64() - t0 > 4000000000LL) return false;
-  }
-  return true;
-}
-__device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) {
-  float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 mm_ld_reduce_add(const float* mc_addr) {
-  float4 v;
-  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void mm_st(float* mc_addr, const float4 v) {
-  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z),
-               "f"(v.w) : "memory");
-}
 
-}  // namespace
-
-// flags inside every rank's symmetric buffer (uint32 words; only ever grow, one epoch pair per step)
-//   [FLAG_A + r]  rank r's backward of step `epoch` is complete (its records are in its buffer, its colour gradients in mine)
-//   [FLAG_B + r]  rank r has broadcast its slice of the sums of step `epoch`
-//   [FLAG_DONE]   local: CTAs of this launch that finished their part of the slice reduction
-//   [FLAG_ERR]    local: 0, or (1 | 2: which barrier timed out) | epoch << 8   (sfb_xchg_status)
-constexpr int FLAG_A = 0, FLAG_B = 16, FLAG_DONE = 32, FLAG_TICKET = 33, FLAG_ERR = 34;
-
-template <int D, bool MC, bool HAS_SH, bool W256>
+template <int D, bool MC, bool HAS_SH, bool W256, int RD = 4>
 __global__ void __launch_bounds__(256, 2)
-xchg_finish_kernel(XchgDev x, uint32_t epoch, int V, int M, const float* __restrict__ means3D,
+xchg_finish_kernel(XchgDev x, uint32_t epoch, int nred_eighths, int V, int M, const float* __restrict__ means3D,
                    const float* __restrict__ campos, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dopacity,
                    float* __restrict__ dL_dscales, float* __restrict__ dL_drot, float* __restrict__ dL_dcolors,
                    float* __restrict__ dL_dsh) {
   __shared__ float s_cam[3 * XCHG_MAX_RANKS];
   __shared__ uint32_t s_ticket;
   const int N = x.world;
+  if (threadIdx.x == 0) xchg_mark(x.flags, 0, true);
   // ---- 0. announce (stream order: this rank's backward has completed) and wait for everybody
   if (blockIdx.x == 0 && threadIdx.x < N) {
     __threadfence_system();
@@ -195,18 +84,19 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int V, int M, const float* __restr
       return;
     }
   }
+  if (threadIdx.x == 0) xchg_mark(x.flags, 1);
 
   // ---- 1. sum this rank's slice of the packed records over the ranks, broadcast the sums (in place)
   // The slice is split over the first `nred` CTAs; the rest start on the SH rows right away (they only need barrier A).
   const size_t C = (size_t)x.P * (size_t)(x.ngeo / 4);                  // 16-byte chunks of the record array
   const size_t c0 = C * (size_t)x.rank / (size_t)N, c1 = C * (size_t)(x.rank + 1) / (size_t)N;
-  const int nred = HAS_SH ? max(1, (int)gridDim.x / 2) : (int)gridDim.x;
+  const int nred = HAS_SH ? min((int)gridDim.x, max(1, ((int)gridDim.x * nred_eighths) / 8)) : (int)gridDim.x;
   if ((int)blockIdx.x < nred) {
     const size_t stride = (size_t)nred * 256;
-    for (size_t c = c0 + (size_t)blockIdx.x * 256 + threadIdx.x; c < c1; c += 4 * stride) {
-      float4 v[4];
+    for (size_t c = c0 + (size_t)blockIdx.x * 256 + threadIdx.x; c < c1; c += RD * stride) {
+      float4 v[RD];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {        // four independent round trips through the switch in flight per thread
+      for (int u = 0; u < RD; u++) {       // RD independent round trips through the switch in flight per thread
         const size_t cu = c + (size_t)u * stride;
         if (cu < c1) {
           if (MC) v[u] = mm_ld_reduce_add(x.geo_mc + 4 * cu);
@@ -220,7 +110,7 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int V, int M, const float* __restr
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < RD; u++) {
         const size_t cu = c + (size_t)u * stride;
         if (cu < c1) {
           if (MC) mm_st(x.geo_mc + 4 * cu, v[u]);
@@ -231,6 +121,7 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int V, int M, const float* __restr
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence_system();
+      xchg_mark(x.flags, 2);
       if (atomicAdd(x.flags + FLAG_DONE, 1u) == (uint32_t)nred - 1u) {    // last CTA of the reduction: tell every rank
         x.flags[FLAG_DONE] = 0u;                                           // (reset for the next launch)
         __threadfence_system();
@@ -251,6 +142,7 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int V, int M, const float* __restr
       const size_t i = (size_t)t * 256 + threadIdx.x;
       if (i < (size_t)x.P) sh_row_rebuild<D, W256>(i, x.gc_slot_floats, V, M, means3D, s_cam, x.gc, dL_dsh);
     }
+    if (threadIdx.x == 0) xchg_mark(x.flags, 3);
   }
 
   // ---- 3. every slice has been broadcast: unpack the summed records into the per-parameter arrays
@@ -261,6 +153,7 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int V, int M, const float* __restr
       return;
     }
   }
+  if (threadIdx.x == 0) xchg_mark(x.flags, 4);
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < (size_t)x.P; i += (size_t)gridDim.x * 256) {
     const float4* rec = reinterpret_cast<const float4*>(x.geo + i * (size_t)x.ngeo);
     const float4 a = __ldcg(rec), b = __ldcg(rec + 1), c = __ldcg(rec + 2);
@@ -273,6 +166,16 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int V, int M, const float* __restr
       dL_dcolors[3 * i] = d.x; dL_dcolors[3 * i + 1] = d.y; dL_dcolors[3 * i + 2] = d.z;
     }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) xchg_mark(x.flags, 5);
+}
+
+// Tuning hooks of the measurement sessions (sfb_xchg_tune): share of the CTAs that start on the slice reduction
+// (eighths of the grid) and reduction round trips in flight per thread (4 or 16).
+static int g_xchg_nred_eighths = 4, g_xchg_depth = 4;
+void xchg_tune(int nred_eighths, int depth) {
+  if (nred_eighths >= 1 && nred_eighths <= 8) g_xchg_nred_eighths = nred_eighths;
+  if (depth == 4 || depth == 16) g_xchg_depth = depth;
 }
 
 void launch_xchg_finish(const XchgDev& x, int max_ctas, uint32_t epoch, int D, int M, const float* means3D, const float* campos,
@@ -283,12 +186,19 @@ void launch_xchg_finish(const XchgDev& x, int max_ctas, uint32_t epoch, int D, i
   const bool w256 = has_sh && (M * 12) % 32 == 0 && (reinterpret_cast<size_t>(dL_dsh) & 31) == 0 && M == (D + 1) * (D + 1) &&
                     (3 * (D + 1) * (D + 1)) % 8 == 0;
   cudaMemsetAsync(x.flags + FLAG_TICKET, 0, sizeof(uint32_t), s);      // the SH work queue's ticket
+  cudaMemsetAsync(x.flags + FLAG_TL, 0, 6 * sizeof(unsigned long long), s);
   // 2 CTAs per SM (launch bound): the whole grid is resident, so CTAs spinning on a flag can never keep the CTAs
   // that produce this rank's own signals off the SMs
   const int grid = max_ctas > 0 ? min(max_ctas, 2 * NUM_SMS_B200) : 2 * NUM_SMS_B200;
 #define SFB_XF(DD, MCV, SHV, WV)                                                                                    \
-  xchg_finish_kernel<DD, MCV, SHV, WV><<<grid, 256, 0, s>>>(x, epoch, x.world, M, means3D, campos, dL_dmeans3D,     \
-                                                            dL_dopacity, dL_dscales, dL_drot, dL_dcolors, dL_dsh)
+  do {                                                                                                              \
+    if (g_xchg_depth == 16)                                                                                         \
+      xchg_finish_kernel<DD, MCV, SHV, WV, 16><<<grid, 256, 0, s>>>(x, epoch, g_xchg_nred_eighths, x.world, M, means3D, campos, \
+                                                                    dL_dmeans3D, dL_dopacity, dL_dscales, dL_drot, dL_dcolors, dL_dsh); \
+    else                                                                                                            \
+      xchg_finish_kernel<DD, MCV, SHV, WV, 4><<<grid, 256, 0, s>>>(x, epoch, g_xchg_nred_eighths, x.world, M, means3D, campos, \
+                                                                   dL_dmeans3D, dL_dopacity, dL_dscales, dL_drot, dL_dcolors, dL_dsh); \
+  } while (0)
 #define SFB_XD(DD)                                                                                                  \
   do {                                                                                                              \
     if (mc) { if (w256) SFB_XF(DD, true, true, true); else SFB_XF(DD, true, true, false); }                         \

@@ -6,12 +6,12 @@
 // ~256 B/Gaussian of gradient tensors — that removes a full memset pass over the largest buffers
 // (dL_dsh alone is 192 B/Gaussian at degree 3).
 #include "common.cuh"
+#include "xchg.cuh"
 #include <cstdlib>
 
 namespace sfb {
 
-constexpr float SH_C0 = 0.28209479177387814f;
-constexpr float SH_C1 = 0.4886025119029199f;
+// (SH_C0 / SH_C1 come from xchg.cuh)
 __constant__ float SHB_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
                                 -1.0925484305920792f, 0.5462742152960396f};
 __constant__ float SHB_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
@@ -34,16 +34,11 @@ struct CamB {
 // kernel's multimem.ld_reduce finds them), and with FACT the clamp-masked colour gradient is written straight into
 // slot `rank` of EVERY rank's buffer while this kernel is still computing — one multimem.st per 16 bytes through
 // the NVSwitch multicast mapping (or one st.global per peer without multicast): the all-gather rides on the kernel.
-template <int D, bool VEC, int MINB = 1, bool W256 = false, bool FACT = false, bool PUSH = false>
-__global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, GeomState g) {
-  __shared__ CamB cam;
-  if (threadIdx.x < 16) {
-    cam.view[threadIdx.x] = p.viewmatrix[threadIdx.x];
-    cam.proj[threadIdx.x] = p.projmatrix[threadIdx.x];
-  }
-  if (threadIdx.x < 3) cam.campos[threadIdx.x] = p.campos[threadIdx.x];
-  __syncthreads();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// The body works on the 256 Gaussians of block `blk`: the plain kernel below runs it once per CTA, the fused
+// backward + exchange kernel (further down) runs it from a work queue.
+template <int D, bool VEC, bool W256, bool FACT, bool PUSH>
+__device__ __forceinline__ void geom_backward_block(const BwdParams& p, const GeomState& g, const CamB& cam, const int blk) {
+  const int idx = blk * 256 + (int)threadIdx.x;
   const bool in_range = idx < p.P;
   if (!PUSH && !in_range) return;          // (PUSH: the whole block meets again at the colour-gradient hand-off)
   const size_t i = (size_t)(in_range ? idx : 0);
@@ -324,7 +319,7 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
     if (FACT) {
       s_gc[3 * threadIdx.x] = gcol[0]; s_gc[3 * threadIdx.x + 1] = gcol[1]; s_gc[3 * threadIdx.x + 2] = gcol[2];
       __syncthreads();
-      const size_t row0 = (size_t)blockIdx.x * 256;
+      const size_t row0 = (size_t)blk * 256;
       const int nfl = 3 * (int)min((size_t)256, (size_t)p.P - row0);       // floats of this block's slab
       if ((int)threadIdx.x * 4 < nfl) {
         const float4 v = reinterpret_cast<const float4*>(s_gc)[threadIdx.x];
@@ -362,6 +357,266 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
   }
   if (p.dL_dscales) { p.dL_dscales[3 * i] = dscale[0]; p.dL_dscales[3 * i + 1] = dscale[1]; p.dL_dscales[3 * i + 2] = dscale[2]; }
   if (p.dL_drot) { p.dL_drot[4 * i] = drot[0]; p.dL_drot[4 * i + 1] = drot[1]; p.dL_drot[4 * i + 2] = drot[2]; p.dL_drot[4 * i + 3] = drot[3]; }
+}
+
+__device__ __forceinline__ void load_cam(CamB& cam, const BwdParams& p) {
+  if (threadIdx.x < 16) {
+    cam.view[threadIdx.x] = p.viewmatrix[threadIdx.x];
+    cam.proj[threadIdx.x] = p.projmatrix[threadIdx.x];
+  }
+  if (threadIdx.x < 3) cam.campos[threadIdx.x] = p.campos[threadIdx.x];
+}
+
+template <int D, bool VEC, int MINB = 1, bool W256 = false, bool FACT = false, bool PUSH = false>
+__global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, GeomState g) {
+  __shared__ CamB cam;
+  load_cam(cam, p);
+  __syncthreads();
+  geom_backward_block<D, VEC, W256, FACT, PUSH>(p, g, cam, (int)blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused geometry backward + view-parallel exchange: ONE persistent kernel per step and rank.
+//
+// The exchange of a step is bound by NVLink (60-150 MB per rank), the geometry backward, the SH row rebuild and the
+// unpacking by HBM; run one after the other (geom_backward_kernel<PUSH>, then sfb_xchg_finish) the two resources idle
+// in turn.  Here the splats are cut into chunks of XCHG_CHUNK and every CTA pulls work units from four queues:
+//   G(c)  geometry backward of chunk c (4 blocks of 256 splats): packed records into this rank's buffer, colour gradients
+//         pushed into every rank's table (multimem.st), then flag A[rank][c] raised in EVERY rank's buffer;
+//   X(c)  NVLink unit, ready when A[*][c] is up on this rank.  Owner mode (c % world == rank): sum the ranks' records of
+//         chunk c inside the switch (multimem.ld_reduce) and broadcast the sums in place (multimem.st; peer loads / stores
+//         without multicast), then raise flag B[c] everywhere.  Direct mode (two ranks): read the peer's records, add
+//         them to this rank's own in rank order and write the per-parameter gradients straight away (no owner, no B);
+//   S(c)  SH gradient rows of chunk c from the local colour table, ready when A[*][c] is up;
+//   U(c)  owner mode: unpack the broadcast sums of chunk c, ready when B[c] is up.
+// Every fourth CTA prefers X over G (the NVLink round trips of a chunk start while later chunks are still being
+// differentiated), the others run G, then S, then U; whatever is ready is taken when a CTA's preferred queue is empty.
+// Queues are tickets in this rank's flag words, claims are CAS, waits are bounded (error word, sfb_xchg_status).
+constexpr int FLAG_TK = 48;        // [+0..3] tickets of the queues G, X, S, U; [+4] abort (a wait timed out)
+enum { FK_EXIT = 0, FK_G = 1, FK_X = 2, FK_S = 3, FK_U = 4 };
+
+__device__ __forceinline__ uint32_t ld_relaxed_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <bool HAS_SH>
+__device__ __forceinline__ void fused_store_sums(const FusedXchg& f, size_t i, const float4 a, const float4 b, const float4 c,
+                                                 const float4 d) {
+  f.dL_dmeans3D[3 * i] = a.x; f.dL_dmeans3D[3 * i + 1] = a.y; f.dL_dmeans3D[3 * i + 2] = a.z;
+  f.dL_dopacity[i] = a.w;
+  f.dL_dscales[3 * i] = b.x; f.dL_dscales[3 * i + 1] = b.y; f.dL_dscales[3 * i + 2] = b.z;
+  f.dL_drot[4 * i] = b.w; f.dL_drot[4 * i + 1] = c.x; f.dL_drot[4 * i + 2] = c.y; f.dL_drot[4 * i + 3] = c.z;
+  if (!HAS_SH) { f.dL_dcolors[3 * i] = d.x; f.dL_dcolors[3 * i + 1] = d.y; f.dL_dcolors[3 * i + 2] = d.z; }
+}
+
+template <int D, bool W256, bool HAS_SH>
+__global__ void __launch_bounds__(256, 2) geom_exchange_fused_kernel(BwdParams p, GeomState g, FusedXchg f) {
+  __shared__ CamB cam;
+  __shared__ float s_camv[3 * XCHG_MAX_RANKS];
+  __shared__ int s_kind, s_unit;
+  const XchgDev& x = f.x;
+  load_cam(cam, p);
+  if (HAS_SH) for (int k = threadIdx.x; k < 3 * f.V; k += 256) s_camv[k] = f.campos_views[k];
+  const int N = x.world, rank = x.rank, nch = x.nch;
+  const int nblk = (x.P + 255) / 256;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t epoch = f.epoch;
+  const uint32_t nG = (uint32_t)nch;
+  const uint32_t nX = f.direct ? (uint32_t)nch : (uint32_t)(nch > rank ? (nch - rank + N - 1) / N : 0);
+  const uint32_t nS = HAS_SH ? (uint32_t)nch : 0u;
+  const uint32_t nU = f.direct ? 0u : (uint32_t)nch;
+  const bool link_cta = (blockIdx.x & 3) == 0;
+  uint32_t* const tk = x.flags + FLAG_TK;
+  uint32_t tG = 0, tX = 0, tS = 0, tU = 0;      // this CTA's view of the tickets (they only grow)
+  constexpr int NG4 = HAS_SH ? 3 : 4;           // 16-byte words per packed record
+  if (threadIdx.x == 0) xchg_mark(x.flags, 0, true);
+  __syncthreads();
+
+  for (;;) {
+    if (warp == 0) {
+      int kind = -1, unit = 0;
+      long long t0 = 0;
+      bool waiting = false;
+      while (kind < 0) {
+        const bool hasG = tG < nG, hasX = tX < nX, hasS = tS < nS, hasU = tU < nU;
+        if (!(hasG | hasX | hasS | hasU)) { kind = FK_EXIT; break; }
+        const uint32_t cX = f.direct ? tX : (uint32_t)rank + tX * (uint32_t)N, cS = tS, cU = tU;
+        uint32_t fx = epoch, fs = epoch, fu = epoch;
+        if (lane < N) {
+          if (hasX) fx = ld_relaxed_sys_u32(x.cflags + (size_t)lane * nch + cX);
+          if (hasS) fs = ld_relaxed_sys_u32(x.cflags + (size_t)lane * nch + cS);
+        }
+        if (lane == 0 && hasU) fu = ld_relaxed_sys_u32(x.cflags + (size_t)XCHG_MAX_RANKS * nch + cU);
+        const bool rX = hasX && __all_sync(0xffffffffu, (int32_t)(fx - epoch) >= 0);
+        const bool rS = hasS && __all_sync(0xffffffffu, (int32_t)(fs - epoch) >= 0);
+        const bool rU = hasU && (int32_t)(__shfl_sync(0xffffffffu, fu, 0) - epoch) >= 0;
+        bool lost = false;      // a claim went to another CTA: look again at once
+        auto claim = [&](int q, uint32_t& t) -> bool {
+          uint32_t old = 0;
+          if (lane == 0) old = atomicCAS(tk + q, t, t + 1u);
+          old = __shfl_sync(0xffffffffu, old, 0);
+          if (old == t) { t = t + 1u; return true; }
+          t = old; lost = true;
+          return false;
+        };
+        if (rX && (link_cta || !hasG)) { if (claim(1, tX)) { kind = FK_X; unit = (int)cX; } }
+        if (kind < 0 && hasG) {
+          uint32_t gt = 0;
+          if (lane == 0) gt = atomicAdd(tk + 0, 1u);
+          gt = __shfl_sync(0xffffffffu, gt, 0);
+          tG = gt + 1u;
+          if (gt < nG) { kind = FK_G; unit = (int)gt; } else lost = true;
+        }
+        if (kind < 0 && rS) { if (claim(2, tS)) { kind = FK_S; unit = (int)cS; } }
+        if (kind < 0 && rU) { if (claim(3, tU)) { kind = FK_U; unit = (int)cU; } }
+        if (kind >= 0 || lost) continue;
+        // nothing is ready: the other ranks are behind.  Bounded wait.
+        if (!waiting) { waiting = true; t0 = clock64(); }
+        bool give_up = ld_relaxed_sys_u32(tk + 4) != 0u;
+        if (!give_up && clock64() - t0 > 4000000000LL) {
+          give_up = true;
+          if (lane == 0) { atomicMax(x.flags + FLAG_ERR, 3u | (epoch << 8)); atomicExch(tk + 4, 1u); }
+        }
+        if (give_up) { kind = FK_EXIT; break; }
+        __nanosleep(256);
+      }
+      if (kind == FK_X || kind == FK_S || kind == FK_U) __threadfence_system();   // acquire side of the relaxed polls
+      if (lane == 0) { s_kind = kind; s_unit = unit; }
+    }
+    __syncthreads();
+    const int kind = s_kind, c = s_unit;
+    if (kind == FK_EXIT) break;
+    const size_t s0 = (size_t)c * XCHG_CHUNK;
+    const size_t s1 = min((size_t)x.P, s0 + XCHG_CHUNK);
+
+    if (kind == FK_G) {
+#pragma unroll 1
+      for (int b = 0; b < XCHG_CHUNK / 256; b++) {
+        const int blk = c * (XCHG_CHUNK / 256) + b;
+        if (blk < nblk) geom_backward_block<D, HAS_SH, W256, HAS_SH, true>(p, g, cam, blk);
+        __syncthreads();
+      }
+      // every store of the chunk has been issued by this CTA: release the flag in every rank's buffer (own included)
+      if (warp == 0 && lane < N) st_release_sys(x.peer_cflags[lane] + (size_t)rank * nch + c, epoch);
+    } else if (kind == FK_X && f.direct) {
+      // two splats per thread and round: their records from every rank in flight together
+#pragma unroll 1
+      for (int k = 0; k < XCHG_CHUNK / 256; k += 2) {
+        const size_t i0 = s0 + threadIdx.x + 256 * k, i1 = i0 + 256;
+        float4 acc[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) acc[h][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < N; r++) {      // rank order: both ranks form the same bits
+          float4 v[2][NG4];
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const size_t i = h ? i1 : i0;
+            if (i < s1) {
+#pragma unroll
+              for (int q = 0; q < NG4; q++) v[h][q] = ld_relaxed_sys_v4(x.peer_geo[r] + (i * NG4 + q) * 4);
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const size_t i = h ? i1 : i0;
+            if (i < s1) {
+#pragma unroll
+              for (int q = 0; q < NG4; q++) {
+                acc[h][q].x += v[h][q].x; acc[h][q].y += v[h][q].y; acc[h][q].z += v[h][q].z; acc[h][q].w += v[h][q].w;
+              }
+            }
+          }
+        }
+        if (i0 < s1) fused_store_sums<HAS_SH>(f, i0, acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+        if (i1 < s1) fused_store_sums<HAS_SH>(f, i1, acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
+      }
+    } else if (kind == FK_X) {
+      const size_t base16 = s0 * NG4;
+      const int n16 = (int)(s1 - s0) * NG4;
+      constexpr int RD = 12;
+#pragma unroll 1
+      for (int j = threadIdx.x; j < n16; j += 256 * RD) {
+        float4 v[RD];
+#pragma unroll
+        for (int u = 0; u < RD; u++) {
+          const int q = j + u * 256;
+          if (q < n16) {
+            if (x.geo_mc) v[u] = mm_ld_reduce_add(x.geo_mc + (base16 + q) * 4);
+            else {
+              v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int r = 0; r < N; r++) {
+                const float4 t = ld_relaxed_sys_v4(x.peer_geo[r] + (base16 + q) * 4);
+                v[u].x += t.x; v[u].y += t.y; v[u].z += t.z; v[u].w += t.w;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < RD; u++) {
+          const int q = j + u * 256;
+          if (q < n16) {
+            if (x.geo_mc) mm_st(x.geo_mc + (base16 + q) * 4, v[u]);
+            else for (int r = 0; r < N; r++) *reinterpret_cast<float4*>(x.peer_geo[r] + (base16 + q) * 4) = v[u];
+          }
+        }
+      }
+      __syncthreads();
+      if (warp == 0 && lane < N) st_release_sys(x.peer_cflags[lane] + (size_t)XCHG_MAX_RANKS * nch + c, epoch);
+    } else if (kind == FK_S) {
+      if (HAS_SH) {
+#pragma unroll 1
+        for (int k = 0; k < XCHG_CHUNK / 256; k++) {
+          const size_t i = s0 + threadIdx.x + 256 * k;
+          if (i < s1) sh_row_rebuild<D, W256>(i, x.gc_slot_floats, f.V, f.M, p.means3D, s_camv, x.gc, f.dL_dsh);
+        }
+      }
+    } else {   // FK_U
+#pragma unroll
+      for (int k = 0; k < XCHG_CHUNK / 256; k++) {
+        const size_t i = s0 + threadIdx.x + 256 * k;
+        if (i < s1) {
+          const float4* rec = reinterpret_cast<const float4*>(x.geo + i * (size_t)x.ngeo);
+          const float4 a = __ldcg(rec), b = __ldcg(rec + 1), cc = __ldcg(rec + 2);
+          const float4 d = HAS_SH ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(rec + 3);
+          fused_store_sums<HAS_SH>(f, i, a, b, cc, d);
+        }
+      }
+    }
+    if (threadIdx.x == 0) xchg_mark(x.flags, kind);      // timeline slots 1..4: last G / X / S / U unit to finish
+    __syncthreads();     // s_kind / s_unit are rewritten by warp 0
+  }
+  if (threadIdx.x == 0) xchg_mark(x.flags, 5);
+}
+
+bool launch_geom_exchange_fused(const BwdParams& p, const GeomState& g, const FusedXchg& f, int max_ctas, cudaStream_t s) {
+  if (p.P <= 0) return true;
+  const bool has_sh = p.shs != nullptr;
+  // SH rows move as 128-bit words (any active degree inside M coefficients), as 256-bit words when the rows are exactly
+  // the active coefficients (degree 3, M = 16); anything else takes the two-kernel path
+  const bool vec = has_sh && ((p.M * 3) % 4 == 0) && ((reinterpret_cast<size_t>(p.shs) & 15) == 0) &&
+                   ((reinterpret_cast<size_t>(f.dL_dsh) & 15) == 0);
+  const bool wide = vec && ((reinterpret_cast<size_t>(p.shs) & 31) == 0) && ((reinterpret_cast<size_t>(f.dL_dsh) & 31) == 0) &&
+                    p.D == 3 && p.M == 16;
+  if (has_sh && !vec) return false;
+  if (p.cov3D_precomp || f.x.world > XCHG_MAX_RANKS) return false;
+  cudaMemsetAsync(f.x.flags + FLAG_TK, 0, 8 * sizeof(uint32_t), s);
+  cudaMemsetAsync(f.x.flags + FLAG_TL, 0, 6 * sizeof(unsigned long long), s);
+  const int grid = max_ctas > 0 ? min(max_ctas, 2 * NUM_SMS_B200) : 2 * NUM_SMS_B200;
+  if (!has_sh) geom_exchange_fused_kernel<0, false, false><<<grid, 256, 0, s>>>(p, g, f);
+  else switch (p.D) {
+    case 0: geom_exchange_fused_kernel<0, false, true><<<grid, 256, 0, s>>>(p, g, f); break;
+    case 1: geom_exchange_fused_kernel<1, false, true><<<grid, 256, 0, s>>>(p, g, f); break;
+    case 2: geom_exchange_fused_kernel<2, false, true><<<grid, 256, 0, s>>>(p, g, f); break;
+    default:
+      if (wide) geom_exchange_fused_kernel<3, true, true><<<grid, 256, 0, s>>>(p, g, f);
+      else      geom_exchange_fused_kernel<3, false, true><<<grid, 256, 0, s>>>(p, g, f);
+      break;
+  }
+  return true;
 }
 
 void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s) {

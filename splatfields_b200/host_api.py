@@ -119,6 +119,9 @@ class ViewParallelRasterizer:
         mc = int(hdl.multicast_ptr) if os.environ.get("SFB_XCHG_NO_MULTICAST", "0") != "1" else 0
         d.mc = mc if mc else None
         d.max_ctas = 0
+        d.campos_views = None
+        # one persistent kernel does the geometry backward AND the exchange (SFB_XCHG_FUSED=0: backward, then sfb_xchg_finish)
+        self.xchg_fused = os.environ.get("SFB_XCHG_FUSED", "1") != "0"
         self.xchg, self._xchg_buf, self._xchg_hdl = d, buf, hdl
         self.xchg_epoch = 0
         self.xchg_multicast = bool(mc)
@@ -179,11 +182,14 @@ class ViewParallelRasterizer:
         n = lib.sfb_last_launch_count()
         factored = self.exchange == "factored"
         nvlink = self.exchange == "nvlink"
+        fused = nvlink and self.xchg_fused
         if nvlink:
             self.xchg_epoch += 1
+            if fused and "shs" in p:
+                self.xchg.campos_views = self.campos_views.data_ptr()
         sh_out = self.dcolor_mine if factored else (self.factored_output if self.world == 1 else None)
         rasterizer.set_grad_arena(self.slab, self.fields, None if sh_out is None else sh_out.view(self.P, 3),
-                                  (self.xchg, self.xchg_epoch) if nvlink else None)
+                                  (self.xchg, self.xchg_epoch, fused) if nvlink else None)
         try:
             # mean over views (train.py:242) folded into the cotangent: backward is linear in it
             color.backward(cotangent if self.world == 1 else cotangent * (1.0 / self.world))
@@ -213,7 +219,9 @@ class ViewParallelRasterizer:
         if self.time_exchange and self.world > 1 and self.device.type == "cuda":
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        if self.exchange == "nvlink":
+        if self.exchange == "nvlink" and self.xchg_fused:
+            pass                             # summed inside the backward call (fused kernel)
+        elif self.exchange == "nvlink":
             lib = _lib.load()
             g = self.grads()
             has_sh = "shs" in p

@@ -45,9 +45,10 @@ _ARENA = None
 # (SFB_BWD_SH_FACTORED); `shs` then gets no .grad from autograd — the caller rebuilds the multi-view sum with
 # sh_grad_combine().
 _SH_COLOR_OUT = None
-# Exchange over NVLink (host_api.ViewParallelRasterizer exchange="nvlink"): (_lib.XchgDesc, epoch) for the NEXT backward.
-# The parameter gradients then leave through the symmetric buffers (sfb_xchg_finish sums them over the ranks) and
-# autograd gets no .grad for the parameters — only means2D's (a per-view quantity).
+# Exchange over NVLink (host_api.ViewParallelRasterizer exchange="nvlink"): (_lib.XchgDesc, epoch[, fused]) for the NEXT
+# backward.  The parameter gradients then leave through the symmetric buffers and autograd gets no .grad for the
+# parameters — only means2D's (a per-view quantity).  fused=True: the backward call itself sums them over the ranks into
+# the arena slab (one persistent kernel: geometry backward + exchange); otherwise sfb_xchg_finish does, afterwards.
 _XCHG = None
 _WARNED_DEPTH = False
 
@@ -294,7 +295,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         """Backward in exchange mode (_XCHG): packed gradient records + pushed colour gradients, no per-parameter
         outputs (include/splat_b200.h: sfb_xchg)."""
         import ctypes as C
-        desc, epoch = _XCHG
+        desc, epoch = _XCHG[0], _XCHG[1]
+        fused = len(_XCHG) > 2 and bool(_XCHG[2])
         rs = ctx.raster_settings
         radii, geom, binning, img, means3D, sh, col, sc, rot, cov, bg, vm, pm, cp = ctx.saved_tensors
         dev = means3D.device
@@ -309,6 +311,19 @@ class _RasterizeGaussians(torch.autograd.Function):
         ga = _prep(grad_out_alpha) if (ctx.with_alpha and grad_out_alpha is not None) else None
         flags = _lib.BWD_ACC_FRESH if ctx.acc_fresh[0] else 0
         ctx.acc_fresh[0] = False
+        o = dict.fromkeys(("means3D", "opacities", "scales", "rotations", "colors_precomp", "shs"))
+        if fused:       # the sums over the ranks land in the caller's slab (set_grad_arena)
+            if _ARENA is None:
+                raise Exception("fused exchange needs a gradient arena (set_grad_arena)")
+            f32 = dict(dtype=torch.float32, device=dev)
+            o["means3D"] = _arena_out("means3D", P, (P, 3), **f32)
+            o["opacities"] = _arena_out("opacities", P, (P, 1), **f32)
+            o["scales"] = _arena_out("scales", P, (P, 3), **f32)
+            o["rotations"] = _arena_out("rotations", P, (P, 4), **f32)
+            if sh is not None:
+                o["shs"] = _arena_out("shs", P, (P, ctx.M, 3), **f32)
+            else:
+                o["colors_precomp"] = _arena_out("colors_precomp", P, (P, 3), **f32)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = lib.sfb_rasterize_backward(
@@ -316,7 +331,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _ptr(bg), _ptr(means3D), _ptr(sh), _ptr(col), _ptr(sc), float(rs.scale_modifier), _ptr(rot),
                 None, _ptr(vm), _ptr(pm), _ptr(cp), float(rs.tanfovx), float(rs.tanfovy), _ptr(radii),
                 _ptr(geom), _ptr(binning), _ptr(img), _ptr(g), _ptr(ga),
-                _ptr(dL_dmeans2D), None, None, None, None, None, None, None, int(bool(rs.debug)), flags,
+                _ptr(dL_dmeans2D), _ptr(o["colors_precomp"]), _ptr(o["opacities"]), _ptr(o["means3D"]), None,
+                _ptr(o["shs"]), _ptr(o["scales"]), _ptr(o["rotations"]), int(bool(rs.debug)), flags,
                 C.byref(desc), int(epoch), stream)
         _lib.check(rc)
         sh_means2D = ctx.shapes[1]

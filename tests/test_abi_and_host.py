@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_lib.SYMBOLS) == declared
-    assert lib.sfb_abi_version() == 5
+    assert lib.sfb_abi_version() == 6
     assert lib.sfb_last_error() == b""
 
 
