@@ -428,7 +428,7 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
   if (!scratch_zeroed)
     cudaMemsetAsync(scratch, 0, sizeof(uint32_t) * (OS_MAX_PASSES * SORT_MAX_BINS + 8 + state_words), s);
   prof_begin(names[0], s);
-  const int hblocks = min(max(1, (n + 2047) / 2048), 8 * NUM_SMS_B200);   // >= 8 keys per thread, all SMs busy from ~0.3 M keys
+  const int hblocks = min(max(1, (n + 2047) / 2048), 4 * NUM_SMS_B200);   // >= 8 keys per thread, all SMs busy from ~0.3 M keys
   radix_hist_all_kernel<<<hblocks, SORT_THREADS, 0, s>>>(keys[0], n, npass, make_int4(shifts[0], shifts[1], shifts[2], shifts[3]),
                                                           make_int4(nbins[0], nbins[1], nbins[2], nbins[3]), hist_all, bias_c);
   prof_end(s);
@@ -535,6 +535,7 @@ duplicate_kernel(int P, int grid_x, SortedIdx sorted,
     for (int i = t0 + threadIdx.x; i < t1; i += DUP_THREADS) ranges_init[i] = make_uint2(0xFFFFFFFFu, 0u);
   }
   const uint32_t* __restrict__ sorted_idx = sorted.get();
+  const bool fast_div = T <= (1 << 16);
   __shared__ uint32_t s_pref[DUP_GPB + 1];
   __shared__ uint32_t s_gidx[DUP_GPB];
   __shared__ uint2 s_rect[DUP_GPB];
@@ -649,7 +650,11 @@ duplicate_kernel(int P, int grid_x, SortedIdx sorted,
       const uint2 r = s_rect[sidx];
       const uint32_t x0 = r.x & 0xFFFFu, y0 = r.x >> 16, x1 = r.y & 0xFFFFu;
       const uint32_t w = x1 - x0;
-      const uint32_t yy = t / w, xx = t - yy * w;
+      // t / w without the ~20-instruction emulated integer division (this loop runs once per instance): (t + 0.5) / w sits
+      // at least 0.5 / w away from an integer and the approximate quotient is off by < 1e-6 relative, so the truncation is
+      // exact while t < 2^16 (t < tiles of one splat <= T; larger grids take the integer division)
+      const uint32_t yy = fast_div ? (uint32_t)__fdividef((float)t + 0.5f, (float)w) : t / w;
+      const uint32_t xx = t - yy * w;
       const uint32_t tile = (y0 + yy) * (uint32_t)grid_x + (x0 + xx);
       const uint32_t gi = s_gidx[sidx];
       if (inst_hi) {

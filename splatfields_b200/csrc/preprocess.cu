@@ -135,6 +135,17 @@ __device__ __forceinline__ void preprocess_body(const FwdParams& p, const GeomSt
     uint8_t clamp_mask = 0;
     float3 mean = make_float3(__ldg(p.means3D + 3 * idx), __ldg(p.means3D + 3 * idx + 1),
                               __ldg(p.means3D + 3 * idx + 2));
+    // Rotation, scale and opacity are requested together with the mean, before the cull decision that depends on it:
+    // one memory round trip instead of three dependent ones (ncu, round 2: 23 % of the kernel's stall samples sat on the
+    // first use of the scale / rotation and of the opacity).  A culled splat costs 32 more bytes of traffic (~2 %).
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if (!p.cov3D_precomp) {
+      q0 = __ldg(p.rotations + 4 * (size_t)idx); q1 = __ldg(p.rotations + 4 * (size_t)idx + 1);
+      q2 = __ldg(p.rotations + 4 * (size_t)idx + 2); q3 = __ldg(p.rotations + 4 * (size_t)idx + 3);
+      s0 = __ldg(p.scales + 3 * (size_t)idx); s1 = __ldg(p.scales + 3 * (size_t)idx + 1);
+      s2 = __ldg(p.scales + 3 * (size_t)idx + 2);
+    }
+    const float opac = __ldg(p.opacities + idx);
     float3 p_view = xform4x3(cam.view, mean);
     if (p_view.z > 0.2f) {
       if (p.shs) {   // start pulling this splat's SH row towards L2 while the projection math runs
@@ -151,8 +162,6 @@ __device__ __forceinline__ void preprocess_body(const FwdParams& p, const GeomSt
 #pragma unroll
         for (int k = 0; k < 6; k++) c6[k] = __ldg(p.cov3D_precomp + 6 * (size_t)idx + k);
       } else {
-        float q0 = __ldg(p.rotations + 4 * (size_t)idx), q1 = __ldg(p.rotations + 4 * (size_t)idx + 1),
-              q2 = __ldg(p.rotations + 4 * (size_t)idx + 2), q3 = __ldg(p.rotations + 4 * (size_t)idx + 3);
         float r = q0, x = q1, y = q2, z = q3;
         float R[9];
         R[0] = fmaf(-2.f, fmaf(y, y, z * z), 1.f);
@@ -164,9 +173,7 @@ __device__ __forceinline__ void preprocess_body(const FwdParams& p, const GeomSt
         R[6] = 2.f * fmaf(x, z, -(r * y));
         R[7] = 2.f * fmaf(y, z, r * x);
         R[8] = fmaf(-2.f, fmaf(x, x, y * y), 1.f);
-        float s0 = p.scale_modifier * __ldg(p.scales + 3 * (size_t)idx),
-              s1 = p.scale_modifier * __ldg(p.scales + 3 * (size_t)idx + 1),
-              s2 = p.scale_modifier * __ldg(p.scales + 3 * (size_t)idx + 2);
+        s0 = p.scale_modifier * s0; s1 = p.scale_modifier * s1; s2 = p.scale_modifier * s2;
         float L[9];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
@@ -243,7 +250,6 @@ __device__ __forceinline__ void preprocess_body(const FwdParams& p, const GeomSt
           // (lambda1/lambda2 > 1e4) and NaN opacities are never culled.  The render kernels use this ONLY to
           // skip (splat, 8x4-pixel patch) pairs that provably fail the reference's own alpha test, so the
           // composited result is unchanged bit for bit.
-          const float opac = __ldg(p.opacities + idx);
           float hx, hy;
           if (opac != opac) { hx = hy = 3.0e38f; }
           else if (opac < 1.0f / 255.0f) { hx = hy = -1.f; }   // alpha <= o < 1/255 everywhere

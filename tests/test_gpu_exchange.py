@@ -17,4 +17,4 @@ def test_exchange_emulated_ranks_match_the_serial_sum(cuda_lib):
     tail = (r.stdout + r.stderr)[-2000:]
     assert r.returncode == 0, tail
     line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
-    assert line["ok"] and len(line["cases"]) == 4, tail
+    assert line["ok"] and len(line["cases"]) == 10 and sum(bool(c.get("fused")) for c in line["cases"]) == 6, tail
