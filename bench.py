@@ -404,6 +404,7 @@ def run_ours(args):
                     acc.setdefault(name, []).append(ms)
     vp.time_exchange = False
     exch_ms = vp.exchange_ms()
+    exch_timeline = vp.exchange_timeline() if (world > 1 and vp.exchange == "nvlink") else None
     if rank == 0:
         _lib.profile_enable(False)
     sync_all()
@@ -454,6 +455,7 @@ def run_ours(args):
                 "fused_with_geometry_backward": bool(getattr(vp, "xchg_fused", False)) if vp.exchange == "nvlink" else False,
                 "ms_per_step": (float(np.mean(exch_ms)) if exch_ms else None)
                 if not (vp.exchange == "nvlink" and getattr(vp, "xchg_fused", False)) else None,
+                "device_timeline_us_rank0": exch_timeline,
                 "fused_kernel_ms_per_step": (stages or {}).get("ms_per_step_by_kernel", {}).get("geom_backward_exchange"),
                 "nvlink_bytes_received_per_splat_per_rank": vp.bytes_on_wire_per_splat(),
                 "nvlink_MB_received_per_rank_per_step": vp.bytes_on_wire_per_splat() * P / 1e6,

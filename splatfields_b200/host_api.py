@@ -300,6 +300,22 @@ class ViewParallelRasterizer:
                                                    torch.cuda.current_stream(self.device).cuda_stream))
         return int(st.value)
 
+    def exchange_timeline(self) -> dict | None:
+        """Device timeline (microseconds from the kernel's first CTA) of the last step's exchange kernel on this rank
+        (include/splat_b200.h: sfb_xchg_timeline); synchronises the stream.  Fused kernel: when the last geometry chunk,
+        the last NVLink unit, the last SH chunk and the last unpack finished; sfb_xchg_finish: its five phases."""
+        if self.xchg is None:
+            return None
+        import ctypes as C
+        t = (C.c_ulonglong * 6)()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().sfb_xchg_timeline(C.byref(self.xchg), t,
+                                                     torch.cuda.current_stream(self.device).cuda_stream))
+        t = [int(v) for v in t]
+        names = (("geometry_done", "nvlink_units_done", "sh_rows_done", "unpack_done", "kernel_end") if self.xchg_fused
+                 else ("barrier_a", "slice_reduced", "sh_rows_done", "barrier_b", "kernel_end"))
+        return {n: (round((v - t[0]) / 1e3, 1) if v else None) for n, v in zip(names, t[1:])}
+
     def exchange_ms(self) -> list:
         """Device time of the gradient exchange (collectives + SH rebuild) of the steps run with time_exchange."""
         torch.cuda.synchronize(self.device)
