@@ -452,48 +452,56 @@ __global__ void __launch_bounds__(256, 2) geom_exchange_fused_kernel(BwdParams p
       int kind = -1, unit = 0;
       long long t0 = 0;
       bool waiting = false;
-      while (kind < 0) {
-        const bool hasG = tG < nG, hasX = tX < nX, hasS = tS < nS, hasU = tU < nU;
-        if (!(hasG | hasX | hasS | hasU)) { kind = FK_EXIT; break; }
-        const uint32_t cX = f.direct ? tX : (uint32_t)rank + tX * (uint32_t)N, cS = tS, cU = tU;
-        uint32_t fx = epoch, fs = epoch, fu = epoch;
-        if (lane < N) {
-          if (hasX) fx = ld_relaxed_sys_u32(x.cflags + (size_t)lane * nch + cX);
-          if (hasS) fs = ld_relaxed_sys_u32(x.cflags + (size_t)lane * nch + cS);
-        }
-        if (lane == 0 && hasU) fu = ld_relaxed_sys_u32(x.cflags + (size_t)XCHG_MAX_RANKS * nch + cU);
-        const bool rX = hasX && __all_sync(0xffffffffu, (int32_t)(fx - epoch) >= 0);
-        const bool rS = hasS && __all_sync(0xffffffffu, (int32_t)(fs - epoch) >= 0);
-        const bool rU = hasU && (int32_t)(__shfl_sync(0xffffffffu, fu, 0) - epoch) >= 0;
-        bool lost = false;      // a claim went to another CTA: look again at once
-        auto claim = [&](int q, uint32_t& t) -> bool {
-          uint32_t old = 0;
-          if (lane == 0) old = atomicCAS(tk + q, t, t + 1u);
-          old = __shfl_sync(0xffffffffu, old, 0);
-          if (old == t) { t = t + 1u; return true; }
-          t = old; lost = true;
-          return false;
-        };
-        if (rX && (link_cta || !hasG)) { if (claim(1, tX)) { kind = FK_X; unit = (int)cX; } }
-        if (kind < 0 && hasG) {
-          uint32_t gt = 0;
-          if (lane == 0) gt = atomicAdd(tk + 0, 1u);
-          gt = __shfl_sync(0xffffffffu, gt, 0);
-          tG = gt + 1u;
-          if (gt < nG) { kind = FK_G; unit = (int)gt; } else lost = true;
-        }
-        if (kind < 0 && rS) { if (claim(2, tS)) { kind = FK_S; unit = (int)cS; } }
-        if (kind < 0 && rU) { if (claim(3, tU)) { kind = FK_U; unit = (int)cU; } }
-        if (kind >= 0 || lost) continue;
-        // nothing is ready: the other ranks are behind.  Bounded wait.
+      // flags of chunk c that gate a unit of queue q (1: X, 2: S -> A[*][c]; 3: U -> B[c]); all lanes get the answer
+      auto chunk_ready = [&](int q, uint32_t c) -> bool {
+        uint32_t fl = epoch;
+        if (q == 3) { if (lane == 0) fl = ld_relaxed_sys_u32(x.cflags + (size_t)XCHG_MAX_RANKS * nch + c); }
+        else if (lane < N) fl = ld_relaxed_sys_u32(x.cflags + (size_t)lane * nch + c);
+        return __all_sync(0xffffffffu, (int32_t)(fl - epoch) >= 0);
+      };
+      // bounded wait (the other ranks are behind); false: gave up, the kernel retires with an error word
+      auto keep_waiting = [&]() -> bool {
         if (!waiting) { waiting = true; t0 = clock64(); }
         bool give_up = ld_relaxed_sys_u32(tk + 4) != 0u;
         if (!give_up && clock64() - t0 > 4000000000LL) {
           give_up = true;
           if (lane == 0) { atomicMax(x.flags + FLAG_ERR, 3u | (epoch << 8)); atomicExch(tk + 4, 1u); }
         }
-        if (give_up) { kind = FK_EXIT; break; }
-        __nanosleep(256);
+        give_up = __any_sync(0xffffffffu, give_up);
+        if (!give_up) __nanosleep(200);
+        return !give_up;
+      };
+      // A unit of queue q is taken with ONE atomicAdd once the queue's next unit (as this CTA last saw it) is ready:
+      // every contender gets a ticket of its own (a compare-and-swap claim lets one CTA through per L2 round trip), and
+      // the ticket it gets may lie a little further on than the one it looked at, in which case it waits for that chunk.
+      auto take = [&](int q, uint32_t& t, uint32_t n, int k) {
+        uint32_t got = 0;
+        if (lane == 0) got = atomicAdd(tk + q, 1u);
+        got = __shfl_sync(0xffffffffu, got, 0);
+        t = got + 1u;
+        if (got >= n) return;                                   // the queue ran out in the meantime
+        const uint32_t c = (q == 1 && !f.direct) ? (uint32_t)rank + got * (uint32_t)N : got;
+        while (!chunk_ready(q, c)) { if (!keep_waiting()) { kind = FK_EXIT; return; } }
+        kind = k; unit = (int)c;
+      };
+      while (kind < 0) {
+        const bool hasG = tG < nG, hasX = tX < nX, hasS = tS < nS, hasU = tU < nU;
+        if (!(hasG | hasX | hasS | hasU)) { kind = FK_EXIT; break; }
+        const uint32_t cX = f.direct ? tX : (uint32_t)rank + tX * (uint32_t)N;
+        if (hasX && (link_cta || !hasG) && chunk_ready(1, cX)) { take(1, tX, nX, FK_X); continue; }
+        if (hasG) {
+          uint32_t gt = 0;
+          if (lane == 0) gt = atomicAdd(tk + 0, 1u);
+          gt = __shfl_sync(0xffffffffu, gt, 0);
+          tG = gt + 1u;
+          if (gt < nG) { kind = FK_G; unit = (int)gt; }
+          continue;
+        }
+        if (hasS && chunk_ready(2, tS)) { take(2, tS, nS, FK_S); continue; }
+        // (U only once every X unit of this rank has been taken: a CTA that waits for another rank's broadcast must
+        //  never be the one that rank is waiting for)
+        if (hasU && !hasX && chunk_ready(3, tU)) { take(3, tU, nU, FK_U); continue; }
+        if (!keep_waiting()) { kind = FK_EXIT; break; }
       }
       if (kind == FK_X || kind == FK_S || kind == FK_U) __threadfence_system();   // acquire side of the relaxed polls
       if (lane == 0) { s_kind = kind; s_unit = unit; }
