@@ -141,12 +141,15 @@ int sfb_xchg_finish(const sfb_xchg* x, unsigned epoch, int sh_degree, int M, con
  * of ready work for too long) | epoch << 8 — the device-side
  * waits are bounded (about 2 s), a kernel that gives up leaves its outputs untouched and records the failure here. */
 int sfb_xchg_status(const sfb_xchg* x, unsigned* status, void* stream);
-/* Measurement hooks.  sfb_xchg_timeline: synchronises `stream` and returns six device timestamps (globaltimer, ns) of
- * the last sfb_xchg_finish launch on this rank: first CTA started, last CTA past the first cross-rank barrier, last CTA
- * done with the slice reduction, with the SH rows, past the second barrier, done unpacking.  sfb_xchg_tune: share of the
- * CTAs that start on the slice reduction (eighths of the grid, default 4) and reduction round trips in flight per
- * thread (4, default, or 16); process-wide. */
-int sfb_xchg_timeline(const sfb_xchg* x, unsigned long long* ns6, void* stream);
+/* Measurement hooks.  sfb_xchg_timeline: synchronises `stream` and returns twelve values about the last exchange kernel
+ * on this rank.  [0..5]: device timestamps (globaltimer, ns).  sfb_xchg_finish: first CTA started, last CTA past the
+ * first cross-rank barrier, done with the slice reduction, with the SH rows, past the second barrier, done unpacking.
+ * Fused kernel: first CTA started, last geometry chunk / NVLink unit / SH chunk / unpack chunk finished, last CTA done.
+ * [6..11] (fused kernel only): SM cycles, summed over the CTAs, spent choosing work (incl. waiting), in geometry chunks,
+ * in their flag releases, in NVLink units, SH chunks, unpack chunks.  sfb_xchg_tune: share of the CTAs that start on the
+ * slice reduction (eighths of the grid, default 4) and reduction round trips in flight per thread (4, default, or 16);
+ * process-wide. */
+int sfb_xchg_timeline(const sfb_xchg* x, unsigned long long* ns12, void* stream);
 void sfb_xchg_tune(int nred_eighths, int depth);
 
 /* Multi-view sum of SH gradients from their factored form (view-parallel training; the serial loop

@@ -38,7 +38,7 @@ def main():
                 torch.cuda.synchronize(); dist.barrier(); e0.record()
             vp.step(G)
             if it >= 4 and it % 4 == 0:       # reading the timeline synchronises: only some of the steps
-                t = (C.c_ulonglong * 6)()
+                t = (C.c_ulonglong * 12)()
                 _lib.check(lib.sfb_xchg_timeline(C.byref(vp.xchg), t, torch.cuda.current_stream(dev).cuda_stream))
                 t = [int(v) for v in t]
                 rows.append([(t[1] - t[0]) / 1e3, (t[2] - t[1]) / 1e3, (t[3] - t[2]) / 1e3, (t[4] - max(t[2], t[3])) / 1e3,

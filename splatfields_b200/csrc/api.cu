@@ -370,7 +370,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
                           (shs ? (dL_dsh != nullptr && xchg->campos_views != nullptr) : dL_dcolors != nullptr);
   if (xchg) {
     const XchgLayout xl = XchgLayout::make((size_t)P, xchg->world, xchg->ngeo, shs != nullptr);
-    const int par = want_fused ? (int)(xchg_epoch & 1u) : 0;
+    const int par = (int)(xchg_epoch & 1u);      // records are double-buffered by step parity
     bp.x_geo = reinterpret_cast<float*>((char*)xchg->local + xl.geo_off[par]);
     bp.x_ngeo = xchg->ngeo;
     bp.x_nranks = xchg->world;
@@ -437,7 +437,7 @@ int sfb_xchg_finish(const sfb_xchg* x, unsigned epoch, int sh_degree, int M, con
   const XchgLayout xl = XchgLayout::make((size_t)x->P, x->world, x->ngeo, has_sh);
   for (int r = 0; r < x->world; r++)
     if (!x->peers[r]) return fail(SFB_ERR_ARG, "sfb_xchg_finish: null peer mapping");
-  XchgDev d = make_xchg_dev(x, xl, 0, epoch);
+  XchgDev d = make_xchg_dev(x, xl, (int)(epoch & 1u), epoch);
   prof_begin("xchg_finish", s);
   launch_xchg_finish(d, x->max_ctas, epoch, sh_degree, M, means3D, campos_views, dL_dmeans3D, dL_dopacity, dL_dscales, dL_drotations,
                      dL_dcolors, has_sh ? dL_dsh : nullptr, s);
@@ -456,14 +456,17 @@ int sfb_xchg_status(const sfb_xchg* x, unsigned* status, void* stream) {
   return SFB_OK;
 }
 
-int sfb_xchg_timeline(const sfb_xchg* x, unsigned long long* ns6, void* stream) {
+int sfb_xchg_timeline(const sfb_xchg* x, unsigned long long* ns12, void* stream) {
   g_err.clear();
-  if (!x || !x->local || !ns6) return fail(SFB_ERR_ARG, "sfb_xchg_timeline: bad arguments");
+  if (!x || !x->local || !ns12) return fail(SFB_ERR_ARG, "sfb_xchg_timeline: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
-  CK(cudaMemcpyAsync(ns6, reinterpret_cast<const uint32_t*>(x->local) + 36, 6 * sizeof(unsigned long long),
+  uint32_t w[6];
+  CK(cudaMemcpyAsync(ns12, reinterpret_cast<const uint32_t*>(x->local) + 36, 6 * sizeof(unsigned long long),
                      cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(w, reinterpret_cast<const uint32_t*>(x->local) + 56, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
-  ns6[0] = ~ns6[0];
+  ns12[0] = ~ns12[0];
+  for (int k = 0; k < 6; k++) ns12[6 + k] = (unsigned long long)w[k] * 64ull;   // SM cycles summed over the CTAs
   return SFB_OK;
 }
 

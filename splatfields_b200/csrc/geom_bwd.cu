@@ -446,6 +446,12 @@ __global__ void __launch_bounds__(256, 2) geom_exchange_fused_kernel(BwdParams p
   constexpr int NG4 = HAS_SH ? 3 : 4;           // 16-byte words per packed record
   if (threadIdx.x == 0) xchg_mark(x.flags, 0, true);
   __syncthreads();
+  // where this CTA's time goes (thread 0; sfb_xchg_timeline): choosing work, G bodies, G flag releases, X, S, U units
+  __shared__ long long s_cyc[7];      // (shared memory: registers are scarce here; [6] = start of the current lap)
+  if (threadIdx.x < 6) s_cyc[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_cyc[6] = clock64();
+  auto lap = [&](int slot) { const long long now = clock64(); s_cyc[slot] += now - s_cyc[6]; s_cyc[6] = now; };
+  __syncthreads();
 
   for (;;) {
     if (warp == 0) {
@@ -508,6 +514,7 @@ __global__ void __launch_bounds__(256, 2) geom_exchange_fused_kernel(BwdParams p
     }
     __syncthreads();
     const int kind = s_kind, c = s_unit;
+    if (threadIdx.x == 0) lap(0);
     if (kind == FK_EXIT) break;
     const size_t s0 = (size_t)c * XCHG_CHUNK;
     const size_t s1 = min((size_t)x.P, s0 + XCHG_CHUNK);
@@ -520,7 +527,10 @@ __global__ void __launch_bounds__(256, 2) geom_exchange_fused_kernel(BwdParams p
         __syncthreads();
       }
       // every store of the chunk has been issued by this CTA: release the flag in every rank's buffer (own included)
+      if (threadIdx.x == 0) lap(1);
       if (warp == 0 && lane < N) st_release_sys(x.peer_cflags[lane] + (size_t)rank * nch + c, epoch);
+      if (warp == 0) __syncwarp();
+      if (threadIdx.x == 0) lap(2);
     } else if (kind == FK_X && f.direct) {
       // two splats per thread and round: their records from every rank in flight together
 #pragma unroll 1
@@ -607,10 +617,17 @@ __global__ void __launch_bounds__(256, 2) geom_exchange_fused_kernel(BwdParams p
         }
       }
     }
-    if (threadIdx.x == 0) xchg_mark(x.flags, kind);      // timeline slots 1..4: last G / X / S / U unit to finish
+    if (threadIdx.x == 0) {
+      xchg_mark(x.flags, kind);      // timeline slots 1..4: last G / X / S / U unit to finish
+      if (kind != FK_G) lap(kind + 1);
+    }
     __syncthreads();     // s_kind / s_unit are rewritten by warp 0
   }
-  if (threadIdx.x == 0) xchg_mark(x.flags, 5);
+  if (threadIdx.x == 0) {
+    xchg_mark(x.flags, 5);
+#pragma unroll
+    for (int k = 0; k < 6; k++) atomicAdd(x.flags + 56 + k, (uint32_t)(s_cyc[k] >> 6));
+  }
 }
 
 bool launch_geom_exchange_fused(const BwdParams& p, const GeomState& g, const FusedXchg& f, int max_ctas, cudaStream_t s) {
@@ -623,7 +640,7 @@ bool launch_geom_exchange_fused(const BwdParams& p, const GeomState& g, const Fu
   const bool wide = vec && ((reinterpret_cast<size_t>(p.shs) & 31) == 0) && ((reinterpret_cast<size_t>(f.dL_dsh) & 31) == 0) &&
                     p.D == 3 && p.M == 16;
   if (p.cov3D_precomp || f.x.world > XCHG_MAX_RANKS) return false;
-  cudaMemsetAsync(f.x.flags + FLAG_TK, 0, 8 * sizeof(uint32_t), s);
+  cudaMemsetAsync(f.x.flags + FLAG_TK, 0, 16 * sizeof(uint32_t), s);      // tickets, abort word, CTA-time counters
   cudaMemsetAsync(f.x.flags + FLAG_TL, 0, 6 * sizeof(unsigned long long), s);
   const int grid = max_ctas > 0 ? min(max_ctas, 2 * NUM_SMS_B200) : 2 * NUM_SMS_B200;
 #define SFB_FX(DD, VV, WW, SS) geom_exchange_fused_kernel<DD, VV, WW, SS><<<grid, 256, 0, s>>>(p, g, f)

@@ -307,14 +307,19 @@ class ViewParallelRasterizer:
         if self.xchg is None:
             return None
         import ctypes as C
-        t = (C.c_ulonglong * 6)()
+        t = (C.c_ulonglong * 12)()
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().sfb_xchg_timeline(C.byref(self.xchg), t,
                                                      torch.cuda.current_stream(self.device).cuda_stream))
         t = [int(v) for v in t]
         names = (("geometry_done", "nvlink_units_done", "sh_rows_done", "unpack_done", "kernel_end") if self.xchg_fused
                  else ("barrier_a", "slice_reduced", "sh_rows_done", "barrier_b", "kernel_end"))
-        return {n: (round((v - t[0]) / 1e3, 1) if v else None) for n, v in zip(names, t[1:])}
+        out = {n: (round((v - t[0]) / 1e3, 1) if v else None) for n, v in zip(names, t[1:6])}
+        if self.xchg_fused and sum(t[6:]) > 0:      # share of the CTAs' time per kind of work
+            tot = float(sum(t[6:]))
+            out["cta_time_share"] = {n: round(v / tot, 3) for n, v in
+                                     zip(("choosing_or_waiting", "geometry", "flag_release", "nvlink_units", "sh_rows", "unpack"), t[6:])}
+        return out
 
     def exchange_ms(self) -> list:
         """Device time of the gradient exchange (collectives + SH rebuild) of the steps run with time_exchange."""
