@@ -244,10 +244,10 @@ def roofline_report(acc, nprof, stats, P, HW, ms_step):
 
 
 EXCHANGE_TEXT = {
-    "nvlink": "own kernel over NVLink symmetric memory - ONE persistent kernel per rank does the geometry backward and "
-              "the exchange chunk by chunk: colour gradients pushed to every rank (multimem.st), packed [P,11] records "
-              "summed in the switch (multimem.ld_reduce) and broadcast - two ranks: peer records read and summed "
-              "directly -, SH rows rebuilt per rank; no NCCL collective on the data path",
+    "nvlink": "own kernels over NVLink symmetric memory - the geometry backward pushes its colour gradients into every "
+              "rank's table while it computes (multimem.st) and leaves packed [P,11] records; one more kernel sums the "
+              "records in the switch (multimem.ld_reduce) and broadcasts them, rebuilds the SH rows and unpacks - two ranks: "
+              "records pushed straight into the peer's inbox and summed locally; no NCCL collective on the data path",
     "factored": "NCCL all-gather of [P,3] colour gradients + all-reduce of [P,11] geometry gradients, SH rows rebuilt per rank",
     "allreduce": "1 NCCL all-reduce of [P,59] fp32 grads",
 }

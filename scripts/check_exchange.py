@@ -27,11 +27,11 @@ def main():
     G = torch.randn(3, H, W, generator=torch.Generator().manual_seed(100 + rank)).to(dev)
     out = {}
     info = {}
-    # nvlink: the fused backward + exchange kernel (multicast); _p2p: the same without the multicast mapping;
-    # _2k: backward, then sfb_xchg_finish (two kernels); _2k_p2p: that without multicast
-    for mode in ("allreduce", "factored", "nvlink", "nvlink_p2p", "nvlink_2k", "nvlink_2k_p2p"):
+    # nvlink: backward (records + pushed colour gradients), then sfb_xchg_finish; _p2p: the same without the multicast
+    # mapping; _fused: the one-kernel variant (geometry backward + exchange); _fused_p2p: that without multicast
+    for mode in ("allreduce", "factored", "nvlink", "nvlink_p2p", "nvlink_fused", "nvlink_fused_p2p"):
         os.environ["SFB_XCHG_NO_MULTICAST"] = "1" if mode.endswith("_p2p") else "0"
-        os.environ["SFB_XCHG_FUSED"] = "0" if "_2k" in mode else "1"
+        os.environ["SFB_XCHG_FUSED"] = "1" if "_fused" in mode else "0"
         vp = ViewParallelRasterizer(sc, cam, H, W, deg, device=dev, world_size=world, exchange=mode.split("_")[0])
         assert vp.exchange == mode.split("_")[0]
         if vp.exchange == "nvlink":
@@ -43,9 +43,9 @@ def main():
         del vp
     # precomputed colours: [14, P] records, plain sum
     sc2 = synth.make_scene(P, 10, scale_mult=1.5, precomp_rgb=True)
-    for mode in ("allreduce", "nvlink", "nvlink_2k"):
+    for mode in ("allreduce", "nvlink", "nvlink_fused"):
         os.environ["SFB_XCHG_NO_MULTICAST"] = "0"
-        os.environ["SFB_XCHG_FUSED"] = "0" if "_2k" in mode else "1"
+        os.environ["SFB_XCHG_FUSED"] = "1" if "_fused" in mode else "0"
         vp = ViewParallelRasterizer(sc2, cam, H, W, 0, device=dev, world_size=world, exchange=mode.split("_")[0])
         for _ in range(2):
             vp.step(G)
@@ -54,10 +54,10 @@ def main():
         del vp
     worst = {}
     ok = True
-    os.environ["SFB_XCHG_FUSED"] = "1"
+    os.environ["SFB_XCHG_FUSED"] = "0"
     for mode, base in (("factored", "allreduce"), ("nvlink", "allreduce"), ("nvlink_p2p", "allreduce"),
-                       ("nvlink_2k", "allreduce"), ("nvlink_2k_p2p", "allreduce"),
-                       ("rgb_nvlink", "rgb_allreduce"), ("rgb_nvlink_2k", "rgb_allreduce")):
+                       ("nvlink_fused", "allreduce"), ("nvlink_fused_p2p", "allreduce"),
+                       ("rgb_nvlink", "rgb_allreduce"), ("rgb_nvlink_fused", "rgb_allreduce")):
         for k in out[base]:
             a, b = out[mode][k], out[base][k]
             scale = float(b.abs().max())

@@ -21,11 +21,9 @@ except Exception as e:
 PY
   tail -2 $OUT/bench_n${N}_$name.err | cut -c1-300
 }
-run_bench fused SFB_X=0
-if [ "$MODE" = full ]; then
-  run_bench fused_p2p SFB_XCHG_NO_MULTICAST=1
-  run_bench twokernel SFB_XCHG_FUSED=0
-fi
+run_bench nvlink SFB_X=0
+if [ "$MODE" = full ]; then run_bench nvlink_p2p SFB_XCHG_NO_MULTICAST=1; fi
+if [ "$MODE" != lean ]; then run_bench fused SFB_XCHG_FUSED=1; fi
 ROUNDS=$((1800 / N))
 timeout 300 $TR scripts/run_view_time.py --rounds $ROUNDS > $OUT/view_time_n$N.json 2> $OUT/view_time_n$N.err; grep '^{' $OUT/view_time_n$N.json; tail -2 $OUT/view_time_n$N.err | cut -c1-300
 ls $OUT

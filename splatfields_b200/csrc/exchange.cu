@@ -91,10 +91,11 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int nred_eighths, int V, int M, co
   const size_t C = (size_t)x.P * (size_t)(x.ngeo / 4);                  // 16-byte chunks of the record array
   const size_t c0 = C * (size_t)x.rank / (size_t)N, c1 = C * (size_t)(x.rank + 1) / (size_t)N;
   const int nred = HAS_SH ? min((int)gridDim.x, max(1, ((int)gridDim.x * nred_eighths) / 8)) : (int)gridDim.x;
-  // Two ranks: every rank reads the peer's records, adds them to its own in rank order (both ranks form the same bits)
-  // and writes the per-parameter gradients straight away — half the NVLink bytes of reduce + broadcast through the
-  // switch (a multimem access also moves this rank's own copy over its link), no second barrier, no unpack pass.  The
-  // records are double-buffered by step parity (api.cu), so the peer's next backward cannot overwrite what is read here.
+  // Two ranks: the peer's geometry backward has pushed its records into this rank's inbox (posted NVLink stores that
+  // travel while it computes; reading them from the peer instead ran at 140 GB/s, round 2).  Every rank adds the two
+  // record sets in rank order (both form the same bits) and writes the per-parameter gradients straight away — 48 B per
+  // splat and direction instead of 72 through the switch (a multimem access also moves this rank's own copy over its
+  // link), no second barrier, no unpack pass.  Records and inboxes are double-buffered by step parity (api.cu).
   const bool direct = N == 2;
   if (direct && (int)blockIdx.x < nred) {
     constexpr int NG4 = HAS_SH ? 3 : 4;
@@ -106,7 +107,8 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int nred_eighths, int V, int M, co
         for (int h = 0; h < 2; h++)
           if (i0 + h < (size_t)x.P) {
 #pragma unroll
-            for (int q = 0; q < NG4; q++) v[r][h][q] = ld_relaxed_sys_v4(x.peer_geo[r] + ((i0 + h) * NG4 + q) * 4);
+            for (int q = 0; q < NG4; q++)
+              v[r][h][q] = __ldcg(reinterpret_cast<const float4*>((r == x.rank ? x.geo : x.inbox) + ((i0 + h) * NG4 + q) * 4));
           }
 #pragma unroll
       for (int h = 0; h < 2; h++) {

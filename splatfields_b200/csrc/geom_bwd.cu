@@ -357,6 +357,13 @@ __device__ __forceinline__ void geom_backward_block(const BwdParams& p, const Ge
     rec[1] = make_float4(dscale[0], dscale[1], dscale[2], drot[0]);
     rec[2] = make_float4(drot[1], drot[2], drot[3], 0.f);
     if (!FACT) rec[3] = make_float4(gcol[0], gcol[1], gcol[2], 0.f);          // precomputed colours: 14 floats (+2 pad)
+    if (p.x_geo_peer) {      // two ranks: the same record straight into the peer's inbox (posted NVLink stores)
+      float4* prec = reinterpret_cast<float4*>(p.x_geo_peer + i * (size_t)p.x_ngeo);
+      prec[0] = make_float4(dmean[0], dmean[1], dmean[2], gop);
+      prec[1] = make_float4(dscale[0], dscale[1], dscale[2], drot[0]);
+      prec[2] = make_float4(drot[1], drot[2], drot[3], 0.f);
+      if (!FACT) prec[3] = make_float4(gcol[0], gcol[1], gcol[2], 0.f);
+    }
     p.dL_dmeans2D[3 * i] = gm2[0]; p.dL_dmeans2D[3 * i + 1] = gm2[1]; p.dL_dmeans2D[3 * i + 2] = 0.f;
     return;
   }
@@ -548,7 +555,7 @@ __global__ void __launch_bounds__(256, 2) geom_exchange_fused_kernel(BwdParams p
             const size_t i = h ? i1 : i0;
             if (i < s1) {
 #pragma unroll
-              for (int q = 0; q < NG4; q++) v[h][q] = ld_relaxed_sys_v4(x.peer_geo[r] + (i * NG4 + q) * 4);
+              for (int q = 0; q < NG4; q++) v[h][q] = ld_relaxed_sys_v4((r == rank ? x.geo : x.inbox) + (i * NG4 + q) * 4);
             }
           }
 #pragma unroll

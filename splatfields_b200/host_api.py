@@ -120,8 +120,10 @@ class ViewParallelRasterizer:
         d.mc = mc if mc else None
         d.max_ctas = 0
         d.campos_views = None
-        # one persistent kernel does the geometry backward AND the exchange (SFB_XCHG_FUSED=0: backward, then sfb_xchg_finish)
-        self.xchg_fused = os.environ.get("SFB_XCHG_FUSED", "1") != "0"
+        # SFB_XCHG_FUSED=1: one persistent kernel does the geometry backward AND the exchange chunk by chunk (measured
+        # slower than backward + sfb_xchg_finish on B200: the per-chunk flag releases wait for the NVLink stores they
+        # cover, profiles/r02d_*); default: the two kernels
+        self.xchg_fused = os.environ.get("SFB_XCHG_FUSED", "0") == "1"
         self.xchg, self._xchg_buf, self._xchg_hdl = d, buf, hdl
         self.xchg_epoch = 0
         self.xchg_multicast = bool(mc)
