@@ -271,7 +271,6 @@ static sfb::XchgDev make_xchg_dev(const sfb_xchg* x, const sfb::XchgLayout& xl, 
   d.flags = reinterpret_cast<uint32_t*>(x->local);
   d.cflags = reinterpret_cast<uint32_t*>((char*)x->local + xl.cflag_off);
   d.geo = reinterpret_cast<float*>((char*)x->local + xl.geo_off[par]);
-  d.inbox = x->world == 2 ? reinterpret_cast<const float*>((char*)x->local + xl.inbox_off[par]) : nullptr;
   d.geo_mc = x->mc ? reinterpret_cast<float*>((char*)x->mc + xl.geo_off[par]) : nullptr;
   for (int r = 0; r < XCHG_MAX_RANKS; r++) { d.peer_flags[r] = nullptr; d.peer_cflags[r] = nullptr; d.peer_geo[r] = nullptr; }
   for (int r = 0; r < x->world; r++) {
@@ -364,7 +363,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   bp.dL_dmeans2D = dL_dmeans2D; bp.dL_dcolors = dL_dcolors; bp.dL_dopacity = dL_dopacity;
   bp.dL_dmeans3D = dL_dmeans3D; bp.dL_dcov3D = dL_dcov3D; bp.dL_dsh = dL_dsh; bp.dL_dscales = dL_dscales;
   bp.dL_drot = dL_drotations;
-  bp.x_geo = nullptr; bp.x_geo_peer = nullptr; bp.x_ngeo = 0; bp.x_mc = 0; bp.x_ndst = 0; bp.x_nranks = 0;
+  bp.x_geo = nullptr; bp.x_ngeo = 0; bp.x_mc = 0; bp.x_ndst = 0; bp.x_nranks = 0;
   // Exchange mode with the summed outputs given: ONE fused kernel does the geometry backward AND the exchange
   // (geom_bwd.cu); without them the records stay in the symmetric buffer for sfb_xchg_finish.
   const bool want_fused = xchg && dL_dmeans3D && dL_dopacity && dL_dscales && dL_drotations &&
@@ -378,10 +377,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
     // slot `rank` of this step's colour-gradient table, on every rank
     const size_t slot = xl.gc_off[xchg_epoch & 1u] + (size_t)xchg->rank * xl.gc_slot_floats * 4;
     for (int r = 0; r < xchg->world; r++) bp.x_gc_peer[r] = reinterpret_cast<float*>((char*)xchg->peers[r] + slot);
-    // two ranks: everything goes to the one peer with plain stores (a multicast store would also come back over this
-    // rank's own link), records included
-    bp.x_geo_peer = xchg->world == 2 ? reinterpret_cast<float*>((char*)xchg->peers[1 - xchg->rank] + xl.inbox_off[par]) : nullptr;
-    if (xchg->mc && xchg->world != 2) { bp.x_mc = 1; bp.x_ndst = 1; bp.x_gc_dst[0] = reinterpret_cast<float*>((char*)xchg->mc + slot); }
+    if (xchg->mc) { bp.x_mc = 1; bp.x_ndst = 1; bp.x_gc_dst[0] = reinterpret_cast<float*>((char*)xchg->mc + slot); }
     else { bp.x_ndst = xchg->world; for (int r = 0; r < xchg->world; r++) bp.x_gc_dst[r] = bp.x_gc_peer[r]; }
   }
   bool fused_done = false;
@@ -389,7 +385,7 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
     const XchgLayout xl = XchgLayout::make((size_t)P, xchg->world, xchg->ngeo, shs != nullptr);
     FusedXchg f;
     f.x = make_xchg_dev(xchg, xl, (int)(xchg_epoch & 1u), xchg_epoch);
-    f.epoch = xchg_epoch; f.V = xchg->world; f.M = M; f.direct = xchg->world == 2 ? 1 : 0;
+    f.epoch = xchg_epoch; f.V = xchg->world; f.M = M;
     f.campos_views = reinterpret_cast<const float*>(xchg->campos_views);
     f.dL_dmeans3D = dL_dmeans3D; f.dL_dopacity = dL_dopacity; f.dL_dscales = dL_dscales; f.dL_drot = dL_drotations;
     f.dL_dcolors = dL_dcolors; f.dL_dsh = dL_dsh;

@@ -451,7 +451,6 @@ struct BwdParams {
   float *dL_dmeans2D, *dL_dcolors, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drot;
   // view-parallel exchange over NVLink (exchange.cu); x_geo == nullptr: off
   float* x_geo;                 // this rank's packed gradient records [P][x_ngeo] (x_ngeo = 12: SH colours, 16: precomputed)
-  float* x_geo_peer;            // two ranks: the peer's inbox — every record is also stored there (nullptr otherwise)
   int x_ngeo, x_mc, x_ndst, x_nranks;
   float* x_gc_dst[XCHG_MAX_RANKS];    // slot `rank` of the colour-gradient table: x_mc ? {multicast address} : one per rank
   float* x_gc_peer[XCHG_MAX_RANKS];   // the same slot through every rank's unicast mapping (ragged tail)
@@ -461,14 +460,13 @@ void launch_geom_backward(const BwdParams& p, const GeomState& g, cudaStream_t s
 // exchange.cu
 // Layout of one rank's symmetric exchange buffer (identical on every rank; include/splat_b200.h: sfb_xchg):
 //   [flags: 256 B][packed gradient records: P * ngeo floats][colour-gradient tables: 2 parities x world x P x 3 floats]
-//   [flags 256 B][chunk flags: (XCHG_MAX_RANKS + 1) x nch words][packed records, 2 parities][two ranks: inbox for the
-//    peer's records, 2 parities][colour tables, 2 parities]
+//   [flags 256 B][chunk flags: (XCHG_MAX_RANKS + 1) x nch words][packed records, 2 parities][colour tables, 2 parities]
 // Chunk flags (fused backward + exchange, geom_bwd.cu): word r * nch + c = rank r has finished the geometry backward of
 // chunk c (XCHG_CHUNK splats) in step `epoch`; word XCHG_MAX_RANKS * nch + c = the sums of chunk c have been broadcast.
 // sfb_xchg_finish (exchange.cu) uses record parity 0 only.
 constexpr int XCHG_CHUNK = 1024;
 struct XchgLayout {
-  size_t cflag_off, geo_off[2], inbox_off[2], gc_off[2], gc_slot_floats, bytes;
+  size_t cflag_off, geo_off[2], gc_off[2], gc_slot_floats, bytes;
   int nch;
   static XchgLayout make(size_t P, int world, int ngeo, bool with_gc) {
     XchgLayout l;
@@ -476,8 +474,6 @@ struct XchgLayout {
     l.nch = (int)((P + XCHG_CHUNK - 1) / XCHG_CHUNK);
     l.cflag_off = o; o = align_up(o + (size_t)(XCHG_MAX_RANKS + 1) * (size_t)l.nch * 4, 256);
     for (int k = 0; k < 2; k++) { l.geo_off[k] = o; o = align_up(o + P * (size_t)ngeo * 4, 256); }
-    // two ranks: the peer's records arrive here (pushed by its geometry backward), one inbox per step parity
-    for (int k = 0; k < 2; k++) { l.inbox_off[k] = o; if (world == 2) o = align_up(o + P * (size_t)ngeo * 4, 256); }
     l.gc_slot_floats = align_up(P * 3, 64);            // one view's [P][3] slot, padded to 256 bytes (16-byte stores)
     for (int k = 0; k < 2; k++) { l.gc_off[k] = o; if (with_gc) o = align_up(o + (size_t)world * l.gc_slot_floats * 4, 256); }
     l.bytes = o;
@@ -492,7 +488,6 @@ struct XchgDev {                 // device-side view of the exchange for one ste
   uint32_t* cflags;              // this rank's chunk flags
   uint32_t* peer_cflags[XCHG_MAX_RANKS];
   float* geo;                    // this rank's packed records (sums after the exchange)
-  const float* inbox;            // two ranks: the peer's records of this step (pushed by its geometry backward), else nullptr
   float* geo_mc;                 // the same array through the multicast mapping, or nullptr
   float* peer_geo[XCHG_MAX_RANKS];
   const float* gc;               // this step's colour-gradient table: world slots of gc_slot_floats floats ([P][3] each)
@@ -507,7 +502,6 @@ struct FusedXchg {
   XchgDev x;                     // geo / geo_mc / peer_geo / gc point at THIS step's parity
   uint32_t epoch;
   int V, M;                      // views (= world), SH coefficients per colour channel
-  int direct;                    // 1: every rank sums the ranks' records itself (two ranks); 0: owner reduces + broadcasts
   const float* campos_views;     // [V][3] (with shs)
   float *dL_dmeans3D, *dL_dopacity, *dL_dscales, *dL_drot, *dL_dcolors, *dL_dsh;   // the SUMS over the ranks
 };

@@ -91,44 +91,12 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int nred_eighths, int V, int M, co
   const size_t C = (size_t)x.P * (size_t)(x.ngeo / 4);                  // 16-byte chunks of the record array
   const size_t c0 = C * (size_t)x.rank / (size_t)N, c1 = C * (size_t)(x.rank + 1) / (size_t)N;
   const int nred = HAS_SH ? min((int)gridDim.x, max(1, ((int)gridDim.x * nred_eighths) / 8)) : (int)gridDim.x;
-  // Two ranks: the peer's geometry backward has pushed its records into this rank's inbox (posted NVLink stores that
-  // travel while it computes; reading them from the peer instead ran at 140 GB/s, round 2).  Every rank adds the two
-  // record sets in rank order (both form the same bits) and writes the per-parameter gradients straight away — 48 B per
-  // splat and direction instead of 72 through the switch (a multimem access also moves this rank's own copy over its
-  // link), no second barrier, no unpack pass.  Records and inboxes are double-buffered by step parity (api.cu).
-  const bool direct = N == 2;
-  if (direct && (int)blockIdx.x < nred) {
-    constexpr int NG4 = HAS_SH ? 3 : 4;
-    for (size_t i0 = ((size_t)blockIdx.x * 256 + threadIdx.x) * 2; i0 < (size_t)x.P; i0 += (size_t)nred * 512) {
-      float4 v[2][2][NG4];            // [rank][splat][word]: twelve (sixteen) 16-byte loads in flight per thread
-#pragma unroll
-      for (int r = 0; r < 2; r++)
-#pragma unroll
-        for (int h = 0; h < 2; h++)
-          if (i0 + h < (size_t)x.P) {
-#pragma unroll
-            for (int q = 0; q < NG4; q++)
-              v[r][h][q] = __ldcg(reinterpret_cast<const float4*>((r == x.rank ? x.geo : x.inbox) + ((i0 + h) * NG4 + q) * 4));
-          }
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const size_t i = i0 + h;
-        if (i < (size_t)x.P) {
-          float4 a[NG4];
-#pragma unroll
-          for (int q = 0; q < NG4; q++)
-            a[q] = make_float4(v[0][h][q].x + v[1][h][q].x, v[0][h][q].y + v[1][h][q].y, v[0][h][q].z + v[1][h][q].z,
-                               v[0][h][q].w + v[1][h][q].w);
-          dL_dmeans3D[3 * i] = a[0].x; dL_dmeans3D[3 * i + 1] = a[0].y; dL_dmeans3D[3 * i + 2] = a[0].z;
-          dL_dopacity[i] = a[0].w;
-          dL_dscales[3 * i] = a[1].x; dL_dscales[3 * i + 1] = a[1].y; dL_dscales[3 * i + 2] = a[1].z;
-          dL_drot[4 * i] = a[1].w; dL_drot[4 * i + 1] = a[2].x; dL_drot[4 * i + 2] = a[2].y; dL_drot[4 * i + 3] = a[2].z;
-          if (!HAS_SH) { dL_dcolors[3 * i] = a[NG4 - 1].x; dL_dcolors[3 * i + 1] = a[NG4 - 1].y; dL_dcolors[3 * i + 2] = a[NG4 - 1].z; }
-        }
-      }
-    }
-    if (threadIdx.x == 0) xchg_mark(x.flags, 2);
-  } else if ((int)blockIdx.x < nred) {
+  // (Two ranks were tried with direct sums — every rank reads the peer's records, or has them pushed into an inbox by
+  // the peer's geometry backward, and adds them itself, 48 instead of 72 B per splat and direction and no second barrier:
+  // SM-issued unicast peer loads ran at 140 GB/s and peer stores at 300 GB/s on B200 against ~585 GB/s through the
+  // switch's multicast path, so reduce + broadcast through the switch is used for every world size;
+  // profiles/r02d_bench_n2_*.)
+  if ((int)blockIdx.x < nred) {
     const size_t stride = (size_t)nred * 256;
     for (size_t c = c0 + (size_t)blockIdx.x * 256 + threadIdx.x; c < c1; c += RD * stride) {
       float4 v[RD];
@@ -182,11 +150,6 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int nred_eighths, int V, int M, co
     if (threadIdx.x == 0) xchg_mark(x.flags, 3);
   }
 
-  if (direct) {
-    __syncthreads();
-    if (threadIdx.x == 0) xchg_mark(x.flags, 5);
-    return;
-  }
   // ---- 3. every slice has been broadcast: unpack the summed records into the per-parameter arrays
   {
     const bool ok = threadIdx.x < N ? spin_until(x.flags + FLAG_B + threadIdx.x, epoch) : true;

@@ -357,13 +357,6 @@ __device__ __forceinline__ void geom_backward_block(const BwdParams& p, const Ge
     rec[1] = make_float4(dscale[0], dscale[1], dscale[2], drot[0]);
     rec[2] = make_float4(drot[1], drot[2], drot[3], 0.f);
     if (!FACT) rec[3] = make_float4(gcol[0], gcol[1], gcol[2], 0.f);          // precomputed colours: 14 floats (+2 pad)
-    if (p.x_geo_peer) {      // two ranks: the same record straight into the peer's inbox (posted NVLink stores)
-      float4* prec = reinterpret_cast<float4*>(p.x_geo_peer + i * (size_t)p.x_ngeo);
-      prec[0] = make_float4(dmean[0], dmean[1], dmean[2], gop);
-      prec[1] = make_float4(dscale[0], dscale[1], dscale[2], drot[0]);
-      prec[2] = make_float4(drot[1], drot[2], drot[3], 0.f);
-      if (!FACT) prec[3] = make_float4(gcol[0], gcol[1], gcol[2], 0.f);
-    }
     p.dL_dmeans2D[3 * i] = gm2[0]; p.dL_dmeans2D[3 * i + 1] = gm2[1]; p.dL_dmeans2D[3 * i + 2] = 0.f;
     return;
   }
@@ -403,12 +396,11 @@ __global__ void __launch_bounds__(256, MINB) geom_backward_kernel(BwdParams p, G
 // in turn.  Here the splats are cut into chunks of XCHG_CHUNK and every CTA pulls work units from four queues:
 //   G(c)  geometry backward of chunk c (4 blocks of 256 splats): packed records into this rank's buffer, colour gradients
 //         pushed into every rank's table (multimem.st), then flag A[rank][c] raised in EVERY rank's buffer;
-//   X(c)  NVLink unit, ready when A[*][c] is up on this rank.  Owner mode (c % world == rank): sum the ranks' records of
-//         chunk c inside the switch (multimem.ld_reduce) and broadcast the sums in place (multimem.st; peer loads / stores
-//         without multicast), then raise flag B[c] everywhere.  Direct mode (two ranks): read the peer's records, add
-//         them to this rank's own in rank order and write the per-parameter gradients straight away (no owner, no B);
+//   X(c)  NVLink unit of the chunk's owner (c % world == rank), ready when A[*][c] is up on this rank: sum the ranks'
+//         records of chunk c inside the switch (multimem.ld_reduce) and broadcast the sums in place (multimem.st; peer
+//         loads / stores without multicast), then raise flag B[c] everywhere;
 //   S(c)  SH gradient rows of chunk c from the local colour table, ready when A[*][c] is up;
-//   U(c)  owner mode: unpack the broadcast sums of chunk c, ready when B[c] is up.
+//   U(c)  unpack the broadcast sums of chunk c, ready when B[c] is up.
 // Every fourth CTA prefers X over G (the NVLink round trips of a chunk start while later chunks are still being
 // differentiated), the others run G, then S, then U; whatever is ready is taken when a CTA's preferred queue is empty.
 // Queues are tickets in this rank's flag words, claims are CAS, waits are bounded (error word, sfb_xchg_status).
@@ -444,9 +436,9 @@ __global__ void __launch_bounds__(256, 2) geom_exchange_fused_kernel(BwdParams p
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t epoch = f.epoch;
   const uint32_t nG = (uint32_t)nch;
-  const uint32_t nX = f.direct ? (uint32_t)nch : (uint32_t)(nch > rank ? (nch - rank + N - 1) / N : 0);
+  const uint32_t nX = (uint32_t)(nch > rank ? (nch - rank + N - 1) / N : 0);
   const uint32_t nS = HAS_SH ? (uint32_t)nch : 0u;
-  const uint32_t nU = f.direct ? 0u : (uint32_t)nch;
+  const uint32_t nU = (uint32_t)nch;
   const bool link_cta = (blockIdx.x & 3) == 0;
   uint32_t* const tk = x.flags + FLAG_TK;
   uint32_t tG = 0, tX = 0, tS = 0, tU = 0;      // this CTA's view of the tickets (they only grow)
@@ -493,14 +485,14 @@ __global__ void __launch_bounds__(256, 2) geom_exchange_fused_kernel(BwdParams p
         got = __shfl_sync(0xffffffffu, got, 0);
         t = got + 1u;
         if (got >= n) return;                                   // the queue ran out in the meantime
-        const uint32_t c = (q == 1 && !f.direct) ? (uint32_t)rank + got * (uint32_t)N : got;
+        const uint32_t c = q == 1 ? (uint32_t)rank + got * (uint32_t)N : got;
         while (!chunk_ready(q, c)) { if (!keep_waiting()) { kind = FK_EXIT; return; } }
         kind = k; unit = (int)c;
       };
       while (kind < 0) {
         const bool hasG = tG < nG, hasX = tX < nX, hasS = tS < nS, hasU = tU < nU;
         if (!(hasG | hasX | hasS | hasU)) { kind = FK_EXIT; break; }
-        const uint32_t cX = f.direct ? tX : (uint32_t)rank + tX * (uint32_t)N;
+        const uint32_t cX = (uint32_t)rank + tX * (uint32_t)N;
         if (hasX && (link_cta || !hasG) && chunk_ready(1, cX)) { take(1, tX, nX, FK_X); continue; }
         if (hasG) {
           uint32_t gt = 0;
@@ -538,40 +530,6 @@ __global__ void __launch_bounds__(256, 2) geom_exchange_fused_kernel(BwdParams p
       if (warp == 0 && lane < N) st_release_sys(x.peer_cflags[lane] + (size_t)rank * nch + c, epoch);
       if (warp == 0) __syncwarp();
       if (threadIdx.x == 0) lap(2);
-    } else if (kind == FK_X && f.direct) {
-      // two splats per thread and round: their records from every rank in flight together
-#pragma unroll 1
-      for (int k = 0; k < XCHG_CHUNK / 256; k += 2) {
-        const size_t i0 = s0 + threadIdx.x + 256 * k, i1 = i0 + 256;
-        float4 acc[2][4];
-#pragma unroll
-        for (int h = 0; h < 2; h++)
-#pragma unroll
-          for (int q = 0; q < 4; q++) acc[h][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < N; r++) {      // rank order: both ranks form the same bits
-          float4 v[2][NG4];
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const size_t i = h ? i1 : i0;
-            if (i < s1) {
-#pragma unroll
-              for (int q = 0; q < NG4; q++) v[h][q] = ld_relaxed_sys_v4((r == rank ? x.geo : x.inbox) + (i * NG4 + q) * 4);
-            }
-          }
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const size_t i = h ? i1 : i0;
-            if (i < s1) {
-#pragma unroll
-              for (int q = 0; q < NG4; q++) {
-                acc[h][q].x += v[h][q].x; acc[h][q].y += v[h][q].y; acc[h][q].z += v[h][q].z; acc[h][q].w += v[h][q].w;
-              }
-            }
-          }
-        }
-        if (i0 < s1) fused_store_sums<HAS_SH>(f, i0, acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
-        if (i1 < s1) fused_store_sums<HAS_SH>(f, i1, acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
-      }
     } else if (kind == FK_X) {
       const size_t base16 = s0 * NG4;
       const int n16 = (int)(s1 - s0) * NG4;
