@@ -179,7 +179,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   fp.tight_rect = tight_rect_enabled() ? 1 : 0;
   fp.wide256 = shs && ((M * 12) % 32 == 0) && ((reinterpret_cast<size_t>(shs) & 31) == 0);
   // the depth sort's scratch is cleared by the preprocess blocks on their way (one memset node less)
-  const size_t dzero = radix_sort_zero_words(P, 32);
+  const size_t dzero = radix_sort_zero_words(P, 32, true);
   fp.zero_ptr = dzero ? g.sort_hist : nullptr;
   fp.zero_words = (uint32_t)dzero;
   fp.nr_host = g_pinned;
@@ -201,8 +201,8 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
                                 g.counters + 2, 0, dzero != 0, nullptr, 0, nullptr, 0, &top_total0);
   CK_LAUNCH("depth sort", debug, s);
   const SortedIdx sorted_idx{g.depth_idx[dfinal], g.depth_idx[dfinal ^ 1], top_total0, (uint32_t)P};
-  launch_instance_block_sums(P, sorted_idx, g.tiles_touched, g.block_sums, s);
-  g_launches += 2;
+  launch_instance_block_sums(P, sorted_idx, g.tiles_touched, g.block_sums, g.counters + 4, s);
+  g_launches += 1;
   CK_LAUNCH("instance scan", debug, s);
 
   CK(cudaEventSynchronize(evt));
@@ -225,7 +225,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   if (R > 0) {
     // stage 2: emit (tile, gaussian) instances in depth order (the blocks also clear the tile sort's scratch and set
     // every tile range to "empty"); stage 3: stable sort by tile id
-    const size_t tzero = radix_sort_zero_words((int)R, tile_bits(T));
+    const size_t tzero = radix_sort_zero_words((int)R, tile_bits(T), false);
     prof_begin("duplicate", s);
     launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, b.tile_key[0], b.inst_hi[0],
                      pk.low_bits, tzero ? b.sort_hist : nullptr, tzero, b.ranges, T, img.tile_bcount, s);

@@ -396,7 +396,7 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n
                      int merge_bits = 0 /* last pass writes (key & ((1 << merge_bits) - 1)) | byte << merge_bits */,
                      const uint32_t** last_total0 = nullptr /* non-null: the last pass may return at once when it is the
                         identity; receives the device word to compare with n (SortedIdx), or nullptr */);
-size_t radix_sort_zero_words(int n, int nbits);
+size_t radix_sort_zero_words(int n, int nbits, bool pairs /* a 32-bit value moves with every key */);
 // Result of the depth sort as its consumers see it.  The most significant radix pass of a bounded scene is the identity
 // (depth keys are rebased to key - min: < 2^24), known on the device only: instead of copying 8 B/Gaussian through
 // that pass, the pass returns at once and the consumers read its input.
@@ -408,7 +408,8 @@ struct SortedIdx {
   __device__ __forceinline__ const uint32_t* get() const { return (total0 && *total0 == n) ? alt : primary; }
 };
 void launch_instance_block_sums(int P, const SortedIdx& sorted_idx, const uint32_t* tiles_touched,
-                                uint32_t* block_sums, cudaStream_t s);
+                                uint32_t* block_sums /* out: exclusive prefix of the per-block instance counts */,
+                                uint32_t* ticket /* zeroed word */, cudaStream_t s);
 void launch_duplicate(int P, int grid_x, const SortedIdx& sorted_idx, const uint32_t* tiles_touched,
                       const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
                       uint8_t* inst_hi /* nullptr: the whole index fits the word */, int idx_bits,

@@ -177,7 +177,10 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int nred_eighths, int V, int M, co
 
 // Tuning hooks of the measurement sessions (sfb_xchg_tune): share of the CTAs that start on the slice reduction
 // (eighths of the grid) and reduction round trips in flight per thread (4 or 16).
-static int g_xchg_nred_eighths = 4, g_xchg_depth = 4;
+// Default: an eighth of the CTAs reduces — the reduction is bound by the links whatever the number of CTAs on it
+// (123 us at N = 2 with 37 or 296 CTAs), while the SH rows are instruction-bound at N = 8 (8 views per row) and were the
+// long pole with half of the grid on them (182 us, profiles/r02d_bench_n8_nvlink.json).
+static int g_xchg_nred_eighths = 1, g_xchg_depth = 4;
 void xchg_tune(int nred_eighths, int depth) {
   if (nred_eighths >= 1 && nred_eighths <= 8) g_xchg_nred_eighths = nred_eighths;
   if (depth == 4 || depth == 16) g_xchg_depth = depth;
