@@ -86,7 +86,11 @@ typedef struct sfb_xchg {
 } sfb_xchg;
 
 /* Backward.  Replaces _C.rasterize_gaussians_backward.  dL_dout_color [3][H][W] is the
- * cotangent of out_color; dL_dout_alpha [1][H][W] (or NULL) the cotangent of the fused out_alpha.  Outputs (all caller-allocated, fully written by the call — no pre-zeroing
+ * cotangent of out_color; dL_dout_alpha [1][H][W] (or NULL) the cotangent of the fused out_alpha; dL_dout_depth
+ * [1][H][W] (or NULL) the cotangent of out_depth — the depth image is one more composited channel (value = the splat's
+ * view-space z, no background), so its gradient reaches the opacities, the 2-D geometry and, through z, the means
+ * (the reference's depth losses, train.py:195-229; whether the pinned extension propagates it is not checkable from the
+ * reference tree, SURVEY A.9-1: pass NULL for a forward-only depth).  Outputs (all caller-allocated, fully written by the call — no pre-zeroing
  * needed): dL_dmeans2D [P][3] (xy = gradient w.r.t. the NDC-scaled screen mean, z = 0; this is what
  * lands in viewspace_points.grad, scene/gaussian_model.py:429), dL_dcolors [P][3], dL_dopacity [P][1],
  * dL_dmeans3D [P][3], dL_dcov3D [P][6], dL_dsh [P][M][3] (may be NULL when shs is NULL),
@@ -118,7 +122,7 @@ int sfb_rasterize_backward(
     const float* viewmatrix, const float* projmatrix, const float* campos,
     float tan_fovx, float tan_fovy, const int* radii,
     void* geom_buffer, void* binning_buffer, void* img_buffer,
-    const float* dL_dout_color, const float* dL_dout_alpha,
+    const float* dL_dout_color, const float* dL_dout_alpha, const float* dL_dout_depth,
     float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D, float* dL_dcov3D,
     float* dL_dsh, float* dL_dscales, float* dL_drotations,
     int debug, int flags,

@@ -135,7 +135,7 @@ def forward(means3D, opacities, scales=None, rotations=None, shs=None, colors_pr
 
 
 def backward(fwd, dL_dcolor, means3D, scales=None, rotations=None, shs=None, cov3D_precomp=None, *,
-             viewmatrix, projmatrix, campos, tanfovx, tanfovy, sh_degree=0, scale_modifier=1.0):
+             viewmatrix, projmatrix, campos, tanfovx, tanfovy, sh_degree=0, scale_modifier=1.0, dL_ddepth=None):
     """Backward for the cotangent dL_dcolor[3,H,W]; returns the gradients in the layout of the
     reference's rasterize_gaussians_backward: dL_dmeans2D[P,3], dL_dcolors[P,3],
     dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscales[P,3], dL_drot[P,4]."""
@@ -150,9 +150,14 @@ def backward(fwd, dL_dcolor, means3D, scales=None, rotations=None, shs=None, cov
     d_opac = np.zeros(P, np.float64)
     d_col = np.zeros((P, 3), np.float64)
     pl = fwd["point_list"] if fwd["num_rendered"] else np.zeros(1, np.uint32)
+    # optional cotangent of the depth image [1,H,W] (the depth is one more composited channel without background)
+    dLd = None if dL_ddepth is None else _f32(dL_ddepth).reshape(H, W)
+    d_depth = None if dLd is None else np.zeros(P, np.float64)
     lib().so_render_backward(C.c_int(W), C.c_int(H), _p(fwd["ranges"]), _p(pl), _p(fwd["means2D"]),
                              _p(fwd["rgb"]), _p(fwd["conic_opacity"]), _p(fwd["bg"]), _p(fwd["final_T"]),
-                             _p(fwd["n_contrib"]), _p(dL), _p(d_mean2D), _p(d_conic), _p(d_opac), _p(d_col))
+                             _p(fwd["n_contrib"]), _p(dL), _p(d_mean2D), _p(d_conic), _p(d_opac), _p(d_col),
+                             _p(fwd["depths"]) if dLd is not None else None, _p(dLd), _p(d_depth))
+    dz = None if d_depth is None else d_depth.astype(np.float32)
     m2 = d_mean2D.astype(np.float32)
     cn = d_conic.astype(np.float32)
     cl = d_col.astype(np.float32)
@@ -167,7 +172,7 @@ def backward(fwd, dL_dcolor, means3D, scales=None, rotations=None, shs=None, cov
         _p(scales), _p(rotations), C.c_float(scale_modifier), _p(fwd["cov3D"]),
         C.c_int(0 if cov3D_precomp is None else 1), _p(vm), _p(pm), _p(cp), C.c_int(W), C.c_int(H),
         C.c_float(tanfovx), C.c_float(tanfovy), _p(m2), _p(cn), _p(cl), _p(d_means3D), _p(d_cov3D), _p(d_sh),
-        _p(d_scales), _p(d_rot))
+        _p(d_scales), _p(d_rot), _p(dz))
     d_means2D = np.zeros((P, 3), np.float32)
     d_means2D[:, :2] = m2
     return dict(dL_dmeans2D=d_means2D, dL_dcolors=cl, dL_dopacity=d_opac.astype(np.float32).reshape(P, 1),

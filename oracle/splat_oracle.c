@@ -476,7 +476,10 @@ void so_render_backward(int W, int H, const uint32_t* ranges, const uint32_t* po
                         const float* means2D, const float* rgb, const float* conic_opacity,
                         const float* bg, const float* final_T, const uint32_t* n_contrib,
                         const float* dL_dpixels /* [3][H][W] */, double* dL_dmean2D, double* dL_dconic,
-                        double* dL_dopacity, double* dL_dcolor) {
+                        double* dL_dopacity, double* dL_dcolor,
+                        const float* depths /* [P] view-space z, or NULL */,
+                        const float* dL_ddepth_img /* [H][W] cotangent of the depth image, or NULL */,
+                        double* dL_ddepth /* [P] out (with dL_ddepth_img) */) {
   const int gx = (W + BLOCK_X - 1) / BLOCK_X, gy = (H + BLOCK_Y - 1) / BLOCK_Y;
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
   /* The pixel sums of one tile are collected per list position in a thread-local fp64 table and added to the
@@ -490,7 +493,10 @@ void so_render_backward(int W, int H, const uint32_t* ranges, const uint32_t* po
   }
 #pragma omp parallel
   {
-  double* loc = (double*)malloc(sizeof(double) * 9 * ((size_t)max_len + 1));
+  /* depth cotangent (the depth image is one more composited channel, "colour" = the splat's view-space z, no
+   * background): tenth sum per list position */
+  const int with_depth = depths && dL_ddepth_img && dL_ddepth;
+  double* loc = (double*)malloc(sizeof(double) * 10 * ((size_t)max_len + 1));
 #pragma omp for schedule(dynamic, 1)
   for (int tile = 0; tile < gx * gy; tile++) {
     int tx = tile % gx, ty = tile / gx;
@@ -502,7 +508,7 @@ void so_render_backward(int W, int H, const uint32_t* ranges, const uint32_t* po
         if (px < W && py < H && n_contrib[(size_t)W * py + px] > deepest) deepest = n_contrib[(size_t)W * py + px];
       }
     if (deepest > r1 - r0) deepest = r1 - r0;
-    memset(loc, 0, sizeof(double) * 9 * (size_t)deepest);
+    memset(loc, 0, sizeof(double) * 10 * (size_t)deepest);
     for (int ly = 0; ly < BLOCK_Y; ly++)
       for (int lx = 0; lx < BLOCK_X; lx++) {
         int px = tx * BLOCK_X + lx, py = ty * BLOCK_Y + ly;
@@ -516,6 +522,8 @@ void so_render_backward(int W, int H, const uint32_t* ranges, const uint32_t* po
         for (int ch = 0; ch < 3; ch++) dLp[ch] = dL_dpixels[(size_t)ch * H * W + pix_id];
         float bg_dot = 0.f;
         for (int ch = 0; ch < 3; ch++) bg_dot += bg[ch] * dLp[ch];
+        const float dLpd = with_depth ? dL_ddepth_img[pix_id] : 0.f;
+        float accum_depth = 0.f, last_depth = 0.f;
         /* walk positions last-1 .. 0 of this tile's list (position = contributor index - 1) */
         for (int64_t pos = (int64_t)last - 1; pos >= 0; pos--) {
           uint32_t g = point_list[r0 + pos];
@@ -536,7 +544,14 @@ void so_render_backward(int W, int H, const uint32_t* ranges, const uint32_t* po
             accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
             last_color[ch] = c;
             dL_dalpha += (c - accum_rec[ch]) * dLp[ch];
-            loc[9 * pos + 6 + ch] += (double)(dchannel_dcolor * dLp[ch]);
+            loc[10 * pos + 6 + ch] += (double)(dchannel_dcolor * dLp[ch]);
+          }
+          if (with_depth) {
+            const float z = depths[g];
+            accum_depth = last_alpha * last_depth + (1.f - last_alpha) * accum_depth;
+            last_depth = z;
+            dL_dalpha += (z - accum_depth) * dLpd;
+            loc[10 * pos + 9] += (double)(dchannel_dcolor * dLpd);
           }
           dL_dalpha *= T;
           last_alpha = alpha;
@@ -549,16 +564,20 @@ void so_render_backward(int W, int H, const uint32_t* ranges, const uint32_t* po
           double cA = (double)(-0.5f * gdx * dx * dL_dG), cB = (double)(-gdx * dy * dL_dG),
                  cC = (double)(-0.5f * gdy * dy * dL_dG);
           double vo = (double)(G * dL_dalpha);
-          double* l = loc + 9 * pos;
+          double* l = loc + 10 * pos;
           l[0] += v0; l[1] += v1; l[2] += cA; l[3] += cB; l[4] += cC; l[5] += vo;
         }
       }
     for (uint32_t pos = 0; pos < deepest; pos++) {
-      const double* l = loc + 9 * (size_t)pos;
+      const double* l = loc + 10 * (size_t)pos;
       uint32_t g = point_list[r0 + pos];
       int any = 0;
-      for (int k = 0; k < 9; k++) any |= (l[k] != 0.0);
+      for (int k = 0; k < 10; k++) any |= (l[k] != 0.0);
       if (!any) continue;
+      if (with_depth) {
+#pragma omp atomic
+        dL_ddepth[g] += l[9];
+      }
 #pragma omp atomic
       dL_dmean2D[2 * g] += l[0];
 #pragma omp atomic
@@ -595,7 +614,7 @@ void so_preprocess_backward(int P, int D, int M, const float* means3D, const int
                             int H, float tan_fovx, float tan_fovy, const float* dL_dmean2D /* [P][2] */,
                             const float* dL_dconic /* [P][3] */, const float* dL_dcolor /* [P][3] */,
                             float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscales,
-                            float* dL_drot) {
+                            float* dL_drot, const float* dL_ddepth /* [P] or NULL: gradient w.r.t. the view-space z */) {
   const float fx = (float)W / (2.0f * tan_fovx), fy = (float)H / (2.0f * tan_fovy);
 #pragma omp parallel for schedule(static)
   for (int idx = 0; idx < P; idx++) {
@@ -647,6 +666,9 @@ void so_preprocess_backward(int P, int D, int M, const float* means3D, const int
     /* dL/dmean = Rw^T dL/dt :  Rw(i,j) = view[4*j+i] */
     for (int j = 0; j < 3; j++)
       dmean[j] = viewmatrix[4 * j + 0] * dtx + viewmatrix[4 * j + 1] * dty + viewmatrix[4 * j + 2] * dtz;
+    /* depth = view[2] x + view[6] y + view[10] z + view[14] */
+    if (dL_ddepth)
+      for (int j = 0; j < 3; j++) dmean[j] += viewmatrix[4 * j + 2] * dL_ddepth[idx];
 
     /* ---- screen mean (NDC) -> mean3D ---- */
     {

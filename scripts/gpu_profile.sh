@@ -7,7 +7,7 @@ timeout 300 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo
 timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -1
 for c in lego_1m lego_100k dtu_500k owlii_2m; do timeout 120 python scripts/quick_perf.py --config $c >> $OUT/quick_perf.jsonl; done; cut -c1-330 $OUT/quick_perf.jsonl
 timeout 300 python bench.py --steps 200 --warmup 10 > $OUT/bench_n1.json 2> $OUT/bench_n1.err; cut -c1-300 $OUT/bench_n1.json; tail -2 $OUT/bench_n1.err
-KERNELS='preprocess_kernel|radix_hist_all_kernel|onesweep_pass_kernel|instance_block_sums_kernel|duplicate_kernel|tile_ranges_kernel|render_forward_kernel|render_backward_mma_kernel|geom_backward_kernel'
+KERNELS='preprocess_kernel|radix_hist_all_kernel|onesweep_pass_kernel|instance_block_sums_kernel|scan_exclusive_kernel|duplicate_kernel|tile_ranges_kernel|render_forward_kernel|render_backward_mma_kernel|geom_backward_kernel'
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
 echo "launch list rows: $(wc -l < $OUT/launches.csv)"

@@ -14,7 +14,7 @@ import sys
 # bench.py's stage names (sfb_profile_name) in launch order of one lego_1m forward + backward
 STAGES = [("preprocess_kernel", "preprocess"), ("radix_hist_all_kernel", "depth_sort.hist"),
           ("onesweep_pass_kernel<16, 2", "depth_sort.scatter"), ("instance_block_sums_kernel", "instance_block_sums"),
-          ("duplicate_kernel", "duplicate"),
+          ("scan_exclusive_kernel", "instance_block_scan"), ("duplicate_kernel", "duplicate"),
           ("radix_hist_all_kernel", "tile_sort.hist"), ("onesweep_pass_kernel<16, 0", "tile_sort.scatter"), ("onesweep_pass_kernel<16, 1", "tile_sort.scatter"),
           ("tile_ranges_kernel", "tile_ranges"), ("render_forward_kernel", "render_forward"),
           ("render_backward", "render_backward"), ("geom_backward_kernel", "geom_backward")]

@@ -12,7 +12,7 @@ timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_r
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
 echo "launch list rows: $(wc -l < $OUT/launches.csv)"
-KERNELS='preprocess_kernel|radix_hist_all_kernel|onesweep_pass_kernel|instance_block_sums_kernel|duplicate_kernel|render_forward_kernel|render_backward_mma_kernel|geom_backward_kernel'
+KERNELS='preprocess_kernel|radix_hist_all_kernel|onesweep_pass_kernel|instance_block_sums_kernel|scan_exclusive_kernel|duplicate_kernel|render_forward_kernel|render_backward_mma_kernel|geom_backward_kernel'
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$KERNELS" -s 45 -c 15 -f -o $OUT/prof \
     python scripts/quick_perf.py --config lego_1m --iters 1 --warmup 3 > $OUT/ncu_full.log 2>&1
 tail -2 $OUT/ncu_full.log | cut -c1-200

@@ -73,7 +73,7 @@ def load():
         ci, ci, ci, ci, ci, ci,                   # P, sh_degree, M, R, W, H
         vp, vp, vp, vp, vp, cf, vp, vp,           # bg, means3D, shs, colors, scales, mod, rot, cov3D
         vp, vp, vp, cf, cf, vp,                   # view, proj, campos, tanfovx, tanfovy, radii
-        vp, vp, vp, vp, vp,                       # geom, binning, img, dL_dout_color, dL_dout_alpha (nullable)
+        vp, vp, vp, vp, vp, vp,                   # geom, binning, img, dL_dout_color, dL_dout_alpha, dL_dout_depth (nullable)
         vp, vp, vp, vp, vp, vp, vp, vp,           # 8 gradient outputs
         ci, ci,                                   # debug, flags (SFB_BWD_ACC_FRESH | SFB_BWD_SH_FACTORED)
         C.POINTER(XchgDesc), C.c_uint, vp]        # xchg (nullable), xchg_epoch, stream

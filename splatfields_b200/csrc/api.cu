@@ -179,7 +179,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   fp.tight_rect = tight_rect_enabled() ? 1 : 0;
   fp.wide256 = shs && ((M * 12) % 32 == 0) && ((reinterpret_cast<size_t>(shs) & 31) == 0);
   // the depth sort's scratch is cleared by the preprocess blocks on their way (one memset node less)
-  const size_t dzero = radix_sort_zero_words(P, 32, true);
+  const size_t dzero = radix_sort_zero_words(P, 32);
   fp.zero_ptr = dzero ? g.sort_hist : nullptr;
   fp.zero_words = (uint32_t)dzero;
   fp.nr_host = g_pinned;
@@ -201,8 +201,8 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
                                 g.counters + 2, 0, dzero != 0, nullptr, 0, nullptr, 0, &top_total0);
   CK_LAUNCH("depth sort", debug, s);
   const SortedIdx sorted_idx{g.depth_idx[dfinal], g.depth_idx[dfinal ^ 1], top_total0, (uint32_t)P};
-  launch_instance_block_sums(P, sorted_idx, g.tiles_touched, g.block_sums, g.counters + 4, s);
-  g_launches += 1;
+  launch_instance_block_sums(P, sorted_idx, g.tiles_touched, g.block_sums, s);
+  g_launches += 2;
   CK_LAUNCH("instance scan", debug, s);
 
   CK(cudaEventSynchronize(evt));
@@ -225,7 +225,7 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   if (R > 0) {
     // stage 2: emit (tile, gaussian) instances in depth order (the blocks also clear the tile sort's scratch and set
     // every tile range to "empty"); stage 3: stable sort by tile id
-    const size_t tzero = radix_sort_zero_words((int)R, tile_bits(T), false);
+    const size_t tzero = radix_sort_zero_words((int)R, tile_bits(T));
     prof_begin("duplicate", s);
     launch_duplicate(P, gx, sorted_idx, g.tiles_touched, g.rect, g.block_sums, b.tile_key[0], b.inst_hi[0],
                      pk.low_bits, tzero ? b.sort_hist : nullptr, tzero, b.ranges, T, img.tile_bcount, s);
@@ -289,7 +289,8 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
                            const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
                            const float* campos, float tan_fovx, float tan_fovy, const int* radii,
                            void* geom_buffer, void* binning_buffer, void* img_buffer,
-                           const float* dL_dout_color, const float* dL_dout_alpha, float* dL_dmeans2D,
+                           const float* dL_dout_color, const float* dL_dout_alpha, const float* dL_dout_depth,
+                           float* dL_dmeans2D,
                            float* dL_dcolors, float* dL_dopacity,
                            float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscales,
                            float* dL_drotations, int debug, int flags, const sfb_xchg* xchg, unsigned xchg_epoch,
@@ -344,7 +345,8 @@ int sfb_rasterize_backward(int P, int sh_degree, int M, int num_rendered, int W,
   }
   prof_begin("render_backward", s);
   if (launch_render_backward(W, H, b.ranges, b.point_list(tfinal), pk.idx_mask, g.rec, (size_t)P, bg, img.final_T,
-                             img.n_contrib, dL_dout_color, dL_dout_alpha, b.hit, img.tile_bcount, img.tile_btile, g.grad,
+                             img.n_contrib, dL_dout_color, dL_dout_alpha, dL_dout_depth, b.hit, img.tile_bcount,
+                             img.tile_btile, g.grad,
                              s) != 0)
     return fail(SFB_ERR_CUDA, g_err.c_str());
   prof_end(s);

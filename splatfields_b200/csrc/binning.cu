@@ -16,6 +16,55 @@
 
 namespace sfb {
 
+// Exclusive scan, in place, of gridDim.x independent rows of `n` words (row r at data + r*n), one block
+// of 1024 threads per row; the row total goes to total_out[r] (if non-null).
+__global__ void __launch_bounds__(1024) scan_exclusive_kernel(uint32_t* __restrict__ data_all, int n,
+                                                              uint32_t* __restrict__ total_out) {
+  uint32_t* __restrict__ data = data_all + (size_t)blockIdx.x * n;
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 4096) {
+    int i0 = base + threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = (i0 + k < n) ? data[i0 + k] : 0u;
+    uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+    uint32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_warp[lane];
+      uint32_t winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      s_warp[lane] = winc - w;  // exclusive prefix of warp sums
+    }
+    __syncthreads();
+    uint32_t carry = s_carry;
+    uint32_t ex = carry + s_warp[warp] + (inc - tsum);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (i0 + k < n) data[i0 + k] = ex;
+      ex += v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = ex;  // ex == carry + everything in this tile
+    __syncthreads();
+  }
+  if (total_out && threadIdx.x == 0) total_out[blockIdx.x] = s_carry;
+}
+
 // ------------------------------------------------------------------ onesweep radix sort (default)
 // One kernel per digit pass: a block takes a ticket, ranks its 4096 (key, value) pairs stably, publishes
 // its per-digit counts and obtains its global offsets by DECOUPLED LOOK-BACK over the predecessors'
@@ -332,22 +381,13 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const void* __restric
 static bool sort_small_tiles(int n) {
   return sort_blocks(n) < 64;
 }
-// Items per block of one onesweep pass: 1024 for really small inputs, 4096 otherwise; pair sorts (the depth sort: 1 M
-// pairs = 245 blocks of 4096 on 148 SMs) can be run with 2048-item tiles (SFB_DSORT_TILE=2048, A/B arm of round 2).
-static int sort_tile_items(int n, bool pairs) {
-  static int mid = -1;
-  if (mid < 0) { const char* e = getenv("SFB_DSORT_TILE"); mid = (e && atoi(e) == 2048) ? 1 : 0; }
-  if (sort_small_tiles(n)) return SORT_THREADS * 4;
-  if (pairs && mid == 1 && sort_blocks(n) < 4 * NUM_SMS_B200) return SORT_THREADS * 8;
-  return SORT_THREADS * 16;
-}
 
 // words of `hist` that have to be zero when radix_sort_pairs starts (the caller may clear them itself, e.g. from a kernel
 // that runs anyway, and pass scratch_zeroed = true)
-size_t radix_sort_zero_words(int n, int nbits, bool pairs) {
+size_t radix_sort_zero_words(int n, int nbits) {
   if (n <= 0 || nbits <= 0) return 0;
   const int npass = (nbits + 7) / 8;
-  const int tile = sort_tile_items(n, pairs);
+  const int tile = sort_small_tiles(n) ? SORT_THREADS * 4 : SORT_THREADS * 16;
   const int nblocks = (n + tile - 1) / tile;
   size_t state_words = 0;
   int shift = 0;
@@ -368,8 +408,8 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
   const int npass = (nbits + 7) / 8;
   // 1024-item tiles only for really small inputs: with the ballot ranking 4096-item tiles win from ~0.3 M items
   // (measured: 1 M pairs 87 -> 65 us, 0.5 M 63 -> 54 us, 0.1 M 43 -> 51 us), although they fill < 2 CTAs per SM
-  const int tile = sort_tile_items(n, vm == 2);
-  const bool small = tile == SORT_THREADS * 4, mid = tile == SORT_THREADS * 8;
+  const bool small = sort_small_tiles(n);
+  const int tile = small ? SORT_THREADS * 4 : SORT_THREADS * 16;
   const int nblocks = (n + tile - 1) / tile;
   // scratch layout: [hist_all: 4*256][tickets: 8][tile_state: npass * nblocks * bins]
   uint32_t* hist_all = scratch;
@@ -410,7 +450,6 @@ static int radix_sort_pairs_onesweep(uint32_t* keys[2], uint32_t* vals[2], uint3
   do { if (nb == 6) SFB_OS2(IPTV, HV, 6); else if (nb == 7) SFB_OS2(IPTV, HV, 7); else SFB_OS2(IPTV, HV, 8); } while (0)
     const int nb = nbins[pass] <= 64 ? 6 : (nbins[pass] <= 128 ? 7 : 8);
     if (small) { if (vm == 2) SFB_OS(4, 2); else if (vm == 1) SFB_OS(4, 1); else SFB_OS(4, 0); }
-    else if (mid) { SFB_OS(8, 2); }
     else       { if (vm == 2) SFB_OS(16, 2); else if (vm == 1) SFB_OS(16, 1); else SFB_OS(16, 0); }
 #undef SFB_OS2
 #undef SFB_OS
@@ -436,15 +475,11 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n
 // ------------------------------------------------------------------ instance emission in depth order
 constexpr int DUP_THREADS = 256;   // DUP_GPB (Gaussians / depth ranks per block) lives in common.cuh: it sizes block_sums
 
-// Per-block instance counts in depth order and, by the LAST block to finish (a ticket in the forward's counter words),
-// their exclusive scan in place: one launch instead of two for the block offsets of the emission kernel.
 __global__ void __launch_bounds__(DUP_THREADS)
 instance_block_sums_kernel(int P, SortedIdx sorted,
-                           const uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ block_sums,
-                           uint32_t* __restrict__ ticket) {
+                           const uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ block_sums) {
   const uint32_t* __restrict__ sorted_idx = sorted.get();
   __shared__ uint32_t s_w[DUP_THREADS / 32];
-  __shared__ bool s_last;
   uint32_t v = 0;
   for (int j = blockIdx.x * DUP_GPB + threadIdx.x; j < min(P, (blockIdx.x + 1) * DUP_GPB); j += DUP_THREADS)
     v += tiles_touched[sorted_idx[j]];
@@ -456,39 +491,17 @@ instance_block_sums_kernel(int P, SortedIdx sorted,
     uint32_t t = 0;
     for (int w = 0; w < DUP_THREADS / 32; w++) t += s_w[w];
     block_sums[blockIdx.x] = t;
-    __threadfence();
-    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
   }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // exclusive scan of block_sums[0, nb): thread t owns a run of `per` consecutive entries
-  const int nb = (int)gridDim.x;
-  const int per = (nb + DUP_THREADS - 1) / DUP_THREADS;
-  const int b0 = min(nb, (int)threadIdx.x * per), b1 = min(nb, b0 + per);
-  uint32_t sum = 0;
-  for (int b = b0; b < b1; b++) sum += __ldcg(block_sums + b);
-  uint32_t inc = sum;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  __syncthreads();
-  if (lane == 31) s_w[warp] = inc;
-  __syncthreads();
-  uint32_t run = inc - sum;
-  for (int w = 0; w < warp; w++) run += s_w[w];
-  for (int b = b0; b < b1; b++) { const uint32_t c = __ldcg(block_sums + b); block_sums[b] = run; run += c; }
-  if (threadIdx.x == 0) *ticket = 0u;      // (the forward clears the counter words anyway)
 }
 
 void launch_instance_block_sums(int P, const SortedIdx& sorted_idx, const uint32_t* tiles_touched,
-                                uint32_t* block_sums, uint32_t* ticket, cudaStream_t s) {
+                                uint32_t* block_sums, cudaStream_t s) {
   int nb = (P + DUP_GPB - 1) / DUP_GPB;
   prof_begin("instance_block_sums", s);
-  instance_block_sums_kernel<<<nb, DUP_THREADS, 0, s>>>(P, sorted_idx, tiles_touched, block_sums, ticket);
+  instance_block_sums_kernel<<<nb, DUP_THREADS, 0, s>>>(P, sorted_idx, tiles_touched, block_sums);
+  prof_end(s);
+  prof_begin("instance_block_scan", s);
+  scan_exclusive_kernel<<<1, 1024, 0, s>>>(block_sums, nb, nullptr);
   prof_end(s);
 }
 

@@ -185,7 +185,7 @@ __device__ __forceinline__ uint32_t refine_patch_mask(uint32_t mask, float x, fl
 struct __align__(16) GradRec {
   float dx, dy, dA, dB;     // d/d(NDC-scaled mean) x,y ; d/d conic A, B (true derivatives)
   float dC, dop, dr, dg;    // d/d conic C ; d/d opacity ; d/d rgb
-  float db, pad0, pad1, pad2;
+  float db, dz, pad1, pad2;   // dz: d/d view-space depth (only with a depth cotangent; stays 0 otherwise)
 };
 static_assert(sizeof(GradRec) == 48, "GradRec must be 48 bytes");
 
@@ -396,7 +396,7 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* hist, int n
                      int merge_bits = 0 /* last pass writes (key & ((1 << merge_bits) - 1)) | byte << merge_bits */,
                      const uint32_t** last_total0 = nullptr /* non-null: the last pass may return at once when it is the
                         identity; receives the device word to compare with n (SortedIdx), or nullptr */);
-size_t radix_sort_zero_words(int n, int nbits, bool pairs /* a 32-bit value moves with every key */);
+size_t radix_sort_zero_words(int n, int nbits);
 // Result of the depth sort as its consumers see it.  The most significant radix pass of a bounded scene is the identity
 // (depth keys are rebased to key - min: < 2^24), known on the device only: instead of copying 8 B/Gaussian through
 // that pass, the pass returns at once and the consumers read its input.
@@ -408,8 +408,7 @@ struct SortedIdx {
   __device__ __forceinline__ const uint32_t* get() const { return (total0 && *total0 == n) ? alt : primary; }
 };
 void launch_instance_block_sums(int P, const SortedIdx& sorted_idx, const uint32_t* tiles_touched,
-                                uint32_t* block_sums /* out: exclusive prefix of the per-block instance counts */,
-                                uint32_t* ticket /* zeroed word */, cudaStream_t s);
+                                uint32_t* block_sums, cudaStream_t s);
 void launch_duplicate(int P, int grid_x, const SortedIdx& sorted_idx, const uint32_t* tiles_touched,
                       const uint2* rect, const uint32_t* block_offsets, uint32_t* tile_keys,
                       uint8_t* inst_hi /* nullptr: the whole index fits the word */, int idx_bits,
@@ -435,7 +434,8 @@ int launch_gather_rows_probe(const SplatRec* table, size_t P, const uint32_t* id
 int launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
                            const SplatRec* rec, size_t P,
                            const float* bg, const float* final_T, const uint32_t* n_contrib,
-                           const float* dL_dpixels, const float* dL_dalpha_img, const uint8_t* hit,
+                           const float* dL_dpixels, const float* dL_dalpha_img,
+                           const float* dL_ddepth_img /* [H][W] cotangent of the depth image, or nullptr */, const uint8_t* hit,
                            const uint32_t* bcount /* [TILE_BUCKETS] tiles per cost bucket (forward) */,
                            const uint32_t* btile /* [TILE_BUCKETS][T] tile ids per bucket */, GradRec* grad, cudaStream_t s);
 

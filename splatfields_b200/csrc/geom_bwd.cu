@@ -162,9 +162,11 @@ __device__ __forceinline__ void geom_backward_block(const BwdParams& p, const Ge
     const float dty = ymul * -fy * itz2 * dJ12;
     const float dtz = -fx * itz2 * dJ00 - fy * itz2 * dJ11 + (2.f * fx * t[0]) * itz3 * dJ02 +
                       (2.f * fy * t[1]) * itz3 * dJ12;
+    // (g2.y = GradRec::dz: gradient w.r.t. the view-space depth, non-zero only when the depth image had a cotangent;
+    //  depth = view[2] x + view[6] y + view[10] z + view[14])
 #pragma unroll
     for (int j = 0; j < 3; j++)
-      dmean[j] = cam.view[4 * j + 0] * dtx + cam.view[4 * j + 1] * dty + cam.view[4 * j + 2] * dtz;
+      dmean[j] = cam.view[4 * j + 0] * dtx + cam.view[4 * j + 1] * dty + cam.view[4 * j + 2] * (dtz + g2.y);
 
     // ---- NDC-scaled screen mean -> mean3D ----
     {

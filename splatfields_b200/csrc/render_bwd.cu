@@ -72,7 +72,7 @@ struct SmemBwdMma {
   float2 stage[NW][MG * 32];        // per warp: [entry row][pixel ^ swizzle] = (sG, w)
   float2 dlp[NW][4][32];            // per warp: (hi, lo) of dL/dC_c per pixel; channel 3 = zeros
   alignas(16) uint8_t list[NW][BBT];   // per warp: compacted entry slots (read 16 at a time)
-  alignas(16) float acc[BBT * 9];
+  alignas(16) float acc[BBT * 10];   // per entry: six moments, three colour sums, [9] = sum of w * dL/ddepth (DEPTH)
   uint64_t bar;
   uint32_t maxc[NW];
   uint32_t tile;
@@ -102,16 +102,21 @@ __device__ __forceinline__ int ordered_tile(int i, int T, const uint32_t* __rest
   return (int)*s_tile;
 }
 
-template <bool ALPHA, int BBT, int MINB, bool TMA, bool PRED>
+// DEPTH: the cotangent of the depth image enters as one more composited channel ("colour" = the splat's view-space z,
+// no background): it adds (z - depth accumulated behind) * dL/dD to dL/dalpha and yields a tenth per-splat sum,
+// sum_p w_p dL/dD_p = dL/dz, which rides in the unused fourth column of the colour product.
+template <bool ALPHA, int BBT, int MINB, bool TMA, bool PRED, bool DEPTH = false>
 __global__ void __launch_bounds__(NT, MINB)
 render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
                            const uint32_t* __restrict__ point_list, uint32_t idx_mask,
                            const SplatRec* __restrict__ rec, const __grid_constant__ CUtensorMap rec_map,
                            const float* __restrict__ bg, const float* __restrict__ final_T,
                            const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
-                           const float* __restrict__ dL_dalpha_img, const uint8_t* __restrict__ hit,
+                           const float* __restrict__ dL_dalpha_img, const float* __restrict__ dL_ddepth_img,
+                           const uint8_t* __restrict__ hit,
                            const uint32_t* __restrict__ bcount, const uint32_t* __restrict__ btile,
                            GradRec* __restrict__ grad) {
+  constexpr int NA = DEPTH ? 10 : 9;      // sums per list entry
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemBwdMma<BBT>& sm = *reinterpret_cast<SmemBwdMma<BBT>*>(smem_raw);
 
@@ -136,6 +141,8 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
   if (inside) { dLp0 = dL_dpixels[pix]; dLp1 = dL_dpixels[HW + pix]; dLp2 = dL_dpixels[2 * HW + pix]; }
   float dLpa = 0.f, acca = 0.f;
   if (ALPHA && inside) dLpa = dL_dalpha_img[pix];
+  float dLpd = 0.f, accd = 0.f;
+  if (DEPTH && inside) dLpd = dL_ddepth_img[pix];
   const float bg_dot = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
   const float Tf_bg = T_final * bg_dot;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
@@ -147,7 +154,8 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
     split_tf32(dLp0, h, l); sm.dlp[warp][0][lane] = make_float2(__uint_as_float(h), __uint_as_float(l));
     split_tf32(dLp1, h, l); sm.dlp[warp][1][lane] = make_float2(__uint_as_float(h), __uint_as_float(l));
     split_tf32(dLp2, h, l); sm.dlp[warp][2][lane] = make_float2(__uint_as_float(h), __uint_as_float(l));
-    sm.dlp[warp][3][lane] = make_float2(0.f, 0.f);
+    if (DEPTH) { split_tf32(dLpd, h, l); sm.dlp[warp][3][lane] = make_float2(__uint_as_float(h), __uint_as_float(l)); }
+    else sm.dlp[warp][3][lane] = make_float2(0.f, 0.f);
   }
   // B operand of the moment product: phi_n at pixel k, n = gid, k = ks*8 + tig (+4); constant per lane.
   // Output column n lands in accumulator slot n (0..5); the colour sums use columns 6, 7, 5 -> slots 6, 7, 8.
@@ -217,7 +225,7 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
       }
     }
     if (threadIdx.x < (unsigned)BBT) sm.mask[threadIdx.x] = (uint8_t)mask;
-    for (int k = threadIdx.x; k < 9 * BBT; k += NT) sm.acc[k] = 0.f;
+    for (int k = threadIdx.x; k < NA * BBT; k += NT) sm.acc[k] = 0.f;
     __syncthreads();
     int nsweep = 0;
     {
@@ -270,6 +278,11 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
             dL_dalpha = fmaf(da, dLpa, dL_dalpha);
             acca = fmaf(ae, da, acca);
           }
+          if (DEPTH) {
+            const float dz = q1.z - accd;
+            dL_dalpha = fmaf(dz, dLpd, dL_dalpha);
+            accd = fmaf(ae, dz, accd);
+          }
           dL_dalpha = fmaf(dL_dalpha, T, -Tf_bg * inv);
           sG = c ? q1.y * dL_dalpha * G : 0.f;
         } else if (j >= jmin) {
@@ -298,6 +311,11 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
               const float da = 1.f - acca;
               dL_dalpha = fmaf(da, dLpa, dL_dalpha);
               acca = fmaf(alpha, da, acca);
+            }
+            if (DEPTH) {
+              const float dz = q1.z - accd;
+              dL_dalpha = fmaf(dz, dLpd, dL_dalpha);
+              accd = fmaf(alpha, dz, accd);
             }
             dL_dalpha = fmaf(dL_dalpha, T, -Tf_bg * inv);
             sG = q1.y * dL_dalpha * G;
@@ -339,26 +357,28 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
       {
         const bool mom = tig < 3;
         if (gid < gn) {
-          float* a = &sm.acc[(int)sm.list[warp][g0 + gid] * 9];
+          float* a = &sm.acc[(int)sm.list[warp][g0 + gid] * NA];
           atomicAdd(a + 2 * tig, mom ? dS[0] : dW[0]);
           atomicAdd(a + 2 * tig + 1, mom ? dS[1] : dW[1]);
           if (tig == 2) atomicAdd(a + 8, dW[1]);
+          if (DEPTH && tig == 2) atomicAdd(a + 9, dW[0]);      // column 4 of the colour product: sum of w * dL/ddepth
         }
         if (gid + 8 < gn) {
-          float* a = &sm.acc[(int)sm.list[warp][g0 + gid + 8] * 9];
+          float* a = &sm.acc[(int)sm.list[warp][g0 + gid + 8] * NA];
           atomicAdd(a + 2 * tig, mom ? dS[2] : dW[2]);
           atomicAdd(a + 2 * tig + 1, mom ? dS[3] : dW[3]);
           if (tig == 2) atomicAdd(a + 8, dW[3]);
+          if (DEPTH && tig == 2) atomicAdd(a + 9, dW[2]);
         }
       }
       __syncwarp();   // staging rows are rewritten by the next group
     }
     __syncthreads();
     if ((int)threadIdx.x < n) {
-      float a[9];
+      float a[NA];
       bool nz = false;
 #pragma unroll
-      for (int k = 0; k < 9; k++) { a[k] = sm.acc[threadIdx.x * 9 + k]; nz |= (a[k] != 0.f); }
+      for (int k = 0; k < NA; k++) { a[k] = sm.acc[threadIdx.x * NA + k]; nz |= (a[k] != 0.f); }
       if (nz) {
         const float4 q0 = sm.row[threadIdx.x][0];
         const float4 q1 = sm.row[threadIdx.x][1];
@@ -380,6 +400,7 @@ render_backward_mma_kernel(int W, int H, int grid_x, const uint2* __restrict__ r
         red_add_v4(gp, gx, gy, gA, gB);
         red_add_v4(gp + 4, gC, S0 != 0.f ? gop : 0.f, a[6], a[7]);
         atomicAdd(gp + 8, a[8]);
+        if (DEPTH) atomicAdd(gp + 9, a[9]);      // GradRec::dz
       }
     }
   }
@@ -399,7 +420,8 @@ static int env_choice(const char* name, const char* alt) {
 int launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, uint32_t idx_mask,
                            const SplatRec* rec, size_t P,
                            const float* bg, const float* final_T, const uint32_t* n_contrib,
-                           const float* dL_dpixels, const float* dL_dalpha_img, const uint8_t* hit,
+                           const float* dL_dpixels, const float* dL_dalpha_img, const float* dL_ddepth_img,
+                           const uint8_t* hit,
                            const uint32_t* bcount, const uint32_t* btile, GradRec* grad,
                            cudaStream_t s) {
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
@@ -417,13 +439,14 @@ int launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* po
   }
   // > 48 KB of dynamic shared memory needs the attribute on EVERY device the process uses (it is per device and the
   // call is cheap: it is made with every launch)
-#define SFB_RBK(A, B, MB, TM) do { if (pred) SFB_RBP(A, B, MB, TM, true); else SFB_RBP(A, B, MB, TM, false); } while (0)
-#define SFB_RBP(A, B, MB, TM, PR)                                                                                   \
+#define SFB_RBK(A, B, MB, TM) do { if (pred) SFB_RBP(A, B, MB, TM, true, false); else SFB_RBP(A, B, MB, TM, false, false); } while (0)
+#define SFB_RBP(A, B, MB, TM, PR, DP)                                                                               \
   do {                                                                                                              \
-    auto kern = render_backward_mma_kernel<A, B, MB, TM, PR>;                                                       \
+    auto kern = render_backward_mma_kernel<A, B, MB, TM, PR, DP>;                                                   \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemBwdMma<B>));            \
     kern<<<gx * gy, NT, sizeof(SmemBwdMma<B>), s>>>(W, H, gx, ranges, point_list, idx_mask, rec, map, bg, final_T,  \
-                                                   n_contrib, dL_dpixels, dL_dalpha_img, hit, bcount, btile, grad); \
+                                                   n_contrib, dL_dpixels, dL_dalpha_img, dL_ddepth_img, hit, bcount, \
+                                                   btile, grad);                                                    \
   } while (0)
 #define SFB_RBA(A)                                                                                                  \
   do {                                                                                                              \
@@ -431,7 +454,9 @@ int launch_render_backward(int W, int H, const uint2* ranges, const uint32_t* po
     else if (b128x3) { SFB_RBK(A, 128, 3, false); }   /* 128-entry batches at 80 registers (3 CTAs / SM) */           \
     else     { if (tma) SFB_RBK(A, 256, 3, true); else SFB_RBK(A, 256, 3, false); }                                 \
   } while (0)
-  if (dL_dalpha_img) SFB_RBA(true); else SFB_RBA(false);
+  if (dL_ddepth_img) {     // depth cotangent: the default configuration of the kernel (the A/B arms do not carry it)
+    if (dL_dalpha_img) SFB_RBP(true, 256, 3, false, false, true); else SFB_RBP(false, 256, 3, false, false, true);
+  } else if (dL_dalpha_img) SFB_RBA(true); else SFB_RBA(false);
 #undef SFB_RBA
 #undef SFB_RBK
 #undef SFB_RBP

@@ -12,6 +12,7 @@ the C ABI (include/splat_b200.h).  torch is used for device memory, streams and 
 """
 from __future__ import annotations
 
+import os
 import threading
 from typing import NamedTuple
 
@@ -51,6 +52,7 @@ _SH_COLOR_OUT = None
 # the arena slab (one persistent kernel: geometry backward + exchange); otherwise sfb_xchg_finish does, afterwards.
 _XCHG = None
 _WARNED_DEPTH = False
+PROPAGATE_DEPTH_GRAD = os.environ.get("SFB_DEPTH_GRAD", "1") != "0"
 
 
 def set_grad_arena(slab, fields, sh_color_out=None, xchg=None):
@@ -221,15 +223,20 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out_color, _grad_radii, _grad_depth, grad_out_alpha=None):
-        # Like the pinned reference build, depth is a forward-only output: its cotangent is not
-        # propagated (every shipped recipe keeps lambda_depth = 0).  Say so once if a loss uses it.
+        # The depth image is differentiable: its cotangent goes to the kernels as one more composited channel (the
+        # reference's depth losses, train.py:195-229).  Whether the pinned depth-diff-gaussian-rasterization build
+        # propagates it is not checkable from the reference tree (every shipped recipe keeps
+        # lambda_depth = 0, where both behaviours coincide).  SFB_DEPTH_GRAD=0 restores a forward-only depth (the
+        # cotangent is dropped with a one-time warning).
         global _WARNED_DEPTH
-        if _grad_depth is not None and not _WARNED_DEPTH:
-            _WARNED_DEPTH = True
-            import warnings
-            warnings.warn("splatfields_b200: the rasterizer's depth output is forward-only (as in the pinned "
-                          "depth-diff-gaussian-rasterization build): the gradient of a depth loss is NOT propagated "
-                          "to the Gaussians", RuntimeWarning, stacklevel=2)
+        if _grad_depth is not None and not PROPAGATE_DEPTH_GRAD:
+            if not _WARNED_DEPTH:
+                _WARNED_DEPTH = True
+                import warnings
+                warnings.warn("splatfields_b200: SFB_DEPTH_GRAD=0 - the gradient of a depth loss is NOT propagated "
+                              "to the Gaussians", RuntimeWarning, stacklevel=2)
+            _grad_depth = None
+        ctx.grad_depth = _grad_depth
         lib = _lib.load()
         rs = ctx.raster_settings
         radii, geom, binning, img, means3D, sh, col, sc, rot, cov, bg, vm, pm, cp = ctx.saved_tensors
@@ -257,7 +264,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         dL_drot = _arena_out("rotations", P, (P, 4), **f32) if cov is None else None
         g = _prep(grad_out_color)
         ga = _prep(grad_out_alpha) if (ctx.with_alpha and grad_out_alpha is not None) else None
-        if g is None:      # only the alpha image was used downstream
+        gd = _prep(ctx.grad_depth)
+        if g is None:      # only the alpha / depth image was used downstream
             g = torch.zeros((3, H, W), **f32)
         flags = (_lib.BWD_ACC_FRESH if ctx.acc_fresh[0] else 0) | (_lib.BWD_SH_FACTORED if factored else 0)
         ctx.acc_fresh[0] = False    # a second backward on the same buffers (retain_graph) must clear them itself
@@ -268,7 +276,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     P, int(rs.sh_degree), int(M), int(ctx.num_rendered), W, H,
                     _ptr(bg), _ptr(means3D), _ptr(sh), _ptr(col), _ptr(sc), float(rs.scale_modifier), _ptr(rot),
                     _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cp), float(rs.tanfovx), float(rs.tanfovy), _ptr(radii),
-                    _ptr(geom), _ptr(binning), _ptr(img), _ptr(g), _ptr(ga),
+                    _ptr(geom), _ptr(binning), _ptr(img), _ptr(g), _ptr(ga), _ptr(gd),
                     _ptr(dL_dmeans2D), _ptr(dL_dcolors), _ptr(dL_dopacity), _ptr(dL_dmeans3D), _ptr(dL_dcov3D),
                     _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drot), int(bool(rs.debug)), flags, None, 0, stream)
             _lib.check(rc)
@@ -309,6 +317,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         if g is None:
             g = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
         ga = _prep(grad_out_alpha) if (ctx.with_alpha and grad_out_alpha is not None) else None
+        gd = _prep(ctx.grad_depth)
         flags = _lib.BWD_ACC_FRESH if ctx.acc_fresh[0] else 0
         ctx.acc_fresh[0] = False
         o = dict.fromkeys(("means3D", "opacities", "scales", "rotations", "colors_precomp", "shs"))
@@ -330,7 +339,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 P, int(rs.sh_degree), int(ctx.M), int(ctx.num_rendered), W, H,
                 _ptr(bg), _ptr(means3D), _ptr(sh), _ptr(col), _ptr(sc), float(rs.scale_modifier), _ptr(rot),
                 None, _ptr(vm), _ptr(pm), _ptr(cp), float(rs.tanfovx), float(rs.tanfovy), _ptr(radii),
-                _ptr(geom), _ptr(binning), _ptr(img), _ptr(g), _ptr(ga),
+                _ptr(geom), _ptr(binning), _ptr(img), _ptr(g), _ptr(ga), _ptr(gd),
                 _ptr(dL_dmeans2D), _ptr(o["colors_precomp"]), _ptr(o["opacities"]), _ptr(o["means3D"]), None,
                 _ptr(o["shs"]), _ptr(o["scales"]), _ptr(o["rotations"]), int(bool(rs.debug)), flags,
                 C.byref(desc), int(epoch), stream)

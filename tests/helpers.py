@@ -30,7 +30,7 @@ def cam_kwargs(cam, H, W, bg):
                 tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5), H=H, W=W)
 
 
-def run_oracle(O, sc, cam, H, W, bg, sh_degree, dL=None, want_margin=True):
+def run_oracle(O, sc, cam, H, W, bg, sh_degree, dL=None, want_margin=True, dLd=None):
     kw = cam_kwargs(cam, H, W, bg)
     n = lambda k: sc[k].numpy() if k in sc else None
     fwd = O.forward(n("means3D"), n("opacities"), n("scales"), n("rotations"), shs=n("shs"),
@@ -40,11 +40,12 @@ def run_oracle(O, sc, cam, H, W, bg, sh_degree, dL=None, want_margin=True):
     if dL is not None:
         bwd = O.backward(fwd, dL, n("means3D"), n("scales"), n("rotations"), shs=n("shs"),
                          cov3D_precomp=n("cov3D_precomp"), viewmatrix=kw["viewmatrix"], projmatrix=kw["projmatrix"],
-                         campos=kw["campos"], tanfovx=kw["tanfovx"], tanfovy=kw["tanfovy"], sh_degree=sh_degree)
+                         campos=kw["campos"], tanfovx=kw["tanfovx"], tanfovy=kw["tanfovy"], sh_degree=sh_degree,
+                         dL_ddepth=dLd)
     return fwd, bwd
 
 
-def run_cuda(sc, cam, H, W, bg, sh_degree, dL=None, device="cuda", debug=False):
+def run_cuda(sc, cam, H, W, bg, sh_degree, dL=None, device="cuda", debug=False, dLd=None):
     """Through GaussianRasterizer (the reference-facing surface) -> C ABI.  Returns numpy dicts."""
     import ctypes as C
     from splatfields_b200 import _lib
@@ -100,7 +101,10 @@ def run_cuda(sc, cam, H, W, bg, sh_degree, dL=None, device="cuda", debug=False):
                    n_contrib=nc.cpu().numpy().astype(np.uint32))
     grads = None
     if dL is not None:
-        (color * torch.as_tensor(dL, device=dev)).sum().backward()
+        loss = (color * torch.as_tensor(dL, device=dev)).sum()
+        if dLd is not None:      # a loss on the depth image as well
+            loss = loss + (depth * torch.as_tensor(dLd, device=dev).reshape(depth.shape)).sum()
+        loss.backward()
         torch.cuda.synchronize()
         grads = dict(dL_dmeans3D=t["means3D"].grad, dL_dmeans2D=means2D.grad, dL_dopacity=t["opacities"].grad)
         for k_in, k_out in (("shs", "dL_dsh"), ("colors_precomp", "dL_dcolors"), ("scales", "dL_dscales"),

@@ -43,6 +43,10 @@ def test_parity_full_size(oracle, cuda_lib, name, k, min_ok):
 VARIANTS = [
     ("no_pack", {"SFB_NO_PACK": "1"}),
     ("exactexp", {"SFB_LIB_VARIANT": "exactexp"}),
+    # the measured A/B arms of round 2 that stay in the library
+    ("tma_staging", {"SFB_FWD_STAGE": "tma", "SFB_BWD_STAGE": "tma"}),
+    ("bwd_b128_pred", {"SFB_BWD_BATCH": "128", "SFB_BWD_SWEEP": "pred"}),
+    ("bwd_b128x3_launch_order", {"SFB_BWD_BATCH": "128x3", "SFB_BWD_ORDER": "0"}),
 ]
 
 

@@ -224,3 +224,32 @@ def test_fused_alpha_matches_two_reference_passes(oracle, cuda_lib):
     o1 = render(camd, gd, None, torch.tensor(bg, device=dev), return_opacity=True, fused_alpha=True)
     assert torch.equal(o1["render"], o2["render"]) and torch.equal(o1["radii"], o2["radii"])
     assert float((o1["opacity"] - o2["opacity"]).abs().max()) <= 1e-6
+
+
+@pytest.mark.parametrize("precomp_rgb", [False, True], ids=["sh3", "rgb"])
+def test_depth_cotangent_matches_the_oracle(oracle, cuda_lib, precomp_rgb):
+    """A loss on the depth image (train.py:195-229) reaches the Gaussians: colour + depth cotangents against the oracle
+    (whose depth backward is checked against fp64 autograd on the CPU, tests/test_oracle_autograd.py)."""
+    P, H, W = 8_000, 160, 208
+    deg = 0 if precomp_rgb else 3
+    sc, cam = scene_and_camera(P, H, W, 61, scale_mult=2.5, precomp_rgb=precomp_rgb)
+    bg = (0.3, 0.6, 0.9)
+    gen = torch.Generator().manual_seed(79)
+    dL = torch.randn(3, H, W, generator=gen).numpy()
+    dLd = torch.randn(1, H, W, generator=gen).numpy()
+    f, _ = run_oracle(oracle, sc, cam, H, W, bg, deg)
+    ok = f["margin"] > 1e-4
+    dL[:, ~ok] = 0
+    dLd[:, ~ok] = 0
+    f, b = run_oracle(oracle, sc, cam, H, W, bg, deg, dL=dL, dLd=dLd)
+    _, b0 = run_oracle(oracle, sc, cam, H, W, bg, deg, dL=dL)
+    c, g = run_cuda(sc, cam, H, W, bg, deg, dL=dL, dLd=dLd)
+    for k in g:
+        ref = b[k] if k != "dL_dopacity" else b[k].reshape(g[k].shape)
+        grad_close(k, g[k], ref)
+    # the depth term matters (not a no-op), and without a depth cotangent nothing changes
+    assert np.abs(b["dL_dmeans3D"] - b0["dL_dmeans3D"]).max() > 1e-2 * np.abs(b0["dL_dmeans3D"]).max()
+    _, g0 = run_cuda(sc, cam, H, W, bg, deg, dL=dL)
+    for k in g0:
+        ref = b0[k] if k != "dL_dopacity" else b0[k].reshape(g0[k].shape)
+        grad_close(k, g0[k], ref)

@@ -11,7 +11,7 @@ from oracle import torch_naive as TN
 from splatfields_b200 import synth
 
 
-def _run(oracle, sc, cam, H, W, deg, bg):
+def _run(oracle, sc, cam, H, W, deg, bg, depth_cotangent=False):
     tfx, tfy = math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5)
     kw = dict(bg=bg.numpy(), viewmatrix=cam.world_view_transform.numpy(), projmatrix=cam.full_proj_transform.numpy(),
               campos=cam.camera_center.numpy(), tanfovx=tfx, tanfovy=tfy, H=H, W=W, sh_degree=deg)
@@ -32,10 +32,17 @@ def _run(oracle, sc, cam, H, W, deg, bg):
     assert np.abs(dep.detach().numpy() - f["depth"])[:, ok].max() < 5e-5
     G = torch.randn(3, H, W, generator=torch.Generator().manual_seed(5))
     G[:, torch.tensor(~ok)] = 0
-    (col * G.double()).sum().backward()
+    Gd = None
+    loss = (col * G.double()).sum()
+    if depth_cotangent:       # a loss on the depth image as well (train.py:217-229, lambda_depth > 0)
+        Gd = torch.randn(1, H, W, generator=torch.Generator().manual_seed(6))
+        Gd[:, torch.tensor(~ok)] = 0
+        loss = loss + (dep * Gd.double()).sum()
+    loss.backward()
     b = oracle.backward(f, G.numpy(), n("means3D"), n("scales"), n("rotations"), shs=n("shs"),
                         cov3D_precomp=n("cov3D_precomp"), viewmatrix=kw["viewmatrix"], projmatrix=kw["projmatrix"],
-                        campos=kw["campos"], tanfovx=tfx, tanfovy=tfy, sh_degree=deg)
+                        campos=kw["campos"], tanfovx=tfx, tanfovy=tfy, sh_degree=deg,
+                        dL_ddepth=None if Gd is None else Gd.numpy())
     return f, b, leaf, aux
 
 
@@ -59,6 +66,24 @@ def test_plumbing_config_sh(oracle, deg):
     assert _rel(b["dL_dmeans2D"][:, :2], aux["ndc"].grad) < 1e-4
     nb = (deg + 1) ** 2
     assert np.all(b["dL_dsh"][:, nb:, :] == 0)
+
+
+def test_depth_cotangent_matches_autograd(oracle):
+    """The depth image is differentiable when its cotangent is given: colour + depth loss against fp64
+    autograd through the dense restatement."""
+    cfg = synth.CONFIGS["plumbing_256"]
+    sc = synth.make_scene(cfg["P"], cfg["seed"], scale_mult=6.0, extent=1.0)
+    cam = synth.config_camera("plumbing_256")
+    f, b, leaf, aux = _run(oracle, sc, cam, cfg["H"], cfg["W"], 2, torch.tensor([1.0, 0.5, 0.2]), depth_cotangent=True)
+    assert _rel(b["dL_dmeans3D"], leaf["means3D"].grad) < 1e-4
+    assert _rel(b["dL_dopacity"], leaf["opacities"].grad.reshape(-1, 1)) < 1e-4
+    assert _rel(b["dL_dscales"], leaf["scales"].grad) < 1e-4
+    assert _rel(b["dL_drotations"], leaf["rotations"].grad) < 1e-4
+    assert _rel(b["dL_dsh"], leaf["shs"].grad) < 1e-4
+    assert _rel(b["dL_dmeans2D"][:, :2], aux["ndc"].grad) < 1e-4
+    # and the depth term is not a no-op: the same scene without it gives different mean gradients
+    _, b0, leaf0, _ = _run(oracle, sc, cam, cfg["H"], cfg["W"], 2, torch.tensor([1.0, 0.5, 0.2]))
+    assert np.abs(b["dL_dmeans3D"] - b0["dL_dmeans3D"]).max() > 1e-3 * np.abs(b0["dL_dmeans3D"]).max()
 
 
 def test_plumbing_config_precomputed_rgb_and_cov(oracle):
