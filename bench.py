@@ -7,8 +7,9 @@
 One "step" = one forward + backward pass of the rasterizer over the workload BASELINE.json's metric is
 quoted on: 1 000 000 synthetic Gaussians, 800x800, SH degree 3 (configs[2], "lego_1m"), one camera per
 rank (view-parallel, splats replicated), followed for N > 1 by the exchange that sums the per-splat gradient
-slab [P, 59] over the ranks (default: all-gather of the [P, 3] colour gradients + all-reduce of the [P, 11]
-geometry gradients, SH rows rebuilt on every rank; SFB_EXCHANGE=allreduce: one all-reduce of the whole slab).
+slab [P, 59] over the ranks (default "nvlink": the library's own kernels over symmetric memory — colour gradients
+pushed to every rank by the geometry backward, packed [P, 11] records summed in the switch, SH rows rebuilt on every
+rank; SFB_EXCHANGE=factored: the same factorisation over NCCL; SFB_EXCHANGE=allreduce: one all-reduce of the whole slab).
 metric = Msplats/s = N * P / t_step.
 
 Printed by rank 0 as one JSON line.  Extra objects: roofline (dominant kernel, live CUDA-event timing on

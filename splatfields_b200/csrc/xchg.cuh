@@ -35,8 +35,9 @@ __device__ __forceinline__ void sh_basis(float x, float y, float z, float* basis
   }
 }
 
-// dL_dsh row of Gaussian i: sum over the V views (index order: bit-reproducible) of basis(dir_v) (x) gc_v, each product
-// rounded on its own (as geom_backward_kernel stores it for a single view) before it enters the sum.
+// dL_dsh row of Gaussian i: sum over the V views (index order: bit-reproducible across ranks and runs) of
+// basis(dir_v) (x) gc_v, one fused multiply-add per term: with 8 views the row costs 8 x 48 of them and the kernel is
+// instruction-bound, not HBM-bound (the first view's products are rounded exactly as geom_backward_kernel stores them).
 template <int D, bool W256>
 __device__ __forceinline__ void sh_row_rebuild(size_t i, size_t view_stride /* floats between the views' [P][3] slots */,
                                                int V, int M, const float* __restrict__ means3D,
@@ -59,9 +60,9 @@ __device__ __forceinline__ void sh_row_rebuild(size_t i, size_t view_stride /* f
     sh_basis<D>(vx * ilen, vy * ilen, vz * ilen, basis);
 #pragma unroll
     for (int k = 0; k < NB; k++) {
-      acc[3 * k] = __fadd_rn(acc[3 * k], __fmul_rn(basis[k], g0));
-      acc[3 * k + 1] = __fadd_rn(acc[3 * k + 1], __fmul_rn(basis[k], g1));
-      acc[3 * k + 2] = __fadd_rn(acc[3 * k + 2], __fmul_rn(basis[k], g2));
+      acc[3 * k] = __fmaf_rn(basis[k], g0, acc[3 * k]);
+      acc[3 * k + 1] = __fmaf_rn(basis[k], g1, acc[3 * k + 1]);
+      acc[3 * k + 2] = __fmaf_rn(basis[k], g2, acc[3 * k + 2]);
     }
   }
   float* dsh = dL_dsh + i * M * 3;
