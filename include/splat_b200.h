@@ -151,7 +151,7 @@ int sfb_xchg_status(const sfb_xchg* x, unsigned* status, void* stream);
  * Fused kernel: first CTA started, last geometry chunk / NVLink unit / SH chunk / unpack chunk finished, last CTA done.
  * [6..11] (fused kernel only): SM cycles, summed over the CTAs, spent choosing work (incl. waiting), in geometry chunks,
  * in their flag releases, in NVLink units, SH chunks, unpack chunks.  sfb_xchg_tune: share of the CTAs that start on the
- * slice reduction (eighths of the grid, default 1) and reduction round trips in flight per thread (4, default, or 16);
+ * slice reduction (eighths of the grid; 0, the default: 2 with two ranks, 1 with more) and reduction round trips in flight per thread (4, default, or 16);
  * process-wide. */
 int sfb_xchg_timeline(const sfb_xchg* x, unsigned long long* ns12, void* stream);
 void sfb_xchg_tune(int nred_eighths, int depth);

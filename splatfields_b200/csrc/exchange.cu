@@ -177,12 +177,13 @@ xchg_finish_kernel(XchgDev x, uint32_t epoch, int nred_eighths, int V, int M, co
 
 // Tuning hooks of the measurement sessions (sfb_xchg_tune): share of the CTAs that start on the slice reduction
 // (eighths of the grid) and reduction round trips in flight per thread (4 or 16).
-// Default: an eighth of the CTAs reduces — the reduction is bound by the links whatever the number of CTAs on it
-// (123 us at N = 2 with 37 or 296 CTAs), while the SH rows are instruction-bound at N = 8 (8 views per row) and were the
-// long pole with half of the grid on them (182 us, profiles/r02d_bench_n8_nvlink.json).
-static int g_xchg_nred_eighths = 1, g_xchg_depth = 4;
+// Default (0 = by world size): a quarter of the CTAs reduces with two ranks, an eighth with more — the reduction is
+// bound by the links whatever the number of CTAs on it (123-135 us at N = 2 with 37 ... 296 CTAs), while the SH rows get
+// instruction-bound as the views multiply and were the long pole at N = 8 with half of the grid on them (182 us,
+// profiles/r02d_bench_n8_nvlink.json).
+static int g_xchg_nred_eighths = 0, g_xchg_depth = 4;
 void xchg_tune(int nred_eighths, int depth) {
-  if (nred_eighths >= 1 && nred_eighths <= 8) g_xchg_nred_eighths = nred_eighths;
+  if (nred_eighths >= 0 && nred_eighths <= 8) g_xchg_nred_eighths = nred_eighths;
   if (depth == 4 || depth == 16) g_xchg_depth = depth;
 }
 
@@ -198,13 +199,14 @@ void launch_xchg_finish(const XchgDev& x, int max_ctas, uint32_t epoch, int D, i
   // 2 CTAs per SM (launch bound): the whole grid is resident, so CTAs spinning on a flag can never keep the CTAs
   // that produce this rank's own signals off the SMs
   const int grid = max_ctas > 0 ? min(max_ctas, 2 * NUM_SMS_B200) : 2 * NUM_SMS_B200;
+  const int nred8 = g_xchg_nred_eighths > 0 ? g_xchg_nred_eighths : (x.world >= 4 ? 1 : 2);
 #define SFB_XF(DD, MCV, SHV, WV)                                                                                    \
   do {                                                                                                              \
     if (g_xchg_depth == 16)                                                                                         \
-      xchg_finish_kernel<DD, MCV, SHV, WV, 16><<<grid, 256, 0, s>>>(x, epoch, g_xchg_nred_eighths, x.world, M, means3D, campos, \
+      xchg_finish_kernel<DD, MCV, SHV, WV, 16><<<grid, 256, 0, s>>>(x, epoch, nred8, x.world, M, means3D, campos, \
                                                                     dL_dmeans3D, dL_dopacity, dL_dscales, dL_drot, dL_dcolors, dL_dsh); \
     else                                                                                                            \
-      xchg_finish_kernel<DD, MCV, SHV, WV, 4><<<grid, 256, 0, s>>>(x, epoch, g_xchg_nred_eighths, x.world, M, means3D, campos, \
+      xchg_finish_kernel<DD, MCV, SHV, WV, 4><<<grid, 256, 0, s>>>(x, epoch, nred8, x.world, M, means3D, campos, \
                                                                    dL_dmeans3D, dL_dopacity, dL_dscales, dL_drot, dL_dcolors, dL_dsh); \
   } while (0)
 #define SFB_XD(DD)                                                                                                  \
