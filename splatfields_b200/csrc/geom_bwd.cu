@@ -46,22 +46,6 @@ __device__ __forceinline__ void geom_backward_block(const BwdParams& p, const Ge
   // depends on it: one memory round trip instead of three dependent ones (ncu, round 2: 21 % of the kernel's stall samples
   // sat on the first use of the radius and of the rotation / scale).  Four of five splats are visible and the rows of
   // neighbouring splats share their 128-byte lines, so the unconditional loads add next to no DRAM traffic.
-  // ... and the same inputs of the splats ~150 k further on (two waves of blocks later) are pulled into L2 now: radius,
-  // accumulator record, mean, rotation, scale = 1 + 12 + 3 + 4 + 3 lines per warp of 32 splats, one prefetch per lane.
-  {
-    constexpr int LOOKAHEAD = 2 * NUM_SMS_B200 * 2 * 256;
-    const int lane = threadIdx.x & 31;
-    const long long w0 = (long long)(idx - lane) + LOOKAHEAD;
-    if (w0 + 32 <= (long long)p.P && lane < 23 && !p.cov3D_precomp) {
-      const char* ptr;
-      if (lane < 12) ptr = reinterpret_cast<const char*>(g.grad + w0) + 128 * lane;
-      else if (lane < 15) ptr = reinterpret_cast<const char*>(p.means3D + 3 * w0) + 128 * (lane - 12);
-      else if (lane < 19) ptr = reinterpret_cast<const char*>(p.rotations + 4 * w0) + 128 * (lane - 15);
-      else if (lane < 22) ptr = reinterpret_cast<const char*>(p.scales + 3 * w0) + 128 * (lane - 19);
-      else ptr = reinterpret_cast<const char*>(p.radii + w0);
-      prefetch_l2(ptr);
-    }
-  }
   int rad = 0;
   float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
   float mean[3] = {0.f, 0.f, 0.f};

@@ -127,23 +127,8 @@ __device__ __forceinline__ void preprocess_body(const FwdParams& p, const GeomSt
   __syncthreads();
 
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  // Look-ahead L2 prefetch: the inputs of the splats some 230 k further on (the blocks that run two waves later) are
-  // pulled into L2 now, so that their first — unavoidable — round trip is an L2 hit instead of a DRAM access (ncu, round
-  // 2: ~20 % of the kernel's stall samples sit on the first use of the mean and of the rotation / scale).  Per warp the
-  // 32 splats cover 3 + 4 + 3 + 1 lines of means / rotations / scales / opacities: one prefetch each from lanes 0..10.
-  {
-    constexpr int LOOKAHEAD = 2 * NUM_SMS_B200 * 3 * 256;
-    const int lane = threadIdx.x & 31;
-    const long long w0 = (long long)(idx - lane) + LOOKAHEAD;          // first splat of this warp's look-ahead group
-    if (w0 + 32 <= (long long)p.P && lane < 11 && !p.cov3D_precomp) {
-      const char* ptr;
-      if (lane < 3) ptr = reinterpret_cast<const char*>(p.means3D + 3 * w0) + 128 * lane;
-      else if (lane < 7) ptr = reinterpret_cast<const char*>(p.rotations + 4 * w0) + 128 * (lane - 3);
-      else if (lane < 10) ptr = reinterpret_cast<const char*>(p.scales + 3 * w0) + 128 * (lane - 7);
-      else ptr = reinterpret_cast<const char*>(p.opacities + w0);
-      prefetch_l2(ptr);
-    }
-  }
+  // (A look-ahead L2 prefetch of the inputs of the blocks two waves further on was measured in round 2: no gain here,
+  //  +8 us in the geometry backward — the first round trip is not where the remaining time goes.)
   uint32_t my_tiles = 0, my_key = 0xFFFFFFFFu;
   if (idx < p.P) {
     int out_radius = 0;
