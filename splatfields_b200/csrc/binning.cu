@@ -535,6 +535,9 @@ duplicate_kernel(int P, int grid_x, SortedIdx sorted,
     for (int i = t0 + threadIdx.x; i < t1; i += DUP_THREADS) ranges_init[i] = make_uint2(0xFFFFFFFFu, 0u);
   }
   const uint32_t* __restrict__ sorted_idx = sorted.get();
+  // (Counting the tile sort's digit histograms here, where every key's tile is known, instead of a separate pass over the
+  //  R keys was measured in round 2: the shared-memory atomics cost this kernel more than the histogram pass saves —
+  //  +12 us against -17 us at 9 M keys, +73 against -64 us at 37 M; profiles/r02f_quick_perf_hist_in_duplicate.jsonl.)
   const bool fast_div = T <= (1 << 16);
   __shared__ uint32_t s_pref[DUP_GPB + 1];
   __shared__ uint32_t s_gidx[DUP_GPB];
