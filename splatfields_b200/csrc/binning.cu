@@ -137,7 +137,10 @@ radix_hist_all_kernel(uint32_t* __restrict__ keys, int n, int npass, int4 shifts
 // shuffle dependency that serialises the rounds is IPT/CH long; the counters of the chains are stitched together by
 // the per-digit exclusive prefix that already runs over the warps.
 template <int IPT, int VM, int NB>
-__global__ void __launch_bounds__(SORT_THREADS, 3)
+// Bare-key passes (the tile sort of packed instances) hold no value registers and run at 64 registers / 4 CTAs per SM
+// (28-72 bytes of spills; 0.119 -> 0.116 ms at 9 M keys, 0.431 -> 0.415 ms at 37 M); with the side byte of split
+// instances the same bound spills 128 bytes and gains nothing, so those and the pair sorts stay at 3.
+__global__ void __launch_bounds__(SORT_THREADS, (VM == 0 && IPT == 16) ? 4 : 3)
 onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const void* __restrict__ vals_in_v,
                      uint32_t* __restrict__ keys_out, void* __restrict__ vals_out_v, int merge_bits, int n, int shift, int bins,
                      const uint32_t* __restrict__ digit_totals /* [SORT_MAX_BINS] for this pass */,
