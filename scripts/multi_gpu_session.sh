@@ -1,5 +1,7 @@
 #!/bin/bash
-# Round-2 multi-GPU session for the fused backward + exchange kernel:  bash scripts/r2/multi3.sh <tag> <N> [full|lean]
+# Multi-GPU session (run under gpurun --gpus N):  bash scripts/multi_gpu_session.sh <tag> <N> [full|mid|lean]
+# exchange equivalence on real NVLink (scripts/check_exchange.py), bench with the default exchange (mid: + the fused
+# one-kernel variant; full: + without multicast), BASELINE configs[4] sharded over the ranks.
 TAG=${1:-r2f}
 N=${2:-2}
 MODE=${3:-full}

@@ -1,4 +1,4 @@
-"""Copy the evidence of one GPU session (gpurun_out/<session>/, written by scripts/gpu_profile.sh) into profiles/
+"""Copy the evidence of one GPU session (gpurun_out/<session>/, written by scripts/gpu_evidence_session.sh) into profiles/
 under a round tag, and derive the two tables bench.py / DESIGN.md cite:
   <tag>_launch_shares.txt   per-kernel share of the ncu launch list of the bench command
   ncu_traffic.json          dram read+write bytes per launch of every library kernel (ncu --set full capture)
