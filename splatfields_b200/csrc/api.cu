@@ -70,14 +70,6 @@ int redzones_check(const sfb::RedzoneList& rz, cudaStream_t s) {
   return -1;
 }
 
-bool knob_on(const char* name, bool dflt) {     // "0" / "1" environment knobs
-  const char* e = getenv(name);
-  if (!e || !e[0]) return dflt;
-  return e[0] != '0';
-}
-
-bool tight_rect_enabled() { static int v = -1; if (v < 0) v = knob_on("SFB_TIGHT_RECT", false); return v == 1; }
-
 int tile_sort_final(int T) {
   int bits = sfb::tile_bits(T);
   int npass = (bits + 7) / 8;
@@ -176,7 +168,6 @@ int sfb_rasterize_forward(int P, int sh_degree, int M, int W, int H, const float
   fp.scales = scales; fp.rotations = rotations; fp.cov3D_precomp = cov3D_precomp;
   fp.viewmatrix = viewmatrix; fp.projmatrix = projmatrix; fp.campos = campos;
   fp.scale_modifier = scale_modifier; fp.tan_fovx = tan_fovx; fp.tan_fovy = tan_fovy; fp.prefiltered = prefiltered;
-  fp.tight_rect = tight_rect_enabled() ? 1 : 0;
   fp.wide256 = shs && ((M * 12) % 32 == 0) && ((reinterpret_cast<size_t>(shs) & 31) == 0);
   // the depth sort's scratch is cleared by the preprocess blocks on their way (one memset node less)
   const size_t dzero = radix_sort_zero_words(P, 32);

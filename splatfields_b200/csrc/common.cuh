@@ -368,7 +368,6 @@ struct FwdParams {
   float scale_modifier, tan_fovx, tan_fovy;
   int prefiltered;
   int wide256;      // SH rows are 32-byte aligned multiples of 32 bytes: use 256-bit loads
-  int tight_rect;   // SFB_TIGHT_RECT=1 (opt-in): tile rectangles clipped to the alpha >= 1/255 footprint box
   uint32_t* zero_ptr;     // or nullptr: words the kernel's blocks clear as a prologue (the depth sort's scratch)
   uint32_t zero_words;
   uint32_t* nr_host;      // or nullptr: pinned host word; the last block to finish stores num_rendered there

@@ -105,11 +105,9 @@ __device__ __forceinline__ void sh_to_rgb(const float* sh, float3 mean, const fl
 
 // (A bulk-copy (cp.async.bulk) staging of the block's SH slab was measured equal to the L2-prefetch + 256-bit-load path
 // used here — 85 vs 86 us at 1M splats, round 1 — while costing 48 KB of shared memory per CTA; it was removed.)
-// TIGHT (opt-in, SFB_TIGHT_RECT=1; NOT reference-identical lists): the tile rectangle is intersected with the
-// footprint box below, so tiles in which the splat provably fails the alpha >= 1/255 test on every pixel are never
-// emitted.  The image and the gradients do not change (those tiles' instances are no-ops), but tiles_touched / R / the
-// key and index buffers shrink, which is why it is a separate instantiation and off by default.
-template <int D, bool VEC_SH, bool TIGHT>
+// (Clipping the tile rectangle to the alpha >= 1/255 footprint box — fewer instances, same image — was an opt-in of round 1;
+// it changes tiles_touched / R / the key and index buffers, i.e. it is not reference-identical, and was removed.)
+template <int D, bool VEC_SH>
 __device__ __forceinline__ void preprocess_body(const FwdParams& p, const GeomState& g, int* __restrict__ radii) {
   __shared__ Cam cam;
   __shared__ uint32_t s_tiles[8];
@@ -261,17 +259,6 @@ __device__ __forceinline__ void preprocess_body(const FwdParams& p, const GeomSt
             hx = ill ? 3.0e38f : 1.02f * sqrtf(tau * a) + 0.5f;
             hy = ill ? 3.0e38f : 1.02f * sqrtf(tau * c) + 0.5f;
           }
-          if (TIGHT && hx < 1.0e30f) {
-            if (hx < 0.f) { area = 0; }
-            else {   // pixel centres sit on integers: pixel px can be touched only if |px - pix| <= hx
-              x0 = max(x0, clampi((int)floorf((pix - hx) / (float)TILE_X), 0, gx));
-              y0 = max(y0, clampi((int)floorf((piy - hy) / (float)TILE_Y), 0, gy));
-              x1 = min(x1, clampi((int)floorf((pix + hx) / (float)TILE_X) + 1, 0, gx));
-              y1 = min(y1, clampi((int)floorf((piy + hy) / (float)TILE_Y) + 1, 0, gy));
-              area = max(x1 - x0, 0) * max(y1 - y0, 0);
-            }
-            if (area == 0) { x0 = x1 = y0 = y1 = 0; }
-          }
           float4* rp = reinterpret_cast<float4*>(g.rec + idx);
           rp[0] = make_float4(pix, piy, conA, conB);
           rp[1] = make_float4(conC, opac, p_view.z, rgb[0]);
@@ -321,38 +308,19 @@ __device__ __forceinline__ void preprocess_body(const FwdParams& p, const GeomSt
   }
 }
 
-template <int D, bool VEC_SH, bool TIGHT = false>
+template <int D, bool VEC_SH>
 __global__ void __launch_bounds__(256)
 preprocess_kernel(FwdParams p, GeomState g, int* __restrict__ radii) {
-  preprocess_body<D, VEC_SH, TIGHT>(p, g, radii);
+  preprocess_body<D, VEC_SH>(p, g, radii);
 }
 
-// Opt-in occupancy variant (SFB_PRE_OCC4=1): the same body under __launch_bounds__(256, 4) — 64 registers and ~50 bytes
-// of spills for 4 instead of 3 resident CTAs per SM.  The kernel is load-latency-bound at 33 % occupancy; whether the
-// extra warps pay for the spills is an A/B for the next GPU session.  (A wrapper of its own: putting the bound on the
-// shared template changes the default's register allocation.)
-template <int D>
-__global__ void __launch_bounds__(256, 4)
-preprocess_kernel_occ4(FwdParams p, GeomState g, int* __restrict__ radii) {
-  preprocess_body<D, true, false>(p, g, radii);
-}
-
-static bool pre_occ4_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SFB_PRE_OCC4"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
-
+// (A variant of the same body under __launch_bounds__(256, 4) — 64 registers, ~50 bytes of spills, 4 instead of 3 resident
+// CTAs per SM — was measured in round 2: 0.086 vs 0.087 ms, no gain, removed.)
 template <int D>
 static void launch_pre_d(const FwdParams& p, const GeomState& g, int* radii, cudaStream_t s) {
   int blocks = (p.P + 255) / 256;
   bool vec = p.shs && ((p.M * 3) % 4 == 0) && ((reinterpret_cast<size_t>(p.shs) & 15) == 0);
-  if (vec && !p.tight_rect && pre_occ4_enabled()) {
-    preprocess_kernel_occ4<D><<<blocks, 256, 0, s>>>(p, g, radii);
-  } else if (p.tight_rect) {
-    if (vec) preprocess_kernel<D, true, true><<<blocks, 256, 0, s>>>(p, g, radii);
-    else     preprocess_kernel<D, false, true><<<blocks, 256, 0, s>>>(p, g, radii);
-  } else if (vec) {
+  if (vec) {
     preprocess_kernel<D, true><<<blocks, 256, 0, s>>>(p, g, radii);
   } else {
     preprocess_kernel<D, false><<<blocks, 256, 0, s>>>(p, g, radii);

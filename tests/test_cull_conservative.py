@@ -67,9 +67,11 @@ def test_patch_culling_never_drops_a_contributing_pair(seed, smax, off):
 
 @pytest.mark.parametrize("seed,smax", [(3, 40), (4, 150), (5, 6)])
 def test_tight_tile_rect_never_drops_a_contributing_tile(seed, smax):
-    """The opt-in SFB_TIGHT_RECT path (preprocess.cu, TIGHT instantiation) clips the reference's tile rectangle to the
-    footprint box.  Restated in float32 numpy (same expressions: floorf, +1 on the exclusive edge, clamps to the grid)
-    and checked by brute force: no pixel of a dropped tile passes the reference's alpha >= 1/255 test."""
+    """The footprint box preprocess stores per splat (SplatRec::hx, hy; the render kernels cull 8x4 patches with it) is
+    conservative at tile granularity too: clipping the reference's tile rectangle to it, restated in float32 numpy
+    (floorf, +1 on the exclusive edge, clamps to the grid), never drops a tile in which some pixel passes the
+    reference's alpha >= 1/255 test (brute force).  (Round 1 shipped that clip as an opt-in preprocess variant; it
+    changed the key / index buffers and was removed — the property it rests on is what the culling relies on.)"""
     N, gx, gy = 4000, 50, 50                     # 800x800 image
     rng = np.random.default_rng(seed)
     a, cc, A, B, C, op, ill, _, _ = _cases(seed, N, smax, 60)
