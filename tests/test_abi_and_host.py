@@ -133,3 +133,23 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "splat_oracle" not in txt, f
+
+
+def test_exchange_buffer_layout_sizes():
+    """sfb_xchg_bytes (host-only arithmetic, no GPU): the symmetric buffer holds the flag page, the chunk flags
+    ((16 + 1) words per 1024 splats), the packed records for both step parities and — with shs — the colour tables
+    for both parities and every rank; everything 256-byte aligned; identical on every rank (no rank argument)."""
+    _built()
+    from splatfields_b200 import _lib
+    lib = _lib.load()
+    al = lambda v: (v + 255) // 256 * 256
+    for P, world, ngeo, with_gc in ((1_000_000, 8, 12, 1), (1_000_000, 2, 12, 1), (2_000_000, 8, 16, 0), (7_777, 3, 12, 1),
+                                    (1, 2, 16, 0)):
+        nch = (P + 1023) // 1024
+        want = 256 + al(17 * nch * 4) + 2 * al(P * ngeo * 4)
+        if with_gc:
+            want += 2 * al(world * al(P * 3 * 4))
+        assert lib.sfb_xchg_bytes(P, world, ngeo, with_gc) == want, (P, world, ngeo, with_gc)
+    assert lib.sfb_xchg_bytes(100, 2, 13, 1) == 0          # records are 12 (shs) or 16 (colors_precomp) floats
+    d = _lib.XchgDesc()
+    assert hasattr(d, "campos_views") and _lib.XCHG_MAX_RANKS == 16
